@@ -1,0 +1,202 @@
+/*
+ * salve_bev.h -- C ABI of the B200-native BEV texture-map renderer (libsalve_bev.so).
+ *
+ * Drop-in boundary for ONE hot path of zillow/salve: equirectangular pano + depth ->
+ * Sim(2)-posed, height-cropped points -> BEV splat (z-order rule) -> linear densification ->
+ * hallucination mask.  The reference has no FFI for this path (it is pure Python); each entry
+ * point below names the reference function(s) it replaces.  Paths are relative to the
+ * reference repository root.
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 on success or a negative SALVE_BEV_E_* code;
+ *     no exception crosses the boundary.  salve_bev_last_error() returns a static message.
+ *   - pointers named host_* are host memory, dev_* are device memory (cudaMalloc'ed by the caller,
+ *     e.g. a torch tensor's data_ptr()).  `stream` is a cudaStream_t passed as void* (NULL = the
+ *     legacy default stream).  Calls taking dev_* outputs are asynchronous on `stream`;
+ *     calls taking host_* outputs synchronise `stream` before returning.
+ *   - the context owns all scratch memory; it is not thread-safe (one context per thread/stream).
+ *   - there is NO CPU fallback: without a CUDA device every entry point fails.
+ */
+#ifndef SALVE_BEV_H
+#define SALVE_BEV_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SALVE_BEV_OK 0
+#define SALVE_BEV_E_INVALID (-1)  /* bad argument */
+#define SALVE_BEV_E_CUDA (-2)     /* CUDA runtime error (see salve_bev_last_error) */
+#define SALVE_BEV_E_CAPACITY (-3) /* request exceeds what the context was created for */
+#define SALVE_BEV_E_NODEVICE (-4) /* no CUDA device */
+
+/* per-image status written by the render calls */
+#define SALVE_BEV_IMG_OK 0
+#define SALVE_BEV_IMG_EMPTY 1      /* no point inside the BEV box: reference returns None (bev_rendering_utils.py:279-280) */
+#define SALVE_BEV_IMG_DEGENERATE 2 /* <4 sites, all in one row or one column: zero image (interpolation_utils.py:37-42) */
+#define SALVE_BEV_IMG_COLLINEAR 3  /* sites on one oblique line: the reference's Qhull call raises */
+
+/* per-image counters, SALVE_BEV_NCOUNTS int32 each */
+#define SALVE_BEV_NCOUNTS 8
+#define SALVE_BEV_CNT_CROP 0     /* points inside the height band      (bev_rendering_utils.py:408-413) */
+#define SALVE_BEV_CNT_BBOX 1     /* ... and inside the BEV box         (bev_rendering_utils.py:38-45)   */
+#define SALVE_BEV_CNT_SITES 2    /* distinct pixels after the z-order rule (zorder_utils.py:49-83)      */
+#define SALVE_BEV_CNT_NONEMPTY 3 /* sites counted non-empty by the uint8 product (interpolation_utils.py:95) */
+#define SALVE_BEV_CNT_KEEP 4     /* pixels of the hallucination keep-mask (interpolation_utils.py:101-115) */
+#define SALVE_BEV_CNT_TRIS 5     /* real Delaunay triangles */
+#define SALVE_BEV_CNT_ROUNDS 6   /* parallel flip rounds */
+#define SALVE_BEV_CNT_FLIPS 7    /* edge flips */
+
+#define SALVE_BEV_SURF_FLOOR 1   /* z band (-inf, -1.0]   (bev_rendering_utils.py:560-562) */
+#define SALVE_BEV_SURF_CEILING 2 /* z band (0.5, +inf)    (bev_rendering_utils.py:564-566) */
+
+typedef struct salve_bev_ctx salve_bev_ctx;
+
+typedef struct salve_bev_config {
+    int32_t device;       /* CUDA device ordinal */
+    int32_t pano_h;       /* equirect height; reference: 512 (bev_rendering_utils.py:373-375) */
+    int32_t pano_w;       /* equirect width;  reference: 1024 */
+    int32_t max_panos;    /* resident pano slots */
+    int32_t max_images;   /* BEV images rendered per internal chunk (scratch is sized for this) */
+    int32_t grid_h;       /* BEV image rows    = BEVParams.img_h + 1 (bev_rendering_utils.py:292): 501 */
+    int32_t grid_w;       /* BEV image columns = BEVParams.img_w + 1: 501 */
+    int32_t kernel_sz;    /* hallucination box size K (interpolation_utils.py:15): 11 */
+    double xmin, ymin;    /* BEV box lower corner, metres (bevparams.py:57-61): -5, -5 */
+    double xmax, ymax;    /* upper corner: 5, 5 */
+    double px_per_m;      /* Sim(2) scale 1/meters_per_px (bevparams.py:78): 50.0 */
+    float depth_scale;    /* float32 multiplier of the uint16 depth (bev_rendering_utils.py:367,611): 0.001f */
+    int32_t crop_rows;    /* int(pano_h * crop_ratio) rows dropped top and bottom (bev_rendering_utils.py:397-401): 80 */
+} salve_bev_config;
+
+/* Fill `cfg` with the reference defaults for a pano of (pano_h, pano_w). */
+void salve_bev_default_config(salve_bev_config* cfg, int32_t pano_h, int32_t pano_w);
+
+const char* salve_bev_last_error(void);
+
+int salve_bev_ctx_create(const salve_bev_config* cfg, salve_bev_ctx** out);
+void salve_bev_ctx_destroy(salve_bev_ctx* ctx);
+
+/*
+ * Unit-sphere factor tables: x = cos_phi[v]*cos_theta[u], y = cos_phi[v]*sin_theta[u],
+ * z = neg_sin_phi[v].  Replaces salve/utils/hohonet_pano_utils.py:10-44 (get_uni_sphere_xyz).
+ * The context computes them itself with libm at creation; a caller that must match numpy's
+ * trig bit-for-bit (the Python layer does) passes numpy's values here.  Host pointers,
+ * pano_h / pano_w doubles.
+ */
+int salve_bev_set_sphere_tables(salve_bev_ctx* ctx, const double* host_cos_phi, const double* host_neg_sin_phi,
+                                const double* host_cos_theta, const double* host_sin_theta);
+/* Write the (pano_h, pano_w, 3) float64 unit-sphere table to host memory (get_uni_sphere_xyz). */
+int salve_bev_get_uni_sphere_xyz(salve_bev_ctx* ctx, double* host_out);
+
+/*
+ * Pano slots.  rgb: (pano_h, pano_w, 3) uint8; depth: (pano_h, pano_w) uint16 millimetres --
+ * what imageio.imread returns at bev_rendering_utils.py:367,370.
+ */
+int salve_bev_upload_pano(salve_bev_ctx* ctx, int32_t slot, const uint8_t* host_rgb, const uint16_t* host_depth, void* stream);
+/* Alias device memory owned by the caller instead of copying (must stay valid while used). */
+int salve_bev_bind_pano(salve_bev_ctx* ctx, int32_t slot, const uint8_t* dev_rgb, const uint16_t* dev_depth);
+
+/*
+ * Render alignment hypotheses.  Replaces render_bev_pair (bev_rendering_utils.py:417-480), once per
+ * requested surface, for n_hyp hypotheses in one call.
+ *   pano1/pano2 : slot of pano i1 / i2 per hypothesis
+ *   R           : n_hyp x 4 float32, i2Ti1 rotation row-major (salve/common/sim2.py:50)
+ *   t           : n_hyp x 2 float32, i2Ti1 translation (un-scaled; the x1.5 of
+ *                 bev_rendering_utils.py:448-451 is applied inside)
+ *   surfaces    : SALVE_BEV_SURF_FLOOR | SALVE_BEV_SURF_CEILING
+ * Output image order per hypothesis: for each requested surface (floor first): img1 (pano 1 posed
+ * into pano 2's frame), img2 (pano 2).  So n_img = n_hyp * nsurf * 2 images of grid_h*grid_w*3 uint8,
+ * rows already flipped (np.flipud, bev_rendering_utils.py:319).
+ *   dev_out     : n_img * grid_h * grid_w * 3 bytes
+ *   dev_counts  : n_img * SALVE_BEV_NCOUNTS int32 (may be NULL)
+ *   dev_status  : n_img int32 SALVE_BEV_IMG_* (may be NULL)
+ * Any n_hyp is accepted; the work is cut into chunks of max_images images.
+ */
+int salve_bev_render_hypotheses(salve_bev_ctx* ctx, int32_t n_hyp, const int32_t* host_pano1, const int32_t* host_pano2,
+                                const float* host_R, const float* host_t, uint32_t surfaces, uint8_t* dev_out,
+                                int32_t* dev_counts, int32_t* dev_status, void* stream);
+/* Same, with host output buffers (device->host copies included; synchronises). */
+int salve_bev_render_hypotheses_host(salve_bev_ctx* ctx, int32_t n_hyp, const int32_t* host_pano1, const int32_t* host_pano2,
+                                     const float* host_R, const float* host_t, uint32_t surfaces, uint8_t* host_out,
+                                     int32_t* host_counts, int32_t* host_status, void* stream);
+
+/*
+ * Render individual images: image k = pano slot[k], surface[k] (SALVE_BEV_SURF_*), posed[k] != 0 ->
+ * apply (R[k], t[k]) as for pano 1 of a pair.  Replaces get_xyzrgb_from_depth + the frame change of
+ * render_bev_pair + render_bev_image (bev_rendering_utils.py:347-414, 443-451, 254-328).
+ */
+int salve_bev_render_images_host(salve_bev_ctx* ctx, int32_t n_img, const int32_t* host_slot, const int32_t* host_surface,
+                                 const int32_t* host_posed, const float* host_R, const float* host_t, uint8_t* host_out,
+                                 int32_t* host_counts, int32_t* host_status, void* stream);
+
+/*
+ * Height-crop + stream compaction: replaces get_xyzrgb_from_depth (bev_rendering_utils.py:347-414).
+ * Keeps z_lo < z <= z_hi after dropping crop_rows rows top and bottom.  First call with
+ * host_xyzrgb == NULL to get *n_out, then with a buffer of n_out*6 doubles (x,y,z,r/255,g/255,b/255),
+ * points in pano raster order.
+ */
+int salve_bev_backproject(salve_bev_ctx* ctx, int32_t slot, double z_lo, double z_hi, double* host_xyzrgb, int64_t* n_out,
+                          void* stream);
+
+/*
+ * Render an arbitrary coloured cloud: replaces render_bev_image (bev_rendering_utils.py:254-328).
+ * host_xyzrgb: n x 6 float64 (rgb in [0,1]).  n < 2^29.  One image to host_out.
+ */
+int salve_bev_render_cloud_host(salve_bev_ctx* ctx, const double* host_xyzrgb, int64_t n, uint8_t* host_out,
+                                int32_t* host_counts, int32_t* host_status, void* stream);
+
+/*
+ * Z-order rule on explicit arrays: replaces choose_elevated_repeated_vals (zorder_utils.py:10-83).
+ * x, y: pixel coordinates (>= 0); valid[i] = 1 iff point i wins its pixel.
+ */
+int salve_bev_choose_elevated(salve_bev_ctx* ctx, const int64_t* host_x, const int64_t* host_y, const double* host_z, int64_t n,
+                              double zmin, double zmax, int32_t num_slices, uint8_t* host_valid, void* stream);
+
+/*
+ * Sparse -> dense: replaces interp_dense_grid_from_sparse (interpolation_utils.py:21-54) for
+ * method="linear".  points: n x 2 int64 (x = column, y = row), distinct; values: n x 3 float64
+ * (truncated to uint8 like interpolation_utils.py:53).  grid_h*grid_w <= 2^20, grid_w <= 2047,
+ * grid_h <= 1023.  host_img: grid_h x grid_w x 3 uint8, fully overwritten unless *status ==
+ * SALVE_BEV_IMG_DEGENERATE (then untouched, as in the reference).  host_hull (may be NULL):
+ * grid_h x grid_w uint8, 1 inside the closed convex hull.
+ */
+int salve_bev_interp_dense(salve_bev_ctx* ctx, const int64_t* host_points_xy, const double* host_values, int64_t n,
+                           int32_t grid_h, int32_t grid_w, uint8_t* host_img, uint8_t* host_hull, int32_t* status, void* stream);
+
+/*
+ * Hallucination mask: replaces remove_hallucinated_content (interpolation_utils.py:74-122).
+ * sparse, interp, out: h x w x 3 uint8.  K odd.
+ */
+int salve_bev_remove_hallucinated(salve_bev_ctx* ctx, const uint8_t* host_sparse, const uint8_t* host_interp, int32_t h, int32_t w,
+                                  int32_t K, uint8_t* host_out, void* stream);
+
+/*
+ * Stage taps of the most recent render call (parity tests).  image = index within the last chunk.
+ * what: see SALVE_BEV_TAP_*.  host_buf must be large enough (sizes in comments, g = grid_h*grid_w,
+ * wpr = (grid_w+31)/32).
+ */
+#define SALVE_BEV_TAP_KEYGRID 0  /* g uint32: (slice<<29 | source index) + 1 of the winner, 0 = empty */
+#define SALVE_BEV_TAP_COLOR 1    /* g uint32: r | g<<8 | b<<16 | 0xFF<<24 at sites, 0 elsewhere */
+#define SALVE_BEV_TAP_OCC 2      /* grid_h*wpr uint32 bit rows: site present */
+#define SALVE_BEV_TAP_NONEMPTY 3 /* same layout: uint8 product != 0 */
+#define SALVE_BEV_TAP_KEEP 4     /* same layout: hallucination keep-mask */
+#define SALVE_BEV_TAP_TRIS 5     /* (2*sites-2) x 3 int32 vertex pixel ids row*grid_w+col, -1 = ghost (hull) */
+#define SALVE_BEV_TAP_INTERP 6   /* g*3 uint8: interpolated image before mask and flip */
+#define SALVE_BEV_TAP_HULL 7     /* g uint8: inside closed convex hull */
+int salve_bev_tap(salve_bev_ctx* ctx, int32_t image, int32_t what, void* host_buf, int64_t host_buf_bytes, void* stream);
+
+/* Per-stage device time (ms, CUDA events) of the most recent render call, summed over its chunks:
+ * [0] splat  [1] sites+zipper+mask  [2] flip  [3] raster  [4] total.  host_ms: 5 floats. */
+int salve_bev_last_timings(salve_bev_ctx* ctx, float* host_ms);
+/* Enable/disable per-stage event timing (off by default: events add sync points at read time only). */
+int salve_bev_enable_timing(salve_bev_ctx* ctx, int32_t on);
+
+/* Number of kernel launches issued by this context since creation (bench.py's gpu_launches). */
+int64_t salve_bev_launch_count(salve_bev_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SALVE_BEV_H */

@@ -117,7 +117,6 @@ def choose_elevated(x, y, z, zmin=-2.0, zmax=2.0, num_slices=4) -> np.ndarray:
     w = int(x.max()) + 1 if n else 1
     pix = y.astype(np.int64) * w + x.astype(np.int64)
     key = sl * n + np.arange(n)
-    best = {}
     valid = np.zeros(n, bool)
     if not ok.any():
         return valid
@@ -139,7 +138,7 @@ class Stages:
     col: Optional[np.ndarray] = None  # (count_bbox,) pixel column
     row: Optional[np.ndarray] = None  # (count_bbox,) pixel row
     z: Optional[np.ndarray] = None  # (count_bbox,)
-    key_grid: Optional[np.ndarray] = None  # (IMG, IMG) int64: (slice<<21 | src_lin) + 1 of the winner, 0 = empty
+    key_grid: Optional[np.ndarray] = None  # (IMG, IMG) int64: (slice<<29 | src_lin) + 1 of the winner, 0 = empty
     site_rc: Optional[np.ndarray] = None  # (S,2) row, col -- ascending source index order (reference order)
     site_rgb: Optional[np.ndarray] = None  # (S,3) u8
     sparse: Optional[np.ndarray] = None  # (IMG,IMG,3) u8
@@ -224,7 +223,7 @@ def render_image(xyzrgb: np.ndarray, src: np.ndarray, W_pano: int, densify: bool
     planes = np.linspace(-2.0, 2.0, 5)
     sl = np.searchsorted(planes, z[valid], side="right") - 1
     st.key_grid = np.zeros((IMG, IMG), np.int64)
-    st.key_grid[row[valid], col[valid]] = ((sl << 21) | src[valid]) + 1
+    st.key_grid[row[valid], col[valid]] = ((sl << 29) | src[valid]) + 1
     site_xy = img_xy[valid]
     site_rgb = rgb[valid]
     st.site_rc = np.stack([site_xy[:, 1], site_xy[:, 0]], 1)

@@ -1,0 +1,720 @@
+// api.cu -- context, scratch management and the extern "C" entry points of libsalve_bev.so.
+// See include/salve_bev.h for the contract of each function and the reference code it replaces.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/salve_bev.h"
+#include "bev_common.cuh"
+#include "k_flip.cuh"
+#include "k_raster.cuh"
+#include "k_sites.cuh"
+#include "k_splat.cuh"
+
+using namespace bev;
+
+static thread_local char g_err[512] = "";
+static void set_err(const char* fmt, const char* a, const char* b, int line) { snprintf(g_err, sizeof(g_err), fmt, a, b, line); }
+#define CU(call)                                                                        \
+    do {                                                                                \
+        cudaError_t e_ = (call);                                                        \
+        if (e_ != cudaSuccess) {                                                        \
+            set_err("CUDA error: %s at %s (api.cu:%d)", cudaGetErrorString(e_), #call, __LINE__); \
+            return SALVE_BEV_E_CUDA;                                                    \
+        }                                                                               \
+    } while (0)
+#define FAIL(code, msg)                                 \
+    do {                                                \
+        set_err("%s%s (api.cu:%d)", msg, "", __LINE__); \
+        return (code);                                  \
+    } while (0)
+
+constexpr int N_TMP = 8;
+constexpr int N_STAGE_EVENTS = 5;
+
+struct salve_bev_ctx {
+    salve_bev_config cfg;
+    GridParams G;
+    size_t img_bytes;
+    // pano slots
+    uint8_t* pano_rgb_store = nullptr;
+    uint16_t* pano_depth_store = nullptr;
+    std::vector<const uint8_t*> h_rgb_ptr;
+    std::vector<const uint16_t*> h_depth_ptr;
+    const uint16_t** d_depth_ptr = nullptr;
+    bool ptr_dirty = true;
+    // sphere tables (cos_phi[H], neg_sin_phi[H], cos_theta[W], sin_theta[W])
+    double* d_tables = nullptr;
+    // per-image scratch (strides in elements)
+    uint32_t *keygrid = nullptr, *color = nullptr, *occ = nullptr, *nonempty = nullptr, *keep = nullptr, *tmpbits = nullptr;
+    uint16_t* wprefix = nullptr;
+    Tri* tris = nullptr;
+    unsigned long long* owner = nullptr;
+    uint32_t *list0 = nullptr, *list1 = nullptr, *cand = nullptr;
+    size_t g_stride = 0, bits_stride = 0, tris_stride = 0, cand_stride = 0;
+    ImgHeader* headers = nullptr;
+    int32_t* counts = nullptr;
+    int32_t* status = nullptr;
+    SplatJob* d_jobs = nullptr;
+    const uint8_t** d_color_src = nullptr;
+    uint8_t* out_store = nullptr;  // max_images images, for the *_host variants
+    // growable temporaries
+    void* tmp[N_TMP] = {nullptr};
+    size_t tmp_bytes[N_TMP] = {0};
+    // timing
+    bool timing = false;
+    std::vector<cudaEvent_t> events;  // N_STAGE_EVENTS per chunk of the last call
+    size_t events_used = 0;
+    int64_t launches = 0;
+    int last_chunk_images = 0;
+    size_t flip_smem = 0;
+};
+
+static int tmp_get(salve_bev_ctx* c, int slot, size_t bytes, void** out) {
+    if (c->tmp_bytes[slot] < bytes) {
+        if (c->tmp[slot]) CU(cudaFree(c->tmp[slot]));
+        c->tmp[slot] = nullptr; c->tmp_bytes[slot] = 0;
+        size_t want = std::max(bytes, (size_t)1 << 20);
+        CU(cudaMalloc(&c->tmp[slot], want));
+        c->tmp_bytes[slot] = want;
+    }
+    *out = c->tmp[slot];
+    return SALVE_BEV_OK;
+}
+
+extern "C" const char* salve_bev_last_error(void) { return g_err; }
+
+extern "C" void salve_bev_default_config(salve_bev_config* cfg, int32_t pano_h, int32_t pano_w) {
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->device = 0;
+    cfg->pano_h = pano_h; cfg->pano_w = pano_w;
+    cfg->max_panos = 64; cfg->max_images = 592;
+    cfg->grid_h = 501; cfg->grid_w = 501; cfg->kernel_sz = 11;
+    cfg->xmin = -5.0; cfg->ymin = -5.0; cfg->xmax = 5.0; cfg->ymax = 5.0; cfg->px_per_m = 1.0 / 0.02;
+    cfg->depth_scale = 0.001f;
+    cfg->crop_rows = (int32_t)(pano_h * (80.0 / 512.0));  // int(H * crop_ratio), bev_rendering_utils.py:399,613
+}
+
+static void compute_tables_libm(int H, int W, std::vector<double>& t) {
+    t.resize(2 * (size_t)H + 2 * (size_t)W);
+    const double pi = 3.141592653589793;
+    for (int v = 0; v < H; v++) {
+        double phi = (v + 0.5) / H; phi -= 0.5; phi *= pi;
+        t[v] = cos(phi); t[H + v] = -sin(phi);
+    }
+    for (int u = 0; u < W; u++) {
+        double th = -(u + 0.5) / W; th *= 2 * pi;
+        t[2 * H + u] = cos(th); t[2 * H + W + u] = sin(th);
+    }
+}
+
+extern "C" int salve_bev_ctx_create(const salve_bev_config* cfg, salve_bev_ctx** out) {
+    if (!cfg || !out) FAIL(SALVE_BEV_E_INVALID, "null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) FAIL(SALVE_BEV_E_NODEVICE, "no CUDA device: this library has no CPU fallback");
+    if (cfg->device < 0 || cfg->device >= ndev) FAIL(SALVE_BEV_E_INVALID, "bad device ordinal");
+    if (cfg->pano_h < 1 || cfg->pano_w < 4 || (cfg->pano_w & 3)) FAIL(SALVE_BEV_E_INVALID, "pano_w must be a positive multiple of 4");
+    if ((int64_t)cfg->pano_h * cfg->pano_w > ((int64_t)1 << KEY_IDX_BITS)) FAIL(SALVE_BEV_E_INVALID, "pano too large");
+    if (cfg->grid_h < 2 || cfg->grid_h > MAX_GRID_H || cfg->grid_w < 2 || cfg->grid_w > 2047 ||
+        (int64_t)cfg->grid_h * cfg->grid_w > (1 << 20))
+        FAIL(SALVE_BEV_E_INVALID, "grid must satisfy 2 <= grid_h <= 1023, 2 <= grid_w <= 2047, grid_h*grid_w <= 2^20");
+    if (cfg->kernel_sz < 1 || !(cfg->kernel_sz & 1) || cfg->kernel_sz > 63) FAIL(SALVE_BEV_E_INVALID, "kernel_sz must be odd, 1..63");
+    if (cfg->max_images < 1 || cfg->max_panos < 1) FAIL(SALVE_BEV_E_INVALID, "max_images/max_panos must be positive");
+    if (cfg->crop_rows < 0 || 2 * cfg->crop_rows >= cfg->pano_h) FAIL(SALVE_BEV_E_INVALID, "bad crop_rows");
+    CU(cudaSetDevice(cfg->device));
+    salve_bev_ctx* c = new salve_bev_ctx();
+    c->cfg = *cfg;
+    c->G.grid_h = cfg->grid_h; c->G.grid_w = cfg->grid_w; c->G.wpr = (cfg->grid_w + 31) / 32;
+    c->G.g = cfg->grid_h * cfg->grid_w; c->G.K = cfg->kernel_sz;
+    c->img_bytes = (size_t)c->G.g * 3;
+    const size_t H = cfg->pano_h, W = cfg->pano_w, P = cfg->max_panos, N = cfg->max_images, g = c->G.g;
+    c->g_stride = (g + 31) & ~(size_t)31;
+    c->bits_stride = ((size_t)c->G.grid_h * c->G.wpr + 31) & ~(size_t)31;
+    c->tris_stride = 2 * c->g_stride;
+    c->cand_stride = 3 * c->g_stride;
+#define ALLOC(ptr, count) CU(cudaMalloc((void**)&(ptr), sizeof(*(ptr)) * (size_t)(count)))
+    ALLOC(c->pano_rgb_store, P * H * W * 3);
+    ALLOC(c->pano_depth_store, P * H * W);
+    ALLOC(c->d_depth_ptr, P);
+    ALLOC(c->d_tables, 2 * H + 2 * W);
+    ALLOC(c->keygrid, N * c->g_stride);
+    ALLOC(c->color, N * c->g_stride);
+    ALLOC(c->occ, N * c->bits_stride);
+    ALLOC(c->nonempty, N * c->bits_stride);
+    ALLOC(c->keep, N * c->bits_stride);
+    ALLOC(c->tmpbits, N * c->bits_stride);
+    ALLOC(c->wprefix, N * c->bits_stride);
+    ALLOC(c->tris, N * c->tris_stride);
+    ALLOC(c->owner, N * c->tris_stride);
+    ALLOC(c->list0, N * c->tris_stride);
+    ALLOC(c->list1, N * c->tris_stride);
+    ALLOC(c->cand, N * c->cand_stride);
+    ALLOC(c->headers, N);
+    ALLOC(c->counts, N * 8);
+    ALLOC(c->status, N);
+    ALLOC(c->d_jobs, N);
+    ALLOC(c->d_color_src, N);
+    ALLOC(c->out_store, N * c->img_bytes);
+#undef ALLOC
+    c->h_rgb_ptr.assign(P, nullptr);
+    c->h_depth_ptr.assign(P, nullptr);
+    for (size_t s = 0; s < P; s++) {
+        c->h_rgb_ptr[s] = c->pano_rgb_store + s * H * W * 3;
+        c->h_depth_ptr[s] = c->pano_depth_store + s * H * W;
+    }
+    std::vector<double> t;
+    compute_tables_libm((int)H, (int)W, t);
+    CU(cudaMemcpy(c->d_tables, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
+    c->flip_smem = ((2 * g + 31) / 32) * 4 + 16;
+    CU(cudaFuncSetAttribute(flip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->flip_smem));
+    *out = c;
+    return SALVE_BEV_OK;
+}
+
+extern "C" void salve_bev_ctx_destroy(salve_bev_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->cfg.device);
+    cudaDeviceSynchronize();
+    void* ptrs[] = {c->pano_rgb_store, c->pano_depth_store, c->d_depth_ptr, c->d_tables, c->keygrid, c->color, c->occ, c->nonempty,
+                    c->keep, c->tmpbits, c->wprefix, c->tris, c->owner, c->list0, c->list1, c->cand, c->headers, c->counts,
+                    c->status, c->d_jobs, c->d_color_src, c->out_store};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    for (int i = 0; i < N_TMP; i++) if (c->tmp[i]) cudaFree(c->tmp[i]);
+    for (cudaEvent_t e : c->events) cudaEventDestroy(e);
+    delete c;
+}
+
+extern "C" int salve_bev_set_sphere_tables(salve_bev_ctx* c, const double* cp, const double* nsp, const double* ct, const double* st) {
+    if (!c || !cp || !nsp || !ct || !st) FAIL(SALVE_BEV_E_INVALID, "null argument");
+    const size_t H = c->cfg.pano_h, W = c->cfg.pano_w;
+    CU(cudaSetDevice(c->cfg.device));
+    CU(cudaMemcpy(c->d_tables, cp, H * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_tables + H, nsp, H * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_tables + 2 * H, ct, W * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_tables + 2 * H + W, st, W * sizeof(double), cudaMemcpyHostToDevice));
+    return SALVE_BEV_OK;
+}
+
+__global__ void sphere_xyz_kernel(const double* t, int H, int W, double* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= H * W) return;
+    const int v = i / W, u = i % W;
+    const double cphi = t[v];
+    out[i * 3 + 0] = __dmul_rn(cphi, t[2 * H + u]);
+    out[i * 3 + 1] = __dmul_rn(cphi, t[2 * H + W + u]);
+    out[i * 3 + 2] = t[H + v];
+}
+
+extern "C" int salve_bev_get_uni_sphere_xyz(salve_bev_ctx* c, double* host_out) {
+    if (!c || !host_out) FAIL(SALVE_BEV_E_INVALID, "null argument");
+    CU(cudaSetDevice(c->cfg.device));
+    const int H = c->cfg.pano_h, W = c->cfg.pano_w;
+    void* buf;
+    int rc = tmp_get(c, 0, (size_t)H * W * 3 * sizeof(double), &buf);
+    if (rc) return rc;
+    sphere_xyz_kernel<<<(H * W + 255) / 256, 256>>>(c->d_tables, H, W, (double*)buf);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(host_out, buf, (size_t)H * W * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    return SALVE_BEV_OK;
+}
+
+extern "C" int salve_bev_upload_pano(salve_bev_ctx* c, int32_t slot, const uint8_t* host_rgb, const uint16_t* host_depth, void* stream) {
+    if (!c || !host_rgb || !host_depth) FAIL(SALVE_BEV_E_INVALID, "null argument");
+    if (slot < 0 || slot >= c->cfg.max_panos) FAIL(SALVE_BEV_E_CAPACITY, "pano slot out of range");
+    CU(cudaSetDevice(c->cfg.device));
+    const size_t H = c->cfg.pano_h, W = c->cfg.pano_w;
+    uint8_t* drgb = c->pano_rgb_store + (size_t)slot * H * W * 3;
+    uint16_t* dd = c->pano_depth_store + (size_t)slot * H * W;
+    CU(cudaMemcpyAsync(drgb, host_rgb, H * W * 3, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    CU(cudaMemcpyAsync(dd, host_depth, H * W * 2, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    if (c->h_rgb_ptr[slot] != drgb || c->h_depth_ptr[slot] != dd) { c->h_rgb_ptr[slot] = drgb; c->h_depth_ptr[slot] = dd; c->ptr_dirty = true; }
+    return SALVE_BEV_OK;
+}
+
+extern "C" int salve_bev_bind_pano(salve_bev_ctx* c, int32_t slot, const uint8_t* dev_rgb, const uint16_t* dev_depth) {
+    if (!c || !dev_rgb || !dev_depth) FAIL(SALVE_BEV_E_INVALID, "null argument");
+    if (slot < 0 || slot >= c->cfg.max_panos) FAIL(SALVE_BEV_E_CAPACITY, "pano slot out of range");
+    if (((uintptr_t)dev_depth & 7) != 0) FAIL(SALVE_BEV_E_INVALID, "depth pointer must be 8-byte aligned");
+    c->h_rgb_ptr[slot] = dev_rgb; c->h_depth_ptr[slot] = dev_depth; c->ptr_dirty = true;
+    return SALVE_BEV_OK;
+}
+
+static SplatParams make_splat_params(salve_bev_ctx* c) {
+    SplatParams P;
+    const int H = c->cfg.pano_h, W = c->cfg.pano_w;
+    P.H = H; P.W = W; P.crop_rows = c->cfg.crop_rows; P.depth_scale = c->cfg.depth_scale;
+    P.xmin = c->cfg.xmin; P.ymin = c->cfg.ymin; P.xmax = c->cfg.xmax; P.ymax = c->cfg.ymax; P.px_per_m = c->cfg.px_per_m;
+    P.floor_hi = -1.0; P.ceil_lo = 0.5;  // bev_rendering_utils.py:560-566
+    P.grid_w = c->G.grid_w; P.g = c->G.g;
+    P.cos_phi = c->d_tables; P.neg_sin_phi = c->d_tables + H; P.cos_theta = c->d_tables + 2 * H; P.sin_theta = c->d_tables + 2 * H + W;
+    P.depth = c->d_depth_ptr;
+    return P;
+}
+
+static int sync_ptr_tables(salve_bev_ctx* c, cudaStream_t st) {
+    if (!c->ptr_dirty) return SALVE_BEV_OK;
+    CU(cudaMemcpyAsync(c->d_depth_ptr, c->h_depth_ptr.data(), sizeof(void*) * c->cfg.max_panos, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));  // the host vector may change before the copy is consumed
+    c->ptr_dirty = false;
+    return SALVE_BEV_OK;
+}
+
+static int stage_event(salve_bev_ctx* c, cudaStream_t st) {
+    if (!c->timing) return SALVE_BEV_OK;
+    if (c->events_used == c->events.size()) { cudaEvent_t e; CU(cudaEventCreate(&e)); c->events.push_back(e); }
+    CU(cudaEventRecord(c->events[c->events_used++], st));
+    return SALVE_BEV_OK;
+}
+
+// Stages 2-4 on images [0, n_img) of the scratch: sites+zipper+mask+base image, flips, raster.
+static int run_mesh_stages(salve_bev_ctx* c, int n_img, const GridParams& G, uint8_t* dev_out, int32_t* dev_counts, int32_t* dev_status,
+                           int raw_mode, int skip_empty, uint8_t* hull, cudaStream_t st) {
+    SitesArgs SA;
+    SA.G = G;
+    SA.keygrid = c->keygrid; SA.keygrid_stride = c->g_stride;
+    SA.color = c->color; SA.color_stride = c->g_stride;
+    SA.occ = c->occ; SA.nonempty = c->nonempty; SA.keep = c->keep; SA.tmpbits = c->tmpbits; SA.bits_stride = c->bits_stride;
+    SA.wprefix = c->wprefix;
+    SA.tris = c->tris; SA.tris_stride = c->tris_stride;
+    SA.headers = c->headers; SA.counts = dev_counts; SA.status = dev_status;
+    SA.color_src = c->d_color_src;
+    SA.out = dev_out; SA.out_stride = (size_t)G.g * 3;
+    SA.raw_mode = raw_mode; SA.skip_empty_check = skip_empty;
+    sites_kernel<<<n_img, SITES_NT, 0, st>>>(SA);
+    c->launches++;
+    CU(cudaGetLastError());
+    int rc = stage_event(c, st); if (rc) return rc;
+
+    FlipArgs FA;
+    FA.grid_w = G.grid_w;
+    FA.tris = c->tris; FA.tris_stride = c->tris_stride;
+    FA.owner = c->owner; FA.owner_stride = c->tris_stride;
+    FA.list0 = c->list0; FA.list1 = c->list1; FA.list_stride = c->tris_stride;
+    FA.cand = c->cand; FA.cand_stride = c->cand_stride;
+    FA.headers = c->headers; FA.counts = dev_counts;
+    flip_kernel<<<n_img, FLIP_NT, ((2 * (size_t)G.g + 31) / 32) * 4 + 16, st>>>(FA);
+    c->launches++;
+    CU(cudaGetLastError());
+    rc = stage_event(c, st); if (rc) return rc;
+
+    RasterArgs RA;
+    RA.G = G;
+    RA.tris = c->tris; RA.tris_stride = c->tris_stride;
+    RA.color = c->color; RA.color_stride = c->g_stride;
+    RA.keep = c->keep; RA.bits_stride = c->bits_stride;
+    RA.headers = c->headers; RA.counts = dev_counts;
+    RA.out = dev_out; RA.out_stride = (size_t)G.g * 3;
+    RA.hull = hull; RA.hull_stride = (size_t)G.g;
+    RA.raw_mode = raw_mode;
+    raster_kernel<<<n_img, RASTER_NT, 0, st>>>(RA);
+    c->launches++;
+    CU(cudaGetLastError());
+    return stage_event(c, st);
+}
+
+// One chunk of pano-sourced images.  jobs / color slots are host arrays.
+static int render_chunk(salve_bev_ctx* c, int n_img, const std::vector<SplatJob>& jobs, const std::vector<int>& img_slot, uint8_t* dev_out,
+                        int32_t* dev_counts, int32_t* dev_status, cudaStream_t st) {
+    if (n_img > c->cfg.max_images || (int)jobs.size() > c->cfg.max_images) FAIL(SALVE_BEV_E_CAPACITY, "chunk exceeds max_images");
+    int rc = sync_ptr_tables(c, st); if (rc) return rc;
+    std::vector<const uint8_t*> src(n_img);
+    for (int i = 0; i < n_img; i++) {
+        if (img_slot[i] < 0 || img_slot[i] >= c->cfg.max_panos) FAIL(SALVE_BEV_E_CAPACITY, "pano slot out of range");
+        src[i] = c->h_rgb_ptr[img_slot[i]];
+    }
+    CU(cudaMemcpyAsync(c->d_jobs, jobs.data(), sizeof(SplatJob) * jobs.size(), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->d_color_src, src.data(), sizeof(void*) * n_img, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));  // host vectors go out of scope; copies from pageable memory are staged anyway
+    if (!dev_counts) dev_counts = c->counts;
+    rc = stage_event(c, st); if (rc) return rc;
+    CU(cudaMemsetAsync(c->keygrid, 0, sizeof(uint32_t) * c->g_stride * n_img, st));
+    CU(cudaMemsetAsync(dev_counts, 0, sizeof(int32_t) * 8 * n_img, st));
+    SplatParams P = make_splat_params(c);
+    const int rows = P.H - 2 * P.crop_rows;
+    const int quads = rows * (P.W >> 2);
+    dim3 grid((quads + 255) / 256, (unsigned)jobs.size());
+    splat_pano_kernel<<<grid, 256, 0, st>>>(P, c->d_jobs, c->keygrid, c->g_stride, dev_counts);
+    c->launches++;
+    CU(cudaGetLastError());
+    rc = stage_event(c, st); if (rc) return rc;
+    c->last_chunk_images = n_img;
+    return run_mesh_stages(c, n_img, c->G, dev_out, dev_counts, dev_status, 0, 0, nullptr, st);
+}
+
+static int render_hyp_impl(salve_bev_ctx* c, int32_t n_hyp, const int32_t* p1, const int32_t* p2, const float* R, const float* t,
+                           uint32_t surfaces, uint8_t* out, int32_t* counts, int32_t* status, bool host_out, cudaStream_t st) {
+    if (!c || !p1 || !p2 || !R || !t || !out) FAIL(SALVE_BEV_E_INVALID, "null argument");
+    if (n_hyp < 0) FAIL(SALVE_BEV_E_INVALID, "negative n_hyp");
+    const bool do_f = surfaces & SALVE_BEV_SURF_FLOOR, do_c = surfaces & SALVE_BEV_SURF_CEILING;
+    const int nsurf = (int)do_f + (int)do_c;
+    if (nsurf == 0 || (surfaces & ~3u)) FAIL(SALVE_BEV_E_INVALID, "bad surface mask");
+    const int per_hyp = nsurf * 2;
+    const int hyp_per_chunk = c->cfg.max_images / per_hyp;
+    if (hyp_per_chunk < 1) FAIL(SALVE_BEV_E_CAPACITY, "max_images too small for one hypothesis");
+    CU(cudaSetDevice(c->cfg.device));
+    c->events_used = 0;
+    std::vector<SplatJob> jobs;
+    std::vector<int> slots;
+    for (int h0 = 0; h0 < n_hyp; h0 += hyp_per_chunk) {
+        const int nh = std::min(hyp_per_chunk, n_hyp - h0);
+        const int n_img = nh * per_hyp;
+        jobs.clear(); slots.assign(n_img, 0);
+        for (int k = 0; k < nh; k++) {
+            const int h = h0 + k;
+            const int base = k * per_hyp;
+            const int f1 = do_f ? base + 0 : -1, f2 = do_f ? base + 1 : -1;
+            const int c1 = do_c ? base + (do_f ? 2 : 0) : -1, c2 = do_c ? base + (do_f ? 3 : 1) : -1;
+            SplatJob a; a.pano_slot = p1[h]; a.posed = 1;
+            memcpy(a.R, R + 4 * (size_t)h, sizeof(float) * 4); memcpy(a.t, t + 2 * (size_t)h, sizeof(float) * 2);
+            a.img_floor = f1; a.img_ceil = c1;
+            SplatJob b; b.pano_slot = p2[h]; b.posed = 0;
+            b.R[0] = 1.f; b.R[1] = 0.f; b.R[2] = 0.f; b.R[3] = 1.f; b.t[0] = 0.f; b.t[1] = 0.f;
+            b.img_floor = f2; b.img_ceil = c2;
+            if (a.pano_slot < 0 || a.pano_slot >= c->cfg.max_panos || b.pano_slot < 0 || b.pano_slot >= c->cfg.max_panos)
+                FAIL(SALVE_BEV_E_CAPACITY, "pano slot out of range");
+            jobs.push_back(a); jobs.push_back(b);
+            if (f1 >= 0) { slots[f1] = a.pano_slot; slots[f2] = b.pano_slot; }
+            if (c1 >= 0) { slots[c1] = a.pano_slot; slots[c2] = b.pano_slot; }
+        }
+        const size_t img0 = (size_t)h0 * per_hyp;
+        uint8_t* d_out = host_out ? c->out_store : out + img0 * c->img_bytes;
+        int32_t* d_counts = host_out ? c->counts : (counts ? counts + img0 * 8 : nullptr);
+        int32_t* d_status = host_out ? c->status : (status ? status + img0 : nullptr);
+        int rc = render_chunk(c, n_img, jobs, slots, d_out, d_counts, d_status, st);
+        if (rc) return rc;
+        if (host_out) {
+            CU(cudaMemcpyAsync(out + img0 * c->img_bytes, c->out_store, (size_t)n_img * c->img_bytes, cudaMemcpyDeviceToHost, st));
+            if (counts) CU(cudaMemcpyAsync(counts + img0 * 8, c->counts, sizeof(int32_t) * 8 * n_img, cudaMemcpyDeviceToHost, st));
+            if (status) CU(cudaMemcpyAsync(status + img0, c->status, sizeof(int32_t) * n_img, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));  // out_store is reused by the next chunk
+        }
+    }
+    return SALVE_BEV_OK;
+}
+
+extern "C" int salve_bev_render_hypotheses(salve_bev_ctx* c, int32_t n_hyp, const int32_t* p1, const int32_t* p2, const float* R,
+                                           const float* t, uint32_t surfaces, uint8_t* dev_out, int32_t* dev_counts, int32_t* dev_status,
+                                           void* stream) {
+    return render_hyp_impl(c, n_hyp, p1, p2, R, t, surfaces, dev_out, dev_counts, dev_status, false, (cudaStream_t)stream);
+}
+extern "C" int salve_bev_render_hypotheses_host(salve_bev_ctx* c, int32_t n_hyp, const int32_t* p1, const int32_t* p2, const float* R,
+                                                const float* t, uint32_t surfaces, uint8_t* host_out, int32_t* host_counts,
+                                                int32_t* host_status, void* stream) {
+    return render_hyp_impl(c, n_hyp, p1, p2, R, t, surfaces, host_out, host_counts, host_status, true, (cudaStream_t)stream);
+}
+
+extern "C" int salve_bev_render_images_host(salve_bev_ctx* c, int32_t n_img, const int32_t* slot, const int32_t* surface,
+                                            const int32_t* posed, const float* R, const float* t, uint8_t* host_out, int32_t* host_counts,
+                                            int32_t* host_status, void* stream) {
+    if (!c || !slot || !surface || !posed || !R || !t || !host_out) FAIL(SALVE_BEV_E_INVALID, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(c->cfg.device));
+    c->events_used = 0;
+    std::vector<SplatJob> jobs;
+    std::vector<int> slots;
+    for (int i0 = 0; i0 < n_img; i0 += c->cfg.max_images) {
+        const int n = std::min(c->cfg.max_images, n_img - i0);
+        jobs.clear(); slots.assign(n, 0);
+        for (int k = 0; k < n; k++) {
+            const int i = i0 + k;
+            SplatJob j; j.pano_slot = slot[i]; j.posed = posed[i] ? 1 : 0;
+            memcpy(j.R, R + 4 * (size_t)i, sizeof(float) * 4); memcpy(j.t, t + 2 * (size_t)i, sizeof(float) * 2);
+            if (surface[i] == SALVE_BEV_SURF_FLOOR) { j.img_floor = k; j.img_ceil = -1; }
+            else if (surface[i] == SALVE_BEV_SURF_CEILING) { j.img_floor = -1; j.img_ceil = k; }
+            else FAIL(SALVE_BEV_E_INVALID, "surface must be SALVE_BEV_SURF_FLOOR or SALVE_BEV_SURF_CEILING");
+            if (j.pano_slot < 0 || j.pano_slot >= c->cfg.max_panos) FAIL(SALVE_BEV_E_CAPACITY, "pano slot out of range");
+            jobs.push_back(j); slots[k] = j.pano_slot;
+        }
+        int rc = render_chunk(c, n, jobs, slots, c->out_store, c->counts, c->status, st);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(host_out + (size_t)i0 * c->img_bytes, c->out_store, (size_t)n * c->img_bytes, cudaMemcpyDeviceToHost, st));
+        if (host_counts) CU(cudaMemcpyAsync(host_counts + (size_t)i0 * 8, c->counts, sizeof(int32_t) * 8 * n, cudaMemcpyDeviceToHost, st));
+        if (host_status) CU(cudaMemcpyAsync(host_status + i0, c->status, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return SALVE_BEV_OK;
+}
+
+extern "C" int salve_bev_backproject(salve_bev_ctx* c, int32_t slot, double z_lo, double z_hi, double* host_xyzrgb, int64_t* n_out,
+                                     void* stream) {
+    if (!c || !n_out) FAIL(SALVE_BEV_E_INVALID, "null argument");
+    if (slot < 0 || slot >= c->cfg.max_panos) FAIL(SALVE_BEV_E_CAPACITY, "pano slot out of range");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(c->cfg.device));
+    SplatParams P = make_splat_params(c);
+    const int rows = P.H - 2 * P.crop_rows;
+    const int total = rows * P.W;
+    const int nblk = (total + COMPACT_BLOCK - 1) / COMPACT_BLOCK;
+    void *bc, *bo;
+    int rc = tmp_get(c, 1, sizeof(int32_t) * nblk, &bc); if (rc) return rc;
+    rc = tmp_get(c, 2, sizeof(long long) * (nblk + 1), &bo); if (rc) return rc;
+    crop_count_kernel<<<nblk, COMPACT_BLOCK, 0, st>>>(P, c->h_depth_ptr[slot], z_lo, z_hi, (int32_t*)bc);
+    exclusive_scan_kernel<<<1, 1024, 0, st>>>((const int32_t*)bc, (long long*)bo, nblk);
+    c->launches += 2;
+    CU(cudaGetLastError());
+    long long total_kept = 0;
+    CU(cudaMemcpyAsync(&total_kept, (long long*)bo + nblk, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *n_out = total_kept;
+    if (!host_xyzrgb || total_kept == 0) return SALVE_BEV_OK;
+    void* ob;
+    rc = tmp_get(c, 0, sizeof(double) * 6 * (size_t)total_kept, &ob); if (rc) return rc;
+    crop_write_kernel<<<nblk, COMPACT_BLOCK, 0, st>>>(P, c->h_depth_ptr[slot], c->h_rgb_ptr[slot], z_lo, z_hi, (const long long*)bo, (double*)ob);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(host_xyzrgb, ob, sizeof(double) * 6 * (size_t)total_kept, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return SALVE_BEV_OK;
+}
+
+extern "C" int salve_bev_render_cloud_host(salve_bev_ctx* c, const double* host_xyzrgb, int64_t n, uint8_t* host_out, int32_t* host_counts,
+                                           int32_t* host_status, void* stream) {
+    if (!c || !host_out || (n > 0 && !host_xyzrgb)) FAIL(SALVE_BEV_E_INVALID, "null argument");
+    if (n < 0 || n >= ((int64_t)1 << KEY_IDX_BITS)) FAIL(SALVE_BEV_E_CAPACITY, "cloud too large (n < 2^29)");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(c->cfg.device));
+    c->events_used = 0;
+    void *dc, *drgb;
+    int rc = tmp_get(c, 0, sizeof(double) * 6 * (size_t)std::max<int64_t>(n, 1), &dc); if (rc) return rc;
+    rc = tmp_get(c, 3, 3 * (size_t)std::max<int64_t>(n, 1), &drgb); if (rc) return rc;
+    if (n) CU(cudaMemcpyAsync(dc, host_xyzrgb, sizeof(double) * 6 * (size_t)n, cudaMemcpyHostToDevice, st));
+    const uint8_t* src = (const uint8_t*)drgb;
+    CU(cudaMemcpyAsync(c->d_color_src, &src, sizeof(void*), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaMemsetAsync(c->keygrid, 0, sizeof(uint32_t) * c->g_stride, st));
+    CU(cudaMemsetAsync(c->counts, 0, sizeof(int32_t) * 8, st));
+    SplatParams P = make_splat_params(c);
+    if (n) {
+        splat_cloud_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P, (const double*)dc, n, c->keygrid, (uint8_t*)drgb, c->counts);
+        c->launches++;
+        CU(cudaGetLastError());
+    }
+    c->last_chunk_images = 1;
+    rc = run_mesh_stages(c, 1, c->G, c->out_store, c->counts, c->status, 0, 0, nullptr, st);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(host_out, c->out_store, c->img_bytes, cudaMemcpyDeviceToHost, st));
+    if (host_counts) CU(cudaMemcpyAsync(host_counts, c->counts, sizeof(int32_t) * 8, cudaMemcpyDeviceToHost, st));
+    if (host_status) CU(cudaMemcpyAsync(host_status, c->status, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return SALVE_BEV_OK;
+}
+
+extern "C" int salve_bev_choose_elevated(salve_bev_ctx* c, const int64_t* hx, const int64_t* hy, const double* hz, int64_t n, double zmin,
+                                         double zmax, int32_t num_slices, uint8_t* host_valid, void* stream) {
+    if (!c || (n > 0 && (!hx || !hy || !hz || !host_valid))) FAIL(SALVE_BEV_E_INVALID, "null argument");
+    if (num_slices < 1 || num_slices > 4096) FAIL(SALVE_BEV_E_INVALID, "bad num_slices");
+    if (n == 0) return SALVE_BEV_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(c->cfg.device));
+    int64_t xmax = 0, ymax = 0;
+    for (int64_t i = 0; i < n; i++) {
+        if (hx[i] < 0 || hy[i] < 0) FAIL(SALVE_BEV_E_INVALID, "negative pixel coordinate");
+        xmax = std::max(xmax, hx[i]); ymax = std::max(ymax, hy[i]);
+    }
+    const int64_t w = xmax + 1, h = ymax + 1;
+    if (w * h > ((int64_t)1 << 28)) FAIL(SALVE_BEV_E_CAPACITY, "z-order grid too large");
+    // np.linspace(zmin, zmax, num_slices + 1): start + i*step with the last element forced to zmax
+    std::vector<double> planes(num_slices + 1);
+    const double step = (zmax - zmin) / num_slices;
+    for (int i = 0; i <= num_slices; i++) planes[i] = zmin + i * step;
+    planes[num_slices] = zmax;
+    void *dx, *dy, *dz, *dp, *dg, *dv;
+    int rc;
+    if ((rc = tmp_get(c, 0, sizeof(int64_t) * n, &dx))) return rc;
+    if ((rc = tmp_get(c, 1, sizeof(int64_t) * n, &dy))) return rc;
+    if ((rc = tmp_get(c, 2, sizeof(double) * n, &dz))) return rc;
+    if ((rc = tmp_get(c, 3, sizeof(double) * (num_slices + 1), &dp))) return rc;
+    if ((rc = tmp_get(c, 4, sizeof(unsigned long long) * (size_t)(w * h), &dg))) return rc;
+    if ((rc = tmp_get(c, 5, (size_t)n, &dv))) return rc;
+    CU(cudaMemcpyAsync(dx, hx, sizeof(int64_t) * n, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(dy, hy, sizeof(int64_t) * n, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(dz, hz, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(dp, planes.data(), sizeof(double) * (num_slices + 1), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(dg, 0, sizeof(unsigned long long) * (size_t)(w * h), st));
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    zorder_mark_kernel<<<nb, 256, 0, st>>>((const long long*)dx, (const long long*)dy, (const double*)dz, n, (const double*)dp, num_slices, w,
+                                           (unsigned long long*)dg);
+    zorder_resolve_kernel<<<nb, 256, 0, st>>>((const long long*)dx, (const long long*)dy, (const double*)dz, n, (const double*)dp, num_slices,
+                                              w, (const unsigned long long*)dg, (uint8_t*)dv);
+    c->launches += 2;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(host_valid, dv, (size_t)n, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return SALVE_BEV_OK;
+}
+
+__global__ void base_raw_kernel(const uint32_t* __restrict__ color, int g, uint8_t* __restrict__ out) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= g) return;
+    const uint32_t cw = color[p];
+    out[p * 3 + 0] = (uint8_t)(cw & 0xFF); out[p * 3 + 1] = (uint8_t)((cw >> 8) & 0xFF); out[p * 3 + 2] = (uint8_t)((cw >> 16) & 0xFF);
+}
+
+extern "C" int salve_bev_interp_dense(salve_bev_ctx* c, const int64_t* host_xy, const double* host_values, int64_t n, int32_t grid_h,
+                                      int32_t grid_w, uint8_t* host_img, uint8_t* host_hull, int32_t* status, void* stream) {
+    if (!c || !host_img || !status || (n > 0 && (!host_xy || !host_values))) FAIL(SALVE_BEV_E_INVALID, "null argument");
+    GridParams G;
+    G.grid_h = grid_h; G.grid_w = grid_w; G.wpr = (grid_w + 31) / 32; G.g = grid_h * grid_w; G.K = c->G.K;
+    if (grid_h < 1 || grid_w < 1 || grid_h > MAX_GRID_H || grid_w > 2047 || (size_t)G.g > c->g_stride ||
+        (size_t)grid_h * G.wpr > c->bits_stride)
+        FAIL(SALVE_BEV_E_CAPACITY, "grid exceeds the context's scratch; create a context with this grid size");
+    if (n < 0 || n > ((int64_t)1 << 28)) FAIL(SALVE_BEV_E_CAPACITY, "too many points");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(c->cfg.device));
+    c->events_used = 0;
+    void *dxy, *dval, *drgb, *derr, *dhull = nullptr;
+    int rc;
+    if ((rc = tmp_get(c, 0, sizeof(int64_t) * 2 * (size_t)std::max<int64_t>(n, 1), &dxy))) return rc;
+    if ((rc = tmp_get(c, 1, sizeof(double) * 3 * (size_t)std::max<int64_t>(n, 1), &dval))) return rc;
+    if ((rc = tmp_get(c, 3, 3 * (size_t)std::max<int64_t>(n, 1), &drgb))) return rc;
+    if ((rc = tmp_get(c, 6, 64, &derr))) return rc;
+    if (host_hull) { if ((rc = tmp_get(c, 7, (size_t)G.g, &dhull))) return rc; CU(cudaMemsetAsync(dhull, 0, (size_t)G.g, st)); }
+    if (n) {
+        CU(cudaMemcpyAsync(dxy, host_xy, sizeof(int64_t) * 2 * (size_t)n, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(dval, host_values, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, st));
+    }
+    const uint8_t* src = (const uint8_t*)drgb;
+    CU(cudaMemcpyAsync(c->d_color_src, &src, sizeof(void*), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaMemsetAsync(derr, 0, sizeof(int), st));
+    CU(cudaMemsetAsync(c->keygrid, 0, sizeof(uint32_t) * c->g_stride, st));
+    CU(cudaMemsetAsync(c->counts, 0, sizeof(int32_t) * 8, st));
+    if (n) {
+        points_to_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const long long*)dxy, (const double*)dval, n, grid_h, grid_w,
+                                                                          c->keygrid, (uint8_t*)drgb, (int*)derr);
+        c->launches++;
+        CU(cudaGetLastError());
+    }
+    c->last_chunk_images = 1;
+    rc = run_mesh_stages(c, 1, G, c->out_store, c->counts, c->status, 1, 1, (uint8_t*)dhull, st);
+    if (rc) return rc;
+    int herr = 0, hstatus = 0;
+    CU(cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&hstatus, c->status, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (herr) FAIL(SALVE_BEV_E_INVALID, "point outside the grid");
+    *status = hstatus;
+    if (hstatus == SALVE_BEV_IMG_DEGENERATE) return SALVE_BEV_OK;  // image left untouched, like the reference
+    CU(cudaMemcpyAsync(host_img, c->out_store, (size_t)G.g * 3, cudaMemcpyDeviceToHost, st));
+    if (host_hull) CU(cudaMemcpyAsync(host_hull, dhull, (size_t)G.g, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return SALVE_BEV_OK;
+}
+
+extern "C" int salve_bev_remove_hallucinated(salve_bev_ctx* c, const uint8_t* host_sparse, const uint8_t* host_interp, int32_t h, int32_t w,
+                                             int32_t K, uint8_t* host_out, void* stream) {
+    if (!c || !host_sparse || !host_interp || !host_out) FAIL(SALVE_BEV_E_INVALID, "null argument");
+    if (h < 1 || w < 1 || K < 1 || !(K & 1)) FAIL(SALVE_BEV_E_INVALID, "bad shape or even K");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(c->cfg.device));
+    const size_t n = (size_t)h * w;
+    void *ds, *di, *dn, *dt, *dout;
+    int rc;
+    if ((rc = tmp_get(c, 0, n * 3, &ds))) return rc;
+    if ((rc = tmp_get(c, 1, n * 3, &di))) return rc;
+    if ((rc = tmp_get(c, 2, n, &dn))) return rc;
+    if ((rc = tmp_get(c, 3, n, &dt))) return rc;
+    if ((rc = tmp_get(c, 4, n * 3, &dout))) return rc;
+    CU(cudaMemcpyAsync(ds, host_sparse, n * 3, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(di, host_interp, n * 3, cudaMemcpyHostToDevice, st));
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    halluc_nonempty_kernel<<<nb, 256, 0, st>>>((const uint8_t*)ds, h, w, (uint8_t*)dn);
+    halluc_rowdilate_kernel<<<nb, 256, 0, st>>>((const uint8_t*)dn, h, w, K / 2, (uint8_t*)dt);
+    halluc_apply_kernel<<<nb, 256, 0, st>>>((const uint8_t*)dt, (const uint8_t*)di, h, w, K / 2, (uint8_t*)dout);
+    c->launches += 3;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(host_out, dout, n * 3, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return SALVE_BEV_OK;
+}
+
+extern "C" int salve_bev_tap(salve_bev_ctx* c, int32_t image, int32_t what, void* host_buf, int64_t host_buf_bytes, void* stream) {
+    if (!c || !host_buf) FAIL(SALVE_BEV_E_INVALID, "null argument");
+    if (image < 0 || image >= c->last_chunk_images) FAIL(SALVE_BEV_E_INVALID, "image index outside the last chunk");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(c->cfg.device));
+    const GridParams& G = c->G;
+    const size_t g = G.g, bits = (size_t)G.grid_h * G.wpr;
+    const void* src = nullptr; size_t bytes = 0;
+    switch (what) {
+        case SALVE_BEV_TAP_KEYGRID: src = c->keygrid + image * c->g_stride; bytes = g * 4; break;
+        case SALVE_BEV_TAP_COLOR: src = c->color + image * c->g_stride; bytes = g * 4; break;
+        case SALVE_BEV_TAP_OCC: src = c->occ + image * c->bits_stride; bytes = bits * 4; break;
+        case SALVE_BEV_TAP_NONEMPTY: src = c->nonempty + image * c->bits_stride; bytes = bits * 4; break;
+        case SALVE_BEV_TAP_KEEP: src = c->keep + image * c->bits_stride; bytes = bits * 4; break;
+        case SALVE_BEV_TAP_TRIS: {
+            ImgHeader hd;
+            CU(cudaMemcpyAsync(&hd, c->headers + image, sizeof(hd), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            bytes = (size_t)hd.n_tris * 3 * 4;
+            if ((int64_t)bytes > host_buf_bytes) FAIL(SALVE_BEV_E_CAPACITY, "tap buffer too small");
+            if (hd.n_tris == 0) return SALVE_BEV_OK;
+            void* d; int rc = tmp_get(c, 0, bytes, &d); if (rc) return rc;
+            tap_tris_kernel<<<(hd.n_tris + 255) / 256, 256, 0, st>>>(c->tris + image * c->tris_stride, hd.n_tris, G.grid_w, (int32_t*)d);
+            c->launches++;
+            CU(cudaGetLastError());
+            CU(cudaMemcpyAsync(host_buf, d, bytes, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            return SALVE_BEV_OK;
+        }
+        case SALVE_BEV_TAP_INTERP:
+        case SALVE_BEV_TAP_HULL: {
+            bytes = (what == SALVE_BEV_TAP_INTERP) ? g * 3 : g;
+            if ((int64_t)bytes > host_buf_bytes) FAIL(SALVE_BEV_E_CAPACITY, "tap buffer too small");
+            void *dimg, *dhull; int rc;
+            if ((rc = tmp_get(c, 0, g * 3, &dimg))) return rc;
+            if ((rc = tmp_get(c, 7, g, &dhull))) return rc;
+            CU(cudaMemsetAsync(dhull, 0, g, st));
+            base_raw_kernel<<<(unsigned)((g + 255) / 256), 256, 0, st>>>(c->color + image * c->g_stride, (int)g, (uint8_t*)dimg);
+            RasterArgs RA;
+            RA.G = G;
+            RA.tris = c->tris + image * c->tris_stride; RA.tris_stride = 0;
+            RA.color = c->color + image * c->g_stride; RA.color_stride = 0;
+            RA.keep = c->keep + image * c->bits_stride; RA.bits_stride = 0;
+            RA.headers = c->headers + image; RA.counts = c->counts + image * 8;
+            RA.out = (uint8_t*)dimg; RA.out_stride = 0; RA.hull = (uint8_t*)dhull; RA.hull_stride = 0; RA.raw_mode = 1;
+            raster_kernel<<<1, RASTER_NT, 0, st>>>(RA);
+            c->launches += 2;
+            CU(cudaGetLastError());
+            CU(cudaMemcpyAsync(host_buf, what == SALVE_BEV_TAP_INTERP ? dimg : dhull, bytes, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            return SALVE_BEV_OK;
+        }
+        default: FAIL(SALVE_BEV_E_INVALID, "unknown tap");
+    }
+    if ((int64_t)bytes > host_buf_bytes) FAIL(SALVE_BEV_E_CAPACITY, "tap buffer too small");
+    CU(cudaMemcpyAsync(host_buf, src, bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return SALVE_BEV_OK;
+}
+
+extern "C" int salve_bev_enable_timing(salve_bev_ctx* c, int32_t on) {
+    if (!c) FAIL(SALVE_BEV_E_INVALID, "null argument");
+    c->timing = on != 0; c->events_used = 0;
+    return SALVE_BEV_OK;
+}
+
+extern "C" int salve_bev_last_timings(salve_bev_ctx* c, float* host_ms) {
+    if (!c || !host_ms) FAIL(SALVE_BEV_E_INVALID, "null argument");
+    for (int i = 0; i < 5; i++) host_ms[i] = 0.f;
+    if (!c->timing || c->events_used == 0) return SALVE_BEV_OK;
+    CU(cudaSetDevice(c->cfg.device));
+    CU(cudaEventSynchronize(c->events[c->events_used - 1]));
+    for (size_t k = 0; k + N_STAGE_EVENTS <= c->events_used; k += N_STAGE_EVENTS) {
+        for (int s = 0; s < 4; s++) {
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, c->events[k + s], c->events[k + s + 1]));
+            host_ms[s] += ms;
+        }
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, c->events[k], c->events[k + 4]));
+        host_ms[4] += ms;
+    }
+    return SALVE_BEV_OK;
+}
+
+extern "C" int64_t salve_bev_launch_count(salve_bev_ctx* c) { return c ? c->launches : 0; }

@@ -1,0 +1,71 @@
+"""Shared helpers for the GPU parity tests: compare every stage of one rendered image with the oracle."""
+
+from __future__ import annotations
+
+import numpy as np
+
+from oracle import bev_oracle as bo
+from oracle import canonical_dt as cdt
+
+
+def oracle_canonical(st: "bo.Stages"):
+    """Canonical-tie Delaunay interpolation of an oracle Stages (sites must be non-degenerate).
+    Returns dict(rc, rgb, tri_v, interp, hull, tri_id, stats, check)."""
+    rc, rgb = cdt.sort_sites(st.site_rc, st.site_rgb)
+    tri_v, stats = cdt.triangulate(rc[:, 0], rc[:, 1], bo.IMG)
+    chk = cdt.check_delaunay(rc[:, 0], rc[:, 1], tri_v)
+    interp, hull, tri_id = cdt.rasterize(rc[:, 0], rc[:, 1], rgb, tri_v, bo.IMG, bo.IMG)
+    return dict(rc=rc, rgb=rgb, tri_v=tri_v, interp=interp, hull=hull, tri_id=tri_id, stats=stats, check=chk)
+
+
+def canonical_final(st: "bo.Stages", can) -> np.ndarray:
+    """Final image built from the canonical interpolation, mask and flip as in the reference."""
+    if st.degenerate:
+        return np.zeros((bo.IMG, bo.IMG, 3), np.uint8)
+    return np.flipud(can["interp"] * st.keep[:, :, None].astype(np.uint8))
+
+
+def tri_pixel_set(tri_v_pix: np.ndarray) -> np.ndarray:
+    """Real triangles (vertex = pixel id) as a lexicographically sorted array of sorted triples."""
+    real = tri_v_pix[(tri_v_pix >= 0).all(1)]
+    t = np.sort(real, axis=1)
+    return t[np.lexsort((t[:, 2], t[:, 1], t[:, 0]))]
+
+
+def oracle_tri_pixel_set(can) -> np.ndarray:
+    rc = can["rc"]
+    pix = rc[:, 0].astype(np.int64) * bo.IMG + rc[:, 1]
+    tv = can["tri_v"]
+    real = tv[(tv >= 0).all(1)]
+    return tri_pixel_set(pix[real].astype(np.int32))
+
+
+def tie_independent_mask(st: "bo.Stages", can) -> np.ndarray:
+    """Pixels whose interpolated value is the same in every Delaunay triangulation: sites and
+    pixels inside strict (tie-free) triangles."""
+    tid = can["tri_id"]
+    ok = tid >= 0
+    strict_px = np.zeros_like(can["hull"])
+    strict_px[ok] = can["check"]["strict_flag"][tid[ok]]
+    site_px = np.zeros_like(can["hull"])
+    site_px[can["rc"][:, 0], can["rc"][:, 1]] = True
+    return strict_px | site_px
+
+
+def rgb_report(gpu_final: np.ndarray, st: "bo.Stages", can) -> dict:
+    """Fractions for the RGB contract, on the un-flipped grid."""
+    ref = np.flipud(st.final).astype(int)
+    got = np.flipud(gpu_final).astype(int)
+    d = np.abs(ref - got).max(2)
+    kept = st.keep & st.hull
+    safe = kept & tie_independent_mask(st, can)
+    return dict(
+        kept=int(kept.sum()),
+        safe_frac=float(safe.sum() / max(kept.sum(), 1)),
+        all_gt0=float((d[kept] > 0).mean()),
+        all_gt1=float((d[kept] > 1).mean()),
+        safe_gt0=float((d[safe] > 0).mean()),
+        safe_gt1=float((d[safe] > 1).mean()),
+        safe_max=int(d[safe].max()) if safe.any() else 0,
+        outside_kept_diff=int((d[~kept] > 0).sum()),
+    )
