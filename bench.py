@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""bench.py -- BEV hypothesis pairs rendered / s on N B200s, with roofline and CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" renders one synthetic building (BASELINE.json configs[1]): 40 panos of 512x1024, 640
+alignment hypotheses, floor + ceiling  =>  2560 BEV images of 501x501x3 per GPU per step.
+One hypothesis = 4 images.  Multi-GPU shards by building (one building per rank, weak scaling,
+no collective on the data path; NCCL only for the barrier and the max-over-ranks time).
+
+`value`  : device-resident inputs and outputs, CUDA events on the launching stream, L2 flushed
+           between timed steps.
+`e2e`    : the same step through the host-buffer C ABI (pinned host panos -> H2D -> render ->
+           D2H of all images), wall clock with synchronize on both sides.
+`roofline`: dominant kernel (the flip kernel), algorithmic bytes per launch / CUDA-event time.
+`cpu_baseline` / `--impl reference`: the oracle port (numpy + SciPy restatement of the reference,
+           bit-identical to it) on all host cores with multiprocessing.Pool -- the reference's own
+           parallel mechanism (scripts/render_dataset_bev.py:111-113).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PANO_H, PANO_W = 512, 1024
+N_PANOS, N_HYP = 40, 640
+IMG = 501
+IMG_BYTES = IMG * IMG * 3
+# compulsory bytes per hypothesis (floor+ceiling), 512x1024 panos
+ALG_BYTES_PER_HYP = 2 * 360448 * 5 + 4 * IMG_BYTES
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: oracle port on host cores
+# ------------------------------------------------------------------------------------------------
+def _cpu_init():
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[k] = "1"
+
+
+def _cpu_warm(_):
+    import scipy.interpolate  # noqa: F401
+    import scipy.spatial  # noqa: F401
+    from oracle import bev_oracle, synth  # noqa: F401
+
+    return 0
+
+
+def _cpu_one(args):
+    """One hypothesis = floor + ceiling pairs through the oracle port."""
+    import warnings
+
+    warnings.simplefilter("ignore")
+    from oracle import bev_oracle as bo
+    from oracle import synth
+
+    k1, k2, j = args
+    rgb1, d1 = synth.synth_pano(PANO_H, PANO_W, k1, "iid", jitter=0.2)
+    rgb2, d2 = synth.synth_pano(PANO_H, PANO_W, k2, "iid", jitter=0.2)
+    R, t = synth.synth_pose(j)
+    t0 = time.perf_counter()
+    for surf in ("floor", "ceiling"):
+        bo.render_pair_images(rgb1, d1, rgb2, d2, R, t, surf)
+    return time.perf_counter() - t0
+
+
+def cpu_throughput(n_hyp: int, procs: int):
+    """hypotheses/s of the oracle port with a Pool of `procs` workers (input synthesis excluded
+    from nothing: it is ~3% of a hypothesis and keeps workers independent)."""
+    import multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    jobs = [(2 * i, 2 * i + 1, i) for i in range(n_hyp)]
+    with ctx.Pool(procs, initializer=_cpu_init) as pool:
+        pool.map(_cpu_warm, range(procs * 2), chunksize=1)  # warm imports, untimed
+        t0 = time.perf_counter()
+        pool.map(_cpu_one, jobs, chunksize=1)
+        dt = time.perf_counter() - t0
+    return n_hyp / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    n_hyp = max(cores, 8)
+    vals = []
+    t_all = time.perf_counter()
+    for _ in range(args.warmup):
+        pass  # worker warm-up happens inside cpu_throughput (imports); no separate untimed pass needed
+    for _ in range(args.steps):
+        v, dt = cpu_throughput(n_hyp, cores)
+        vals.append((v, dt))
+    value = sum(n_hyp for _ in vals) / sum(dt for _, dt in vals)
+    line = {
+        "impl": "reference",
+        "metric": "BEV hypothesis pairs rendered/sec",
+        "value": value,
+        "unit": "hypotheses/s",
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": 1e3 * sum(dt for _, dt in vals) / len(vals),
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f64",
+        "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {
+            "value": value, "unit": "hypotheses/s", "cores": cores, "kind": "port",
+            "sample": f"{n_hyp} hypotheses (floor+ceiling, 4 images each) per step x {args.steps} steps, multiprocessing.Pool({cores})",
+        },
+        "e2e": {"value": value, "unit": "hypotheses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "wall_s": time.perf_counter() - t_all,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(n_gpus: int):
+    return {
+        "workload": "one synthetic building per GPU: 40 panos 512x1024 (u8 RGB + u16 depth), 640 alignment hypotheses, "
+        "floor+ceiling BEV pairs (4 images of 501x501x3 per hypothesis), default BEVParams",
+        "panos": N_PANOS, "hypotheses_per_gpu": N_HYP, "images_per_hypothesis": 4, "pano_hw": [PANO_H, PANO_W],
+        "bev_grid": [IMG, IMG], "parallelism": f"dp{n_gpus} (sharded by building, no collective)",
+        "l2": "256 MiB scratch write between timed steps (L2 flush); per-step working set is > 2 GB",
+        "unposed_render_cache": False,
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {
+            "sm_mhz": float(np.median(sm)) if sm else None,
+            "sm_max_mhz": max(mx) if mx else None,
+            "reasons": sorted(reasons),
+            "samples": len(sm),
+        }
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+
+    from oracle import synth  # input generator only (no rendering arithmetic)
+    from salve_b200.renderer import BevRenderer
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    # ---- synthetic building for this rank ----------------------------------------------------------
+    rgbs, depths, p1, p2, R, t = synth.synth_building(N_PANOS, N_HYP, PANO_H, PANO_W, seed=rank)
+    n_img = N_HYP * 4
+    r = BevRenderer(pano_h=PANO_H, pano_w=PANO_W, max_panos=N_PANOS, max_images=592, device=local)
+    stream = torch.cuda.current_stream(dev)
+    sh = stream.cuda_stream
+
+    # device-resident inputs
+    d_rgb = torch.from_numpy(rgbs).to(dev)
+    d_depth = torch.from_numpy(depths.view(np.int16)).to(dev)
+    for k in range(N_PANOS):
+        r.bind_pano(k, d_rgb[k].data_ptr(), d_depth[k].data_ptr())
+    d_out = torch.empty(n_img * IMG_BYTES, dtype=torch.uint8, device=dev)
+    d_counts = torch.zeros(n_img * 8, dtype=torch.int32, device=dev)
+    d_status = torch.zeros(n_img, dtype=torch.int32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step_device():
+        r.render_hypotheses_device(p1, p2, R, t, d_out, d_counts, d_status, stream=sh)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+
+    # ---- `value`: K timed steps, CUDA events on the launching stream, L2 flush between ------------
+    r.enable_timing(True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = r.launch_count()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    stage_ms = {"splat": 0.0, "sites": 0.0, "flip": 0.0, "raster": 0.0, "total": 0.0}
+    barrier()
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)
+        evs[k][0].record(stream)
+        step_device()
+        evs[k][1].record(stream)
+        torch.cuda.synchronize(dev)
+        tm = r.last_timings()
+        for key in stage_ms:
+            stage_ms[key] += tm[key]
+    barrier()
+    launches = r.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    r.enable_timing(False)
+    t_ms = sum(a.elapsed_time(b) for a, b in evs)
+    tt = torch.tensor([t_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_ms = float(tt.item())
+    value = world * N_HYP * args.steps / (t_ms / 1e3)
+    counts_h = d_counts.cpu().numpy().reshape(n_img, 8)
+    status_h = d_status.cpu().numpy()
+
+    # ---- `e2e`: host buffers through the C ABI, H2D + D2H inside the timed region --------------------
+    h_rgb = torch.from_numpy(rgbs).pin_memory()
+    h_depth = torch.from_numpy(depths.view(np.int16)).pin_memory()
+    h_out = torch.empty(n_img * IMG_BYTES, dtype=torch.uint8).pin_memory()
+    r2 = BevRenderer(pano_h=PANO_H, pano_w=PANO_W, max_panos=N_PANOS, max_images=592, device=local)
+    h_out_np = h_out.numpy()
+
+    def step_e2e():
+        for k in range(N_PANOS):
+            r2.upload_pano_ptr(k, h_rgb[k].data_ptr(), h_depth[k].data_ptr(), stream=sh)
+        r2.render_hypotheses(p1, p2, R, t, out=h_out_np, stream=sh)
+
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    torch.cuda.synchronize(dev)
+    te = time.perf_counter() - t0
+    te_t = torch.tensor([te], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
+    te = float(te_t.item())
+    e2e_value = world * N_HYP * args.steps / te
+    same = bool(np.array_equal(h_out_np[: 8 * IMG_BYTES], d_out[: 8 * IMG_BYTES].cpu().numpy()))
+    h2d = N_PANOS * PANO_H * PANO_W * 5 + N_HYP * (2 * 4 + 6 * 4)
+    d2h = n_img * IMG_BYTES + n_img * 9 * 4
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------------------
+    peak, peak_src = load_peaks()
+    n_tris = counts_h[:, 2].astype(np.int64) * 2 - 2
+    n_tris[status_h != 0] = 0
+    sites = counts_h[:, 2].astype(np.int64)
+    n_launch = args.steps * ((n_img + 591) // 592)
+    # algorithmic bytes per stage and step (DESIGN.md section "Kernels")
+    alg = {
+        "splat": 2 * N_HYP * 360448 * 2 + int(counts_h[:, 1].sum()) * 4,         # depth in (2 B/px per pano pass) + one 4 B key update per point in the box
+        "sites": n_img * IMG * IMG * 4 + int(sites.sum()) * 3 + int(n_tris.sum()) * 16 + n_img * IMG_BYTES,  # key grid in, winner colours in, mesh out, base image out
+        "flip": int(n_tris.sum()) * 16 * 2,                                       # mesh in + mesh out
+        "raster": int(n_tris.sum()) * 16 + int(sites.sum()) * 4 + int(counts_h[:, 4].sum() - counts_h[:, 2].sum()) * 3,  # mesh in, colours in, non-site kept pixels out
+    }
+    kernels = {}
+    for name in ("splat", "sites", "flip", "raster"):
+        ms = stage_ms[name] / args.steps
+        gbs = alg[name] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        kernels[name] = {"ms_per_step": ms, "alg_bytes_per_step": alg[name], "achieved_gbs": gbs, "frac": gbs / peak,
+                         "share_of_step": stage_ms[name] / max(stage_ms["total"], 1e-9)}
+    dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
+    chunks_per_step = (n_img + 591) // 592
+    roofline = {
+        "kernel": {"splat": "splat_pano_kernel", "sites": "sites_kernel", "flip": "flip_kernel", "raster": "raster_kernel"}[dom],
+        "bound": "hbm",
+        "achieved": kernels[dom]["achieved_gbs"],
+        "peak": peak,
+        "unit": "GB/s",
+        "frac": kernels[dom]["frac"],
+        "traffic": None,
+        "peak_source": peak_src,
+        "alg_bytes_per_launch": alg[dom] / chunks_per_step,
+        "avg_launch_ms": kernels[dom]["ms_per_step"] / chunks_per_step,
+        "launches_timed": n_launch,
+        "path": {"alg_bytes_per_hypothesis": ALG_BYTES_PER_HYP, "achieved_gbs": value / world * ALG_BYTES_PER_HYP / 1e9,
+                 "frac": value / world * ALG_BYTES_PER_HYP / 1e9 / peak},
+        "kernels": kernels,
+    }
+
+    # ---- CPU baseline (bounded sample) -------------------------------------------------------------------
+    cpu = None
+    if not args.no_cpu and world >= 1:
+        cores = os.cpu_count() or 1
+        n_s = max(cores, 8)
+        v, dt = cpu_throughput(n_s, cores)
+        cpu = {"value": v, "unit": "hypotheses/s", "cores": cores, "kind": "port",
+               "sample": f"{n_s} hypotheses (floor+ceiling) in {dt:.1f} s, multiprocessing.Pool({cores}), oracle port (numpy+SciPy)"}
+
+    line = {
+        "metric": "BEV hypothesis pairs rendered/sec",
+        "value": value,
+        "unit": "hypotheses/s",
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": max(args.warmup, 3),
+        "ms_per_step": t_ms / args.steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f64 geometry, int64 predicates, u8 colour",
+        "data": "synthetic",
+        "config": workload_config(world),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "hypotheses/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "matches_device_path": same},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "images_ok": int((status_h == 0).sum()), "images": int(n_img),
+        "mean_sites": float(sites.mean()), "mean_flip_rounds": float(counts_h[:, 6].mean()),
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
