@@ -99,6 +99,13 @@ int salve_bev_upload_pano(salve_bev_ctx* ctx, int32_t slot, const uint8_t* host_
 int salve_bev_bind_pano(salve_bev_ctx* ctx, int32_t slot, const uint8_t* dev_rgb, const uint16_t* dev_depth);
 
 /*
+ * Height bands of the two surfaces, each keeps lo < z <= hi.  Defaults are the reference's
+ * floor (-inf, -1.0] and ceiling (0.5, +inf) (bev_rendering_utils.py:560-566); a caller that
+ * renders with another args.crop_z_range (render_bev_pair takes it from `args`) sets band A.
+ */
+int salve_bev_set_bands(salve_bev_ctx* ctx, double a_lo, double a_hi, double b_lo, double b_hi);
+
+/*
  * Render alignment hypotheses.  Replaces render_bev_pair (bev_rendering_utils.py:417-480), once per
  * requested surface, for n_hyp hypotheses in one call.
  *   pano1/pano2 : slot of pano i1 / i2 per hypothesis
@@ -136,9 +143,13 @@ int salve_bev_render_images_host(salve_bev_ctx* ctx, int32_t n_img, const int32_
  * Keeps z_lo < z <= z_hi after dropping crop_rows rows top and bottom.  First call with
  * host_xyzrgb == NULL to get *n_out, then with a buffer of n_out*6 doubles (x,y,z,r/255,g/255,b/255),
  * points in pano raster order.
+ * frame: 0 = HoHoNet frame, as get_xyzrgb_from_depth returns;
+ *        1 = ZInD frame, xy @ rotmat2d(-90).T          (bev_rendering_utils.py:443-446);
+ *        2 = additionally xy @ R.T + t*1.5 (pano 1 of a pair; host_R 4 floats, host_t 2 floats)
+ *            -- 1 and 2 together replace get_bev_pair_xyzrgb (bev_rendering_utils.py:483-522).
  */
-int salve_bev_backproject(salve_bev_ctx* ctx, int32_t slot, double z_lo, double z_hi, double* host_xyzrgb, int64_t* n_out,
-                          void* stream);
+int salve_bev_backproject(salve_bev_ctx* ctx, int32_t slot, double z_lo, double z_hi, int32_t frame, const float* host_R,
+                          const float* host_t, double* host_xyzrgb, int64_t* n_out, void* stream);
 
 /*
  * Render an arbitrary coloured cloud: replaces render_bev_image (bev_rendering_utils.py:254-328).
@@ -157,8 +168,8 @@ int salve_bev_choose_elevated(salve_bev_ctx* ctx, const int64_t* host_x, const i
 /*
  * Sparse -> dense: replaces interp_dense_grid_from_sparse (interpolation_utils.py:21-54) for
  * method="linear".  points: n x 2 int64 (x = column, y = row), distinct; values: n x 3 float64
- * (truncated to uint8 like interpolation_utils.py:53).  grid_h*grid_w <= 2^20, grid_w <= 2047,
- * grid_h <= 1023.  host_img: grid_h x grid_w x 3 uint8, fully overwritten unless *status ==
+ * (truncated to uint8 like interpolation_utils.py:53).  grid_h*grid_w <= 800000 (the flip kernel keeps
+ * one bit per triangle in shared memory), grid_w <= 2047, grid_h <= 1023.  host_img: grid_h x grid_w x 3 uint8, fully overwritten unless *status ==
  * SALVE_BEV_IMG_DEGENERATE (then untouched, as in the reference).  host_hull (may be NULL):
  * grid_h x grid_w uint8, 1 inside the closed convex hull.
  */

@@ -55,7 +55,8 @@ SYMBOLS = {
     "salve_bev_render_hypotheses": (ctypes.c_int, [c_vp, ctypes.c_int32, c_i32p, c_i32p, c_f32p, c_f32p, ctypes.c_uint32, c_vp, c_vp, c_vp, c_vp]),
     "salve_bev_render_hypotheses_host": (ctypes.c_int, [c_vp, ctypes.c_int32, c_i32p, c_i32p, c_f32p, c_f32p, ctypes.c_uint32, c_vp, c_vp, c_vp, c_vp]),
     "salve_bev_render_images_host": (ctypes.c_int, [c_vp, ctypes.c_int32, c_i32p, c_i32p, c_i32p, c_f32p, c_f32p, c_vp, c_vp, c_vp, c_vp]),
-    "salve_bev_backproject": (ctypes.c_int, [c_vp, ctypes.c_int32, ctypes.c_double, ctypes.c_double, c_f64p, c_i64p, c_vp]),
+    "salve_bev_set_bands": (ctypes.c_int, [c_vp, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double]),
+    "salve_bev_backproject": (ctypes.c_int, [c_vp, ctypes.c_int32, ctypes.c_double, ctypes.c_double, ctypes.c_int32, c_f32p, c_f32p, c_f64p, c_i64p, c_vp]),
     "salve_bev_render_cloud_host": (ctypes.c_int, [c_vp, c_f64p, ctypes.c_int64, c_u8p, c_i32p, c_i32p, c_vp]),
     "salve_bev_choose_elevated": (ctypes.c_int, [c_vp, c_i64p, c_i64p, c_f64p, ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_int32, c_u8p, c_vp]),
     "salve_bev_interp_dense": (ctypes.c_int, [c_vp, c_i64p, c_f64p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, c_u8p, c_u8p, c_i32p, c_vp]),

@@ -71,6 +71,7 @@ struct salve_bev_ctx {
     int64_t launches = 0;
     int last_chunk_images = 0;
     size_t flip_smem = 0;
+    double band[4] = {-INFINITY, -1.0, 0.5, INFINITY};  // bev_rendering_utils.py:560-566
 };
 
 static int tmp_get(salve_bev_ctx* c, int slot, size_t bytes, void** out) {
@@ -119,8 +120,8 @@ extern "C" int salve_bev_ctx_create(const salve_bev_config* cfg, salve_bev_ctx**
     if (cfg->pano_h < 1 || cfg->pano_w < 4 || (cfg->pano_w & 3)) FAIL(SALVE_BEV_E_INVALID, "pano_w must be a positive multiple of 4");
     if ((int64_t)cfg->pano_h * cfg->pano_w > ((int64_t)1 << KEY_IDX_BITS)) FAIL(SALVE_BEV_E_INVALID, "pano too large");
     if (cfg->grid_h < 2 || cfg->grid_h > MAX_GRID_H || cfg->grid_w < 2 || cfg->grid_w > 2047 ||
-        (int64_t)cfg->grid_h * cfg->grid_w > (1 << 20))
-        FAIL(SALVE_BEV_E_INVALID, "grid must satisfy 2 <= grid_h <= 1023, 2 <= grid_w <= 2047, grid_h*grid_w <= 2^20");
+        (int64_t)cfg->grid_h * cfg->grid_w > 800000)
+        FAIL(SALVE_BEV_E_INVALID, "grid must satisfy 2 <= grid_h <= 1023, 2 <= grid_w <= 2047, grid_h*grid_w <= 800000");
     if (cfg->kernel_sz < 1 || !(cfg->kernel_sz & 1) || cfg->kernel_sz > 63) FAIL(SALVE_BEV_E_INVALID, "kernel_sz must be odd, 1..63");
     if (cfg->max_images < 1 || cfg->max_panos < 1) FAIL(SALVE_BEV_E_INVALID, "max_images/max_panos must be positive");
     if (cfg->crop_rows < 0 || 2 * cfg->crop_rows >= cfg->pano_h) FAIL(SALVE_BEV_E_INVALID, "bad crop_rows");
@@ -248,7 +249,7 @@ static SplatParams make_splat_params(salve_bev_ctx* c) {
     const int H = c->cfg.pano_h, W = c->cfg.pano_w;
     P.H = H; P.W = W; P.crop_rows = c->cfg.crop_rows; P.depth_scale = c->cfg.depth_scale;
     P.xmin = c->cfg.xmin; P.ymin = c->cfg.ymin; P.xmax = c->cfg.xmax; P.ymax = c->cfg.ymax; P.px_per_m = c->cfg.px_per_m;
-    P.floor_hi = -1.0; P.ceil_lo = 0.5;  // bev_rendering_utils.py:560-566
+    P.a_lo = c->band[0]; P.a_hi = c->band[1]; P.b_lo = c->band[2]; P.b_hi = c->band[3];
     P.grid_w = c->G.grid_w; P.g = c->G.g;
     P.cos_phi = c->d_tables; P.neg_sin_phi = c->d_tables + H; P.cos_theta = c->d_tables + 2 * H; P.sin_theta = c->d_tables + 2 * H + W;
     P.depth = c->d_depth_ptr;
@@ -296,7 +297,10 @@ static int run_mesh_stages(salve_bev_ctx* c, int n_img, const GridParams& G, uin
     FA.list0 = c->list0; FA.list1 = c->list1; FA.list_stride = c->tris_stride;
     FA.cand = c->cand; FA.cand_stride = c->cand_stride;
     FA.headers = c->headers; FA.counts = dev_counts;
-    flip_kernel<<<n_img, FLIP_NT, ((2 * (size_t)G.g + 31) / 32) * 4 + 16, st>>>(FA);
+    const size_t flip_smem = ((2 * (size_t)G.g + 31) / 32) * 4 + 16;
+    // the attribute is per function, not per context: (re)assert it for this launch
+    CU(cudaFuncSetAttribute(flip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(flip_smem, (size_t)49152)));
+    flip_kernel<<<n_img, FLIP_NT, flip_smem, st>>>(FA);
     c->launches++;
     CU(cudaGetLastError());
     rc = stage_event(c, st); if (rc) return rc;
@@ -306,7 +310,7 @@ static int run_mesh_stages(salve_bev_ctx* c, int n_img, const GridParams& G, uin
     RA.tris = c->tris; RA.tris_stride = c->tris_stride;
     RA.color = c->color; RA.color_stride = c->g_stride;
     RA.keep = c->keep; RA.bits_stride = c->bits_stride;
-    RA.headers = c->headers; RA.counts = dev_counts;
+    RA.headers = c->headers; RA.counts = dev_counts; RA.status = dev_status;
     RA.out = dev_out; RA.out_stride = (size_t)G.g * 3;
     RA.hull = hull; RA.hull_stride = (size_t)G.g;
     RA.raw_mode = raw_mode;
@@ -439,9 +443,18 @@ extern "C" int salve_bev_render_images_host(salve_bev_ctx* c, int32_t n_img, con
     return SALVE_BEV_OK;
 }
 
-extern "C" int salve_bev_backproject(salve_bev_ctx* c, int32_t slot, double z_lo, double z_hi, double* host_xyzrgb, int64_t* n_out,
-                                     void* stream) {
+extern "C" int salve_bev_set_bands(salve_bev_ctx* c, double a_lo, double a_hi, double b_lo, double b_hi) {
+    if (!c) FAIL(SALVE_BEV_E_INVALID, "null argument");
+    c->band[0] = a_lo; c->band[1] = a_hi; c->band[2] = b_lo; c->band[3] = b_hi;
+    return SALVE_BEV_OK;
+}
+
+extern "C" int salve_bev_backproject(salve_bev_ctx* c, int32_t slot, double z_lo, double z_hi, int32_t frame, const float* host_R,
+                                     const float* host_t, double* host_xyzrgb, int64_t* n_out, void* stream) {
     if (!c || !n_out) FAIL(SALVE_BEV_E_INVALID, "null argument");
+    if (frame < 0 || frame > 2 || (frame == 2 && (!host_R || !host_t))) FAIL(SALVE_BEV_E_INVALID, "bad frame / missing pose");
+    PoseArg pose = {{1.f, 0.f, 0.f, 1.f}, {0.f, 0.f}};
+    if (frame == 2) { memcpy(pose.R, host_R, sizeof(float) * 4); memcpy(pose.t, host_t, sizeof(float) * 2); }
     if (slot < 0 || slot >= c->cfg.max_panos) FAIL(SALVE_BEV_E_CAPACITY, "pano slot out of range");
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaSetDevice(c->cfg.device));
@@ -463,7 +476,7 @@ extern "C" int salve_bev_backproject(salve_bev_ctx* c, int32_t slot, double z_lo
     if (!host_xyzrgb || total_kept == 0) return SALVE_BEV_OK;
     void* ob;
     rc = tmp_get(c, 0, sizeof(double) * 6 * (size_t)total_kept, &ob); if (rc) return rc;
-    crop_write_kernel<<<nblk, COMPACT_BLOCK, 0, st>>>(P, c->h_depth_ptr[slot], c->h_rgb_ptr[slot], z_lo, z_hi, (const long long*)bo, (double*)ob);
+    crop_write_kernel<<<nblk, COMPACT_BLOCK, 0, st>>>(P, c->h_depth_ptr[slot], c->h_rgb_ptr[slot], z_lo, z_hi, (const long long*)bo, frame, pose, (double*)ob);
     c->launches++;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(host_xyzrgb, ob, sizeof(double) * 6 * (size_t)total_kept, cudaMemcpyDeviceToHost, st));
@@ -675,7 +688,7 @@ extern "C" int salve_bev_tap(salve_bev_ctx* c, int32_t image, int32_t what, void
             RA.tris = c->tris + image * c->tris_stride; RA.tris_stride = 0;
             RA.color = c->color + image * c->g_stride; RA.color_stride = 0;
             RA.keep = c->keep + image * c->bits_stride; RA.bits_stride = 0;
-            RA.headers = c->headers + image; RA.counts = c->counts + image * 8;
+            RA.headers = c->headers + image; RA.counts = c->counts + image * 8; RA.status = nullptr;
             RA.out = (uint8_t*)dimg; RA.out_stride = 0; RA.hull = (uint8_t*)dhull; RA.hull_stride = 0; RA.raw_mode = 1;
             raster_kernel<<<1, RASTER_NT, 0, st>>>(RA);
             c->launches += 2;

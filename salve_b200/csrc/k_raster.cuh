@@ -23,6 +23,7 @@ struct RasterArgs {
     const uint32_t* keep; size_t bits_stride;
     const ImgHeader* headers;
     int32_t* counts;
+    int32_t* status;  // optional: set to SALVE_BEV_IMG_COLLINEAR when the mesh has no real triangle
     uint8_t* out; size_t out_stride;
     uint8_t* hull; size_t hull_stride;  // optional (tap): 1 inside the closed hull
     int32_t raw_mode;
@@ -113,7 +114,10 @@ __global__ void __launch_bounds__(RASTER_NT) raster_kernel(RasterArgs A) {
         if (!tri_setup(A, T, color, s, true)) continue;
         raster_pixels(A, s, keep, out, hull, lane, 32);
     }
-    if (tid == 0) A.counts[img * 8 + 5] = s_real;
+    if (tid == 0) {
+        A.counts[img * 8 + 5] = s_real;
+        if (s_real == 0 && A.status) A.status[img] = 3;  // all sites on one oblique line
+    }
 }
 
 // ---- stand-alone hallucination mask on explicit images (remove_hallucinated_content) ------------

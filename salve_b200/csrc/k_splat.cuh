@@ -31,8 +31,8 @@ struct SplatParams {
     int32_t H, W, crop_rows;
     float depth_scale;
     double xmin, ymin, xmax, ymax, px_per_m;
-    double floor_hi;  // floor band (-inf, floor_hi]
-    double ceil_lo;   // ceiling band (ceil_lo, +inf)
+    double a_lo, a_hi;  // band A ("floor")   keeps a_lo < z <= a_hi; reference (-inf, -1.0]
+    double b_lo, b_hi;  // band B ("ceiling") keeps b_lo < z <= b_hi; reference (0.5, +inf)
     int32_t grid_w, g;
     const double* cos_phi;
     const double* neg_sin_phi;
@@ -93,23 +93,25 @@ __global__ void __launch_bounds__(256) splat_pano_kernel(SplatParams P, const Sp
             const int u = u0 + k;
             const double d = (double)__fmul_rn((float)d16[k], P.depth_scale);
             const double z = __dmul_rn(d, sz);
-            const bool is_f = (z <= P.floor_hi);  // (-inf, floor_hi]
-            const bool is_c = (z > P.ceil_lo);    // (ceil_lo, +inf)
-            uint32_t* kg = is_f ? kg_f : (is_c ? kg_c : nullptr);
+            const bool is_f = (z > P.a_lo && z <= P.a_hi);
+            const bool is_c = (z > P.b_lo && z <= P.b_hi);
             if (is_f) n_crop_f++;
             if (is_c) n_crop_c++;
-            if (kg == nullptr) continue;
+            const bool do_f = is_f && kg_f != nullptr, do_c = is_c && kg_c != nullptr;
+            if (!do_f && !do_c) continue;
             const double x = __dmul_rn(d, __dmul_rn(cphi, __ldg(P.cos_theta + u)));
             const double y = __dmul_rn(d, __dmul_rn(cphi, __ldg(P.sin_theta + u)));
             double wx, wy;
             rot_pose(x, y, job.posed != 0, job.R, tx, ty, wx, wy);
             int row, col;
             if (!bbox_pixel(P, wx, wy, row, col)) continue;
-            if (is_f) n_box_f++; else n_box_c++;
+            if (do_f) n_box_f++;
+            if (do_c) n_box_c++;
             const int sl = z_slice4(z);
             if (sl < 0) continue;
             const uint32_t key = (((uint32_t)sl << KEY_IDX_BITS) | (uint32_t)(v * P.W + u)) + 1u;
-            atomicMax(kg + row * P.grid_w + col, key);
+            if (do_f) atomicMax(kg_f + row * P.grid_w + col, key);
+            if (do_c) atomicMax(kg_c + row * P.grid_w + col, key);
         }
     }
     if (counts != nullptr) {
@@ -234,9 +236,12 @@ __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int32_t* __r
     if (threadIdx.x == 0) out[n] = carry;
 }
 
+// frame: 0 = HoHoNet frame (get_xyzrgb_from_depth), 1 = ZInD frame (after rotmat2d(-90)),
+// 2 = posed into pano 2's frame (get_bev_pair_xyzrgb, bev_rendering_utils.py:483-522)
+struct PoseArg { float R[4]; float t[2]; };
 __global__ void __launch_bounds__(COMPACT_BLOCK) crop_write_kernel(SplatParams P, const uint16_t* __restrict__ depth,
                                                                    const uint8_t* __restrict__ rgb, double lo, double hi,
-                                                                   const long long* __restrict__ block_offsets,
+                                                                   const long long* __restrict__ block_offsets, int frame, PoseArg pose,
                                                                    double* __restrict__ out_xyzrgb) {
     __shared__ int warp_cnt[COMPACT_BLOCK / 32];
     const int idx = blockIdx.x * COMPACT_BLOCK + threadIdx.x;
@@ -251,6 +256,12 @@ __global__ void __launch_bounds__(COMPACT_BLOCK) crop_write_kernel(SplatParams P
     for (int w = 0; w < warp; w++) off += warp_cnt[w];
     off += __popc(b & ((1u << lane) - 1u));
     double* o = out_xyzrgb + off * 6;
+    if (frame > 0) {
+        const double tx = (double)__fmul_rn(pose.t[0], 1.5f), ty = (double)__fmul_rn(pose.t[1], 1.5f);
+        double wx, wy;
+        rot_pose(x, y, frame == 2, pose.R, tx, ty, wx, wy);
+        x = wx; y = wy;
+    }
     o[0] = x; o[1] = y; o[2] = z;
     o[3] = __ddiv_rn((double)rgb[src * 3 + 0], 255.0);  // rgb / 255.0, bev_rendering_utils.py:394
     o[4] = __ddiv_rn((double)rgb[src * 3 + 1], 255.0);

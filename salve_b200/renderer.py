@@ -195,12 +195,19 @@ class BevRenderer:
         )
         return out, counts, status
 
-    def backproject(self, slot: int, z_lo: float, z_hi: float, stream: int = 0) -> np.ndarray:
+    def set_bands(self, a=(-float("inf"), -1.0), b=(0.5, float("inf"))) -> None:
+        nat.check(self._lib.salve_bev_set_bands(self._h, float(a[0]), float(a[1]), float(b[0]), float(b[1])))
+
+    def backproject(self, slot: int, z_lo: float, z_hi: float, frame: int = 0, R=None, t=None, stream: int = 0) -> np.ndarray:
+        """frame 0: HoHoNet frame; 1: ZInD frame; 2: posed by (R, t) into pano 2's frame."""
         n = ctypes.c_int64(0)
-        nat.check(self._lib.salve_bev_backproject(self._h, slot, float(z_lo), float(z_hi), None, ctypes.byref(n), stream or None))
+        R = None if R is None else np.ascontiguousarray(R, np.float32).reshape(4)
+        t = None if t is None else np.ascontiguousarray(t, np.float32).reshape(2)
+        a = (self._h, slot, float(z_lo), float(z_hi), int(frame), _ptr(R, ctypes.c_float), _ptr(t, ctypes.c_float))
+        nat.check(self._lib.salve_bev_backproject(*a, None, ctypes.byref(n), stream or None))
         out = np.empty((n.value, 6), np.float64)
         if n.value:
-            nat.check(self._lib.salve_bev_backproject(self._h, slot, float(z_lo), float(z_hi), _ptr(out, ctypes.c_double), ctypes.byref(n), stream or None))
+            nat.check(self._lib.salve_bev_backproject(*a, _ptr(out, ctypes.c_double), ctypes.byref(n), stream or None))
         return out
 
     def render_cloud(self, xyzrgb: np.ndarray, stream: int = 0):

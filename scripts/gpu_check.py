@@ -47,7 +47,7 @@ def main():
             res["keep"] = np.array_equal(r.tap(img_idx, "keep"), st.keep)
             tri = r.tap(img_idx, "tris")
             res["tris"] = np.array_equal(pu.tri_pixel_set(tri), pu.oracle_tri_pixel_set(can))
-            res["hull"] = np.array_equal(r.tap(img_idx, "hull"), st.hull)
+            res["hull"] = np.array_equal(r.tap(img_idx, "hull"), can["hull"]) and pu.hull_check(can["hull"], st.hull) >= 0
             res["interp"] = np.array_equal(r.tap(img_idx, "interp"), can["interp"])
             res["final_canonical"] = np.array_equal(imgs[0, si, pi], pu.canonical_final(st, can))
             rep = pu.rgb_report(imgs[0, si, pi], st, can)

@@ -52,11 +52,35 @@ def tie_independent_mask(st: "bo.Stages", can) -> np.ndarray:
     return strict_px | site_px
 
 
+def hull_check(exact_hull: np.ndarray, scipy_hull: np.ndarray) -> int:
+    """The exact closed convex hull vs SciPy's `defined` mask.
+
+    They must agree except, at most, on pixels lying on the hull *boundary*: SciPy decides
+    inside/outside with float64 barycentrics and a 100-ulp tolerance, which misclassifies a pixel
+    that sits exactly on the long hull edge of a needle triangle (observed: twice-area 3 over a
+    ~90 px edge).  Returns the number of such pixels; asserts everything else.
+    """
+    diff = exact_hull != scipy_hull
+    if not diff.any():
+        return 0
+    assert not (scipy_hull & ~exact_hull).any(), "SciPy defines a pixel outside the exact hull"
+    pad = np.pad(exact_hull, 1)
+    interior = np.ones_like(exact_hull)
+    for dy in (0, 1, 2):
+        for dx in (0, 1, 2):
+            interior &= pad[dy : dy + exact_hull.shape[0], dx : dx + exact_hull.shape[1]]
+    assert not (diff & interior).any(), "hull masks differ away from the hull boundary"
+    n = int(diff.sum())
+    assert n <= max(4, 1e-4 * exact_hull.sum()), f"{n} boundary pixels differ"
+    return n
+
+
 def rgb_report(gpu_final: np.ndarray, st: "bo.Stages", can) -> dict:
     """Fractions for the RGB contract, on the un-flipped grid."""
     ref = np.flipud(st.final).astype(int)
     got = np.flipud(gpu_final).astype(int)
     d = np.abs(ref - got).max(2)
+    d[can["hull"] & ~st.hull] = 0  # hull-boundary pixels SciPy's float tolerance drops (see hull_check)
     kept = st.keep & st.hull
     safe = kept & tie_independent_mask(st, can)
     return dict(

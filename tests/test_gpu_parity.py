@@ -1,0 +1,421 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle on identical inputs.
+
+Bar: integer stages bit-exact (crop / bbox counts, winner keys, non-empty mask incl. the uint8 wrap,
+keep mask, hull mask, triangle set); interpolated RGB bit-exact against the canonical-tie oracle and
+within 1/255 of the reference (SciPy) on 100 % of tie-independent pixels (RGB_TOL, RGB_FRAC below),
+with the overall differing fraction reported (it is the reference's own tie-break ambiguity,
+SURVEY.md Appendix C).
+"""
+
+import json
+import os
+
+import numpy as np
+import pytest
+
+import parity_utils as pu
+from oracle import bev_oracle as bo
+from oracle import canonical_dt as cdt
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+RGB_TOL = 1  # per channel, /255
+RGB_FRAC = 0.999  # of tie-independent kept pixels within RGB_TOL of the reference
+
+
+@pytest.fixture(scope="module")
+def R():
+    from salve_b200.renderer import BevRenderer
+
+    r = BevRenderer(pano_h=512, pano_w=1024, max_panos=8, max_images=16)
+    yield r
+    r.close()
+
+
+def check_image_against_oracle(r, img_idx, img, counts, st, report=None):
+    """All stages of one rendered image vs the oracle Stages `st`."""
+    assert counts[0] == st.count_crop, "crop count"
+    assert counts[1] == st.count_bbox, "bbox count"
+    assert counts[2] == len(st.site_rc), "site count"
+    assert np.array_equal(r.tap(img_idx, "keygrid").astype(np.int64), st.key_grid), "winner keys"
+    assert np.array_equal(r.tap(img_idx, "occ"), st.key_grid != 0)
+    assert np.array_equal(r.tap(img_idx, "nonempty"), st.nonempty), "non-empty mask (uint8 wrap)"
+    assert counts[3] == int(st.nonempty.sum())
+    assert np.array_equal(r.tap(img_idx, "keep"), st.keep), "keep mask"
+    assert counts[4] == int(st.keep.sum())
+    col = r.tap(img_idx, "color")
+    sparse = np.stack([col & 0xFF, (col >> 8) & 0xFF, (col >> 16) & 0xFF], -1).astype(np.uint8)
+    assert np.array_equal(sparse, st.sparse), "sparse image"
+    can = pu.oracle_canonical(st)
+    assert can["stats"]["residual_ties"] == 0
+    tris = r.tap(img_idx, "tris")
+    assert np.array_equal(pu.tri_pixel_set(tris), pu.oracle_tri_pixel_set(can)), "triangle set"
+    assert counts[5] == int((can["tri_v"] >= 0).all(1).sum())
+    assert np.array_equal(r.tap(img_idx, "hull"), can["hull"]), "hull mask vs exact oracle"
+    n_hull_extra = pu.hull_check(can["hull"], st.hull)  # vs SciPy: identical up to float-tolerance boundary pixels
+    assert np.array_equal(r.tap(img_idx, "interp"), can["interp"]), "interpolated image vs canonical oracle"
+    assert np.array_equal(img, pu.canonical_final(st, can)), "final image vs canonical oracle"
+    rep = pu.rgb_report(img, st, can)
+    rep["hull_boundary_px_scipy_drops"] = n_hull_extra
+    assert rep["outside_kept_diff"] == 0
+    assert 1.0 - rep["safe_gt1"] >= RGB_FRAC and rep["safe_max"] <= RGB_TOL, rep
+    if report is not None:
+        report.append(rep)
+    return rep
+
+
+@pytest.mark.parametrize("seed,tex", [(0, "iid"), (1, "smooth"), (2, "iid")])
+def test_c1_single_hypothesis_all_stages(R, seed, tex):
+    """BASELINE configs[0]: one hypothesis, 512x1024, stage by stage, floor and ceiling."""
+    rgb1, d1 = synth.synth_pano(512, 1024, 10 * seed, tex)
+    rgb2, d2 = synth.synth_pano(512, 1024, 10 * seed + 1, tex, jitter=0.2)
+    Rm, t = synth.synth_pose(seed)
+    R.upload_pano(0, rgb1, d1)
+    R.upload_pano(1, rgb2, d2)
+    imgs, counts, status = R.render_hypotheses([0], [1], Rm[None], t[None])
+    assert (status == 0).all()
+    reps = []
+    for si, surf in enumerate(("floor", "ceiling")):
+        s1, s2 = bo.render_pair(rgb1, d1, rgb2, d2, Rm, t, surf)
+        for pi, st in enumerate((s1, s2)):
+            check_image_against_oracle(R, si * 2 + pi, imgs[0, si, pi], counts[0, si, pi], st, reps)
+    print("RGB vs reference (SciPy):", json.dumps(reps))
+
+
+def test_golden_reference_images(R, golden, golden_inputs):
+    """Against images produced by the unmodified reference (tests/golden, scripts/make_golden.py)."""
+    g, meta = golden
+    rgb1, d1, rgb2, d2, Rm, t = golden_inputs
+    R.upload_pano(0, rgb1, d1)
+    R.upload_pano(1, rgb2, d2)
+    imgs, counts, status = R.render_hypotheses([0], [1], Rm[None], t[None])
+    for si, surf in enumerate(("floor", "ceiling")):
+        for pi in range(2):
+            name = f"{surf}_{pi + 1}"
+            m = meta["images"][name]
+            c = counts[0, si, pi]
+            assert (c[0], c[1], c[2]) == (m["count_crop"], m["count_bbox"], m["n_sites"])
+            idx = si * 2 + pi
+            assert np.array_equal(np.packbits(R.tap(idx, "nonempty")), g[f"{name}_nonempty"])
+            assert np.array_equal(np.packbits(R.tap(idx, "keep")), g[f"{name}_keep"])
+            ref_hull = np.unpackbits(g[f"{name}_hull"])[: 501 * 501].reshape(501, 501).astype(bool)
+            pu.hull_check(R.tap(idx, "hull"), ref_hull)
+            ref = g[f"{name}_final"]
+            got = imgs[0, si, pi]
+            # defined (non-zero) support identical up to pixels whose value is legitimately 0/1
+            d = np.abs(ref.astype(int) - got.astype(int)).max(2)
+            keep = np.flipud(np.unpackbits(g[f"{name}_keep"])[: 501 * 501].reshape(501, 501).astype(bool))
+            assert d[~keep].max() == 0
+            assert (d[keep] > 1).mean() < 0.08  # tie-break ambiguity floor of the reference itself (5-7 %)
+
+
+def test_c3_full_resolution_panos():
+    """BASELINE configs[2]: 1024x2048 panos (an extension: the reference hard-codes 512x1024)."""
+    from salve_b200.renderer import BevRenderer
+
+    H, W = 1024, 2048
+    rgb1, d1 = synth.synth_pano(H, W, 21, "smooth")
+    rgb2, d2 = synth.synth_pano(H, W, 22, "iid")
+    Rm, t = synth.synth_pose(9)
+    r = BevRenderer(pano_h=H, pano_w=W, max_panos=2, max_images=4)
+    r.upload_pano(0, rgb1, d1)
+    r.upload_pano(1, rgb2, d2)
+    imgs, counts, status = r.render_hypotheses([0], [1], Rm[None], t[None])
+    for si, surf in enumerate(("floor", "ceiling")):
+        s1, s2 = bo.render_pair(rgb1, d1, rgb2, d2, Rm, t, surf)
+        for pi, st in enumerate((s1, s2)):
+            check_image_against_oracle(r, si * 2 + pi, imgs[0, si, pi], counts[0, si, pi], st)
+    r.close()
+
+
+def test_batch_chunking_determinism_and_independence():
+    """C2-style batch (size-independent properties): chunked batch == one-by-one, run twice == same bytes,
+    img2 depends only on (pano 2, surface)."""
+    from salve_b200.renderer import BevRenderer
+
+    n_p, n_h = 5, 22
+    rgbs, depths, p1, p2, Rm, t = synth.synth_building(n_p, n_h, 512, 1024, seed=3)
+    r = BevRenderer(max_panos=n_p, max_images=12)  # 3 hypotheses per chunk -> 8 chunks
+    for k in range(n_p):
+        r.upload_pano(k, rgbs[k], depths[k])
+    a, ca, sa = r.render_hypotheses(p1, p2, Rm, t)
+    b, cb, sb = r.render_hypotheses(p1, p2, Rm, t)
+    assert np.array_equal(a, b) and np.array_equal(ca, cb), "not deterministic"
+    assert (sa == 0).all()
+    for h in range(n_h):  # one-by-one through the per-image entry point
+        one, c1, s1 = r.render_images([p1[h], p2[h], p1[h], p2[h]], ["floor", "floor", "ceiling", "ceiling"], [1, 0, 1, 0],
+                                      np.repeat(Rm[h][None], 4, 0), np.repeat(t[h][None], 4, 0))
+        assert np.array_equal(one.reshape(2, 2, 501, 501, 3), a[h]), f"hypothesis {h}"
+    seen = {}
+    for h in range(n_h):
+        for si in range(2):
+            key = (int(p2[h]), si)
+            if key in seen:
+                assert np.array_equal(a[h, si, 1], seen[key])
+            seen[key] = a[h, si, 1]
+    r.close()
+
+
+def test_device_output_path_equals_host_path():
+    import torch
+
+    from salve_b200.renderer import BevRenderer
+
+    rgbs, depths, p1, p2, Rm, t = synth.synth_building(3, 5, 512, 1024, seed=4)
+    r = BevRenderer(max_panos=3, max_images=8)
+    d_rgb = torch.from_numpy(rgbs).cuda()
+    d_dep = torch.from_numpy(depths.view(np.int16)).cuda()
+    for k in range(3):
+        r.bind_pano(k, d_rgb[k], d_dep[k])
+    out = torch.zeros(5 * 4 * 501 * 501 * 3, dtype=torch.uint8, device="cuda")
+    cnt = torch.zeros(5 * 4 * 8, dtype=torch.int32, device="cuda")
+    st = torch.full((5 * 4,), -1, dtype=torch.int32, device="cuda")
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        n = r.render_hypotheses_device(p1, p2, Rm, t, out, cnt, st, stream=s.cuda_stream)
+    s.synchronize()
+    assert n == 20 and (st == 0).all()
+    r2 = BevRenderer(max_panos=3, max_images=8)
+    for k in range(3):
+        r2.upload_pano(k, rgbs[k], depths[k])
+    host, hc, hs = r2.render_hypotheses(p1, p2, Rm, t)
+    assert np.array_equal(out.cpu().numpy().reshape(host.shape), host)
+    assert np.array_equal(cnt.cpu().numpy().reshape(hc.shape)[..., :6], hc[..., :6])
+    r.close(); r2.close()
+
+
+# ---- stream compaction / back-projection -----------------------------------------------------------------
+@pytest.mark.parametrize("surf", ["floor", "ceiling"])
+def test_backproject_compaction_bit_exact(R, surf):
+    rgb, d = synth.synth_pano(512, 1024, 31, "iid")
+    Rm, t = synth.synth_pose(4)
+    R.upload_pano(2, rgb, d)
+    band = bo.BANDS[surf]
+    want, src, _ = bo.backproject(rgb, d, band)
+    got = R.backproject(2, band[0], band[1], frame=0)
+    assert got.shape == want.shape and np.array_equal(got, want)  # order-preserving, float64 bit-exact
+    z = want.copy(); bo.to_zind_frame(z)
+    assert np.array_equal(R.backproject(2, band[0], band[1], frame=1), z)
+    bo.apply_pose(z, Rm, t)
+    assert np.array_equal(R.backproject(2, band[0], band[1], frame=2, R=Rm, t=t), z)
+
+
+def test_sphere_table_bit_exact(R):
+    assert np.array_equal(R.uni_sphere_xyz(), bo.uni_sphere_xyz(512, 1024))
+
+
+# ---- drop-in entry points: the reference's known-answer tests, replayed on the CUDA path ---------------
+def test_dropin_zorder_kats():
+    from salve_b200.utils.zorder_utils import choose_elevated_repeated_vals
+    from test_oracle_cpu import ZORDER_KATS
+
+    for xyz, slices, expected in ZORDER_KATS:
+        xyz = np.array(xyz)
+        got = choose_elevated_repeated_vals(xyz[:, 0], xyz[:, 1], xyz[:, 2], zmin=0, zmax=10, num_slices=slices)
+        assert got.dtype == bool and got.tolist() == expected
+    rng = np.random.default_rng(0)
+    x = rng.integers(0, 60, 20000); y = rng.integers(0, 50, 20000); z = rng.uniform(-2.6, 2.6, 20000)
+    assert np.array_equal(choose_elevated_repeated_vals(x, y, z), bo.choose_elevated(x, y, z))
+
+
+def test_dropin_hallucination_kat_and_wrap():
+    from salve_b200.utils.interpolation_utils import remove_hallucinated_content
+
+    sparse = np.zeros((6, 6), np.int64)
+    sparse[0, 1] = 2; sparse[0, 3] = 4; sparse[2, 1] = 2; sparse[4, 1] = 2
+    sparse = np.stack([sparse] * 3, -1)
+    interp = np.stack([np.tile(np.arange(1, 7), (6, 1))] * 3, -1)
+    out = remove_hallucinated_content(sparse, interp, K=3)
+    expected = np.array([[1, 2, 3, 4, 5, 0], [1, 2, 3, 4, 5, 0], [1, 2, 3, 0, 0, 0], [1, 2, 3, 0, 0, 0], [1, 2, 3, 0, 0, 0], [1, 2, 3, 0, 0, 0]], np.uint8)
+    assert out.dtype == np.uint8
+    for ch in range(3):
+        assert np.array_equal(out[:, :, ch], expected)
+    rng = np.random.default_rng(2)
+    sp = rng.integers(0, 256, (77, 93, 3)).astype(np.uint8); sp[rng.random((77, 93)) < 0.93] = 0
+    sp[5, 5] = (16, 16, 1)  # product wraps to 0 in uint8: counts as empty
+    it = rng.integers(0, 256, (77, 93, 3)).astype(np.uint8)
+    want = (np.repeat(bo.keep_mask(bo.nonempty_mask(sp), 11)[:, :, None], 3, 2) * it).astype(np.uint8)
+    assert np.array_equal(remove_hallucinated_content(sp, it), want)
+
+
+def test_dropin_interp_guards_and_shape():
+    """reference tests/utils/test_interpolation_utils.py:8-79."""
+    from salve_b200.utils.interpolation_utils import interp_dense_grid_from_sparse
+
+    rgb = np.full((4, 3), 200.0)
+    for pts in (np.array([[1, 1], [1, 5], [1, 7], [1, 9]]), np.array([[1, 3], [5, 3], [7, 3], [9, 3]])):
+        img = np.zeros((10, 10, 3), np.uint8)
+        out = interp_dense_grid_from_sparse(img, pts, rgb, grid_h=10, grid_w=10, is_semantics=False)
+        assert out is img and not out.any()
+    img = np.zeros((10, 10, 3), np.uint8)
+    assert not interp_dense_grid_from_sparse(img, np.array([[0, 0], [3, 3]]), rgb[:2], 10, 10, False).any()
+    img = np.zeros((4, 4, 3), np.uint8)
+    pts = np.array([[0, 0], [3, 0], [3, 3], [0, 3]])
+    vals = np.array([[10, 20, 30], [40, 50, 60], [70, 80, 90], [100, 110, 120]], float)
+    out = interp_dense_grid_from_sparse(img, pts, vals, 4, 4, False)
+    assert isinstance(out, np.ndarray) and out.shape == (4, 4, 3) and out is img
+    assert out[0, 0].tolist() == [10, 20, 30] and out[3, 3].tolist() == [70, 80, 90]
+    with pytest.raises(NotImplementedError):
+        interp_dense_grid_from_sparse(img, pts, vals, 4, 4, True)
+
+
+def test_dropin_bbox_sphere_bevparams():
+    from salve_b200.utils import bev_rendering_utils as bru
+    from salve_b200.utils.hohonet_pano_utils import get_uni_sphere_xyz
+
+    pts = np.array([[-2, 2], [2, 0], [1, 2], [0, 1]])
+    rgb = np.array([[255, 128, 0], [1, 2, 3], [4, 5, 6], [7, 8, 9]])
+    vp, vr = bru.prune_to_2d_bbox(pts, rgb, -1, -1, 1, 2)  # reference tests/utils/test_bev_rendering_utils.py:8-40
+    assert vp.tolist() == [[1, 2], [0, 1]] and vr.tolist() == [[4, 5, 6], [7, 8, 9]]
+    s = get_uni_sphere_xyz(512, 1024)  # reference tests/test_hohonet_pano_utils.py:8-24
+    assert np.allclose(s[256, 512], [-1, 0, 0], atol=4e-3) and np.allclose(s[0, 0], [0, 0, 1], atol=4e-3)
+    assert np.array_equal(s, bo.uni_sphere_xyz(512, 1024))
+
+
+# ---- edge cases -----------------------------------------------------------------------------------------------
+def _cloud(xy, z=-1.2, rgb=(0.5, 0.25, 1.0)):
+    xy = np.asarray(xy, float)
+    n = len(xy)
+    return np.concatenate([xy, np.full((n, 1), z), np.tile(np.asarray(rgb, float), (n, 1))], 1)
+
+
+def test_edge_empty_cloud_returns_none():
+    from salve_b200.common.bevparams import BEVParams
+    from salve_b200.utils.bev_rendering_utils import render_bev_image
+
+    assert render_bev_image(BEVParams(), _cloud([[9.0, 9.0], [-7.0, 0.0]]), False) is None
+    assert render_bev_image(BEVParams(), np.zeros((0, 6)), False) is None
+
+
+def test_edge_degenerate_clouds_render_zero():
+    from salve_b200.common.bevparams import BEVParams
+    from salve_b200.utils.bev_rendering_utils import render_bev_image
+
+    p = BEVParams()
+    for xy in ([[0, 0], [1, 1], [2, 0.5]], [[0, 0], [1, 0], [2, 0], [3, 0]], [[1, -2], [1, -1], [1, 0], [1, 3]]):
+        img = render_bev_image(p, _cloud(xy), False)
+        assert img.shape == (501, 501, 3) and not img.any()
+    img = render_bev_image(p, _cloud([[0, 0], [1, 0], [0, 1], [1, 1]], z=5.0), False)  # z outside [-2, 2): no site
+    assert not img.any()
+    img = render_bev_image(p, _cloud([[5.0, 5.0], [-5.0, -5.0], [5.0, -5.0], [-5.0, 5.0]]), False)  # inclusive bbox -> corners
+    assert img[0, 500].tolist() == [127, 63, 255] and img[500, 0].tolist() == [127, 63, 255]
+
+
+def test_edge_oblique_collinear_raises_like_qhull():
+    from salve_b200.utils.interpolation_utils import QhullError, interp_dense_grid_from_sparse
+
+    pts = np.array([[i, i] for i in range(6)])
+    with pytest.raises(QhullError):
+        interp_dense_grid_from_sparse(np.zeros((8, 8, 3), np.uint8), pts, np.full((6, 3), 9.0), 8, 8, False)
+
+
+def test_interp_dense_fuzz_against_oracle_and_scipy():
+    """Random site sets on small grids: every zipper / ghost / flip corner case (single-site rows, gaps,
+    full rows, diagonals).  Interpolation bit-exact vs the canonical oracle; hull mask equal to SciPy's."""
+    import scipy.interpolate
+
+    from salve_b200.renderer import BevRenderer
+
+    r = BevRenderer(max_panos=1, max_images=1, grid_h=48, grid_w=96)
+    rng = np.random.default_rng(123)
+    n_cases = 0
+    for it in range(400):
+        h = int(rng.integers(2, 48)); w = int(rng.integers(2, 96))
+        occ = rng.random((h, w)) < rng.choice([0.03, 0.1, 0.3, 0.7, 1.0])
+        mode = it % 6
+        if mode == 1:
+            occ[:] = False
+            for rr in range(h):
+                occ[rr, rng.integers(0, w)] = True
+        elif mode == 2:
+            occ[:] = False
+            for rr in range(min(h, w)):
+                occ[rr, rr] = True
+            occ[rng.integers(0, h), rng.integers(0, w)] = True
+        elif mode == 3:
+            occ[rng.integers(0, h)] = True  # one full row
+        rows, cols = np.nonzero(occ)
+        if len(rows) < 4 or len(set(rows)) < 2 or len(set(cols)) < 2:
+            continue
+        vals = rng.integers(0, 256, (len(rows), 3)).astype(np.float64)
+        perm = rng.permutation(len(rows))  # the GPU result must not depend on input order
+        img, hull, status = r.interp_dense(np.stack([cols, rows], 1)[perm], vals[perm], h, w, want_hull=True)
+        tri_v, _ = cdt.triangulate(rows, cols, w)
+        if not (tri_v >= 0).all(1).any():
+            assert status == 3
+            continue
+        assert status == 0
+        want, want_hull, _ = cdt.rasterize(rows, cols, vals.astype(np.uint8), tri_v, h, w)
+        assert np.array_equal(img, want), f"case {it} ({h}x{w}, {len(rows)} sites)"
+        assert np.array_equal(hull, want_hull)
+        xg, yg = np.meshgrid(np.arange(w), np.arange(h))
+        sv = scipy.interpolate.griddata(np.stack([cols, rows], 1).astype(float), vals, np.stack([xg.ravel(), yg.ravel()], 1).astype(float), "linear")
+        pu.hull_check(want_hull, ~np.isnan(sv[:, 0]).reshape(h, w))
+        n_cases += 1
+    assert n_cases > 250
+    r.close()
+
+
+def test_render_cloud_equals_pano_path(R):
+    """render_bev_image on the oracle's posed cloud == the fused pano path (same winners, same image)."""
+    from salve_b200.common.bevparams import BEVParams
+    from salve_b200.utils.bev_rendering_utils import render_bev_image
+
+    rgb, d = synth.synth_pano(512, 1024, 41, "smooth")
+    Rm, t = synth.synth_pose(6)
+    R.upload_pano(3, rgb, d)
+    img, _, st = R.render_images([3], ["floor"], [1], Rm[None], t[None])
+    cloud, _, _ = bo.backproject(rgb, d, bo.BANDS["floor"])
+    bo.to_zind_frame(cloud); bo.apply_pose(cloud, Rm, t)
+    got = render_bev_image(BEVParams(), cloud, False)
+    assert np.array_equal(got, img[0])
+
+
+def test_file_driver_roundtrip(tmp_path):
+    """generate_texture_maps_for_pair: naming, outputs, skip-if-exists (reference bev_rendering_utils.py:525-663)."""
+    import cv2
+
+    from salve_b200.common.sim2 import Sim2
+    from salve_b200.utils import bev_rendering_utils as bru
+
+    b = "0001"
+    (tmp_path / "panos").mkdir(); (tmp_path / "depth" / b).mkdir(parents=True); (tmp_path / "hyp").mkdir()
+    paths = {}
+    for k in (3, 7):
+        rgb, d = synth.synth_pano(512, 1024, 50 + k, "smooth")
+        p = tmp_path / "panos" / f"floor_01_partial_room_0{k}_pano_{k}.png"
+        cv2.imwrite(str(p), rgb[:, :, ::-1])
+        cv2.imwrite(str(tmp_path / "depth" / b / f"{p.stem}.depth.png"), d)
+        paths[k] = str(p)
+    Rm, t = synth.synth_pose(8)
+    pair = tmp_path / "hyp" / "3_7__door_0_0_identity.json"
+    Sim2(Rm.astype(np.float64), t.astype(np.float64), 1.0).save_as_json(str(pair))
+    kw = dict(img_fpaths_dict=paths, surface_type="floor", pair_fpath=str(pair), pair_idx=58, label_type="gt_alignment_approx",
+              bev_save_root=str(tmp_path / "bev"), building_id=b, floor_id="floor_01", depth_save_root=str(tmp_path / "depth"),
+              render_modalities=["rgb_texture"], layout_save_root=None, floor_pose_graph=None)
+    bru.generate_texture_maps_for_pair(**kw)
+    out = sorted(os.listdir(tmp_path / "bev" / "gt_alignment_approx" / b))
+    assert out == [
+        "pair_58___door_0_0_identity_floor_rgb_floor_01_partial_room_03_pano_3.jpg",
+        "pair_58___door_0_0_identity_floor_rgb_floor_01_partial_room_07_pano_7.jpg",
+    ]
+    im = cv2.imread(str(tmp_path / "bev" / "gt_alignment_approx" / b / out[0]))
+    assert im.shape == (501, 501, 3) and im.any()
+    m0 = os.path.getmtime(tmp_path / "bev" / "gt_alignment_approx" / b / out[0])
+    bru.generate_texture_maps_for_pair(**kw)  # resume: skip
+    assert os.path.getmtime(tmp_path / "bev" / "gt_alignment_approx" / b / out[0]) == m0
+    # pixel parity of the arrays path behind it, against the oracle
+    rgb1 = cv2.imread(paths[3])[:, :, ::-1]; d1 = cv2.imread(str(tmp_path / "depth" / b / f"{os.path.basename(paths[3])[:-4]}.depth.png"), cv2.IMREAD_UNCHANGED)
+    rgb2 = cv2.imread(paths[7])[:, :, ::-1]; d2 = cv2.imread(str(tmp_path / "depth" / b / f"{os.path.basename(paths[7])[:-4]}.depth.png"), cv2.IMREAD_UNCHANGED)
+    args = type("A", (), {})()
+    args.__dict__.update(img_i1=paths[3], img_i2=paths[7], depth_i1=str(tmp_path / "depth" / b / f"{os.path.basename(paths[3])[:-4]}.depth.png"),
+                         depth_i2=str(tmp_path / "depth" / b / f"{os.path.basename(paths[7])[:-4]}.depth.png"), scale=0.001, crop_ratio=80 / 512,
+                         crop_z_range=[-float("inf"), -1.0])
+    i1, i2 = bru.render_bev_pair(args, b, "floor_01", 3, 7, Sim2.from_json(str(pair)), False)
+    s1, s2 = bo.render_pair(np.ascontiguousarray(rgb1), d1, np.ascontiguousarray(rgb2), d2, Rm, t, "floor")
+    for img, st in ((i1, s1), (i2, s2)):
+        assert np.array_equal(img, pu.canonical_final(st, pu.oracle_canonical(st)))
+    bad = type("A", (), {})(); bad.__dict__.update(scale=0.001, crop_z_range=[0, 1])
+    with pytest.raises(ValueError):
+        bru.get_xyzrgb_from_depth(bad, "x", "y", False)

@@ -1,0 +1,109 @@
+"""Host-side mirror types and the multi-GPU sharding logic (gloo, world_size 2)."""
+
+import json
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from salve_b200.common.bevparams import BEVParams, get_line_width_by_resolution
+from salve_b200.common.sim2 import Sim2
+from salve_b200.utils.mesh_grid import get_mesh_grid_as_point_cloud
+from salve_b200 import sharding
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_bevparams_kat():
+    """reference tests/common/test_bevparams.py:9-50."""
+    p = BEVParams(img_h=20, img_w=20, meters_per_px=0.5)
+    got = p.bevimg_Sim2_world.transform_from(np.array([[2, 2], [-5, -5], [5, 5]]))
+    assert np.allclose(got, [[14, 14], [0, 0], [20, 20]])
+    assert [get_line_width_by_resolution(r) for r in (0.005, 0.01, 0.02)] == [30, 15, 8]
+    d = BEVParams()
+    assert d.xlims == [-5, 5] and d.ylims == [-5, 5] and d.img_h == 500
+
+
+def test_sim2_contract(tmp_path):
+    """reference tests/common/test_sim2.py: constructor errors, float32 storage, transform, JSON, compose/inverse."""
+    with pytest.raises(ValueError):
+        Sim2(np.eye(3), np.zeros(2), 1.0)
+    with pytest.raises(ValueError):
+        Sim2(np.eye(2), np.zeros(3), 1.0)
+    with pytest.raises(ValueError):
+        Sim2([[1, 0], [0, 1]], np.zeros(2), 1.0)
+    with pytest.raises(ZeroDivisionError):
+        Sim2(np.eye(2), np.zeros(2), 0.0)
+    th = np.deg2rad(30)
+    R = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+    s = Sim2(R, np.array([1.0, 2.0]), 3.0)
+    assert s.rotation.dtype == np.float32 and s.translation.dtype == np.float32 and isinstance(s.scale, float)
+    assert abs(s.theta_deg - 30) < 1e-4
+    pts = np.array([[1.0, 0.0], [0.0, 1.0]])
+    assert np.allclose(s.transform_from(pts), (pts @ R.T + [1, 2]) * 3, atol=1e-6)
+    with pytest.raises(ValueError):
+        s.transform_from(np.zeros((3, 3)))
+    ident = s.compose(s.inverse())
+    assert np.allclose(ident.rotation, np.eye(2), atol=1e-6) and np.allclose(ident.translation, 0, atol=1e-5) and np.isclose(ident.scale, 1)
+    f = tmp_path / "a_Sim2_b.json"
+    s.save_as_json(str(f))
+    d = json.load(open(f))
+    assert set(d) == {"R", "t", "s"} and len(d["R"]) == 4 and len(d["t"]) == 2
+    assert Sim2.from_json(str(f)) == s
+    assert Sim2.from_matrix(s.matrix) == s
+
+
+def test_mesh_grid_order():
+    g = get_mesh_grid_as_point_cloud(0, 2, 0, 1)
+    assert g.tolist() == [[0, 0], [1, 0], [2, 0], [0, 1], [1, 1], [2, 1]]  # x fastest
+
+
+def test_shard_assignment_balances_and_partitions():
+    counts = [633, 10, 400, 399, 50, 700, 1, 1, 300, 300]
+    for world in (1, 2, 4, 8):
+        parts = sharding.assign_buildings(counts, world)
+        flat = sorted(b for p in parts for b in p)
+        assert flat == list(range(len(counts)))
+        loads = [sum(counts[b] for b in p) for p in parts]
+        assert max(loads) - min(loads) <= max(counts)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    counts = [5, 3, 8, 1, 9, 2]
+    mine = sharding.assign_buildings(counts, world)[rank]
+    local = {b: counts[b] for b in mine}  # pretend each hypothesis was rendered
+    total, per_rank = sharding.gather_totals(sum(local.values()), elapsed_s=0.5 + rank)
+    q.put((rank, sorted(mine), total, per_rank))
+    dist.destroy_process_group()
+
+
+def test_gloo_world_size_2_shards_without_data_collective():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+    (r0, b0, tot0, pr0), (r1, b1, tot1, pr1) = res
+    assert sorted(b0 + b1) == [0, 1, 2, 3, 4, 5] and not set(b0) & set(b1)
+    assert tot0 == tot1 == dict(units=28, max_elapsed_s=1.5)
+    assert pr0 == pr1 and sum(pr0) == 28
