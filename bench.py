@@ -13,7 +13,7 @@ no collective on the data path; NCCL only for the barrier and the max-over-ranks
            between timed steps.
 `e2e`    : the same step through the host-buffer C ABI (pinned host panos -> H2D -> render ->
            D2H of all images), wall clock with synchronize on both sides.
-`roofline`: dominant kernel (the flip kernel), algorithmic bytes per launch / CUDA-event time.
+`roofline`: dominant kernel (image_kernel), algorithmic bytes per launch / CUDA-event time.
 `cpu_baseline` / `--impl reference`: the oracle port (numpy + SciPy restatement of the reference,
            bit-identical to it) on all host cores with multiprocessing.Pool -- the reference's own
            parallel mechanism (scripts/render_dataset_bev.py:111-113).
@@ -267,7 +267,7 @@ def run_ours(args):
         sampler.start()
     launches0 = r.launch_count()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    stage_ms = {"splat": 0.0, "sites": 0.0, "flip": 0.0, "raster": 0.0, "total": 0.0}
+    stage_ms = {"splat": 0.0, "image": 0.0, "total": 0.0}
     barrier()
     for k in range(args.steps):
         flush.fill_(k & 0xFF)
@@ -326,19 +326,18 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel ---------------------------------------------------------------
     peak, peak_src = load_peaks()
-    n_tris = counts_h[:, 2].astype(np.int64) * 2 - 2
-    n_tris[status_h != 0] = 0
     sites = counts_h[:, 2].astype(np.int64)
+    filled = counts_h[:, 5].astype(np.int64)
     n_launch = args.steps * ((n_img + 591) // 592)
-    # algorithmic bytes per stage and step (DESIGN.md section "Kernels")
+    # algorithmic bytes per stage and step
     alg = {
-        "splat": 2 * N_HYP * 360448 * 2 + int(counts_h[:, 1].sum()) * 4,         # depth in (2 B/px per pano pass) + one 4 B key update per point in the box
-        "sites": n_img * IMG * IMG * 4 + int(sites.sum()) * 3 + int(n_tris.sum()) * 16 + n_img * IMG_BYTES,  # key grid in, winner colours in, mesh out, base image out
-        "flip": int(n_tris.sum()) * 16 * 2,                                       # mesh in + mesh out
-        "raster": int(n_tris.sum()) * 16 + int(sites.sum()) * 4 + int(counts_h[:, 4].sum() - counts_h[:, 2].sum()) * 3,  # mesh in, colours in, non-site kept pixels out
+        # depth in (2 B/px per pano pass) + one 4 B key update per point inside the box
+        "splat": 2 * N_HYP * 360448 * 2 + int(counts_h[:, 1].sum()) * 4,
+        # key grid in, winner colours in (3 B gathered per site), final image out
+        "image": n_img * IMG * IMG * 4 + int(sites.sum()) * 3 + n_img * IMG_BYTES,
     }
     kernels = {}
-    for name in ("splat", "sites", "flip", "raster"):
+    for name in ("splat", "image"):
         ms = stage_ms[name] / args.steps
         gbs = alg[name] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
         kernels[name] = {"ms_per_step": ms, "alg_bytes_per_step": alg[name], "achieved_gbs": gbs, "frac": gbs / peak,
@@ -346,7 +345,7 @@ def run_ours(args):
     dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
     chunks_per_step = (n_img + 591) // 592
     roofline = {
-        "kernel": {"splat": "splat_pano_kernel", "sites": "sites_kernel", "flip": "flip_kernel", "raster": "raster_kernel"}[dom],
+        "kernel": {"splat": "splat_pano_kernel", "image": "image_kernel"}[dom],
         "bound": "hbm",
         "achieved": kernels[dom]["achieved_gbs"],
         "peak": peak,
@@ -392,7 +391,7 @@ def run_ours(args):
         "roofline": roofline,
         "cpu_baseline": cpu,
         "images_ok": int((status_h == 0).sum()), "images": int(n_img),
-        "mean_sites": float(sites.mean()), "mean_flip_rounds": float(counts_h[:, 6].mean()),
+        "mean_sites": float(sites.mean()), "mean_filled_px": float(filled.mean()), "mean_flips_per_filled_px": float(counts_h[:, 7].sum() / max(filled.sum(), 1)),
     }
     print(json.dumps(line))
     if dist is not None:

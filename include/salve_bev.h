@@ -45,9 +45,10 @@ extern "C" {
 #define SALVE_BEV_CNT_SITES 2    /* distinct pixels after the z-order rule (zorder_utils.py:49-83)      */
 #define SALVE_BEV_CNT_NONEMPTY 3 /* sites counted non-empty by the uint8 product (interpolation_utils.py:95) */
 #define SALVE_BEV_CNT_KEEP 4     /* pixels of the hallucination keep-mask (interpolation_utils.py:101-115) */
-#define SALVE_BEV_CNT_TRIS 5     /* real Delaunay triangles */
-#define SALVE_BEV_CNT_ROUNDS 6   /* parallel flip rounds */
-#define SALVE_BEV_CNT_FLIPS 7    /* edge flips */
+#define SALVE_BEV_CNT_FILLED 5   /* non-site pixels interpolated (inside hull and keep-mask)          */
+#define SALVE_BEV_CNT_MAXFLIPS 6 /* longest flip descent of one query pixel (diagnostic)            */
+#define SALVE_BEV_CNT_FLIPS 7    /* Lawson flips in total (diagnostic; like MAXFLIPS it depends on how often two warps
+                                    reach the same large triangle, i.e. on timing -- images and counters 0..5 do not) */
 
 #define SALVE_BEV_SURF_FLOOR 1   /* z band (-inf, -1.0]   (bev_rendering_utils.py:560-562) */
 #define SALVE_BEV_SURF_CEILING 2 /* z band (0.5, +inf)    (bev_rendering_utils.py:564-566) */
@@ -124,7 +125,8 @@ int salve_bev_set_bands(salve_bev_ctx* ctx, double a_lo, double a_hi, double b_l
 int salve_bev_render_hypotheses(salve_bev_ctx* ctx, int32_t n_hyp, const int32_t* host_pano1, const int32_t* host_pano2,
                                 const float* host_R, const float* host_t, uint32_t surfaces, uint8_t* dev_out,
                                 int32_t* dev_counts, int32_t* dev_status, void* stream);
-/* Same, with host output buffers (device->host copies included; synchronises). */
+/* Same, with host output buffers (device->host copies included; synchronises).  Chunks are double buffered:
+ * chunk k+1 renders while chunk k is copied out on a private copy stream; pass page-locked host_out to get the overlap. */
 int salve_bev_render_hypotheses_host(salve_bev_ctx* ctx, int32_t n_hyp, const int32_t* host_pano1, const int32_t* host_pano2,
                                      const float* host_R, const float* host_t, uint32_t surfaces, uint8_t* host_out,
                                      int32_t* host_counts, int32_t* host_status, void* stream);
@@ -168,8 +170,8 @@ int salve_bev_choose_elevated(salve_bev_ctx* ctx, const int64_t* host_x, const i
 /*
  * Sparse -> dense: replaces interp_dense_grid_from_sparse (interpolation_utils.py:21-54) for
  * method="linear".  points: n x 2 int64 (x = column, y = row), distinct; values: n x 3 float64
- * (truncated to uint8 like interpolation_utils.py:53).  grid_h*grid_w <= 800000 (the flip kernel keeps
- * one bit per triangle in shared memory), grid_w <= 2047, grid_h <= 1023.  host_img: grid_h x grid_w x 3 uint8, fully overwritten unless *status ==
+ * (truncated to uint8 like interpolation_utils.py:53).  grid_h*grid_w <= 800000, grid_w <= 2047, grid_h <= 1023; grids whose
+ * bit rows fit shared memory (e.g. 501x501) use image_kernel, larger ones the explicit-mesh path.  host_img: grid_h x grid_w x 3 uint8, fully overwritten unless *status ==
  * SALVE_BEV_IMG_DEGENERATE (then untouched, as in the reference).  host_hull (may be NULL):
  * grid_h x grid_w uint8, 1 inside the closed convex hull.
  */
@@ -193,16 +195,24 @@ int salve_bev_remove_hallucinated(salve_bev_ctx* ctx, const uint8_t* host_sparse
 #define SALVE_BEV_TAP_OCC 2      /* grid_h*wpr uint32 bit rows: site present */
 #define SALVE_BEV_TAP_NONEMPTY 3 /* same layout: uint8 product != 0 */
 #define SALVE_BEV_TAP_KEEP 4     /* same layout: hallucination keep-mask */
-#define SALVE_BEV_TAP_TRIS 5     /* (2*sites-2) x 3 int32 vertex pixel ids row*grid_w+col, -1 = ghost (hull) */
+#define SALVE_BEV_TAP_TRIS 5     /* (2*sites-2) x 3 int32 vertex pixel ids row*grid_w+col, -1 = ghost (hull): the full Delaunay
+                                    mesh of the image, built on demand by the explicit-mesh path (zipper + parallel Lawson flips) */
 #define SALVE_BEV_TAP_INTERP 6   /* g*3 uint8: interpolated image before mask and flip */
 #define SALVE_BEV_TAP_HULL 7     /* g uint8: inside closed convex hull */
+#define SALVE_BEV_TAP_QTRI 8     /* g*3 int32: per interpolated pixel the vertex pixel ids of the Delaunay triangle its flip descent
+                                    ended in; -1 elsewhere */
 int salve_bev_tap(salve_bev_ctx* ctx, int32_t image, int32_t what, void* host_buf, int64_t host_buf_bytes, void* stream);
 
 /* Per-stage device time (ms, CUDA events) of the most recent render call, summed over its chunks:
- * [0] splat  [1] sites+zipper+mask  [2] flip  [3] raster  [4] total.  host_ms: 5 floats. */
+ * [0] splat (memset + splat_pano_kernel)  [1] image_kernel  [2], [3] reserved (0)  [4] total.  host_ms: 5 floats. */
 int salve_bev_last_timings(salve_bev_ctx* ctx, float* host_ms);
 /* Enable/disable per-stage event timing (off by default: events add sync points at read time only). */
 int salve_bev_enable_timing(salve_bev_ctx* ctx, int32_t on);
+
+/* Diagnostics of image_kernel for the images of the most recent chunk: 16 int64 per image.  [0..11] SM clock at the phase
+ * boundaries (start, sites, hull+masks, list, pass 1, shade, list, pass 1b, shade, list, pass 2, end); [12..14] number of
+ * pixels entering pass 1, pass 1b, pass 2.  host_clk: n_img * 16 int64.  Synchronises the device. */
+int salve_bev_last_phase_clocks(salve_bev_ctx* ctx, int64_t* host_clk, int32_t n_img);
 
 /* Number of kernel launches issued by this context since creation (bench.py's gpu_launches). */
 int64_t salve_bev_launch_count(salve_bev_ctx* ctx);

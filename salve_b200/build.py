@@ -10,7 +10,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.path.join(_PKG, "libsalve_bev.so")
 SOURCES = ["api.cu"]
-HEADERS = ["bev_common.cuh", "k_splat.cuh", "k_sites.cuh", "k_flip.cuh", "k_raster.cuh", "../../include/salve_bev.h"]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + ["../../include/salve_bev.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -10,6 +10,7 @@
 #include "../../include/salve_bev.h"
 #include "bev_common.cuh"
 #include "k_flip.cuh"
+#include "k_image.cuh"
 #include "k_raster.cuh"
 #include "k_sites.cuh"
 #include "k_splat.cuh"
@@ -33,7 +34,7 @@ static void set_err(const char* fmt, const char* a, const char* b, int line) { s
     } while (0)
 
 constexpr int N_TMP = 8;
-constexpr int N_STAGE_EVENTS = 5;
+constexpr int N_STAGE_EVENTS = 3;  // chunk start, after splat, after the image kernel
 
 struct salve_bev_ctx {
     salve_bev_config cfg;
@@ -54,13 +55,25 @@ struct salve_bev_ctx {
     Tri* tris = nullptr;
     unsigned long long* owner = nullptr;
     uint32_t *list0 = nullptr, *list1 = nullptr, *cand = nullptr;
+    uint32_t* qlist = nullptr;  // per image work list of image_kernel (g entries)
+    unsigned long long* qres = nullptr;  // per image, per list entry: the resolved triangle
+    long long* phase_clk = nullptr;      // diagnostics: 16 slots per image of the last chunk
+    uint32_t* keepbits = nullptr;        // per image keep-mask bit rows of image_kernel
     size_t g_stride = 0, bits_stride = 0, tris_stride = 0, cand_stride = 0;
     ImgHeader* headers = nullptr;
     int32_t* counts = nullptr;
     int32_t* status = nullptr;
     SplatJob* d_jobs = nullptr;
     const uint8_t** d_color_src = nullptr;
-    uint8_t* out_store = nullptr;  // max_images images, for the *_host variants
+    uint8_t* out_store = nullptr;  // 2 x max_images images (double buffered), for the *_host variants
+    // host-output pipeline: chunk k+1 renders while chunk k is copied device->host on copy_stream
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr}, ev_staged[2] = {nullptr, nullptr};
+    SplatJob* h_jobs[2] = {nullptr, nullptr};          // pinned staging of the per-chunk job tables
+    const uint8_t** h_src[2] = {nullptr, nullptr};
+    int stage_parity = 0;
+    int32_t* h_meta = nullptr;  // pinned staging of counts/status for the *_host variants (user arrays may be pageable,
+    size_t h_meta_cap = 0;      //  and a device->pageable async copy would block the host and serialise the pipeline)
     // growable temporaries
     void* tmp[N_TMP] = {nullptr};
     size_t tmp_bytes[N_TMP] = {0};
@@ -70,7 +83,10 @@ struct salve_bev_ctx {
     size_t events_used = 0;
     int64_t launches = 0;
     int last_chunk_images = 0;
+    int32_t* last_counts = nullptr;  // device counters of the last chunk (taps re-run the image kernel on a copy)
     size_t flip_smem = 0;
+    size_t image_smem = 0;           // dynamic shared memory of image_kernel for the context's grid
+    int max_smem_optin = 0;
     double band[4] = {-INFINITY, -1.0, 0.5, INFINITY};  // bev_rendering_utils.py:560-566
 };
 
@@ -142,24 +158,37 @@ extern "C" int salve_bev_ctx_create(const salve_bev_config* cfg, salve_bev_ctx**
     ALLOC(c->d_depth_ptr, P);
     ALLOC(c->d_tables, 2 * H + 2 * W);
     ALLOC(c->keygrid, N * c->g_stride);
-    ALLOC(c->color, N * c->g_stride);
-    ALLOC(c->occ, N * c->bits_stride);
-    ALLOC(c->nonempty, N * c->bits_stride);
-    ALLOC(c->keep, N * c->bits_stride);
-    ALLOC(c->tmpbits, N * c->bits_stride);
-    ALLOC(c->wprefix, N * c->bits_stride);
-    ALLOC(c->tris, N * c->tris_stride);
-    ALLOC(c->owner, N * c->tris_stride);
-    ALLOC(c->list0, N * c->tris_stride);
-    ALLOC(c->list1, N * c->tris_stride);
-    ALLOC(c->cand, N * c->cand_stride);
+    ALLOC(c->qlist, N * c->g_stride);
+    ALLOC(c->qres, N * c->g_stride);
+    ALLOC(c->phase_clk, N * 16);
+    ALLOC(c->keepbits, N * c->bits_stride);
+    // mesh scratch (explicit triangulation: grids too large for image_kernel's shared memory, and the triangle tap): ONE image
+    ALLOC(c->color, c->g_stride);
+    ALLOC(c->occ, c->bits_stride);
+    ALLOC(c->nonempty, c->bits_stride);
+    ALLOC(c->keep, c->bits_stride);
+    ALLOC(c->tmpbits, c->bits_stride);
+    ALLOC(c->wprefix, c->bits_stride);
+    ALLOC(c->tris, c->tris_stride);
+    ALLOC(c->owner, c->tris_stride);
+    ALLOC(c->list0, c->tris_stride);
+    ALLOC(c->list1, c->tris_stride);
+    ALLOC(c->cand, c->cand_stride);
     ALLOC(c->headers, N);
-    ALLOC(c->counts, N * 8);
-    ALLOC(c->status, N);
+    ALLOC(c->counts, 2 * N * 8);
+    ALLOC(c->status, 2 * N);
     ALLOC(c->d_jobs, N);
     ALLOC(c->d_color_src, N);
-    ALLOC(c->out_store, N * c->img_bytes);
+    ALLOC(c->out_store, 2 * N * c->img_bytes);
 #undef ALLOC
+    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++) {
+        CU(cudaEventCreateWithFlags(&c->ev_done[k], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_copied[k], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_staged[k], cudaEventDisableTiming));
+        CU(cudaMallocHost((void**)&c->h_jobs[k], sizeof(SplatJob) * N));
+        CU(cudaMallocHost((void**)&c->h_src[k], sizeof(void*) * N));
+    }
     c->h_rgb_ptr.assign(P, nullptr);
     c->h_depth_ptr.assign(P, nullptr);
     for (size_t s = 0; s < P; s++) {
@@ -171,6 +200,14 @@ extern "C" int salve_bev_ctx_create(const salve_bev_config* cfg, salve_bev_ctx**
     CU(cudaMemcpy(c->d_tables, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
     c->flip_smem = ((2 * g + 31) / 32) * 4 + 16;
     CU(cudaFuncSetAttribute(flip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->flip_smem));
+    CU(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
+    c->image_smem = image_smem_bytes(c->G.grid_h, c->G.wpr);
+    {
+        cudaFuncAttributes fa;
+        CU(cudaFuncGetAttributes(&fa, image_kernel));
+        c->max_smem_optin -= (int)fa.sharedSizeBytes;  // what is left for dynamic shared memory
+        CU(cudaFuncSetAttribute(image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
+    }
     *out = c;
     return SALVE_BEV_OK;
 }
@@ -180,11 +217,20 @@ extern "C" void salve_bev_ctx_destroy(salve_bev_ctx* c) {
     cudaSetDevice(c->cfg.device);
     cudaDeviceSynchronize();
     void* ptrs[] = {c->pano_rgb_store, c->pano_depth_store, c->d_depth_ptr, c->d_tables, c->keygrid, c->color, c->occ, c->nonempty,
-                    c->keep, c->tmpbits, c->wprefix, c->tris, c->owner, c->list0, c->list1, c->cand, c->headers, c->counts,
+                    c->keep, c->tmpbits, c->wprefix, c->tris, c->owner, c->list0, c->list1, c->cand, c->qlist, c->qres, c->phase_clk, c->keepbits, c->headers, c->counts,
                     c->status, c->d_jobs, c->d_color_src, c->out_store};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < N_TMP; i++) if (c->tmp[i]) cudaFree(c->tmp[i]);
     for (cudaEvent_t e : c->events) cudaEventDestroy(e);
+    for (int k = 0; k < 2; k++) {
+        if (c->ev_done[k]) cudaEventDestroy(c->ev_done[k]);
+        if (c->ev_copied[k]) cudaEventDestroy(c->ev_copied[k]);
+        if (c->ev_staged[k]) cudaEventDestroy(c->ev_staged[k]);
+        if (c->h_jobs[k]) cudaFreeHost(c->h_jobs[k]);
+        if (c->h_src[k]) cudaFreeHost(c->h_src[k]);
+    }
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->h_meta) cudaFreeHost(c->h_meta);
     delete c;
 }
 
@@ -271,24 +317,47 @@ static int stage_event(salve_bev_ctx* c, cudaStream_t st) {
     return SALVE_BEV_OK;
 }
 
-// Stages 2-4 on images [0, n_img) of the scratch: sites+zipper+mask+base image, flips, raster.
-static int run_mesh_stages(salve_bev_ctx* c, int n_img, const GridParams& G, uint8_t* dev_out, int32_t* dev_counts, int32_t* dev_status,
-                           int raw_mode, int skip_empty, uint8_t* hull, cudaStream_t st) {
+// Everything after the splat for images [0, n_img): image_kernel (sites, masks, hull, query-driven flips).
+static int run_image_stage(salve_bev_ctx* c, int n_img, const GridParams& G, const uint32_t* keygrid, const uint8_t* const* color_src,
+                           uint8_t* dev_out, int32_t* dev_counts, int32_t* dev_status, int raw_mode, int skip_empty, uint8_t* hull,
+                           int32_t* qtri, uint32_t* bits, cudaStream_t st) {
+    const size_t smem = image_smem_bytes(G.grid_h, G.wpr);
+    if (smem > (size_t)c->max_smem_optin) FAIL(SALVE_BEV_E_CAPACITY, "grid too large for image_kernel's shared memory");
+    ImageArgs IA;
+    IA.G = G;
+    IA.keygrid = keygrid; IA.keygrid_stride = c->g_stride;
+    IA.color_src = color_src;
+    IA.counts = dev_counts; IA.status = dev_status;
+    IA.out = dev_out; IA.out_stride = (size_t)G.g * 3;
+    IA.hull = hull; IA.hull_stride = (size_t)G.g;
+    IA.qtri = qtri; IA.qtri_stride = (size_t)G.g * 3;
+    IA.bits = bits; IA.bits_stride = 3 * (size_t)G.grid_h * G.wpr;
+    IA.qlist = c->qlist; IA.qlist_stride = c->g_stride; IA.qres = c->qres; IA.keepbits = c->keepbits; IA.keepbits_stride = c->bits_stride; IA.phase_clk = (n_img <= c->cfg.max_images && keygrid == c->keygrid) ? c->phase_clk : nullptr;
+    IA.raw_mode = raw_mode; IA.skip_empty_check = skip_empty;
+    image_kernel<<<n_img, IMAGE_NT, smem, st>>>(IA);
+    c->launches++;
+    CU(cudaGetLastError());
+    return stage_event(c, st);
+}
+
+// Explicit-mesh path on ONE image (mesh scratch): sites + zipper, parallel Lawson flips, and (optionally) the rasteriser.
+// Used for grids that exceed image_kernel's shared memory and for the triangle tap.
+static int run_mesh_stages(salve_bev_ctx* c, const GridParams& G, const uint32_t* keygrid, const uint8_t* const* color_src, uint8_t* dev_out,
+                           int32_t* dev_counts, int32_t* dev_status, int raw_mode, int skip_empty, uint8_t* hull, bool raster, cudaStream_t st) {
     SitesArgs SA;
     SA.G = G;
-    SA.keygrid = c->keygrid; SA.keygrid_stride = c->g_stride;
+    SA.keygrid = const_cast<uint32_t*>(keygrid); SA.keygrid_stride = c->g_stride;
     SA.color = c->color; SA.color_stride = c->g_stride;
     SA.occ = c->occ; SA.nonempty = c->nonempty; SA.keep = c->keep; SA.tmpbits = c->tmpbits; SA.bits_stride = c->bits_stride;
     SA.wprefix = c->wprefix;
     SA.tris = c->tris; SA.tris_stride = c->tris_stride;
     SA.headers = c->headers; SA.counts = dev_counts; SA.status = dev_status;
-    SA.color_src = c->d_color_src;
+    SA.color_src = color_src;
     SA.out = dev_out; SA.out_stride = (size_t)G.g * 3;
     SA.raw_mode = raw_mode; SA.skip_empty_check = skip_empty;
-    sites_kernel<<<n_img, SITES_NT, 0, st>>>(SA);
+    sites_kernel<<<1, SITES_NT, 0, st>>>(SA);
     c->launches++;
     CU(cudaGetLastError());
-    int rc = stage_event(c, st); if (rc) return rc;
 
     FlipArgs FA;
     FA.grid_w = G.grid_w;
@@ -300,10 +369,10 @@ static int run_mesh_stages(salve_bev_ctx* c, int n_img, const GridParams& G, uin
     const size_t flip_smem = ((2 * (size_t)G.g + 31) / 32) * 4 + 16;
     // the attribute is per function, not per context: (re)assert it for this launch
     CU(cudaFuncSetAttribute(flip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(flip_smem, (size_t)49152)));
-    flip_kernel<<<n_img, FLIP_NT, flip_smem, st>>>(FA);
+    flip_kernel<<<1, FLIP_NT, flip_smem, st>>>(FA);
     c->launches++;
     CU(cudaGetLastError());
-    rc = stage_event(c, st); if (rc) return rc;
+    if (!raster) return SALVE_BEV_OK;
 
     RasterArgs RA;
     RA.G = G;
@@ -314,10 +383,10 @@ static int run_mesh_stages(salve_bev_ctx* c, int n_img, const GridParams& G, uin
     RA.out = dev_out; RA.out_stride = (size_t)G.g * 3;
     RA.hull = hull; RA.hull_stride = (size_t)G.g;
     RA.raw_mode = raw_mode;
-    raster_kernel<<<n_img, RASTER_NT, 0, st>>>(RA);
+    raster_kernel<<<1, RASTER_NT, 0, st>>>(RA);
     c->launches++;
     CU(cudaGetLastError());
-    return stage_event(c, st);
+    return SALVE_BEV_OK;
 }
 
 // One chunk of pano-sourced images.  jobs / color slots are host arrays.
@@ -325,14 +394,17 @@ static int render_chunk(salve_bev_ctx* c, int n_img, const std::vector<SplatJob>
                         int32_t* dev_counts, int32_t* dev_status, cudaStream_t st) {
     if (n_img > c->cfg.max_images || (int)jobs.size() > c->cfg.max_images) FAIL(SALVE_BEV_E_CAPACITY, "chunk exceeds max_images");
     int rc = sync_ptr_tables(c, st); if (rc) return rc;
-    std::vector<const uint8_t*> src(n_img);
+    // job tables go through pinned, double-buffered staging so that the chunk loop never blocks the host
+    const int sp = c->stage_parity; c->stage_parity ^= 1;
+    CU(cudaEventSynchronize(c->ev_staged[sp]));  // the copy issued two chunks ago from this staging buffer has been consumed
     for (int i = 0; i < n_img; i++) {
         if (img_slot[i] < 0 || img_slot[i] >= c->cfg.max_panos) FAIL(SALVE_BEV_E_CAPACITY, "pano slot out of range");
-        src[i] = c->h_rgb_ptr[img_slot[i]];
+        c->h_src[sp][i] = c->h_rgb_ptr[img_slot[i]];
     }
-    CU(cudaMemcpyAsync(c->d_jobs, jobs.data(), sizeof(SplatJob) * jobs.size(), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(c->d_color_src, src.data(), sizeof(void*) * n_img, cudaMemcpyHostToDevice, st));
-    CU(cudaStreamSynchronize(st));  // host vectors go out of scope; copies from pageable memory are staged anyway
+    memcpy(c->h_jobs[sp], jobs.data(), sizeof(SplatJob) * jobs.size());
+    CU(cudaMemcpyAsync(c->d_jobs, c->h_jobs[sp], sizeof(SplatJob) * jobs.size(), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->d_color_src, c->h_src[sp], sizeof(void*) * n_img, cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(c->ev_staged[sp], st));
     if (!dev_counts) dev_counts = c->counts;
     rc = stage_event(c, st); if (rc) return rc;
     CU(cudaMemsetAsync(c->keygrid, 0, sizeof(uint32_t) * c->g_stride * n_img, st));
@@ -346,7 +418,8 @@ static int render_chunk(salve_bev_ctx* c, int n_img, const std::vector<SplatJob>
     CU(cudaGetLastError());
     rc = stage_event(c, st); if (rc) return rc;
     c->last_chunk_images = n_img;
-    return run_mesh_stages(c, n_img, c->G, dev_out, dev_counts, dev_status, 0, 0, nullptr, st);
+    c->last_counts = dev_counts;
+    return run_image_stage(c, n_img, c->G, c->keygrid, c->d_color_src, dev_out, dev_counts, dev_status, 0, 0, nullptr, nullptr, nullptr, st);
 }
 
 static int render_hyp_impl(salve_bev_ctx* c, int32_t n_hyp, const int32_t* p1, const int32_t* p2, const float* R, const float* t,
@@ -363,6 +436,17 @@ static int render_hyp_impl(salve_bev_ctx* c, int32_t n_hyp, const int32_t* p1, c
     c->events_used = 0;
     std::vector<SplatJob> jobs;
     std::vector<int> slots;
+    const size_t n_img_total = (size_t)n_hyp * per_hyp;
+    if (host_out && (counts || status)) {
+        if (c->h_meta_cap < n_img_total * 9) {
+            if (c->h_meta) CU(cudaFreeHost(c->h_meta));
+            c->h_meta = nullptr; c->h_meta_cap = 0;
+            CU(cudaMallocHost((void**)&c->h_meta, sizeof(int32_t) * n_img_total * 9));
+            c->h_meta_cap = n_img_total * 9;
+        }
+    }
+    int32_t* h_counts = c->h_meta;
+    int32_t* h_status = c->h_meta ? c->h_meta + n_img_total * 8 : nullptr;
     for (int h0 = 0; h0 < n_hyp; h0 += hyp_per_chunk) {
         const int nh = std::min(hyp_per_chunk, n_hyp - h0);
         const int n_img = nh * per_hyp;
@@ -385,17 +469,29 @@ static int render_hyp_impl(salve_bev_ctx* c, int32_t n_hyp, const int32_t* p1, c
             if (c1 >= 0) { slots[c1] = a.pano_slot; slots[c2] = b.pano_slot; }
         }
         const size_t img0 = (size_t)h0 * per_hyp;
-        uint8_t* d_out = host_out ? c->out_store : out + img0 * c->img_bytes;
-        int32_t* d_counts = host_out ? c->counts : (counts ? counts + img0 * 8 : nullptr);
-        int32_t* d_status = host_out ? c->status : (status ? status + img0 : nullptr);
+        const int par = (int)((h0 / hyp_per_chunk) & 1);
+        const size_t N = c->cfg.max_images;
+        uint8_t* d_out = host_out ? c->out_store + par * N * c->img_bytes : out + img0 * c->img_bytes;
+        int32_t* d_counts = host_out ? c->counts + par * N * 8 : (counts ? counts + img0 * 8 : nullptr);
+        int32_t* d_status = host_out ? c->status + par * N : (status ? status + img0 : nullptr);
+        if (host_out) CU(cudaStreamWaitEvent(st, c->ev_copied[par], 0));  // buffer `par` was drained (chunk k-2)
         int rc = render_chunk(c, n_img, jobs, slots, d_out, d_counts, d_status, st);
         if (rc) return rc;
         if (host_out) {
-            CU(cudaMemcpyAsync(out + img0 * c->img_bytes, c->out_store, (size_t)n_img * c->img_bytes, cudaMemcpyDeviceToHost, st));
-            if (counts) CU(cudaMemcpyAsync(counts + img0 * 8, c->counts, sizeof(int32_t) * 8 * n_img, cudaMemcpyDeviceToHost, st));
-            if (status) CU(cudaMemcpyAsync(status + img0, c->status, sizeof(int32_t) * n_img, cudaMemcpyDeviceToHost, st));
-            CU(cudaStreamSynchronize(st));  // out_store is reused by the next chunk
+            // device->host on the copy stream, overlapping the next chunk's kernels
+            CU(cudaEventRecord(c->ev_done[par], st));
+            CU(cudaStreamWaitEvent(c->copy_stream, c->ev_done[par], 0));
+            CU(cudaMemcpyAsync(out + img0 * c->img_bytes, d_out, (size_t)n_img * c->img_bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+            if (counts) CU(cudaMemcpyAsync(h_counts + img0 * 8, d_counts, sizeof(int32_t) * 8 * n_img, cudaMemcpyDeviceToHost, c->copy_stream));
+            if (status) CU(cudaMemcpyAsync(h_status + img0, d_status, sizeof(int32_t) * n_img, cudaMemcpyDeviceToHost, c->copy_stream));
+            CU(cudaEventRecord(c->ev_copied[par], c->copy_stream));
         }
+    }
+    if (host_out) {
+        CU(cudaStreamSynchronize(c->copy_stream));
+        CU(cudaStreamSynchronize(st));
+        if (counts) memcpy(counts, h_counts, sizeof(int32_t) * 8 * n_img_total);
+        if (status) memcpy(status, h_status, sizeof(int32_t) * n_img_total);
     }
     return SALVE_BEV_OK;
 }
@@ -507,7 +603,8 @@ extern "C" int salve_bev_render_cloud_host(salve_bev_ctx* c, const double* host_
         CU(cudaGetLastError());
     }
     c->last_chunk_images = 1;
-    rc = run_mesh_stages(c, 1, c->G, c->out_store, c->counts, c->status, 0, 0, nullptr, st);
+    c->last_counts = c->counts;
+    rc = run_image_stage(c, 1, c->G, c->keygrid, c->d_color_src, c->out_store, c->counts, c->status, 0, 0, nullptr, nullptr, nullptr, st);
     if (rc) return rc;
     CU(cudaMemcpyAsync(host_out, c->out_store, c->img_bytes, cudaMemcpyDeviceToHost, st));
     if (host_counts) CU(cudaMemcpyAsync(host_counts, c->counts, sizeof(int32_t) * 8, cudaMemcpyDeviceToHost, st));
@@ -603,7 +700,11 @@ extern "C" int salve_bev_interp_dense(salve_bev_ctx* c, const int64_t* host_xy, 
         CU(cudaGetLastError());
     }
     c->last_chunk_images = 1;
-    rc = run_mesh_stages(c, 1, G, c->out_store, c->counts, c->status, 1, 1, (uint8_t*)dhull, st);
+    c->last_counts = c->counts;
+    if (image_smem_bytes(G.grid_h, G.wpr) <= (size_t)c->max_smem_optin)
+        rc = run_image_stage(c, 1, G, c->keygrid, c->d_color_src, c->out_store, c->counts, c->status, 1, 1, (uint8_t*)dhull, nullptr, nullptr, st);
+    else
+        rc = run_mesh_stages(c, G, c->keygrid, c->d_color_src, c->out_store, c->counts, c->status, 1, 1, (uint8_t*)dhull, true, st);
     if (rc) return rc;
     int herr = 0, hstatus = 0;
     CU(cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -645,6 +746,11 @@ extern "C" int salve_bev_remove_hallucinated(salve_bev_ctx* c, const uint8_t* ho
     return SALVE_BEV_OK;
 }
 
+__global__ void fill_i32_kernel(int32_t* p, size_t n, int32_t v) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
 extern "C" int salve_bev_tap(salve_bev_ctx* c, int32_t image, int32_t what, void* host_buf, int64_t host_buf_bytes, void* stream) {
     if (!c || !host_buf) FAIL(SALVE_BEV_E_INVALID, "null argument");
     if (image < 0 || image >= c->last_chunk_images) FAIL(SALVE_BEV_E_INVALID, "image index outside the last chunk");
@@ -652,55 +758,89 @@ extern "C" int salve_bev_tap(salve_bev_ctx* c, int32_t image, int32_t what, void
     CU(cudaSetDevice(c->cfg.device));
     const GridParams& G = c->G;
     const size_t g = G.g, bits = (size_t)G.grid_h * G.wpr;
-    const void* src = nullptr; size_t bytes = 0;
+    const uint32_t* kg = c->keygrid + (size_t)image * c->g_stride;
+    const uint8_t* const* csrc = c->d_color_src + image;
+    const bool img_ok = image_smem_bytes(G.grid_h, G.wpr) <= (size_t)c->max_smem_optin;
+    // taps recompute from the image's key grid (which the render leaves intact) on a private copy of its counters
+    void* dcnt; int rc;
+    if ((rc = tmp_get(c, 6, 64, &dcnt))) return rc;
+    if (c->last_counts) CU(cudaMemcpyAsync(dcnt, c->last_counts + (size_t)image * 8, 32, cudaMemcpyDeviceToDevice, st));
+    size_t bytes = 0;
     switch (what) {
-        case SALVE_BEV_TAP_KEYGRID: src = c->keygrid + image * c->g_stride; bytes = g * 4; break;
-        case SALVE_BEV_TAP_COLOR: src = c->color + image * c->g_stride; bytes = g * 4; break;
-        case SALVE_BEV_TAP_OCC: src = c->occ + image * c->bits_stride; bytes = bits * 4; break;
-        case SALVE_BEV_TAP_NONEMPTY: src = c->nonempty + image * c->bits_stride; bytes = bits * 4; break;
-        case SALVE_BEV_TAP_KEEP: src = c->keep + image * c->bits_stride; bytes = bits * 4; break;
+        case SALVE_BEV_TAP_KEYGRID: {
+            bytes = g * 4;
+            if ((int64_t)bytes > host_buf_bytes) FAIL(SALVE_BEV_E_CAPACITY, "tap buffer too small");
+            CU(cudaMemcpyAsync(host_buf, kg, bytes, cudaMemcpyDeviceToHost, st));
+            break;
+        }
+        case SALVE_BEV_TAP_COLOR: {
+            bytes = g * 4;
+            if ((int64_t)bytes > host_buf_bytes) FAIL(SALVE_BEV_E_CAPACITY, "tap buffer too small");
+            void* d; if ((rc = tmp_get(c, 0, bytes, &d))) return rc;
+            const uint8_t* src1 = nullptr;
+            CU(cudaMemcpyAsync(&src1, csrc, sizeof(void*), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            tap_color_kernel<<<(unsigned)((g + 255) / 256), 256, 0, st>>>(kg, src1, (int)g, (uint32_t*)d);
+            c->launches++;
+            CU(cudaGetLastError());
+            CU(cudaMemcpyAsync(host_buf, d, bytes, cudaMemcpyDeviceToHost, st));
+            break;
+        }
+        case SALVE_BEV_TAP_OCC:
+        case SALVE_BEV_TAP_NONEMPTY:
+        case SALVE_BEV_TAP_KEEP:
+        case SALVE_BEV_TAP_QTRI: {
+            if (!img_ok) FAIL(SALVE_BEV_E_CAPACITY, "tap not available for this grid size");
+            bytes = (what == SALVE_BEV_TAP_QTRI) ? g * 3 * 4 : bits * 4;
+            if ((int64_t)bytes > host_buf_bytes) FAIL(SALVE_BEV_E_CAPACITY, "tap buffer too small");
+            void *dimg, *dbits, *dq = nullptr;
+            if ((rc = tmp_get(c, 0, g * 3, &dimg))) return rc;
+            if ((rc = tmp_get(c, 1, bits * 4 * 3, &dbits))) return rc;
+            if (what == SALVE_BEV_TAP_QTRI) {
+                if ((rc = tmp_get(c, 2, g * 3 * 4, &dq))) return rc;
+                fill_i32_kernel<<<(unsigned)((g * 3 + 255) / 256), 256, 0, st>>>((int32_t*)dq, g * 3, -1);
+                c->launches++;
+            }
+            rc = run_image_stage(c, 1, G, kg, csrc, (uint8_t*)dimg, (int32_t*)dcnt, nullptr, 0, 0, nullptr, (int32_t*)dq, (uint32_t*)dbits, st);
+            if (rc) return rc;
+            const void* src = what == SALVE_BEV_TAP_QTRI ? dq
+                              : (const void*)((uint32_t*)dbits + (what == SALVE_BEV_TAP_OCC ? 0 : what == SALVE_BEV_TAP_NONEMPTY ? 1 : 2) * bits);
+            CU(cudaMemcpyAsync(host_buf, src, bytes, cudaMemcpyDeviceToHost, st));
+            break;
+        }
         case SALVE_BEV_TAP_TRIS: {
+            // explicit mesh of this image by the mesh path (zipper + parallel Lawson flips)
+            rc = run_mesh_stages(c, G, kg, csrc, nullptr, (int32_t*)dcnt, nullptr, 0, 0, nullptr, false, st);
+            if (rc) return rc;
             ImgHeader hd;
-            CU(cudaMemcpyAsync(&hd, c->headers + image, sizeof(hd), cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(&hd, c->headers, sizeof(hd), cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
             bytes = (size_t)hd.n_tris * 3 * 4;
             if ((int64_t)bytes > host_buf_bytes) FAIL(SALVE_BEV_E_CAPACITY, "tap buffer too small");
             if (hd.n_tris == 0) return SALVE_BEV_OK;
-            void* d; int rc = tmp_get(c, 0, bytes, &d); if (rc) return rc;
-            tap_tris_kernel<<<(hd.n_tris + 255) / 256, 256, 0, st>>>(c->tris + image * c->tris_stride, hd.n_tris, G.grid_w, (int32_t*)d);
+            void* d; if ((rc = tmp_get(c, 0, bytes, &d))) return rc;
+            tap_tris_kernel<<<(hd.n_tris + 255) / 256, 256, 0, st>>>(c->tris, hd.n_tris, G.grid_w, (int32_t*)d);
             c->launches++;
             CU(cudaGetLastError());
             CU(cudaMemcpyAsync(host_buf, d, bytes, cudaMemcpyDeviceToHost, st));
-            CU(cudaStreamSynchronize(st));
-            return SALVE_BEV_OK;
+            break;
         }
         case SALVE_BEV_TAP_INTERP:
         case SALVE_BEV_TAP_HULL: {
             bytes = (what == SALVE_BEV_TAP_INTERP) ? g * 3 : g;
             if ((int64_t)bytes > host_buf_bytes) FAIL(SALVE_BEV_E_CAPACITY, "tap buffer too small");
-            void *dimg, *dhull; int rc;
+            void *dimg, *dhull;
             if ((rc = tmp_get(c, 0, g * 3, &dimg))) return rc;
             if ((rc = tmp_get(c, 7, g, &dhull))) return rc;
             CU(cudaMemsetAsync(dhull, 0, g, st));
-            base_raw_kernel<<<(unsigned)((g + 255) / 256), 256, 0, st>>>(c->color + image * c->g_stride, (int)g, (uint8_t*)dimg);
-            RasterArgs RA;
-            RA.G = G;
-            RA.tris = c->tris + image * c->tris_stride; RA.tris_stride = 0;
-            RA.color = c->color + image * c->g_stride; RA.color_stride = 0;
-            RA.keep = c->keep + image * c->bits_stride; RA.bits_stride = 0;
-            RA.headers = c->headers + image; RA.counts = c->counts + image * 8; RA.status = nullptr;
-            RA.out = (uint8_t*)dimg; RA.out_stride = 0; RA.hull = (uint8_t*)dhull; RA.hull_stride = 0; RA.raw_mode = 1;
-            raster_kernel<<<1, RASTER_NT, 0, st>>>(RA);
-            c->launches += 2;
-            CU(cudaGetLastError());
+            if (img_ok) rc = run_image_stage(c, 1, G, kg, csrc, (uint8_t*)dimg, (int32_t*)dcnt, nullptr, 1, 0, (uint8_t*)dhull, nullptr, nullptr, st);
+            else rc = run_mesh_stages(c, G, kg, csrc, (uint8_t*)dimg, (int32_t*)dcnt, nullptr, 1, 0, (uint8_t*)dhull, true, st);
+            if (rc) return rc;
             CU(cudaMemcpyAsync(host_buf, what == SALVE_BEV_TAP_INTERP ? dimg : dhull, bytes, cudaMemcpyDeviceToHost, st));
-            CU(cudaStreamSynchronize(st));
-            return SALVE_BEV_OK;
+            break;
         }
         default: FAIL(SALVE_BEV_E_INVALID, "unknown tap");
     }
-    if ((int64_t)bytes > host_buf_bytes) FAIL(SALVE_BEV_E_CAPACITY, "tap buffer too small");
-    CU(cudaMemcpyAsync(host_buf, src, bytes, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return SALVE_BEV_OK;
 }
@@ -718,15 +858,23 @@ extern "C" int salve_bev_last_timings(salve_bev_ctx* c, float* host_ms) {
     CU(cudaSetDevice(c->cfg.device));
     CU(cudaEventSynchronize(c->events[c->events_used - 1]));
     for (size_t k = 0; k + N_STAGE_EVENTS <= c->events_used; k += N_STAGE_EVENTS) {
-        for (int s = 0; s < 4; s++) {
-            float ms = 0.f;
-            CU(cudaEventElapsedTime(&ms, c->events[k + s], c->events[k + s + 1]));
-            host_ms[s] += ms;
-        }
         float ms = 0.f;
-        CU(cudaEventElapsedTime(&ms, c->events[k], c->events[k + 4]));
+        CU(cudaEventElapsedTime(&ms, c->events[k], c->events[k + 1]));
+        host_ms[0] += ms;
+        CU(cudaEventElapsedTime(&ms, c->events[k + 1], c->events[k + 2]));
+        host_ms[1] += ms;
+        CU(cudaEventElapsedTime(&ms, c->events[k], c->events[k + 2]));
         host_ms[4] += ms;
     }
+    return SALVE_BEV_OK;
+}
+
+extern "C" int salve_bev_last_phase_clocks(salve_bev_ctx* c, int64_t* host_clk, int32_t n_img) {
+    if (!c || !host_clk) FAIL(SALVE_BEV_E_INVALID, "null argument");
+    if (n_img < 0 || n_img > c->cfg.max_images) FAIL(SALVE_BEV_E_CAPACITY, "more images than a chunk holds");
+    CU(cudaSetDevice(c->cfg.device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(host_clk, c->phase_clk, sizeof(long long) * 16 * (size_t)n_img, cudaMemcpyDeviceToHost));
     return SALVE_BEV_OK;
 }
 

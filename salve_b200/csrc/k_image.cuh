@@ -1,0 +1,938 @@
+// k_image.cuh -- one CTA per BEV image, everything after the splat:
+//   winners -> site bit rows (shared memory), sparse colours, emptiness / keep masks, convex hull,
+//   and the densification itself, with NO triangle mesh in memory.
+//
+// Reference stages covered:
+//   sparse_bev_img[y, x] = rgb of the z-order winner            bev_rendering_utils.py:298-308
+//   degenerate-input guards (<4 points, one row, one column)     interpolation_utils.py:37-42, 57-71
+//   griddata(points, values, grid, "linear") + u8 truncation     interpolation_utils.py:46-53
+//   nonempty = uint8(r*g*b) > 0  (wraps mod 256)                 interpolation_utils.py:95-98
+//   keep = KxK zero-padded box count > 0, out = keep * interp    interpolation_utils.py:101-121
+//   np.flipud of the result                                      bev_rendering_utils.py:319
+//
+// Densification = "query-driven Lawson flips".  The value of linear interpolation at a non-site pixel q
+// is fixed by the Delaunay triangle that contains q.  For each such pixel a thread holds ONE triangle
+// (a,b,c) of sites with q inside it and repeats the Lawson step restricted to q: find a site d that
+// violates the empty-circumcircle property of (a,b,c) (exact int64 in-circle test; co-circular ties
+// by the same symbolic perturbation as the mesh path and the CPU checker), flip inside the 4-point
+// configuration {a,b,c,d} and keep the one new triangle that still contains q.  The lifted plane over
+// q rises strictly with every flip, so the descent ends at the unique triangle of the canonical
+// (perturbed) Delaunay triangulation over q -- bit-identical to rasterising the full mesh, but the
+// only state is the 32 KB occupancy bitmap in shared memory: no mesh, no atomics, no rounds.
+// Violators are searched row by row outward from q inside the circumcircle's per-row chord; the
+// chord is estimated in float64 (with a margin) and every candidate is confirmed exactly.
+// Consecutive query pixels of a row reuse the previous triangle while they stay inside it.
+//
+// The closed convex hull (pixels outside get 0, like griddata's NaN) is computed exactly from the
+// per-row first/last sites (two monotone chains) concurrently with the first phase of queries, which
+// only handles pixels between the first and last site of their own row and therefore needs no hull.
+#pragma once
+#include <type_traits>
+
+#include "bev_common.cuh"
+
+namespace bev {
+
+constexpr int IMAGE_NT = 512;
+constexpr int IMAGE_MAX_FLIPS = 100000;  // safety cap on one descent (never reached: the lift is strictly monotone)
+constexpr int IMAGE_MAX_GAP = 24;        // pass 1: row gap (nearest site left to nearest site right) at most this,
+constexpr int IMAGE_TRIP_BUDGET = 24;    //   and at most this many five-row trips + flips per query
+constexpr int IMAGE_MAX_GAP_B = 64;      // pass 1b: the same for the int64 / float64 state machine;
+constexpr int IMAGE_ROW_BUDGET_B = 160;  //   what is left goes to the cooperative pass
+
+struct ImageArgs {
+    GridParams G;
+    const uint32_t* keygrid; size_t keygrid_stride;
+    const uint8_t* const* color_src;  // per image: u8 rgb triples indexed by the key's source index
+    int32_t* counts;                  // [n_img][8]
+    int32_t* status;                  // [n_img] or null
+    uint8_t* out; size_t out_stride;  // final images (bytes per image)
+    uint8_t* hull; size_t hull_stride;        // optional tap: 1 inside the closed convex hull
+    int32_t* qtri; size_t qtri_stride;        // optional tap: per pixel the 3 vertex pixel ids of its triangle (pre-filled with -1)
+    uint32_t* bits; size_t bits_stride;       // optional tap: occ, nonempty, keep bit planes (3 * grid_h * wpr words per image)
+    uint32_t* qlist; size_t qlist_stride;     // per image work list of query pixels (row << 11 | col), capacity g
+    unsigned long long* qres;                 // per image, per list entry: resolved triangle (3 x 21-bit vertex labels | bit 63)
+    uint32_t* keepbits; size_t keepbits_stride;  // per image scratch: non-empty, then keep bit rows (grid_h * wpr words)
+    long long* phase_clk;                     // optional diagnostics: per image 16 slots, SM clock at the phase boundaries + list sizes
+    int32_t raw_mode;                 // 1: no keep mask, no flip (interp_dense_grid_from_sparse semantics)
+    int32_t skip_empty_check;         // 1: generic interp path (no EMPTY status)
+};
+
+// shared memory carve-up (bytes) for a grid of (h, wpr)
+__host__ __device__ inline size_t image_smem_bytes(int h, int wpr) {
+    const size_t plane = (size_t)h * wpr * 4;
+    const size_t rows = ((size_t)h * 2 + 15) & ~(size_t)15;
+    return 2 * plane + 13 * rows + 2 * (((size_t)h * 4 + 15) & ~(size_t)15) + 64;
+}
+
+struct Tri2 { int ax, ay, bx, by, cx, cy; };
+
+__device__ __forceinline__ int orient_i(int ax, int ay, int bx, int by, int cx, int cy) {
+    return (bx - ax) * (cy - ay) - (by - ay) * (cx - ax);  // |.| <= 2*2047^2: exact in int32
+}
+__device__ __forceinline__ bool tri_contains(const Tri2& t, int qx, int qy) {
+    return orient_i(t.ax, t.ay, t.bx, t.by, qx, qy) >= 0 && orient_i(t.bx, t.by, t.cx, t.cy, qx, qy) >= 0 &&
+           orient_i(t.cx, t.cy, t.ax, t.ay, qx, qy) >= 0;
+}
+__device__ __forceinline__ bool ccw_contains(int ax, int ay, int bx, int by, int cx, int cy, int qx, int qy) {
+    return orient_i(ax, ay, bx, by, cx, cy) > 0 && orient_i(ax, ay, bx, by, qx, qy) >= 0 && orient_i(bx, by, cx, cy, qx, qy) >= 0 &&
+           orient_i(cx, cy, ax, ay, qx, qy) >= 0;
+}
+
+// bits lo..hi (absolute columns, inclusive) that fall into word wi
+__device__ __forceinline__ uint32_t range_mask(int wi, int lo, int hi) {
+    int a = lo - wi * 32, b = hi - wi * 32;
+    if (lo > hi || b < 0 || a > 31) return 0u;
+    a = max(a, 0); b = min(b, 31);
+    return (0xFFFFFFFFu >> (31 - b)) & (0xFFFFFFFFu << a);
+}
+// highest set bit p with xmin <= p <= x, or -1
+__device__ __forceinline__ int prev_bit(const uint32_t* row, int x, int xmin) {
+    if (x < xmin) return -1;
+    int wi = x >> 5;
+    const int wmin = xmin >> 5;
+    uint32_t m = row[wi] & (0xFFFFFFFFu >> (31 - (x & 31)));
+    while (true) {
+        if (m) { const int p = wi * 32 + 31 - __clz(m); return p >= xmin ? p : -1; }
+        if (--wi < wmin) return -1;
+        m = row[wi];
+    }
+}
+// lowest set bit p with x <= p <= xmax, or -1
+__device__ __forceinline__ int next_bit(const uint32_t* row, int x, int xmax) {
+    if (x > xmax) return -1;
+    int wi = x >> 5;
+    const int wmax = xmax >> 5;
+    uint32_t m = row[wi] & (0xFFFFFFFFu << (x & 31));
+    while (true) {
+        if (m) { const int p = wi * 32 + __ffs(m) - 1; return p <= xmax ? p : -1; }
+        if (++wi > wmax) return -1;
+        m = row[wi];
+    }
+}
+
+__device__ __forceinline__ uint32_t load_rgb(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16); }
+
+struct ImageShared {
+    uint32_t* occ; uint32_t* keep; uint32_t* tmp;
+    int16_t *cnt, *first, *last, *up, *dn, *hlo, *hhi, *hl0, *hl1, *hr0, *hr1, *stk_l, *stk_r;
+    float *hlf, *hrf;  // real-valued hull cross-section per row (left, right); empty rows: +inf, -inf
+};
+
+// Initial triangle for pixel (x, r) lying strictly between two sites of its own row: nearest site left, nearest right,
+// and the nearest site of the closest non-empty row above (else below).
+__device__ __forceinline__ bool init_tri_row(const ImageShared& S, int wpr, int w, int x, int r, Tri2& t) {
+    const uint32_t* row = S.occ + r * wpr;
+    const int xl = prev_bit(row, x - 1, 0), xr = next_bit(row, x + 1, w - 1);
+    if (xl < 0 || xr < 0) return false;
+    int yy = S.up[r];
+    const bool above = yy >= 0;
+    if (!above) yy = S.dn[r];
+    if (yy < 0) return false;
+    const uint32_t* r2 = S.occ + yy * wpr;
+    const int pl = prev_bit(r2, x, 0), pr = next_bit(r2, x + 1, w - 1);
+    const int xc = (pr < 0 || (pl >= 0 && x - pl <= pr - x)) ? pl : pr;
+    if (above) { t.ax = xl; t.ay = r; t.bx = xr; t.by = r; }
+    else { t.ax = xr; t.ay = r; t.bx = xl; t.by = r; }
+    t.cx = xc; t.cy = yy;
+    return true;
+}
+// Initial triangle for a pixel inside the hull but outside its row's site extent: the hull edge on its side plus the
+// nearest site of its own row; if the row is empty, split the quad spanned by the two hull edges that cross row r.
+__device__ __forceinline__ bool init_tri_hull(const ImageShared& S, int x, int r, Tri2& t) {
+    const int l0 = S.hl0[r], l1 = S.hl1[r], r0 = S.hr0[r], r1 = S.hr1[r];
+    const int L0x = S.first[l0], L1x = S.first[l1], R0x = S.last[r0], R1x = S.last[r1];
+    if (S.cnt[r] > 0) {
+        if (x < S.first[r]) {
+            const int px = S.first[r];
+            if (ccw_contains(L0x, l0, px, r, L1x, l1, x, r)) { t = {L0x, l0, px, r, L1x, l1}; return true; }
+        } else {
+            const int px = S.last[r];
+            if (ccw_contains(R0x, r0, R1x, r1, px, r, x, r)) { t = {R0x, r0, R1x, r1, px, r}; return true; }
+        }
+    }
+    if (ccw_contains(L0x, l0, R0x, r0, R1x, r1, x, r)) { t = {L0x, l0, R0x, r0, R1x, r1}; return true; }
+    if (ccw_contains(L0x, l0, R1x, r1, L1x, l1, x, r)) { t = {L0x, l0, R1x, r1, L1x, l1}; return true; }
+    if (ccw_contains(L0x, l0, R0x, r0, L1x, l1, x, r)) { t = {L0x, l0, R0x, r0, L1x, l1}; return true; }
+    if (ccw_contains(R0x, r0, R1x, r1, L1x, l1, x, r)) { t = {R0x, r0, R1x, r1, L1x, l1}; return true; }
+    return false;
+}
+
+// ---- pass 1 / 1b: one query pixel per LANE, as a state machine -----------------------------------------------------------
+// Every trip of the loop, each active lane examines ONE row of its current circumcircle scan (rows outward from the query:
+// r, r+1, r-1, r+2, ...).  A lane that finds a violator flips and restarts its scan; a lane whose scan ends has resolved its
+// query and stores the triangle; idle lanes are refilled from the work list.  Lanes therefore stay converged on the row step
+// whatever the length of their own descent.
+// SMALL (pass 1): only triangles that stay within 32 px of vertex a with circumradius <= 30 px -- the exact in-circle test
+// fits int32 and the chord estimate float32 (margin 0.05 px); everything else is deferred.  !SMALL (pass 1b): int64 / float64
+// (margin 1e-3 px), bounded by a row budget.  The estimate only proposes candidates; each is confirmed exactly.
+constexpr unsigned long long QRES_DONE = 1ull << 63;
+
+template <bool SMALL>
+__device__ __forceinline__ void resolve_pass(const ImageShared& S, int wpr, int W, int H, const uint32_t* __restrict__ qlist,
+                                             unsigned long long* __restrict__ qres, int n, int* s_next, uint32_t* defer, int max_gap,
+                                             int row_budget, int lane, int& my_flips, int& my_maxflips) {
+    typedef typename std::conditional<SMALL, float, double>::type real;
+    typedef typename std::conditional<SMALL, int, long long>::type exact;
+    const unsigned FULL = 0xffffffffu;
+    const real margin = SMALL ? (real)0.05 : (real)1e-3, neg_tol = SMALL ? (real)-0.5 : (real)-1e-6;
+    bool active = false, exhausted = false;
+    int x = 0, r = 0, idx = 0, k = 0, budget = 0, flips = 0;
+    bool down = false, up_ok = true, dn_ok = true;
+    Tri2 t = {0, 0, 0, 0, 0, 0};
+    real ux2 = 0, uy2 = 0, cxa = 0;
+    exact eA2 = 1, eU = 0, eV = 0;
+    uint32_t va = 0, vb = 0, vc = 0;
+    int wa = 0, wb = 0, wc = 0;
+
+    // circle of the current triangle; false: not a triangle this pass handles
+    auto setup = [&]() -> bool {
+        const int bx = t.bx - t.ax, by = t.by - t.ay, cx = t.cx - t.ax, cy = t.cy - t.ay;
+        if (SMALL && max(max(abs(bx), abs(by)), max(abs(cx), abs(cy))) > 32) return false;
+        const exact b2 = (exact)bx * bx + (exact)by * by, c2 = (exact)cx * cx + (exact)cy * cy;
+        eA2 = (exact)bx * cy - (exact)by * cx;  // > 0
+        // in-circle determinant of d = a + (dx, dy):  inc = eU*dx + eV*dy - eA2*(dx^2+dy^2)   (> 0: strictly inside)
+        eU = b2 * cy - by * c2; eV = bx * c2 - b2 * cx;
+        if (SMALL) {
+            const float fu = (float)eU, fv = (float)eV, fa = (float)eA2;
+            if (fu * fu + fv * fv > 3600.0f * fa * fa) return false;  // circumradius^2 = (U^2+V^2) / (4 A2^2) > 30^2
+        }
+        const real inv = (real)1 / (real)eA2;
+        const real ux = (real)0.5 * (real)eU * inv;
+        uy2 = (real)eV * inv; ux2 = ux * ux; cxa = (real)t.ax + ux;
+        va = vlabel(t.ay, t.ax); vb = vlabel(t.by, t.bx); vc = vlabel(t.cy, t.cx);
+        wa = (int)pert_weight(va, W); wb = (int)pert_weight(vb, W); wc = (int)pert_weight(vc, W);
+        k = 0; down = false; up_ok = true; dn_ok = true;
+        return true;
+    };
+    auto give_up = [&]() {  // hand the query to the next pass
+        atomicOr(&defer[r * wpr + (x >> 5)], 1u << (x & 31));
+        qres[idx] = 0ull;
+        active = false;
+    };
+
+    while (true) {
+        // ---- refill idle lanes
+        const unsigned idle = __ballot_sync(FULL, !active);
+        if (idle && !exhausted && (__popc(idle) >= 8 || idle == FULL)) {
+            const int leader = __ffs(idle) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(s_next, __popc(idle));
+            base = __shfl_sync(FULL, base, leader);
+            if (base + __popc(idle) >= n) exhausted = true;
+            if (!active) {
+                const int i = base + __popc(idle & ((1u << lane) - 1u));
+                if (i < n) {
+                    const uint32_t code = qlist[i];
+                    x = (int)(code & COL_MASK); r = (int)(code >> COL_BITS); idx = i;
+                    active = true; budget = row_budget; flips = 0;
+                    bool ok = S.cnt[r] > 1 && x > S.first[r] && x < S.last[r] && init_tri_row(S, wpr, W, x, r, t);
+                    if (ok) ok = abs(t.bx - t.ax) <= max_gap;
+                    if (ok) ok = setup();
+                    if (!ok) give_up();
+                }
+            }
+        }
+        if (!__any_sync(FULL, active)) { if (exhausted) break; continue; }
+        if (!active) continue;
+
+        // ---- one row of the scan
+        const int y = down ? r - k : r + k;
+        bool dead = false;
+        int vx = -1;
+        if (y < 0 || y >= H) dead = true;
+        else {
+            const real dyr = (real)(y - t.ay);
+            const real tt = ux2 + dyr * (uy2 - dyr);  // squared half chord of the circle on this row
+            if (tt < neg_tol) dead = true;
+            else {
+                const real hw = sqrt(max(tt, (real)0)) + margin;
+                // circle (with margin) and hull are convex and both contain q: once a row misses their intersection, so do
+                // all rows beyond it.  This bounds the scan of the huge circumcircles of flat triangles along the hull.
+                const real lo = max(cxa - hw, (real)S.hlf[y] - (real)1e-2), hi = min(cxa + hw, (real)S.hrf[y] + (real)1e-2);
+                if (!(lo <= hi)) dead = true;
+                else {
+                    const int x0 = (int)ceil(lo), x1 = (int)floor(hi);
+                    if (x0 <= x1) {
+                        const uint32_t* row = S.occ + y * wpr;
+                        int pl = prev_bit(row, min(x, x1), x0);
+                        int pr = next_bit(row, max(x + 1, x0), x1);
+                        while (pl >= 0 || pr >= 0) {
+                            const bool take_l = pr < 0 || (pl >= 0 && x - pl <= pr - x);
+                            const int cxx = take_l ? pl : pr;
+                            const uint32_t vd = vlabel(y, cxx);
+                            if (vd != va && vd != vb && vd != vc) {
+                                const exact dx = cxx - t.ax, dy = y - t.ay;
+                                const exact inc = eU * dx + eV * dy - eA2 * (dx * dx + dy * dy);
+                                if (inc > 0) { vx = cxx; break; }
+                                if (inc == 0) {  // co-circular: symbolic perturbation, same rule as incircle_pert()
+                                    const long long pert = (long long)wa * orient_v(vb, vc, vd) - (long long)wb * orient_v(va, vc, vd) +
+                                                           (long long)wc * orient_v(va, vb, vd) - pert_weight(vd, W) * (long long)eA2;
+                                    if (pert > 0) { vx = cxx; break; }
+                                }
+                            }
+                            if (take_l) pl = prev_bit(row, cxx - 1, x0); else pr = next_bit(row, cxx + 1, x1);
+                        }
+                    }
+                }
+            }
+        }
+        if (vx >= 0) {
+            // Lawson flip inside {a,b,c,d}: keep the new triangle that contains q
+            bool ok = true;
+            if (ccw_contains(vx, y, t.bx, t.by, t.cx, t.cy, x, r)) { t.ax = vx; t.ay = y; }
+            else if (ccw_contains(t.ax, t.ay, vx, y, t.cx, t.cy, x, r)) { t.bx = vx; t.by = y; }
+            else if (ccw_contains(t.ax, t.ay, t.bx, t.by, vx, y, x, r)) { t.cx = vx; t.cy = y; }
+            else ok = false;  // cannot happen (d is inside the triangle or across exactly one edge)
+            flips++;
+            if (!ok || !setup() || --budget < 0) give_up();
+            continue;
+        }
+        if (dead) { if (down) dn_ok = false; else up_ok = false; }
+        if (!up_ok && !dn_ok) {  // scan complete: t is the triangle of the canonical triangulation over q
+            qres[idx] = QRES_DONE | (unsigned long long)va | ((unsigned long long)vb << 21) | ((unsigned long long)vc << 42);
+            my_flips += flips; my_maxflips = max(my_maxflips, flips);
+            active = false;
+            continue;
+        }
+        if (--budget < 0) { give_up(); continue; }
+        // next row: r, r+1, r-1, r+2, r-2, ... skipping finished directions
+        do {
+            if (k == 0) { k = 1; down = false; }
+            else if (!down) down = true;
+            else { k++; down = false; }
+        } while (down ? !dn_ok : !up_ok);
+    }
+}
+
+// ---- pass 1: small circles, FIVE rows of the scan per trip ----------------------------------------------------------------
+// Same state machine, specialised for the bulk of the queries (holes of a few pixels): triangles within 32 px of vertex a
+// and circumradius <= 14 px.  Then the exact in-circle determinant fits int32, the chord of a row fits a 32-bit window of the
+// occupancy row (one funnel shift), and float32 locates the chord to < 0.02 px: bits further than 0.05 px inside the chord are
+// violators without any test, only bits within 0.05 px of its ends (lattice points on the circle: ties) take the exact test.
+// A trip scans the next five rows (r, r+1, r-1, r+2, r-2, then r+3, ...), keeps the deepest violator (largest determinant)
+// and flips once, so the flip / circle-setup code runs converged instead of for two or three lanes at a time.
+__device__ __forceinline__ float sqrt_approx(float v) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+
+__device__ __forceinline__ void resolve_small(const ImageShared& S, int wpr, int W, int H, const uint32_t* __restrict__ qlist,
+                                              unsigned long long* __restrict__ qres, int n, int* s_next, uint32_t* defer, int max_gap,
+                                              int trip_budget, int lane, int& my_flips, int& my_maxflips) {
+    const unsigned FULL = 0xffffffffu;
+    bool active = false, exhausted = false, need_setup = false;
+    int x = 0, r = 0, idx = 0, obase = 0, budget = 0, flips = 0;
+    bool up_ok = true, dn_ok = true;
+    Tri2 t = {0, 0, 0, 0, 0, 0};
+    float ux2 = 0.f, uy2 = 0.f, cxa = 0.f;
+    int eA2 = 1, eU = 0, eV = 0;
+    uint32_t va = 0, vb = 0, vc = 0;
+    int wa = 0, wb = 0, wc = 0;
+
+    auto give_up = [&]() {  // hand the query to the next pass
+        atomicOr(&defer[r * wpr + (x >> 5)], 1u << (x & 31));
+        qres[idx] = 0ull;
+        active = false;
+    };
+
+    while (true) {
+        // ---- refill idle lanes
+        const unsigned idle = __ballot_sync(FULL, !active);
+        if (idle && !exhausted && (__popc(idle) >= 8 || idle == FULL)) {
+            const int leader = __ffs(idle) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(s_next, __popc(idle));
+            base = __shfl_sync(FULL, base, leader);
+            if (base + __popc(idle) >= n) exhausted = true;
+            if (!active) {
+                const int i = base + __popc(idle & ((1u << lane) - 1u));
+                if (i < n) {
+                    const uint32_t code = qlist[i];
+                    x = (int)(code & COL_MASK); r = (int)(code >> COL_BITS); idx = i;
+                    active = true; budget = trip_budget; flips = 0; need_setup = true;
+                    bool ok = S.cnt[r] > 1 && x > S.first[r] && x < S.last[r] && init_tri_row(S, wpr, W, x, r, t);
+                    if (ok) ok = abs(t.bx - t.ax) <= max_gap;
+                    if (!ok) give_up();
+                }
+            }
+        }
+        if (!__any_sync(FULL, active)) { if (exhausted) break; continue; }
+
+        // ---- circle of a new triangle
+        if (active && need_setup) {
+            need_setup = false;
+            const int bx = t.bx - t.ax, by = t.by - t.ay, cx = t.cx - t.ax, cy = t.cy - t.ay;
+            bool ok = max(max(abs(bx), abs(by)), max(abs(cx), abs(cy))) <= 32;
+            if (ok) {
+                const int b2 = bx * bx + by * by, c2 = cx * cx + cy * cy;
+                eA2 = bx * cy - by * cx;  // > 0
+                // in-circle determinant of d = a + (dx, dy):  inc = eU*dx + eV*dy - eA2*(dx^2+dy^2)   (> 0: strictly inside)
+                eU = b2 * cy - by * c2; eV = bx * c2 - b2 * cx;
+                const float fu = (float)eU, fv = (float)eV, fa = (float)eA2;
+                ok = fu * fu + fv * fv <= 784.0f * fa * fa;  // circumradius^2 = (U^2+V^2) / (4 A2^2) <= 14^2
+                const float inv = 1.0f / fa;
+                const float ux = 0.5f * fu * inv;
+                uy2 = fv * inv; ux2 = ux * ux; cxa = (float)t.ax + ux;
+                va = vlabel(t.ay, t.ax); vb = vlabel(t.by, t.bx); vc = vlabel(t.cy, t.cx);
+                wa = (int)pert_weight(va, W); wb = (int)pert_weight(vb, W); wc = (int)pert_weight(vc, W);
+                obase = 0; up_ok = true; dn_ok = true;
+            }
+            if (!ok) give_up();
+        }
+
+        // ---- five rows of the scan
+        int best_inc = -1, best_x = 0, best_y = 0;
+#pragma unroll
+        for (int j = 0; j < 5; j++) {
+            const int o = obase + j;
+            const int k = (o + 1) >> 1;
+            const bool down = (o & 1) != 0;
+            const bool on = active && (down ? dn_ok : up_ok);
+            if (!__any_sync(FULL, on)) continue;
+            if (!on) continue;
+            const int y = down ? r - k : r + k;
+            bool dead = (y < 0 || y >= H);
+            if (!dead) {
+                const float dyr = (float)(y - t.ay);
+                const float tt = fmaf(dyr, uy2 - dyr, ux2);  // squared half chord of the circle on this row
+                if (tt < -0.5f) dead = true;
+                else {
+                    const float hw = sqrt_approx(fmaxf(tt, 0.0f));
+                    const float lo = cxa - hw, hi = cxa + hw;
+                    // circle and hull are convex and both contain q: a row that misses their intersection ends its direction
+                    if (!(fmaxf(lo - 0.05f, S.hlf[y] - 0.01f) <= fminf(hi + 0.05f, S.hrf[y] + 0.01f))) dead = true;
+                    else {
+                        const int xo0 = max((int)ceilf(lo - 0.05f), 0), xo1 = min((int)floorf(hi + 0.05f), W - 1);
+                        if (xo0 <= xo1) {
+                            const uint32_t* row = S.occ + y * wpr;
+                            const int w0 = xo0 >> 5;
+                            const uint32_t lo32 = row[w0], hi32 = (w0 + 1 < wpr) ? row[w0 + 1] : 0u;
+                            const int nb = xo1 - xo0 + 1;  // <= 30: the chord is at most 2 * 14.05 + 1 wide
+                            uint32_t win = __funnelshift_r(lo32, hi32, xo0 & 31) & ((1u << nb) - 1u);  // bit i <-> column xo0 + i
+                            if (win) {
+                                const int i0 = max((int)ceilf(lo + 0.05f) - xo0, 0), i1 = min((int)floorf(hi - 0.05f) - xo0, nb - 1);  // certainly inside
+                                const uint32_t inner = (i0 <= i1) ? (((2u << i1) - 1u) & ~((1u << i0) - 1u)) : 0u;  // i0 >= 0, i1 <= nb - 1 <= 29
+                                const uint32_t sure = win & inner;
+                                uint32_t amb = win & ~inner;  // within 0.05 px of the chord ends: at most one lattice point per end
+                                if (sure) {
+                                    // the determinant is a concave parabola along the row: deepest at the bit nearest the centre
+                                    const int cpos = min(max(__float2int_rn(cxa) - xo0, 0), nb - 1);
+                                    const uint32_t below = sure & ((2u << cpos) - 1u), above = sure & ~((2u << cpos) - 1u);
+                                    const int pb = below ? 31 - __clz(below) : -64, pa = above ? __ffs(above) - 1 : 128;
+                                    const int pos = (cpos - pb <= pa - cpos) ? pb : pa;
+                                    const int dx = xo0 + pos - t.ax, dy = y - t.ay;
+                                    const int inc = eU * dx + eV * dy - eA2 * (dx * dx + dy * dy);
+                                    if (inc > best_inc) { best_inc = inc; best_x = xo0 + pos; best_y = y; }
+                                }
+                                while (amb) {
+                                    const int b = __ffs(amb) - 1; amb &= amb - 1;
+                                    const int cxx = xo0 + b;
+                                    const uint32_t vd = vlabel(y, cxx);
+                                    if (vd == va || vd == vb || vd == vc) continue;
+                                    const int dx = cxx - t.ax, dy = y - t.ay;
+                                    const int inc = eU * dx + eV * dy - eA2 * (dx * dx + dy * dy);
+                                    if (inc > 0) { if (inc > best_inc) { best_inc = inc; best_x = cxx; best_y = y; } }
+                                    else if (inc == 0 && best_inc < 0) {  // co-circular: symbolic perturbation, same rule as incircle_pert()
+                                        const long long pert = (long long)wa * orient_v(vb, vc, vd) - (long long)wb * orient_v(va, vc, vd) +
+                                                               (long long)wc * orient_v(va, vb, vd) - pert_weight(vd, W) * (long long)eA2;
+                                        if (pert > 0) { best_inc = 0; best_x = cxx; best_y = y; }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            if (dead) { if (down) dn_ok = false; else up_ok = false; }
+        }
+        if (!active) continue;
+        obase += 5;
+        if (best_inc >= 0) {
+            // Lawson flip inside {a,b,c,d}: keep the new triangle that contains q
+            bool ok = true;
+            if (ccw_contains(best_x, best_y, t.bx, t.by, t.cx, t.cy, x, r)) { t.ax = best_x; t.ay = best_y; }
+            else if (ccw_contains(t.ax, t.ay, best_x, best_y, t.cx, t.cy, x, r)) { t.bx = best_x; t.by = best_y; }
+            else if (ccw_contains(t.ax, t.ay, t.bx, t.by, best_x, best_y, x, r)) { t.cx = best_x; t.cy = best_y; }
+            else ok = false;  // cannot happen (d is inside the triangle or across exactly one edge)
+            flips++; need_setup = true;
+            if (!ok || --budget < 0) give_up();
+        } else if (!up_ok && !dn_ok) {  // scan complete: t is the triangle of the canonical triangulation over q
+            qres[idx] = QRES_DONE | (unsigned long long)va | ((unsigned long long)vb << 21) | ((unsigned long long)vc << 42);
+            my_flips += flips; my_maxflips = max(my_maxflips, flips);
+            active = false;
+        } else if (--budget < 0) give_up();
+    }
+}
+
+// ---- warp-cooperative versions for queries whose triangles are large (wide gaps, hull pockets) -------------------------
+// One lane per row of each 32-row wave (row offsets 0, -1, +1, -2, ... from qy).  Returns, in every lane, the violator
+// nearest to q found in the first wave that has one (x | y << 16), or -1.
+__device__ __forceinline__ int coop_find_violator(const uint32_t* __restrict__ occ, const float* __restrict__ hlf, const float* __restrict__ hrf, int wpr,
+                                                  int W, int H, const Tri2& t, int qx, int qy, int grid_w, int lane) {
+    const long long bx = t.bx - t.ax, by = t.by - t.ay, cx = t.cx - t.ax, cy = t.cy - t.ay;
+    const long long b2 = bx * bx + by * by, c2 = cx * cx + cy * cy;
+    const long long A2 = bx * cy - by * cx;
+    const long long U = b2 * cy - by * c2, V = bx * c2 - b2 * cx;
+    const double inv = 1.0 / (double)A2;
+    const double ux = 0.5 * (double)U * inv, uy2 = (double)V * inv, ux2 = ux * ux, cxa = (double)t.ax + ux;
+    const uint32_t va = vlabel(t.ay, t.ax), vb = vlabel(t.by, t.bx), vc = vlabel(t.cy, t.cx);
+    bool up_dead = false, dn_dead = false;
+    for (int wave = 0;; wave++) {
+        const int o = wave * 32 + lane;
+        const int k = (o + 1) >> 1;
+        const bool down = (o & 1) != 0;
+        const int y = down ? qy - k : qy + k;
+        bool row_dead = false;
+        unsigned long long best = ~0ull;
+        if (!(down ? dn_dead : up_dead)) {
+            if (y < 0 || y >= H) row_dead = true;
+            else {
+                const double dyr = (double)(y - t.ay);
+                const double tt = ux2 + dyr * (uy2 - dyr);
+                if (tt < -1e-6) row_dead = true;
+                else {
+                    const double hw = sqrt(fmax(tt, 0.0)) + 1e-3;
+                    const double lo = fmax(cxa - hw, (double)hlf[y] - 1e-2), hi = fmin(cxa + hw, (double)hrf[y] + 1e-2);
+                    if (!(lo <= hi)) row_dead = true;
+                    else {
+                        const int x0 = (int)ceil(lo), x1 = (int)floor(hi);
+                        if (x0 <= x1) {
+                            const uint32_t* row = occ + y * wpr;
+                            int pl = prev_bit(row, min(qx, x1), x0);
+                            int pr = next_bit(row, max(qx + 1, x0), x1);
+                            while (pl >= 0 || pr >= 0) {
+                                const bool take_l = pr < 0 || (pl >= 0 && qx - pl <= pr - qx);
+                                const int x = take_l ? pl : pr;
+                                const uint32_t vd = vlabel(y, x);
+                                if (vd != va && vd != vb && vd != vc) {
+                                    const long long dx = x - t.ax, dy = y - t.ay;
+                                    const long long inc = U * dx + V * dy - A2 * (dx * dx + dy * dy);
+                                    if (inc > 0 || (inc == 0 && incircle_pert(va, vb, vc, vd, grid_w) > 0)) {
+                                        const long long ddx = x - qx, ddy = y - qy;
+                                        best = ((unsigned long long)(ddx * ddx + ddy * ddy) << 32) | (uint32_t)(x | (y << 16));
+                                        break;
+                                    }
+                                }
+                                if (take_l) pl = prev_bit(row, x - 1, x0); else pr = next_bit(row, x + 1, x1);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) { const unsigned long long ob = __shfl_xor_sync(0xffffffffu, best, sft); best = ob < best ? ob : best; }
+        if (best != ~0ull) return (int)(uint32_t)best;
+        // convexity of circle /\ hull: a dead row kills every row beyond it in its direction
+        if (__ballot_sync(0xffffffffu, row_dead && !down)) up_dead = true;
+        if (__ballot_sync(0xffffffffu, row_dead && down)) dn_dead = true;
+        if (up_dead && dn_dead) return -1;
+    }
+}
+
+__global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
+    const int img = blockIdx.x;
+    const int h = A.G.grid_h, w = A.G.grid_w, wpr = A.G.wpr;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = IMAGE_NT / 32;
+    const int nwords = h * wpr;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ImageShared S;
+    {
+        const size_t plane = (size_t)nwords * 4;
+        const size_t rows = ((size_t)h * 2 + 15) & ~(size_t)15;
+        unsigned char* p = smem_raw;
+        S.occ = (uint32_t*)p; p += plane;
+        S.keep = A.keepbits + (size_t)img * A.keepbits_stride;  // global (L2): only list building and the final masking read it
+        S.tmp = (uint32_t*)p; p += plane;
+        int16_t** arr[13] = {&S.cnt, &S.first, &S.last, &S.up, &S.dn, &S.hlo, &S.hhi, &S.hl0, &S.hl1, &S.hr0, &S.hr1, &S.stk_l, &S.stk_r};
+        for (int i = 0; i < 13; i++) { *arr[i] = (int16_t*)p; p += rows; }
+        const size_t frows = ((size_t)h * 4 + 15) & ~(size_t)15;
+        S.hlf = (float*)p; p += frows; S.hrf = (float*)p; p += frows;
+    }
+    __shared__ int s_S, s_M, s_mincol, s_maxcol, s_ne_cnt, s_keep_cnt, s_nitems, s_next, s_filled, s_flips, s_maxflips, s_hull_ok;
+
+    const uint32_t* keygrid = A.keygrid + (size_t)img * A.keygrid_stride;
+    const uint8_t* csrc = A.color_src[img];
+    uint8_t* out = A.out + (size_t)img * A.out_stride;
+    int32_t* counts = A.counts + img * 8;
+    const bool raw = A.raw_mode != 0;
+    long long* pclk = A.phase_clk ? A.phase_clk + (size_t)img * 16 : nullptr;
+    auto mark = [&](int slot) { if (pclk && tid == 0) pclk[slot] = clock64(); };
+    mark(0);
+
+    if (tid == 0) {
+        s_S = 0; s_M = 0; s_mincol = 1 << 30; s_maxcol = -1; s_ne_cnt = 0; s_keep_cnt = 0; s_nitems = 0; s_next = 0;
+        s_filled = 0; s_flips = 0; s_maxflips = 0; s_hull_ok = 0;
+    }
+    __syncthreads();
+
+    // ---- A. winners -> occupancy / non-empty bit rows, sparse image (site colours, rest zero) --------
+    // Loads are issued in batches of 8 words per lane (keys, then the colour gathers) so that a warp keeps 8 independent
+    // requests in flight instead of one dependent pair.
+    for (int r = warp; r < h; r += NW) {
+        int running = 0, first = -1, last = -1, ne_cnt = 0;
+        uint8_t* orow = out + (size_t)(raw ? r : (h - 1 - r)) * w * 3;
+        const uint32_t* krow = keygrid + (size_t)r * w;
+        for (int wi0 = 0; wi0 < wpr; wi0 += 8) {
+            uint32_t key[8], col[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int c = (wi0 + j) * 32 + lane;
+                key[j] = (wi0 + j < wpr && c < w) ? __ldg(krow + c) : 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                col[j] = 0u;
+                if (key[j]) col[j] = load_rgb(csrc + (size_t)((key[j] - 1u) & KEY_IDX_MASK) * 3);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int wi = wi0 + j;
+                if (wi >= wpr) break;
+                const int c = wi * 32 + lane;
+                const uint32_t cr = col[j] & 0xFF, cg = (col[j] >> 8) & 0xFF, cb = col[j] >> 16;
+                const bool ne = ((cr * cg * cb) & 0xFFu) != 0u;  // uint8 product wraps (interpolation_utils.py:95)
+                if (c < w) { orow[c * 3 + 0] = (uint8_t)cr; orow[c * 3 + 1] = (uint8_t)cg; orow[c * 3 + 2] = (uint8_t)cb; }
+                const uint32_t ob = __ballot_sync(0xffffffffu, key[j] != 0u);
+                const uint32_t nb = __ballot_sync(0xffffffffu, ne);
+                if (lane == 0) { S.occ[r * wpr + wi] = ob; S.keep[r * wpr + wi] = nb; }  // keep plane holds `nonempty` until stage D
+                if (ob) { if (first < 0) first = wi * 32 + __ffs(ob) - 1; last = wi * 32 + 31 - __clz(ob); }
+                running += __popc(ob); ne_cnt += __popc(nb);
+            }
+        }
+        if (lane == 0) {
+            S.cnt[r] = (int16_t)running; S.first[r] = (int16_t)first; S.last[r] = (int16_t)last;
+            if (running) { atomicMin(&s_mincol, first); atomicMax(&s_maxcol, last); atomicAdd(&s_S, running); atomicAdd(&s_M, 1); }
+            if (ne_cnt) atomicAdd(&s_ne_cnt, ne_cnt);
+        }
+    }
+    __syncthreads();
+    if (A.bits) {
+        uint32_t* b = A.bits + (size_t)img * A.bits_stride;
+        for (int i = tid; i < nwords; i += IMAGE_NT) { b[i] = S.occ[i]; b[nwords + i] = S.keep[i]; }
+    }
+
+    mark(1);
+    // ---- B. guards (interpolation_utils.py:37-42, 57-71) ---------------------------------------------
+    const int nS = s_S, M = s_M;
+    int status = 0;  // SALVE_BEV_IMG_OK
+    if (!A.skip_empty_check && counts[1] == 0) status = 1;                         // EMPTY -> None
+    else if (nS < 4 || M < 2 || s_mincol == s_maxcol) status = 2;                  // DEGENERATE -> zeros
+
+    // nearest non-empty row above / below every row
+    for (int r = tid; r < h; r += IMAGE_NT) {
+        int u = r + 1; while (u < h && S.cnt[u] == 0) u++;
+        int d = r - 1; while (d >= 0 && S.cnt[d] == 0) d--;
+        S.up[r] = (int16_t)(u < h ? u : -1); S.dn[r] = (int16_t)d;
+        S.hlo[r] = 1; S.hhi[r] = 0;  // rows outside the hull: empty range
+        S.hlf[r] = __int_as_float(0x7f800000); S.hrf[r] = __int_as_float(0xff800000);
+    }
+
+    // ---- C. exact convex hull from the per-row first / last sites: two monotone chains (threads 0 and 32) ------------
+    __syncthreads();
+    if (status == 0 && (tid == 0 || tid == 32)) {
+        const bool left = tid == 0;
+        const int16_t* xs = left ? S.first : S.last;
+        int16_t* e0 = left ? S.hl0 : S.hr0;   // per row: rows of the two end points of the hull edge crossing it
+        int16_t* e1 = left ? S.hl1 : S.hr1;
+        int16_t* stk = left ? S.stk_l : S.stk_r;
+        int16_t* bound = left ? S.hlo : S.hhi;
+        int top = 0;
+        int r = S.cnt[0] > 0 ? 0 : S.up[0];
+        while (r >= 0) {
+            const int x = xs[r];
+            while (top >= 2) {
+                const int r1 = stk[top - 1], r0 = stk[top - 2];
+                const int o = orient_i(xs[r0], r0, xs[r1], r1, x, r);
+                // going up, the left chain turns clockwise at every vertex and the right chain counter-clockwise
+                if (left ? (o >= 0) : (o <= 0)) top--; else break;
+            }
+            stk[top++] = (int16_t)r;
+            r = S.up[r];
+        }
+        for (int k = 1; k < top; k++) {
+            const int r0 = stk[k - 1], r1 = stk[k];
+            const int x0 = xs[r0], x1 = xs[r1], dy = r1 - r0;
+            for (int rr = r0; rr <= r1; rr++) {
+                const int num = x0 * dy + (x1 - x0) * (rr - r0);  // >= 0: a convex combination scaled by dy
+                bound[rr] = (int16_t)(left ? (num + dy - 1) / dy : num / dy);  // ceil on the left, floor on the right
+                e0[rr] = (int16_t)r0; e1[rr] = (int16_t)r1;
+                (left ? S.hlf : S.hrf)[rr] = (float)num / (float)dy;
+            }
+        }
+        if (top <= 2) atomicAdd(&s_hull_ok, left ? 1 : 2);  // this chain has no interior vertex
+    }
+
+    // ---- D. keep mask = Chebyshev dilation of `nonempty` by K/2, zero padded ---------------------------
+    if (!raw) {
+        const int rad = A.G.K / 2;
+        for (int item = tid; item < nwords; item += IMAGE_NT) {
+            const int r = item / wpr, wi = item - r * wpr;
+            const uint32_t cur = S.keep[item];
+            const uint32_t prv = (wi > 0) ? S.keep[item - 1] : 0u;
+            const uint32_t nxt = (wi + 1 < wpr) ? S.keep[item + 1] : 0u;
+            const unsigned long long L = ((unsigned long long)cur << 32) | prv, R = ((unsigned long long)nxt << 32) | cur;
+            uint32_t o = cur;
+            for (int d = 1; d <= rad; d++) o |= (uint32_t)(L >> (32 - d)) | (uint32_t)(R >> d);
+            const int valid = w - wi * 32;
+            if (valid < 32) o &= (1u << valid) - 1u;
+            S.tmp[item] = o;
+        }
+        __syncthreads();
+        int kc = 0;
+        for (int item = tid; item < nwords; item += IMAGE_NT) {
+            const int r = item / wpr, wi = item - r * wpr;
+            uint32_t o = 0;
+            const int r0 = max(r - rad, 0), r1 = min(r + rad, h - 1);
+            for (int rr = r0; rr <= r1; rr++) o |= S.tmp[rr * wpr + wi];
+            S.keep[item] = o;
+            kc += __popc(o);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) kc += __shfl_xor_sync(0xffffffffu, kc, o);
+        if (lane == 0 && kc) atomicAdd(&s_keep_cnt, kc);
+    } else {
+        for (int item = tid; item < nwords; item += IMAGE_NT) {
+            const int wi = item % wpr;
+            S.keep[item] = range_mask(wi, 0, w - 1);  // raw mode: every pixel is kept
+        }
+    }
+    __syncthreads();
+    if (A.bits) {
+        uint32_t* b = A.bits + (size_t)img * A.bits_stride;
+        for (int i = tid; i < nwords; i += IMAGE_NT) b[2 * nwords + i] = S.keep[i];
+    }
+    if (tid == 0) {
+        counts[2] = nS; counts[3] = s_ne_cnt; counts[4] = raw ? 0 : s_keep_cnt;
+    }
+
+    mark(2);
+    // all sites on one oblique line: every row has one site and neither chain has an interior vertex
+    if (status == 0 && s_hull_ok == 3 && nS == M) status = 3;  // COLLINEAR: the reference's Qhull call raises
+
+    // ---- F. work list of query pixels (row << 11 | col) in global memory, one warp per row -------------------------
+    // query = kept, not a site, inside the closed hull
+    uint32_t* qlist = A.qlist + (size_t)img * A.qlist_stride;
+    if (status == 0) {
+        for (int r = warp; r < h; r += NW) {
+            for (int wi0 = 0; wi0 < wpr; wi0 += 32) {
+                const int wi = wi0 + lane;
+                uint32_t q = 0;
+                if (wi < wpr) {
+                    const int item = r * wpr + wi;
+                    const uint32_t hm = range_mask(wi, S.hlo[r], S.hhi[r]);
+                    q = S.keep[item] & ~S.occ[item] & hm;
+                    if (A.hull && hm) {
+                        uint8_t* hp = A.hull + (size_t)img * A.hull_stride + (size_t)r * w + wi * 32;
+                        uint32_t m = hm;
+                        while (m) { const int b = __ffs(m) - 1; m &= m - 1; hp[b] = 1; }
+                    }
+                }
+                int n = __popc(q), incl = n;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                if (total == 0) continue;
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_nitems, total);
+                base = __shfl_sync(0xffffffffu, base, 0) + incl - n;
+                while (q) { const int b = __ffs(q) - 1; q &= q - 1; qlist[base++] = ((uint32_t)r << COL_BITS) | (uint32_t)(wi * 32 + b); }
+            }
+        }
+    }
+    __syncthreads();
+
+    int my_filled = 0, my_flips = 0, my_maxflips = 0;
+    int32_t* qtri = A.qtri ? A.qtri + (size_t)img * A.qtri_stride : nullptr;
+
+    // one query pixel: initial triangle, flip descent, exact barycentric value
+    auto site_rgb = [&](int sx, int sy) { return load_rgb(out + ((size_t)(raw ? sy : h - 1 - sy) * w + sx) * 3); };
+    auto write_px = [&](const Tri2& t, uint32_t ca, uint32_t cb, uint32_t cc, int x, int r) {
+        const uint32_t ua = (uint32_t)orient_i(t.bx, t.by, t.cx, t.cy, x, r), ub = (uint32_t)orient_i(t.cx, t.cy, t.ax, t.ay, x, r),
+                       uc = (uint32_t)orient_i(t.ax, t.ay, t.bx, t.by, x, r);
+        const uint32_t A2 = ua + ub + uc;
+        uint8_t* o = out + ((size_t)(raw ? r : h - 1 - r) * w + x) * 3;
+        o[0] = (uint8_t)((ua * (ca & 0xFF) + ub * (cb & 0xFF) + uc * (cc & 0xFF)) / A2);
+        o[1] = (uint8_t)((ua * ((ca >> 8) & 0xFF) + ub * ((cb >> 8) & 0xFF) + uc * ((cc >> 8) & 0xFF)) / A2);
+        o[2] = (uint8_t)((ua * ((ca >> 16) & 0xFF) + ub * ((cb >> 16) & 0xFF) + uc * ((cc >> 16) & 0xFF)) / A2);
+        if (qtri) {
+            int32_t* q = qtri + ((size_t)r * w + x) * 3;
+            q[0] = t.ay * w + t.ax; q[1] = t.by * w + t.bx; q[2] = t.cy * w + t.cx;
+        }
+    };
+    auto flip_to = [&](Tri2& t, int v, int x, int r) {
+        const int dx = v & 0xFFFF, dy = v >> 16;
+        // flip inside {a,b,c,d}: keep the new triangle that contains q
+        if (ccw_contains(dx, dy, t.bx, t.by, t.cx, t.cy, x, r)) { t.ax = dx; t.ay = dy; return true; }
+        if (ccw_contains(t.ax, t.ay, dx, dy, t.cx, t.cy, x, r)) { t.bx = dx; t.by = dy; return true; }
+        if (ccw_contains(t.ax, t.ay, t.bx, t.by, dx, dy, x, r)) { t.cx = dx; t.cy = dy; return true; }
+        return false;  // cannot happen (d is inside the triangle or across exactly one edge)
+    };
+    uint32_t* defer = S.tmp;  // bit plane: queries handed to the next pass (the row-dilated plane is dead now)
+    unsigned long long* qres = A.qres + (size_t)img * A.qlist_stride;
+
+    // list of the pixels whose bit is set in `plane` (row-major, one warp per row); `plane` is cleared
+    auto build_list = [&](uint32_t* plane, bool clear) {
+        for (int r = warp; r < h; r += NW) {
+            for (int wi0 = 0; wi0 < wpr; wi0 += 32) {
+                const int wi = wi0 + lane;
+                uint32_t q = wi < wpr ? plane[r * wpr + wi] : 0u;
+                if (clear && q) plane[r * wpr + wi] = 0u;
+                int n = __popc(q), incl = n;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                if (total == 0) continue;
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_nitems, total);
+                base = __shfl_sync(0xffffffffu, base, 0) + incl - n;
+                while (q) { const int b = __ffs(q) - 1; q &= q - 1; qlist[base++] = ((uint32_t)r << COL_BITS) | (uint32_t)(wi * 32 + b); }
+            }
+        }
+    };
+    // interpolate the pixels a pass resolved: gathers, exact barycentrics and stores with every lane busy
+    auto shade = [&](int n) {
+        for (int i = tid; i < n; i += IMAGE_NT) {
+            const unsigned long long rs = qres[i];
+            if (!(rs & QRES_DONE)) continue;
+            const uint32_t code = qlist[i];
+            const uint32_t a = (uint32_t)rs & M21, b = (uint32_t)(rs >> 21) & M21, c = (uint32_t)(rs >> 42) & M21;
+            const Tri2 t = {vcol(a), vrow(a), vcol(b), vrow(b), vcol(c), vrow(c)};
+            write_px(t, site_rgb(t.ax, t.ay), site_rgb(t.bx, t.by), site_rgb(t.cx, t.cy), (int)(code & COL_MASK), (int)(code >> COL_BITS));
+            my_filled++;
+        }
+    };
+
+    // ---- G1. pass 1 (small circles) and pass 1b (any circle, bounded work): one query per lane ---------------------------
+    for (int i = tid; i < nwords; i += IMAGE_NT) defer[i] = 0u;
+    __syncthreads();
+    mark(3);
+    if (pclk && tid == 0) pclk[12] = s_nitems;
+    if (status == 0) resolve_small(S, wpr, w, h, qlist, qres, s_nitems, &s_next, defer, IMAGE_MAX_GAP, IMAGE_TRIP_BUDGET, lane, my_flips, my_maxflips);
+    __syncthreads();
+    mark(4);
+    if (status == 0) shade(s_nitems);
+    __syncthreads();
+    mark(5);
+    if (tid == 0) { s_nitems = 0; s_next = 0; }
+    __syncthreads();
+    if (status == 0) build_list(defer, true);
+    __syncthreads();
+    mark(6);
+    if (pclk && tid == 0) pclk[13] = s_nitems;
+    if (status == 0) resolve_pass<false>(S, wpr, w, h, qlist, qres, s_nitems, &s_next, defer, IMAGE_MAX_GAP_B, IMAGE_ROW_BUDGET_B, lane, my_flips, my_maxflips);
+    __syncthreads();
+    mark(7);
+    if (status == 0) shade(s_nitems);
+    __syncthreads();
+    mark(8);
+
+    // ---- G2. pass 2: what is left (hull pockets, wide gaps, long descents), one warp per query ---------------------------
+    // The final triangle of a descent is rasterised over ALL deferred pixels it contains (they share it), which are then
+    // taken off the list: a big triangle across a hole is found about once instead of once per pixel.  Warps take
+    // row-major bands of the list, so that the pixels of one triangle mostly meet the same warp.
+    if (tid == 0) { s_nitems = 0; s_next = 0; }
+    __syncthreads();
+    if (status == 0) build_list(defer, false);
+    __syncthreads();
+    mark(9);
+    if (pclk && tid == 0) pclk[14] = s_nitems;
+    if (status == 0) {
+        const int n = s_nitems;
+        const int band = max(16, (n + 4 * NW - 1) / (4 * NW));
+        while (true) {
+            int i0 = 0;
+            if (lane == 0) i0 = atomicAdd(&s_next, band);
+            i0 = __shfl_sync(0xffffffffu, i0, 0);
+            if (i0 >= n) break;
+            const int i_end = min(n, i0 + band);
+          for (int i = i0; i < i_end; i++) {
+            const uint32_t code = qlist[i];
+            const int x = (int)(code & COL_MASK), r = (int)(code >> COL_BITS);
+            if (!((defer[r * wpr + (x >> 5)] >> (x & 31)) & 1u)) continue;  // already filled by another descent's triangle
+            Tri2 t;
+            const bool in_row = S.cnt[r] > 1 && x > S.first[r] && x < S.last[r];
+            if (!(in_row ? init_tri_row(S, wpr, w, x, r, t) : init_tri_hull(S, x, r, t))) continue;
+            int flips = 0;
+            while (flips < IMAGE_MAX_FLIPS) {
+                const int v = coop_find_violator(S.occ, S.hlf, S.hrf, wpr, w, h, t, x, r, w, lane);
+                if (v < 0 || !flip_to(t, v, x, r)) break;
+                flips++;
+            }
+            if (lane == 0) { my_flips += flips; my_maxflips = max(my_maxflips, flips); }
+            // rasterise t over the deferred pixels it contains: one lane per row of its bounding box
+            const uint32_t ca = site_rgb(t.ax, t.ay), cb = site_rgb(t.bx, t.by), cc = site_rgb(t.cx, t.cy);
+            const int y0 = min(t.ay, min(t.by, t.cy)), y1 = max(t.ay, max(t.by, t.cy));
+            const int bx0 = min(t.ax, min(t.bx, t.cx)), bx1 = max(t.ax, max(t.bx, t.cx));
+            for (int y = y0 + lane; y <= y1; y += 32) {
+                for (int wi = bx0 >> 5; wi <= (bx1 >> 5); wi++) {
+                    uint32_t m = defer[y * wpr + wi] & range_mask(wi, bx0, bx1);
+                    uint32_t done = 0;
+                    while (m) {
+                        const int b = __ffs(m) - 1; m &= m - 1;
+                        const int px = wi * 32 + b;
+                        if (tri_contains(t, px, y)) { write_px(t, ca, cb, cc, px, y); done |= 1u << b; }
+                    }
+                    // count a pixel once even when two concurrent descents reach the same triangle (same value either way)
+                    if (done) my_filled += __popc(atomicAnd(&defer[y * wpr + wi], ~done) & done);
+                }
+            }
+            __syncwarp();
+          }
+        }
+    }
+    __syncthreads();
+
+    mark(10);
+    // ---- H. masked-out sites, degenerate images, counters ------------------------------------------------------------
+    if (status == 1 || status == 2) {
+        // the reference returns None (empty) or an all-zero interpolation (degenerate): clear the site colours
+        for (int item = tid; item < nwords; item += IMAGE_NT) {
+            uint32_t m = S.occ[item];
+            const int r = item / wpr, wi = item - r * wpr;
+            while (m) {
+                const int b = __ffs(m) - 1; m &= m - 1;
+                uint8_t* o = out + ((size_t)(raw ? r : h - 1 - r) * w + wi * 32 + b) * 3;
+                o[0] = 0; o[1] = 0; o[2] = 0;
+            }
+        }
+    } else if (!raw) {
+        for (int item = tid; item < nwords; item += IMAGE_NT) {
+            uint32_t m = S.occ[item] & ~S.keep[item];  // sites the hallucination mask removes
+            const int r = item / wpr, wi = item - r * wpr;
+            while (m) {
+                const int b = __ffs(m) - 1; m &= m - 1;
+                uint8_t* o = out + ((size_t)(h - 1 - r) * w + wi * 32 + b) * 3;
+                o[0] = 0; o[1] = 0; o[2] = 0;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        my_filled += __shfl_xor_sync(0xffffffffu, my_filled, o);
+        my_flips += __shfl_xor_sync(0xffffffffu, my_flips, o);
+        my_maxflips = max(my_maxflips, __shfl_xor_sync(0xffffffffu, my_maxflips, o));
+    }
+    if (lane == 0) { atomicAdd(&s_filled, my_filled); atomicAdd(&s_flips, my_flips); atomicMax(&s_maxflips, my_maxflips); }
+    __syncthreads();
+    if (tid == 0) {
+        counts[5] = s_filled; counts[6] = s_maxflips; counts[7] = s_flips;
+        if (pclk) pclk[11] = clock64();
+        if (A.status) A.status[img] = status;
+    }
+}
+
+// colour word tap: r | g<<8 | b<<16 | 0xFF<<24 at sites, 0 elsewhere
+__global__ void tap_color_kernel(const uint32_t* __restrict__ keygrid, const uint8_t* __restrict__ csrc, int g, uint32_t* __restrict__ outc) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= g) return;
+    const uint32_t key = keygrid[p];
+    uint32_t cw = 0;
+    if (key) {
+        const uint8_t* s = csrc + (size_t)((key - 1u) & KEY_IDX_MASK) * 3;
+        cw = (uint32_t)s[0] | ((uint32_t)s[1] << 8) | ((uint32_t)s[2] << 16) | 0xFF000000u;
+    }
+    outc[p] = cw;
+}
+
+}  // namespace bev

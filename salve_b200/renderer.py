@@ -18,7 +18,7 @@ SURF_CEILING = 2
 SURFACE_BITS = {"floor": SURF_FLOOR, "ceiling": SURF_CEILING}
 NCOUNTS = 8
 IMG_OK, IMG_EMPTY, IMG_DEGENERATE, IMG_COLLINEAR = 0, 1, 2, 3
-TAP = dict(keygrid=0, color=1, occ=2, nonempty=3, keep=4, tris=5, interp=6, hull=7)
+TAP = dict(keygrid=0, color=1, occ=2, nonempty=3, keep=4, tris=5, interp=6, hull=7, qtri=8)
 
 
 def numpy_sphere_tables(H: int, W: int):
@@ -282,6 +282,8 @@ class BevRenderer:
             buf = np.zeros((self.grid_h, self.grid_w, 3), np.uint8)
         elif what == "hull":
             buf = np.zeros((self.grid_h, self.grid_w), np.uint8)
+        elif what == "qtri":
+            buf = np.full((self.grid_h, self.grid_w, 3), -1, np.int32)
         else:
             raise ValueError(what)
         nat.check(self._lib.salve_bev_tap(self._h, image, TAP[what], buf.ctypes.data, buf.nbytes, None))
@@ -300,7 +302,13 @@ class BevRenderer:
     def last_timings(self) -> dict:
         ms = np.zeros(5, np.float32)
         nat.check(self._lib.salve_bev_last_timings(self._h, _ptr(ms, ctypes.c_float)))
-        return dict(splat=float(ms[0]), sites=float(ms[1]), flip=float(ms[2]), raster=float(ms[3]), total=float(ms[4]))
+        return dict(splat=float(ms[0]), image=float(ms[1]), total=float(ms[4]))
+
+    def last_phase_clocks(self, n_img: int) -> np.ndarray:
+        """(n_img, 16) int64 diagnostics of image_kernel for the last chunk (see salve_bev_last_phase_clocks)."""
+        clk = np.zeros((n_img, 16), np.int64)
+        nat.check(self._lib.salve_bev_last_phase_clocks(self._h, _ptr(clk, ctypes.c_int64), n_img))
+        return clk
 
     def launch_count(self) -> int:
         return int(self._lib.salve_bev_launch_count(self._h))

@@ -40,6 +40,24 @@ def oracle_tri_pixel_set(can) -> np.ndarray:
     return tri_pixel_set(pix[real].astype(np.int32))
 
 
+def check_query_triangles(qtri: np.ndarray, queries: np.ndarray, oracle_tris: np.ndarray) -> None:
+    """Each query pixel's triangle (vertex pixel ids) is a triangle of the canonical mesh and contains the pixel."""
+    W = queries.shape[1]
+    rows, cols = np.nonzero(queries)
+    t = np.sort(qtri[rows, cols].astype(np.int64), axis=1)
+    base = np.int64(W) * queries.shape[0]
+    code = lambda a: (a[:, 0] * base + a[:, 1]) * base + a[:, 2]
+    assert np.isin(code(t), code(oracle_tris.astype(np.int64))).all(), "a query ended in a triangle that is not in the canonical mesh"
+    v = qtri[rows, cols].astype(np.int64)
+    vx, vy = v % W, v // W
+    def orient(i, j, px, py):
+        return (vx[:, j] - vx[:, i]) * (py - vy[:, i]) - (vy[:, j] - vy[:, i]) * (px - vx[:, i])
+    a2 = orient(0, 1, vx[:, 2], vy[:, 2])
+    assert (a2 > 0).all(), "query triangle not counter-clockwise"
+    for i, j in ((0, 1), (1, 2), (2, 0)):
+        assert (orient(i, j, cols, rows) >= 0).all(), "query pixel outside its triangle"
+
+
 def tie_independent_mask(st: "bo.Stages", can) -> np.ndarray:
     """Pixels whose interpolated value is the same in every Delaunay triangulation: sites and
     pixels inside strict (tie-free) triangles."""

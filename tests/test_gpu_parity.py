@@ -49,9 +49,17 @@ def check_image_against_oracle(r, img_idx, img, counts, st, report=None):
     assert np.array_equal(sparse, st.sparse), "sparse image"
     can = pu.oracle_canonical(st)
     assert can["stats"]["residual_ties"] == 0
+    # explicit-mesh path (zipper + parallel Lawson flips), built on demand: the whole triangle set
     tris = r.tap(img_idx, "tris")
-    assert np.array_equal(pu.tri_pixel_set(tris), pu.oracle_tri_pixel_set(can)), "triangle set"
-    assert counts[5] == int((can["tri_v"] >= 0).all(1).sum())
+    oracle_tris = pu.oracle_tri_pixel_set(can)
+    assert np.array_equal(pu.tri_pixel_set(tris), oracle_tris), "triangle set"
+    # render path (query-driven flips): every interpolated pixel ended in a triangle of the canonical mesh that contains it
+    occ = st.key_grid != 0
+    queries = st.keep & can["hull"] & ~occ
+    assert counts[5] == int(queries.sum()), "interpolated pixel count"
+    qtri = r.tap(img_idx, "qtri")
+    assert np.array_equal((qtri >= 0).all(2), queries)
+    pu.check_query_triangles(qtri, queries, oracle_tris)
     assert np.array_equal(r.tap(img_idx, "hull"), can["hull"]), "hull mask vs exact oracle"
     n_hull_extra = pu.hull_check(can["hull"], st.hull)  # vs SciPy: identical up to float-tolerance boundary pixels
     assert np.array_equal(r.tap(img_idx, "interp"), can["interp"]), "interpolated image vs canonical oracle"
@@ -141,7 +149,9 @@ def test_batch_chunking_determinism_and_independence():
         r.upload_pano(k, rgbs[k], depths[k])
     a, ca, sa = r.render_hypotheses(p1, p2, Rm, t)
     b, cb, sb = r.render_hypotheses(p1, p2, Rm, t)
-    assert np.array_equal(a, b) and np.array_equal(ca, cb), "not deterministic"
+    # counters 6 and 7 (longest descent, flips in total) are diagnostics of the schedule: how often two warps of the
+    # cooperative pass reach the same large triangle depends on timing.  Images and every other counter do not.
+    assert np.array_equal(a, b) and np.array_equal(ca[..., :6], cb[..., :6]), "not deterministic"
     assert (sa == 0).all()
     for h in range(n_h):  # one-by-one through the per-image entry point
         one, c1, s1 = r.render_images([p1[h], p2[h], p1[h], p2[h]], ["floor", "floor", "ceiling", "ceiling"], [1, 0, 1, 0],
