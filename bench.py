@@ -149,7 +149,9 @@ def workload_config(n_gpus: int):
         "panos": N_PANOS, "hypotheses_per_gpu": N_HYP, "images_per_hypothesis": 4, "pano_hw": [PANO_H, PANO_W],
         "bev_grid": [IMG, IMG], "parallelism": f"dp{n_gpus} (sharded by building, no collective)",
         "l2": "256 MiB scratch write between timed steps (L2 flush); per-step working set is > 2 GB",
-        "unposed_render_cache": False,
+        "unposed_render_dedup": "within a step every distinct (pano 2, surface) image is rendered once and copied into each hypothesis' slot "
+        "(img2 does not depend on the hypothesis, reference bev_rendering_utils.py:451-455); all 4 images of every hypothesis are "
+        "materialised in the output; nothing is carried across steps; value_no_dedup renders all 2560 images from scratch",
     }
 
 
@@ -234,7 +236,9 @@ def run_ours(args):
     # ---- synthetic building for this rank ----------------------------------------------------------
     rgbs, depths, p1, p2, R, t = synth.synth_building(N_PANOS, N_HYP, PANO_H, PANO_W, seed=rank)
     n_img = N_HYP * 4
-    r = BevRenderer(pano_h=PANO_H, pano_w=PANO_W, max_panos=N_PANOS, max_images=592, device=local)
+    dev_chunk = int(os.environ.get("BENCH_DEV_CHUNK", "1480"))  # images per internal chunk (10 per SM): one launch per step
+    e2e_chunk = int(os.environ.get("BENCH_E2E_CHUNK", "296"))   # host path: smaller chunks so that D2H overlaps rendering
+    r = BevRenderer(pano_h=PANO_H, pano_w=PANO_W, max_panos=N_PANOS, max_images=dev_chunk, device=local)
     stream = torch.cuda.current_stream(dev)
     sh = stream.cuda_stream
 
@@ -290,18 +294,42 @@ def run_ours(args):
     value = world * N_HYP * args.steps / (t_ms / 1e3)
     counts_h = d_counts.cpu().numpy().reshape(n_img, 8)
     status_h = d_status.cpu().numpy()
+    d_ref = d_out[: 8 * IMG_BYTES].cpu().numpy().copy()
+
+    # ---- the same without the de-duplication of un-posed renders (every image from scratch) -------------------
+    r.set_dedup_unposed(False)
+    step_device()
+    torch.cuda.synchronize(dev)
+    same_nd = bool(np.array_equal(d_out[: 8 * IMG_BYTES].cpu().numpy(), d_ref))
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)
+        ev2[k][0].record(stream)
+        step_device()
+        ev2[k][1].record(stream)
+    barrier()
+    t2 = torch.tensor([sum(a.elapsed_time(b) for a, b in ev2)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    value_nd = world * N_HYP * args.steps / (float(t2.item()) / 1e3)
+    r.set_dedup_unposed(True)
 
     # ---- `e2e`: host buffers through the C ABI, H2D + D2H inside the timed region --------------------
     h_rgb = torch.from_numpy(rgbs).pin_memory()
     h_depth = torch.from_numpy(depths.view(np.int16)).pin_memory()
-    h_out = torch.empty(n_img * IMG_BYTES, dtype=torch.uint8).pin_memory()
-    r2 = BevRenderer(pano_h=PANO_H, pano_w=PANO_W, max_panos=N_PANOS, max_images=592, device=local)
-    h_out_np = h_out.numpy()
+    # compact host layout: img1 per hypothesis and surface + img2 once per distinct (pano 2, surface); every hypothesis' four
+    # images are in host memory when the call returns (img2 shared through the returned index)
+    h_posed = torch.empty(N_HYP * 2 * IMG_BYTES, dtype=torch.uint8).pin_memory()
+    h_unposed = torch.empty(N_PANOS * 2 * IMG_BYTES, dtype=torch.uint8).pin_memory()
+    r2 = BevRenderer(pano_h=PANO_H, pano_w=PANO_W, max_panos=N_PANOS, max_images=e2e_chunk, device=local)
+    h_posed_np, h_unposed_np = h_posed.numpy(), h_unposed.numpy()
+    e2e_ret = {}
 
     def step_e2e():
         for k in range(N_PANOS):
             r2.upload_pano_ptr(k, h_rgb[k].data_ptr(), h_depth[k].data_ptr(), stream=sh)
-        r2.render_hypotheses(p1, p2, R, t, out=h_out_np, stream=sh)
+        e2e_ret["r"] = r2.render_hypotheses_compact(p1, p2, R, t, posed_out=h_posed_np, unposed_out=h_unposed_np, stream=sh)
 
     step_e2e()
     barrier()
@@ -315,9 +343,14 @@ def run_ours(args):
         dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
     te = float(te_t.item())
     e2e_value = world * N_HYP * args.steps / te
-    same = bool(np.array_equal(h_out_np[: 8 * IMG_BYTES], d_out[: 8 * IMG_BYTES].cpu().numpy()))
+    posed_h, unposed_h, idx_h = e2e_ret["r"][:3]
+    full0 = d_ref.reshape(2, 2, 2, IMG, IMG, 3)  # hypotheses 0, 1 of the device path: (surface, posed/un-posed)
+    same = all(
+        np.array_equal(posed_h[h, s], full0[h, s, 0]) and np.array_equal(unposed_h[idx_h[h], s], full0[h, s, 1]) for h in range(2) for s in range(2)
+    )
+    n_unique = int(unposed_h.shape[0])
     h2d = N_PANOS * PANO_H * PANO_W * 5 + N_HYP * (2 * 4 + 6 * 4)
-    d2h = n_img * IMG_BYTES + n_img * 9 * 4
+    d2h = (N_HYP * 2 + n_unique * 2) * (IMG_BYTES + 9 * 4)
 
     if rank != 0:
         if dist is not None:
@@ -326,15 +359,22 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel ---------------------------------------------------------------
     peak, peak_src = load_peaks()
-    sites = counts_h[:, 2].astype(np.int64)
-    filled = counts_h[:, 5].astype(np.int64)
-    n_launch = args.steps * ((n_img + 591) // 592)
+    # images the kernels really rendered in a (de-duplicated) step: all posed ones + one per distinct (pano 2, surface)
+    c4 = counts_h.reshape(N_HYP, 2, 2, 8)
+    first = {int(p): h for h, p in reversed(list(enumerate(p2)))}
+    rendered = np.concatenate([c4[:, :, 0].reshape(-1, 8), c4[sorted(first.values())][:, :, 1].reshape(-1, 8)])
+    n_rendered = rendered.shape[0]
+    n_jobs = N_HYP + len(first)  # pano passes of the splat (each serves floor and ceiling)
+    sites = rendered[:, 2].astype(np.int64)
+    filled = rendered[:, 5].astype(np.int64)
+    chunks_per_step = (n_rendered + dev_chunk - 1) // dev_chunk
+    n_launch = args.steps * chunks_per_step
     # algorithmic bytes per stage and step
     alg = {
         # depth in (2 B/px per pano pass) + one 4 B key update per point inside the box
-        "splat": 2 * N_HYP * 360448 * 2 + int(counts_h[:, 1].sum()) * 4,
+        "splat": n_jobs * 360448 * 2 + int(rendered[:, 1].sum()) * 4,
         # key grid in, winner colours in (3 B gathered per site), final image out
-        "image": n_img * IMG * IMG * 4 + int(sites.sum()) * 3 + n_img * IMG_BYTES,
+        "image": n_rendered * IMG * IMG * 4 + int(sites.sum()) * 3 + n_rendered * IMG_BYTES,
     }
     kernels = {}
     for name in ("splat", "image"):
@@ -343,7 +383,6 @@ def run_ours(args):
         kernels[name] = {"ms_per_step": ms, "alg_bytes_per_step": alg[name], "achieved_gbs": gbs, "frac": gbs / peak,
                          "share_of_step": stage_ms[name] / max(stage_ms["total"], 1e-9)}
     dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
-    chunks_per_step = (n_img + 591) // 592
     roofline = {
         "kernel": {"splat": "splat_pano_kernel", "image": "image_kernel"}[dom],
         "bound": "hbm",
@@ -388,6 +427,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "hypotheses/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "matches_device_path": same},
         "gpu_launches": int(launches),
+        "value_no_dedup": value_nd, "no_dedup_matches": same_nd, "images_rendered_per_step": int(n_rendered),
         "roofline": roofline,
         "cpu_baseline": cpu,
         "images_ok": int((status_h == 0).sum()), "images": int(n_img),

@@ -132,6 +132,31 @@ int salve_bev_render_hypotheses_host(salve_bev_ctx* ctx, int32_t n_hyp, const in
                                      int32_t* host_counts, int32_t* host_status, void* stream);
 
 /*
+ * De-duplicated layout.  img2 of render_bev_pair does not depend on the hypothesis: only pano 1's cloud is posed
+ * (bev_rendering_utils.py:451), pano 2 is rendered in its own frame (:455).  These entry points render every distinct
+ * (pano 2, surface) once and return
+ *   posed          : n_hyp * nsurf images, hypothesis-major, surface-minor (floor first): img1 of each pair
+ *   unposed        : n_unique * nsurf images (n_unique <= min(n_hyp, max_panos)): img2 of the pairs, one per distinct pano 2 in
+ *                    order of first appearance; the caller provides room for min(n_hyp, max_panos) * nsurf images
+ *   unposed_of_hyp : n_hyp int32 (host), index u of hypothesis h's pano 2: its img2 for surface s is unposed[u * nsurf + s]
+ *   n_unique       : 1 int32 (host)
+ * counts / status arrays (may be NULL) follow the two image arrays.  salve_bev_render_hypotheses[_host] use the same
+ * machinery whenever a pano 2 repeats and then copy the shared image into every hypothesis' slot, so their output is
+ * unchanged; salve_bev_set_dedup_unposed(ctx, 0) turns that off (every image rendered from scratch).
+ */
+int salve_bev_render_hypotheses_compact(salve_bev_ctx* ctx, int32_t n_hyp, const int32_t* host_pano1, const int32_t* host_pano2,
+                                        const float* host_R, const float* host_t, uint32_t surfaces, uint8_t* dev_posed,
+                                        uint8_t* dev_unposed, int32_t* host_unposed_of_hyp, int32_t* host_n_unique,
+                                        int32_t* dev_counts_posed, int32_t* dev_counts_unposed, int32_t* dev_status_posed,
+                                        int32_t* dev_status_unposed, void* stream);
+int salve_bev_render_hypotheses_compact_host(salve_bev_ctx* ctx, int32_t n_hyp, const int32_t* host_pano1, const int32_t* host_pano2,
+                                             const float* host_R, const float* host_t, uint32_t surfaces, uint8_t* host_posed,
+                                             uint8_t* host_unposed, int32_t* host_unposed_of_hyp, int32_t* host_n_unique,
+                                             int32_t* host_counts_posed, int32_t* host_counts_unposed, int32_t* host_status_posed,
+                                             int32_t* host_status_unposed, void* stream);
+int salve_bev_set_dedup_unposed(salve_bev_ctx* ctx, int32_t on);
+
+/*
  * Render individual images: image k = pano slot[k], surface[k] (SALVE_BEV_SURF_*), posed[k] != 0 ->
  * apply (R[k], t[k]) as for pano 1 of a pair.  Replaces get_xyzrgb_from_depth + the frame change of
  * render_bev_pair + render_bev_image (bev_rendering_utils.py:347-414, 443-451, 254-328).
@@ -186,7 +211,8 @@ int salve_bev_remove_hallucinated(salve_bev_ctx* ctx, const uint8_t* host_sparse
                                   int32_t K, uint8_t* host_out, void* stream);
 
 /*
- * Stage taps of the most recent render call (parity tests).  image = index within the last chunk.
+ * Stage taps of the most recent render call (parity tests).  image = index within the last internal chunk (for a call that
+ * was de-duplicated the chunks hold the unique un-posed images first, then the posed ones).
  * what: see SALVE_BEV_TAP_*.  host_buf must be large enough (sizes in comments, g = grid_h*grid_w,
  * wpr = (grid_w+31)/32).
  */

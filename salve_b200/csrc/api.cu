@@ -58,7 +58,14 @@ struct salve_bev_ctx {
     uint32_t* qlist = nullptr;  // per image work list of image_kernel (g entries)
     unsigned long long* qres = nullptr;  // per image, per list entry: the resolved triangle
     long long* phase_clk = nullptr;      // diagnostics: 16 slots per image of the last chunk
-    uint32_t* keepbits = nullptr;        // per image keep-mask bit rows of image_kernel
+    uint32_t* keepbits = nullptr;        // per CTA slot keep-mask bit rows of image_kernel
+    int32_t* work_counter = nullptr;     // image_kernel's dynamic image counter
+    int image_slots = 0;                 // persistent CTAs of image_kernel (scratch slots)
+    // hypothesis-independent (un-posed pano 2) renders of the current call: max_panos x 2 surfaces
+    uint8_t* cache_out = nullptr; int32_t* cache_counts = nullptr; int32_t* cache_status = nullptr;
+    int32_t* d_dest = nullptr;           // per image of the chunk: destination (see ImageArgs::dest)
+    int32_t* h_dest[2] = {nullptr, nullptr};
+    bool dedup_unposed = true;
     size_t g_stride = 0, bits_stride = 0, tris_stride = 0, cand_stride = 0;
     ImgHeader* headers = nullptr;
     int32_t* counts = nullptr;
@@ -69,6 +76,7 @@ struct salve_bev_ctx {
     // host-output pipeline: chunk k+1 renders while chunk k is copied device->host on copy_stream
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr}, ev_staged[2] = {nullptr, nullptr};
+    cudaEvent_t ev_cache = nullptr;  // the un-posed cache of the current call is complete
     SplatJob* h_jobs[2] = {nullptr, nullptr};          // pinned staging of the per-chunk job tables
     const uint8_t** h_src[2] = {nullptr, nullptr};
     int stage_parity = 0;
@@ -158,10 +166,20 @@ extern "C" int salve_bev_ctx_create(const salve_bev_config* cfg, salve_bev_ctx**
     ALLOC(c->d_depth_ptr, P);
     ALLOC(c->d_tables, 2 * H + 2 * W);
     ALLOC(c->keygrid, N * c->g_stride);
-    ALLOC(c->qlist, N * c->g_stride);
-    ALLOC(c->qres, N * c->g_stride);
+    {
+        int n_sm = 0;
+        CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
+        c->image_slots = (int)std::min<size_t>(N, (size_t)2 * n_sm);  // persistent CTAs of image_kernel: 2 per SM
+    }
+    ALLOC(c->qlist, (size_t)c->image_slots * c->g_stride);
+    ALLOC(c->qres, (size_t)c->image_slots * c->g_stride);
     ALLOC(c->phase_clk, N * 16);
-    ALLOC(c->keepbits, N * c->bits_stride);
+    ALLOC(c->keepbits, (size_t)c->image_slots * c->bits_stride);
+    ALLOC(c->work_counter, 1);
+    ALLOC(c->cache_out, 2 * P * c->img_bytes + 64);  // +64: replicate_images_kernel reads whole words
+    ALLOC(c->cache_counts, 2 * P * 8);
+    ALLOC(c->cache_status, 2 * P);
+    ALLOC(c->d_dest, N);
     // mesh scratch (explicit triangulation: grids too large for image_kernel's shared memory, and the triangle tap): ONE image
     ALLOC(c->color, c->g_stride);
     ALLOC(c->occ, c->bits_stride);
@@ -182,12 +200,14 @@ extern "C" int salve_bev_ctx_create(const salve_bev_config* cfg, salve_bev_ctx**
     ALLOC(c->out_store, 2 * N * c->img_bytes);
 #undef ALLOC
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->ev_cache, cudaEventDisableTiming));
     for (int k = 0; k < 2; k++) {
         CU(cudaEventCreateWithFlags(&c->ev_done[k], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&c->ev_copied[k], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&c->ev_staged[k], cudaEventDisableTiming));
         CU(cudaMallocHost((void**)&c->h_jobs[k], sizeof(SplatJob) * N));
         CU(cudaMallocHost((void**)&c->h_src[k], sizeof(void*) * N));
+        CU(cudaMallocHost((void**)&c->h_dest[k], sizeof(int32_t) * N));
     }
     c->h_rgb_ptr.assign(P, nullptr);
     c->h_depth_ptr.assign(P, nullptr);
@@ -217,7 +237,7 @@ extern "C" void salve_bev_ctx_destroy(salve_bev_ctx* c) {
     cudaSetDevice(c->cfg.device);
     cudaDeviceSynchronize();
     void* ptrs[] = {c->pano_rgb_store, c->pano_depth_store, c->d_depth_ptr, c->d_tables, c->keygrid, c->color, c->occ, c->nonempty,
-                    c->keep, c->tmpbits, c->wprefix, c->tris, c->owner, c->list0, c->list1, c->cand, c->qlist, c->qres, c->phase_clk, c->keepbits, c->headers, c->counts,
+                    c->keep, c->tmpbits, c->wprefix, c->tris, c->owner, c->list0, c->list1, c->cand, c->qlist, c->qres, c->phase_clk, c->keepbits, c->work_counter, c->cache_out, c->cache_counts, c->cache_status, c->d_dest, c->headers, c->counts,
                     c->status, c->d_jobs, c->d_color_src, c->out_store};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < N_TMP; i++) if (c->tmp[i]) cudaFree(c->tmp[i]);
@@ -228,7 +248,9 @@ extern "C" void salve_bev_ctx_destroy(salve_bev_ctx* c) {
         if (c->ev_staged[k]) cudaEventDestroy(c->ev_staged[k]);
         if (c->h_jobs[k]) cudaFreeHost(c->h_jobs[k]);
         if (c->h_src[k]) cudaFreeHost(c->h_src[k]);
+        if (c->h_dest[k]) cudaFreeHost(c->h_dest[k]);
     }
+    if (c->ev_cache) cudaEventDestroy(c->ev_cache);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->h_meta) cudaFreeHost(c->h_meta);
     delete c;
@@ -320,21 +342,25 @@ static int stage_event(salve_bev_ctx* c, cudaStream_t st) {
 // Everything after the splat for images [0, n_img): image_kernel (sites, masks, hull, query-driven flips).
 static int run_image_stage(salve_bev_ctx* c, int n_img, const GridParams& G, const uint32_t* keygrid, const uint8_t* const* color_src,
                            uint8_t* dev_out, int32_t* dev_counts, int32_t* dev_status, int raw_mode, int skip_empty, uint8_t* hull,
-                           int32_t* qtri, uint32_t* bits, cudaStream_t st) {
+                           int32_t* qtri, uint32_t* bits, cudaStream_t st, const int32_t* dest = nullptr, int32_t* counts_out = nullptr) {
     const size_t smem = image_smem_bytes(G.grid_h, G.wpr);
     if (smem > (size_t)c->max_smem_optin) FAIL(SALVE_BEV_E_CAPACITY, "grid too large for image_kernel's shared memory");
     ImageArgs IA;
     IA.G = G;
+    IA.n_img = n_img; IA.work_counter = c->work_counter;
+    CU(cudaMemsetAsync(c->work_counter, 0, sizeof(int32_t), st));
     IA.keygrid = keygrid; IA.keygrid_stride = c->g_stride;
     IA.color_src = color_src;
     IA.counts = dev_counts; IA.status = dev_status;
     IA.out = dev_out; IA.out_stride = (size_t)G.g * 3;
+    IA.dest = dest; IA.counts_out = counts_out;
+    IA.cache_out = c->cache_out; IA.cache_counts = c->cache_counts; IA.cache_status = c->cache_status;
     IA.hull = hull; IA.hull_stride = (size_t)G.g;
     IA.qtri = qtri; IA.qtri_stride = (size_t)G.g * 3;
     IA.bits = bits; IA.bits_stride = 3 * (size_t)G.grid_h * G.wpr;
     IA.qlist = c->qlist; IA.qlist_stride = c->g_stride; IA.qres = c->qres; IA.keepbits = c->keepbits; IA.keepbits_stride = c->bits_stride; IA.phase_clk = (n_img <= c->cfg.max_images && keygrid == c->keygrid) ? c->phase_clk : nullptr;
     IA.raw_mode = raw_mode; IA.skip_empty_check = skip_empty;
-    image_kernel<<<n_img, IMAGE_NT, smem, st>>>(IA);
+    image_kernel<<<std::min(n_img, c->image_slots), IMAGE_NT, smem, st>>>(IA);
     c->launches++;
     CU(cudaGetLastError());
     return stage_event(c, st);
@@ -391,7 +417,8 @@ static int run_mesh_stages(salve_bev_ctx* c, const GridParams& G, const uint32_t
 
 // One chunk of pano-sourced images.  jobs / color slots are host arrays.
 static int render_chunk(salve_bev_ctx* c, int n_img, const std::vector<SplatJob>& jobs, const std::vector<int>& img_slot, uint8_t* dev_out,
-                        int32_t* dev_counts, int32_t* dev_status, cudaStream_t st) {
+                        int32_t* dev_counts, int32_t* dev_status, cudaStream_t st, const std::vector<int32_t>* dest = nullptr,
+                        int32_t* counts_out = nullptr) {
     if (n_img > c->cfg.max_images || (int)jobs.size() > c->cfg.max_images) FAIL(SALVE_BEV_E_CAPACITY, "chunk exceeds max_images");
     int rc = sync_ptr_tables(c, st); if (rc) return rc;
     // job tables go through pinned, double-buffered staging so that the chunk loop never blocks the host
@@ -404,6 +431,10 @@ static int render_chunk(salve_bev_ctx* c, int n_img, const std::vector<SplatJob>
     memcpy(c->h_jobs[sp], jobs.data(), sizeof(SplatJob) * jobs.size());
     CU(cudaMemcpyAsync(c->d_jobs, c->h_jobs[sp], sizeof(SplatJob) * jobs.size(), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(c->d_color_src, c->h_src[sp], sizeof(void*) * n_img, cudaMemcpyHostToDevice, st));
+    if (dest) {
+        memcpy(c->h_dest[sp], dest->data(), sizeof(int32_t) * n_img);
+        CU(cudaMemcpyAsync(c->d_dest, c->h_dest[sp], sizeof(int32_t) * n_img, cudaMemcpyHostToDevice, st));
+    }
     CU(cudaEventRecord(c->ev_staged[sp], st));
     if (!dev_counts) dev_counts = c->counts;
     rc = stage_event(c, st); if (rc) return rc;
@@ -419,7 +450,207 @@ static int render_chunk(salve_bev_ctx* c, int n_img, const std::vector<SplatJob>
     rc = stage_event(c, st); if (rc) return rc;
     c->last_chunk_images = n_img;
     c->last_counts = dev_counts;
-    return run_image_stage(c, n_img, c->G, c->keygrid, c->d_color_src, dev_out, dev_counts, dev_status, 0, 0, nullptr, nullptr, nullptr, st);
+    return run_image_stage(c, n_img, c->G, c->keygrid, c->d_color_src, dev_out, dev_counts, dev_status, 0, 0, nullptr, nullptr, nullptr, st,
+                           dest ? c->d_dest : nullptr, counts_out);
+}
+
+// Copy images between two device buffers at any alignment (an image is 753 003 bytes: consecutive images share no
+// alignment).  Copy k: cache image src_idx[k] -> out image dst_idx[k], plus its counters and status.
+__global__ void __launch_bounds__(256) replicate_images_kernel(const uint8_t* __restrict__ cache, uint8_t* __restrict__ out,
+                                                              const int32_t* __restrict__ src_idx, const int32_t* __restrict__ dst_idx,
+                                                              size_t bytes, const int32_t* __restrict__ cache_counts,
+                                                              int32_t* __restrict__ counts, const int32_t* __restrict__ cache_status,
+                                                              int32_t* __restrict__ status) {
+    const int k = blockIdx.y;
+    const int si = src_idx[k], di = dst_idx[k];
+    if (blockIdx.x == 0 && threadIdx.x < 9) {
+        if (threadIdx.x < 8) { if (counts) counts[(size_t)di * 8 + threadIdx.x] = cache_counts[(size_t)si * 8 + threadIdx.x]; }
+        else if (status) status[di] = cache_status[si];
+    }
+    if (!out) return;
+    const uint8_t* s = cache + (size_t)si * bytes;
+    uint8_t* d = out + (size_t)di * bytes;
+    size_t head = (16 - ((uintptr_t)d & 15)) & 15;
+    if (head > bytes) head = bytes;
+    const size_t nchunks = (bytes - head) / 16;
+    const size_t tail0 = head + nchunks * 16;
+    for (size_t ch = (size_t)blockIdx.x * blockDim.x + threadIdx.x; ch < nchunks; ch += (size_t)gridDim.x * blockDim.x) {
+        const uintptr_t sa = (uintptr_t)(s + head + ch * 16);
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(sa & ~(uintptr_t)3);
+        const int sh = (int)(sa & 3) * 8;
+        const uint32_t a0 = w[0], a1 = w[1], a2 = w[2], a3 = w[3], a4 = sh ? w[4] : 0u;
+        uint4 v;
+        v.x = __funnelshift_r(a0, a1, sh); v.y = __funnelshift_r(a1, a2, sh); v.z = __funnelshift_r(a2, a3, sh); v.w = __funnelshift_r(a3, a4, sh);
+        *reinterpret_cast<uint4*>(d + head + ch * 16) = v;
+    }
+    if (blockIdx.x == 0) {
+        if (threadIdx.x < head) d[threadIdx.x] = s[threadIdx.x];
+        if (tail0 + threadIdx.x < bytes) d[tail0 + threadIdx.x] = s[tail0 + threadIdx.x];
+    }
+}
+
+// ---- de-duplicated rendering ----------------------------------------------------------------------------------------------
+// img2 of render_bev_pair does not depend on the hypothesis: only xyzrgb1 is posed (bev_rendering_utils.py:451), pano 2 is
+// rendered in its own frame (:455).  A call that names the same pano 2 in several hypotheses renders it once per surface
+// into the context's cache; every hypothesis then gets a copy (full layout) or an index (compact layout).
+// Image stream of a call: first the unique un-posed images (unique pano 2's in order of first appearance x surfaces), then the
+// posed images (hypothesis-major, surface-minor), cut into chunks of whole jobs.
+struct HypPlan {
+    std::vector<int32_t> uniq;        // unique pano-2 slots
+    std::vector<int32_t> uniq_of_hyp; // per hypothesis: index into uniq
+};
+static void make_plan(int32_t n_hyp, const int32_t* p2, int max_panos, HypPlan& P) {
+    std::vector<int32_t> where(max_panos, -1);
+    P.uniq.clear(); P.uniq_of_hyp.resize(n_hyp);
+    for (int h = 0; h < n_hyp; h++) {
+        int32_t& w = where[p2[h]];
+        if (w < 0) { w = (int32_t)P.uniq.size(); P.uniq.push_back(p2[h]); }
+        P.uniq_of_hyp[h] = w;
+    }
+}
+
+// full = true : out holds n_hyp * nsurf * 2 images in the order of salve_bev_render_hypotheses (posed, un-posed per surface)
+// full = false: out holds the n_hyp * nsurf posed images, out_unposed the uniq * nsurf un-posed ones
+static int render_hyp_dedup(salve_bev_ctx* c, int32_t n_hyp, const int32_t* p1, const float* R, const float* t, uint32_t surfaces,
+                            bool full, bool host_out, uint8_t* out, uint8_t* out_unposed, int32_t* counts, int32_t* counts_unposed,
+                            int32_t* status, int32_t* status_unposed, const HypPlan& plan, cudaStream_t st) {
+    const bool do_f = surfaces & SALVE_BEV_SURF_FLOOR, do_c = surfaces & SALVE_BEV_SURF_CEILING;
+    const int nsurf = (int)do_f + (int)do_c;
+    const int nU = (int)plan.uniq.size();
+    const int jobs_per_chunk = c->cfg.max_images / nsurf;
+    if (jobs_per_chunk < 1) FAIL(SALVE_BEV_E_CAPACITY, "max_images too small for one hypothesis");
+    const int n_jobs = nU + n_hyp;
+    const size_t n_posed = (size_t)n_hyp * nsurf, n_unposed = (size_t)nU * nsurf;
+    const size_t n_user = full ? 2 * n_posed : n_posed;  // images in `out`
+    const size_t ib = c->img_bytes;
+    const size_t N = c->cfg.max_images;
+    int rc;
+    int32_t *hm_counts = nullptr, *hm_status = nullptr, *hm_ucounts = nullptr, *hm_ustatus = nullptr;
+    if (host_out) {
+        const size_t need = (n_user + n_unposed) * 9;
+        if (c->h_meta_cap < need) {
+            if (c->h_meta) CU(cudaFreeHost(c->h_meta));
+            c->h_meta = nullptr; c->h_meta_cap = 0;
+            CU(cudaMallocHost((void**)&c->h_meta, sizeof(int32_t) * need));
+            c->h_meta_cap = need;
+        }
+        hm_counts = c->h_meta; hm_status = hm_counts + n_user * 8;
+        hm_ucounts = hm_status + n_user; hm_ustatus = hm_ucounts + n_unposed * 8;
+    }
+    std::vector<SplatJob> jobs;
+    std::vector<int> slots;
+    std::vector<int32_t> dest;
+    int chunk_no = 0;
+    for (int j0 = 0; j0 < n_jobs; j0 += jobs_per_chunk, chunk_no++) {
+        const int nj = std::min(jobs_per_chunk, n_jobs - j0);
+        const int n_img = nj * nsurf;
+        const int par = chunk_no & 1;
+        jobs.clear(); slots.assign(n_img, 0); dest.assign(n_img, 0);
+        int first_posed = -1;  // chunk-local index of the first posed image (posed images are a suffix of the chunk)
+        for (int k = 0; k < nj; k++) {
+            const int j = j0 + k;
+            SplatJob a;
+            a.img_floor = do_f ? k * nsurf : -1;
+            a.img_ceil = do_c ? k * nsurf + (do_f ? 1 : 0) : -1;
+            if (j < nU) {
+                a.pano_slot = plan.uniq[j]; a.posed = 0;
+                a.R[0] = 1.f; a.R[1] = 0.f; a.R[2] = 0.f; a.R[3] = 1.f; a.t[0] = 0.f; a.t[1] = 0.f;
+                for (int s = 0; s < nsurf; s++) dest[k * nsurf + s] = -1 - (j * nsurf + s);
+            } else {
+                const int h = j - nU;
+                a.pano_slot = p1[h]; a.posed = 1;
+                memcpy(a.R, R + 4 * (size_t)h, sizeof(float) * 4); memcpy(a.t, t + 2 * (size_t)h, sizeof(float) * 2);
+                if (first_posed < 0) first_posed = k * nsurf;
+                for (int s = 0; s < nsurf; s++) {
+                    const int li = k * nsurf + s;
+                    // host output: posed images go through the double-buffered staging store in chunk-local order
+                    dest[li] = host_out ? li : (full ? (h * nsurf + s) * 2 : h * nsurf + s);
+                }
+            }
+            if (a.pano_slot < 0 || a.pano_slot >= c->cfg.max_panos) FAIL(SALVE_BEV_E_CAPACITY, "pano slot out of range");
+            for (int s = 0; s < nsurf; s++) slots[k * nsurf + s] = a.pano_slot;
+            jobs.push_back(a);
+        }
+        if (host_out) {
+            CU(cudaStreamWaitEvent(st, c->ev_copied[par], 0));  // staging buffer `par` was drained (chunk k-2)
+            uint8_t* stage = c->out_store + par * N * ib;
+            int32_t* cnt_stage = c->counts + par * N * 8;
+            int32_t* st_stage = c->status + par * N;
+            rc = render_chunk(c, n_img, jobs, slots, stage, cnt_stage, st_stage, st, &dest, nullptr);
+            if (rc) return rc;
+            if (first_posed >= 0) {
+                const int np = n_img - first_posed;
+                const size_t fin0 = (size_t)(std::max(j0, nU) - nU) * nsurf;  // index among the posed images
+                CU(cudaEventRecord(c->ev_done[par], st));
+                CU(cudaStreamWaitEvent(c->copy_stream, c->ev_done[par], 0));
+                const uint8_t* src = stage + (size_t)first_posed * ib;
+                const size_t k = full ? 2 : 1;  // posed image i of the call is image k*i of `out`
+                if (full) CU(cudaMemcpy2DAsync(out + fin0 * 2 * ib, 2 * ib, src, ib, ib, np, cudaMemcpyDeviceToHost, c->copy_stream));
+                else CU(cudaMemcpyAsync(out + fin0 * ib, src, (size_t)np * ib, cudaMemcpyDeviceToHost, c->copy_stream));
+                CU(cudaMemcpy2DAsync(hm_counts + fin0 * k * 8, k * 32, cnt_stage + (size_t)first_posed * 8, 32, 32, np, cudaMemcpyDeviceToHost, c->copy_stream));
+                CU(cudaMemcpy2DAsync(hm_status + fin0 * k, k * 4, st_stage + first_posed, 4, 4, np, cudaMemcpyDeviceToHost, c->copy_stream));
+                CU(cudaEventRecord(c->ev_copied[par], c->copy_stream));
+            }
+            if (j0 < nU && j0 + nj >= nU) {
+                // the cache is complete once this chunk is done: its device->host copies overlap the posed chunks that follow
+                CU(cudaEventRecord(c->ev_cache, st));
+                CU(cudaStreamWaitEvent(c->copy_stream, c->ev_cache, 0));
+                if (full) {
+                    for (int h = 0; h < n_hyp; h++)
+                        for (int s = 0; s < nsurf; s++)
+                            CU(cudaMemcpyAsync(out + ((size_t)(h * nsurf + s) * 2 + 1) * ib, c->cache_out + (size_t)(plan.uniq_of_hyp[h] * nsurf + s) * ib, ib,
+                                               cudaMemcpyDeviceToHost, c->copy_stream));
+                } else {
+                    CU(cudaMemcpyAsync(out_unposed, c->cache_out, n_unposed * ib, cudaMemcpyDeviceToHost, c->copy_stream));
+                }
+                CU(cudaMemcpyAsync(hm_ucounts, c->cache_counts, sizeof(int32_t) * 8 * n_unposed, cudaMemcpyDeviceToHost, c->copy_stream));
+                CU(cudaMemcpyAsync(hm_ustatus, c->cache_status, sizeof(int32_t) * n_unposed, cudaMemcpyDeviceToHost, c->copy_stream));
+            }
+        } else {
+            rc = render_chunk(c, n_img, jobs, slots, out, c->counts, status, st, &dest, counts);
+            if (rc) return rc;
+        }
+    }
+    // ---- device output: un-posed images from the cache to their destinations
+    if (!host_out && full && n_posed) {
+        void *dsrc, *ddst;
+        if ((rc = tmp_get(c, 5, sizeof(int32_t) * n_posed, &dsrc))) return rc;
+        if ((rc = tmp_get(c, 6, sizeof(int32_t) * n_posed, &ddst))) return rc;
+        std::vector<int32_t> hs(n_posed), hd(n_posed);
+        for (int h = 0; h < n_hyp; h++)
+            for (int s = 0; s < nsurf; s++) {
+                hs[(size_t)h * nsurf + s] = plan.uniq_of_hyp[h] * nsurf + s;
+                hd[(size_t)h * nsurf + s] = (h * nsurf + s) * 2 + 1;
+            }
+        CU(cudaMemcpyAsync(dsrc, hs.data(), sizeof(int32_t) * n_posed, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ddst, hd.data(), sizeof(int32_t) * n_posed, cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));  // hs / hd are pageable locals
+        replicate_images_kernel<<<dim3(16, (unsigned)n_posed), 256, 0, st>>>(c->cache_out, out, (const int32_t*)dsrc, (const int32_t*)ddst, ib,
+                                                                            c->cache_counts, counts, c->cache_status, status);
+        c->launches++;
+        CU(cudaGetLastError());
+    } else if (!host_out && n_unposed) {
+        CU(cudaMemcpyAsync(out_unposed, c->cache_out, n_unposed * ib, cudaMemcpyDeviceToDevice, st));
+        if (counts_unposed) CU(cudaMemcpyAsync(counts_unposed, c->cache_counts, sizeof(int32_t) * 8 * n_unposed, cudaMemcpyDeviceToDevice, st));
+        if (status_unposed) CU(cudaMemcpyAsync(status_unposed, c->cache_status, sizeof(int32_t) * n_unposed, cudaMemcpyDeviceToDevice, st));
+    }
+    if (host_out) {
+        CU(cudaStreamSynchronize(c->copy_stream));
+        CU(cudaStreamSynchronize(st));
+        if (full) {
+            for (int h = 0; h < n_hyp; h++)
+                for (int s = 0; s < nsurf; s++) {
+                    const size_t d = (size_t)(h * nsurf + s) * 2 + 1, u = (size_t)plan.uniq_of_hyp[h] * nsurf + s;
+                    memcpy(hm_counts + d * 8, hm_ucounts + u * 8, 32);
+                    hm_status[d] = hm_ustatus[u];
+                }
+        }
+        if (counts) memcpy(counts, hm_counts, sizeof(int32_t) * 8 * n_user);
+        if (status) memcpy(status, hm_status, sizeof(int32_t) * n_user);
+        if (counts_unposed) memcpy(counts_unposed, hm_ucounts, sizeof(int32_t) * 8 * n_unposed);
+        if (status_unposed) memcpy(status_unposed, hm_ustatus, sizeof(int32_t) * n_unposed);
+    }
+    return SALVE_BEV_OK;
 }
 
 static int render_hyp_impl(salve_bev_ctx* c, int32_t n_hyp, const int32_t* p1, const int32_t* p2, const float* R, const float* t,
@@ -434,6 +665,14 @@ static int render_hyp_impl(salve_bev_ctx* c, int32_t n_hyp, const int32_t* p1, c
     if (hyp_per_chunk < 1) FAIL(SALVE_BEV_E_CAPACITY, "max_images too small for one hypothesis");
     CU(cudaSetDevice(c->cfg.device));
     c->events_used = 0;
+    for (int h = 0; h < n_hyp; h++)
+        if (p1[h] < 0 || p1[h] >= c->cfg.max_panos || p2[h] < 0 || p2[h] >= c->cfg.max_panos) FAIL(SALVE_BEV_E_CAPACITY, "pano slot out of range");
+    if (c->dedup_unposed && n_hyp > 1) {
+        HypPlan plan;
+        make_plan(n_hyp, p2, c->cfg.max_panos, plan);
+        if ((int)plan.uniq.size() < n_hyp)  // some pano 2 repeats: render each un-posed image once
+            return render_hyp_dedup(c, n_hyp, p1, R, t, surfaces, true, host_out, out, nullptr, counts, nullptr, status, nullptr, plan, st);
+    }
     std::vector<SplatJob> jobs;
     std::vector<int> slots;
     const size_t n_img_total = (size_t)n_hyp * per_hyp;
@@ -505,6 +744,45 @@ extern "C" int salve_bev_render_hypotheses_host(salve_bev_ctx* c, int32_t n_hyp,
                                                 const float* t, uint32_t surfaces, uint8_t* host_out, int32_t* host_counts,
                                                 int32_t* host_status, void* stream) {
     return render_hyp_impl(c, n_hyp, p1, p2, R, t, surfaces, host_out, host_counts, host_status, true, (cudaStream_t)stream);
+}
+
+static int render_compact(salve_bev_ctx* c, int32_t n_hyp, const int32_t* p1, const int32_t* p2, const float* R, const float* t, uint32_t surfaces,
+                          bool host_out, uint8_t* out_posed, uint8_t* out_unposed, int32_t* unposed_of_hyp, int32_t* n_unique, int32_t* counts_posed,
+                          int32_t* counts_unposed, int32_t* status_posed, int32_t* status_unposed, cudaStream_t st) {
+    if (!c || !p1 || !p2 || !R || !t || !out_posed || !out_unposed || !unposed_of_hyp || !n_unique) FAIL(SALVE_BEV_E_INVALID, "null argument");
+    if (n_hyp < 0) FAIL(SALVE_BEV_E_INVALID, "negative n_hyp");
+    if ((surfaces & 3u) == 0 || (surfaces & ~3u)) FAIL(SALVE_BEV_E_INVALID, "bad surface mask");
+    for (int h = 0; h < n_hyp; h++)
+        if (p1[h] < 0 || p1[h] >= c->cfg.max_panos || p2[h] < 0 || p2[h] >= c->cfg.max_panos) FAIL(SALVE_BEV_E_CAPACITY, "pano slot out of range");
+    CU(cudaSetDevice(c->cfg.device));
+    c->events_used = 0;
+    HypPlan plan;
+    make_plan(n_hyp, p2, c->cfg.max_panos, plan);
+    *n_unique = (int32_t)plan.uniq.size();
+    for (int h = 0; h < n_hyp; h++) unposed_of_hyp[h] = plan.uniq_of_hyp[h];
+    return render_hyp_dedup(c, n_hyp, p1, R, t, surfaces, false, host_out, out_posed, out_unposed, counts_posed, counts_unposed, status_posed,
+                            status_unposed, plan, st);
+}
+extern "C" int salve_bev_render_hypotheses_compact(salve_bev_ctx* c, int32_t n_hyp, const int32_t* p1, const int32_t* p2, const float* R,
+                                                   const float* t, uint32_t surfaces, uint8_t* dev_posed, uint8_t* dev_unposed,
+                                                   int32_t* host_unposed_of_hyp, int32_t* host_n_unique, int32_t* dev_counts_posed,
+                                                   int32_t* dev_counts_unposed, int32_t* dev_status_posed, int32_t* dev_status_unposed,
+                                                   void* stream) {
+    return render_compact(c, n_hyp, p1, p2, R, t, surfaces, false, dev_posed, dev_unposed, host_unposed_of_hyp, host_n_unique, dev_counts_posed,
+                          dev_counts_unposed, dev_status_posed, dev_status_unposed, (cudaStream_t)stream);
+}
+extern "C" int salve_bev_render_hypotheses_compact_host(salve_bev_ctx* c, int32_t n_hyp, const int32_t* p1, const int32_t* p2, const float* R,
+                                                        const float* t, uint32_t surfaces, uint8_t* host_posed, uint8_t* host_unposed,
+                                                        int32_t* host_unposed_of_hyp, int32_t* host_n_unique, int32_t* host_counts_posed,
+                                                        int32_t* host_counts_unposed, int32_t* host_status_posed, int32_t* host_status_unposed,
+                                                        void* stream) {
+    return render_compact(c, n_hyp, p1, p2, R, t, surfaces, true, host_posed, host_unposed, host_unposed_of_hyp, host_n_unique, host_counts_posed,
+                          host_counts_unposed, host_status_posed, host_status_unposed, (cudaStream_t)stream);
+}
+extern "C" int salve_bev_set_dedup_unposed(salve_bev_ctx* c, int32_t on) {
+    if (!c) FAIL(SALVE_BEV_E_INVALID, "null argument");
+    c->dedup_unposed = on != 0;
+    return SALVE_BEV_OK;
 }
 
 extern "C" int salve_bev_render_images_host(salve_bev_ctx* c, int32_t n_img, const int32_t* slot, const int32_t* surface,

@@ -39,20 +39,28 @@ constexpr int IMAGE_MAX_GAP = 24;        // pass 1: row gap (nearest site left t
 constexpr int IMAGE_TRIP_BUDGET = 24;    //   and at most this many five-row trips + flips per query
 constexpr int IMAGE_MAX_GAP_B = 64;      // pass 1b: the same for the int64 / float64 state machine;
 constexpr int IMAGE_ROW_BUDGET_B = 160;  //   what is left goes to the cooperative pass
+constexpr double IMAGE_MAX_R_B = 12.0;   // pass 1b: largest circumradius (px)
 
 struct ImageArgs {
     GridParams G;
+    int32_t n_img;                    // images of this launch; CTAs are persistent and take images from *work_counter
+    int32_t* work_counter;            // zeroed by the host before the launch
     const uint32_t* keygrid; size_t keygrid_stride;
     const uint8_t* const* color_src;  // per image: u8 rgb triples indexed by the key's source index
-    int32_t* counts;                  // [n_img][8]
-    int32_t* status;                  // [n_img] or null
-    uint8_t* out; size_t out_stride;  // final images (bytes per image)
+    int32_t* counts;                  // [n_img][8] working counters, indexed like the key grids ([0], [1] come from the splat)
+    int32_t* status;                  // by destination, or null
+    uint8_t* out; size_t out_stride;  // final images by destination (bytes per image)
+    // Destination of image i (null: i).  d >= 0: out / counts_out / status slot d.  d < 0: slot -1-d of the context's cache of
+    // hypothesis-independent renders (cache_out / cache_counts / cache_status).
+    const int32_t* dest;
+    int32_t* counts_out;              // final counters by destination, or null (then `counts` is the final array)
+    uint8_t* cache_out; int32_t* cache_counts; int32_t* cache_status;
     uint8_t* hull; size_t hull_stride;        // optional tap: 1 inside the closed convex hull
     int32_t* qtri; size_t qtri_stride;        // optional tap: per pixel the 3 vertex pixel ids of its triangle (pre-filled with -1)
     uint32_t* bits; size_t bits_stride;       // optional tap: occ, nonempty, keep bit planes (3 * grid_h * wpr words per image)
-    uint32_t* qlist; size_t qlist_stride;     // per image work list of query pixels (row << 11 | col), capacity g
-    unsigned long long* qres;                 // per image, per list entry: resolved triangle (3 x 21-bit vertex labels | bit 63)
-    uint32_t* keepbits; size_t keepbits_stride;  // per image scratch: non-empty, then keep bit rows (grid_h * wpr words)
+    uint32_t* qlist; size_t qlist_stride;     // per CTA work list of query pixels (row << 11 | col), capacity g
+    unsigned long long* qres;                 // per CTA, per list entry: resolved triangle (3 x 21-bit vertex labels | bit 63)
+    uint32_t* keepbits; size_t keepbits_stride;  // per CTA scratch: non-empty, then keep bit rows (grid_h * wpr words)
     long long* phase_clk;                     // optional diagnostics: per image 16 slots, SM clock at the phase boundaries + list sizes
     int32_t raw_mode;                 // 1: no keep mask, no flip (interp_dense_grid_from_sparse semantics)
     int32_t skip_empty_check;         // 1: generic interp path (no EMPTY status)
@@ -196,6 +204,11 @@ __device__ __forceinline__ void resolve_pass(const ImageShared& S, int wpr, int 
         if (SMALL) {
             const float fu = (float)eU, fv = (float)eV, fa = (float)eA2;
             if (fu * fu + fv * fv > 3600.0f * fa * fa) return false;  // circumradius^2 = (U^2+V^2) / (4 A2^2) > 30^2
+        } else {
+            // a lane walks one row per trip: circles taller than ~one warp of rows are cheaper in the cooperative pass,
+            // which scans 32 rows per trip and shares the triangle it ends in among all the pixels inside it
+            const double fu = (double)eU, fv = (double)eV, fa = (double)eA2;
+            if (fu * fu + fv * fv > (4.0 * IMAGE_MAX_R_B * IMAGE_MAX_R_B) * fa * fa) return false;
         }
         const real inv = (real)1 / (real)eA2;
         const real ux = (real)0.5 * (real)eU * inv;
@@ -529,7 +542,7 @@ __device__ __forceinline__ int coop_find_violator(const uint32_t* __restrict__ o
 }
 
 __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
-    const int img = blockIdx.x;
+    const int slot = blockIdx.x;  // scratch slot of this (persistent) CTA
     const int h = A.G.grid_h, w = A.G.grid_w, wpr = A.G.wpr;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = IMAGE_NT / 32;
@@ -542,22 +555,31 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
         const size_t rows = ((size_t)h * 2 + 15) & ~(size_t)15;
         unsigned char* p = smem_raw;
         S.occ = (uint32_t*)p; p += plane;
-        S.keep = A.keepbits + (size_t)img * A.keepbits_stride;  // global (L2): only list building and the final masking read it
+        S.keep = A.keepbits + (size_t)slot * A.keepbits_stride;  // global (L2): only list building and the final masking read it
         S.tmp = (uint32_t*)p; p += plane;
         int16_t** arr[13] = {&S.cnt, &S.first, &S.last, &S.up, &S.dn, &S.hlo, &S.hhi, &S.hl0, &S.hl1, &S.hr0, &S.hr1, &S.stk_l, &S.stk_r};
         for (int i = 0; i < 13; i++) { *arr[i] = (int16_t*)p; p += rows; }
         const size_t frows = ((size_t)h * 4 + 15) & ~(size_t)15;
         S.hlf = (float*)p; p += frows; S.hrf = (float*)p; p += frows;
     }
-    __shared__ int s_S, s_M, s_mincol, s_maxcol, s_ne_cnt, s_keep_cnt, s_nitems, s_next, s_filled, s_flips, s_maxflips, s_hull_ok;
+    __shared__ int s_S, s_M, s_mincol, s_maxcol, s_ne_cnt, s_keep_cnt, s_nitems, s_next, s_filled, s_flips, s_maxflips, s_hull_ok, s_img;
 
+  for (;;) {  // images are handed out dynamically: their cost varies by 3x
+    __syncthreads();  // the previous image is finished by every thread (shared state is reused)
+    if (tid == 0) s_img = atomicAdd(A.work_counter, 1);
+    __syncthreads();
+    const int img = s_img;
+    if (img >= A.n_img) break;
     const uint32_t* keygrid = A.keygrid + (size_t)img * A.keygrid_stride;
     const uint8_t* csrc = A.color_src[img];
-    uint8_t* out = A.out + (size_t)img * A.out_stride;
+    const int dst = A.dest ? A.dest[img] : img;
+    uint8_t* out = dst >= 0 ? A.out + (size_t)dst * A.out_stride : A.cache_out + (size_t)(-1 - dst) * A.out_stride;
     int32_t* counts = A.counts + img * 8;
+    int32_t* counts_final = dst >= 0 ? (A.counts_out ? A.counts_out + (size_t)dst * 8 : nullptr) : A.cache_counts + (size_t)(-1 - dst) * 8;
+    int32_t* status_final = dst >= 0 ? (A.status ? A.status + dst : nullptr) : A.cache_status + (-1 - dst);
     const bool raw = A.raw_mode != 0;
     long long* pclk = A.phase_clk ? A.phase_clk + (size_t)img * 16 : nullptr;
-    auto mark = [&](int slot) { if (pclk && tid == 0) pclk[slot] = clock64(); };
+    auto mark = [&](int k) { if (pclk && tid == 0) pclk[k] = clock64(); };
     mark(0);
 
     if (tid == 0) {
@@ -710,39 +732,72 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
     // all sites on one oblique line: every row has one site and neither chain has an interior vertex
     if (status == 0 && s_hull_ok == 3 && nS == M) status = 3;  // COLLINEAR: the reference's Qhull call raises
 
-    // ---- F. work list of query pixels (row << 11 | col) in global memory, one warp per row -------------------------
-    // query = kept, not a site, inside the closed hull
-    uint32_t* qlist = A.qlist + (size_t)img * A.qlist_stride;
+    // ---- F. edge rule + work list of query pixels (row << 11 | col) in global memory -------------------------------------
+    // query = kept, not a site, inside the closed hull.
+    // Edge rule: a query whose W and E (or N and S) neighbours are both sites lies at the midpoint of a Delaunay edge --
+    // the circle of radius 1 around it has no lattice point strictly inside but the query itself -- so its interpolated value is
+    // the exact mean of the two site colours whichever triangle it is attributed to (third barycentric weight 0).  With all
+    // four neighbours present they are co-circular and the canonical diagonal is decided by the symbolic perturbation
+    // (incircle_pert on (E, N, W, S) = 2 * (wE + wW - wN - wS): positive keeps N-S).  About half of all queries end here.
+    int my_filled = 0, my_flips = 0, my_maxflips = 0;
+    uint32_t* qlist = A.qlist + (size_t)slot * A.qlist_stride;
+    const bool edge_rule = A.qtri == nullptr;  // the triangle tap wants every query resolved to a triangle
     if (status == 0) {
-        for (int r = warp; r < h; r += NW) {
-            for (int wi0 = 0; wi0 < wpr; wi0 += 32) {
-                const int wi = wi0 + lane;
-                uint32_t q = 0;
-                if (wi < wpr) {
-                    const int item = r * wpr + wi;
-                    const uint32_t hm = range_mask(wi, S.hlo[r], S.hhi[r]);
-                    q = S.keep[item] & ~S.occ[item] & hm;
-                    if (A.hull && hm) {
-                        uint8_t* hp = A.hull + (size_t)img * A.hull_stride + (size_t)r * w + wi * 32;
-                        uint32_t m = hm;
-                        while (m) { const int b = __ffs(m) - 1; m &= m - 1; hp[b] = 1; }
+        const int nw_pad = (nwords + 31) & ~31;
+        const ptrdiff_t dn = raw ? (ptrdiff_t)w * 3 : -(ptrdiff_t)w * 3;  // address step to row r + 1 in the (flipped) output
+        for (int item = tid; item < nw_pad; item += IMAGE_NT) {  // a warp takes 32 consecutive words
+            uint32_t q = 0;
+            if (item < nwords) {
+                const int r = item / wpr, wi = item - r * wpr;
+                const uint32_t hm = range_mask(wi, S.hlo[r], S.hhi[r]);
+                const uint32_t oc = S.occ[item];
+                q = S.keep[item] & ~oc & hm;
+                if (A.hull && hm) {
+                    uint8_t* hp = A.hull + (size_t)img * A.hull_stride + (size_t)r * w + wi * 32;
+                    uint32_t m = hm;
+                    while (m) { const int b = __ffs(m) - 1; m &= m - 1; hp[b] = 1; }
+                }
+                if (q && edge_rule) {
+                    const uint32_t ol = wi > 0 ? S.occ[item - 1] : 0u, orr = wi + 1 < wpr ? S.occ[item + 1] : 0u;
+                    const uint32_t he = q & ((oc << 1) | (ol >> 31)) & ((oc >> 1) | (orr << 31));
+                    const uint32_t ve = q & (r + 1 < h ? S.occ[item + wpr] : 0u) & (r > 0 ? S.occ[item - wpr] : 0u);
+                    uint32_t e = he | ve;
+                    uint8_t* orow = out + (size_t)(raw ? r : h - 1 - r) * w * 3;
+                    while (e) {
+                        const int b = __ffs(e) - 1; e &= e - 1;
+                        const int x = wi * 32 + b;
+                        bool horiz = (he >> b) & 1u;
+                        if (horiz && ((ve >> b) & 1u)) {
+                            const long long wh = pert_weight(vlabel(r, x - 1), w) + pert_weight(vlabel(r, x + 1), w);
+                            const long long wv = pert_weight(vlabel(r - 1, x), w) + pert_weight(vlabel(r + 1, x), w);
+                            if (wh == wv) continue;  // residual tie of the perturbation: the general path decides
+                            horiz = wh < wv;
+                        }
+                        uint8_t* p = orow + x * 3;
+                        const uint8_t* pa = horiz ? p - 3 : p + dn;
+                        const uint8_t* pb = horiz ? p + 3 : p - dn;
+                        p[0] = (uint8_t)(((uint32_t)pa[0] + pb[0]) >> 1);
+                        p[1] = (uint8_t)(((uint32_t)pa[1] + pb[1]) >> 1);
+                        p[2] = (uint8_t)(((uint32_t)pa[2] + pb[2]) >> 1);
+                        q &= ~(1u << b);
+                        my_filled++;
                     }
                 }
-                int n = __popc(q), incl = n;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-                const int total = __shfl_sync(0xffffffffu, incl, 31);
-                if (total == 0) continue;
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&s_nitems, total);
-                base = __shfl_sync(0xffffffffu, base, 0) + incl - n;
-                while (q) { const int b = __ffs(q) - 1; q &= q - 1; qlist[base++] = ((uint32_t)r << COL_BITS) | (uint32_t)(wi * 32 + b); }
             }
+            int n = __popc(q), incl = n;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            if (total == 0) continue;
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_nitems, total);
+            base = __shfl_sync(0xffffffffu, base, 0) + incl - n;
+            const int r = item / wpr, wi = item - r * wpr;
+            while (q) { const int b = __ffs(q) - 1; q &= q - 1; qlist[base++] = ((uint32_t)r << COL_BITS) | (uint32_t)(wi * 32 + b); }
         }
     }
     __syncthreads();
 
-    int my_filled = 0, my_flips = 0, my_maxflips = 0;
     int32_t* qtri = A.qtri ? A.qtri + (size_t)img * A.qtri_stride : nullptr;
 
     // one query pixel: initial triangle, flip descent, exact barycentric value
@@ -769,25 +824,24 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
         return false;  // cannot happen (d is inside the triangle or across exactly one edge)
     };
     uint32_t* defer = S.tmp;  // bit plane: queries handed to the next pass (the row-dilated plane is dead now)
-    unsigned long long* qres = A.qres + (size_t)img * A.qlist_stride;
+    unsigned long long* qres = A.qres + (size_t)slot * A.qlist_stride;
 
     // list of the pixels whose bit is set in `plane` (row-major, one warp per row); `plane` is cleared
     auto build_list = [&](uint32_t* plane, bool clear) {
-        for (int r = warp; r < h; r += NW) {
-            for (int wi0 = 0; wi0 < wpr; wi0 += 32) {
-                const int wi = wi0 + lane;
-                uint32_t q = wi < wpr ? plane[r * wpr + wi] : 0u;
-                if (clear && q) plane[r * wpr + wi] = 0u;
-                int n = __popc(q), incl = n;
+        const int nw_pad = (nwords + 31) & ~31;
+        for (int item = tid; item < nw_pad; item += IMAGE_NT) {
+            uint32_t q = item < nwords ? plane[item] : 0u;
+            if (clear && q) plane[item] = 0u;
+            int n = __popc(q), incl = n;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-                const int total = __shfl_sync(0xffffffffu, incl, 31);
-                if (total == 0) continue;
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&s_nitems, total);
-                base = __shfl_sync(0xffffffffu, base, 0) + incl - n;
-                while (q) { const int b = __ffs(q) - 1; q &= q - 1; qlist[base++] = ((uint32_t)r << COL_BITS) | (uint32_t)(wi * 32 + b); }
-            }
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            if (total == 0) continue;
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_nitems, total);
+            base = __shfl_sync(0xffffffffu, base, 0) + incl - n;
+            const int r = item / wpr, wi = item - r * wpr;
+            while (q) { const int b = __ffs(q) - 1; q &= q - 1; qlist[base++] = ((uint32_t)r << COL_BITS) | (uint32_t)(wi * 32 + b); }
         }
     };
     // interpolate the pixels a pass resolved: gathers, exact barycentrics and stores with every lane busy
@@ -918,8 +972,13 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
     if (tid == 0) {
         counts[5] = s_filled; counts[6] = s_maxflips; counts[7] = s_flips;
         if (pclk) pclk[11] = clock64();
-        if (A.status) A.status[img] = status;
+        if (status_final) *status_final = status;
+        if (counts_final) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) counts_final[k] = counts[k];
+        }
     }
+  }  // next image
 }
 
 // colour word tap: r | g<<8 | b<<16 | 0xFF<<24 at sites, 0 elsewhere

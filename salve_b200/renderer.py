@@ -176,6 +176,60 @@ class BevRenderer:
         )
         return n * bin(mask).count("1") * 2
 
+    def render_hypotheses_compact(self, pano1, pano2, R, t, surfaces=("floor", "ceiling"), posed_out: Optional[np.ndarray] = None,
+                                  unposed_out: Optional[np.ndarray] = None, stream: int = 0):
+        """Host-output render without duplicates: img2 of a pair does not depend on the hypothesis
+        (reference bev_rendering_utils.py:451-455), so every distinct (pano 2, surface) is rendered and copied out once.
+        Returns (posed (n, nsurf, gh, gw, 3), unposed (n_unique, nsurf, gh, gw, 3), unposed_of_hyp (n,),
+        counts_posed (n, nsurf, 8), counts_unposed (n_unique, nsurf, 8), status_posed (n, nsurf), status_unposed (n_unique, nsurf)).
+        Hypothesis h, surface s: img1 = posed[h, s], img2 = unposed[unposed_of_hyp[h], s]."""
+        n, p1, p2, R, t = self._hyp_args(pano1, pano2, R, t)
+        mask = self._surf_mask(surfaces)
+        nsurf = bin(mask).count("1")
+        cap = min(n, int(self.cfg.max_panos))
+        if posed_out is None:
+            posed_out = np.empty((n, nsurf) + self.img_shape, np.uint8)
+        if unposed_out is None:
+            unposed_out = np.empty((cap, nsurf) + self.img_shape, np.uint8)
+        assert posed_out.dtype == np.uint8 and posed_out.size == n * nsurf * int(np.prod(self.img_shape)) and posed_out.flags.c_contiguous
+        assert unposed_out.dtype == np.uint8 and unposed_out.size >= cap * nsurf * int(np.prod(self.img_shape)) and unposed_out.flags.c_contiguous
+        idx = np.zeros(n, np.int32)
+        nu = ctypes.c_int32(0)
+        cp = np.zeros((n, nsurf, NCOUNTS), np.int32)
+        cu = np.zeros((cap, nsurf, NCOUNTS), np.int32)
+        sp = np.zeros((n, nsurf), np.int32)
+        su = np.zeros((cap, nsurf), np.int32)
+        nat.check(
+            self._lib.salve_bev_render_hypotheses_compact_host(
+                self._h, n, _ptr(p1, ctypes.c_int32), _ptr(p2, ctypes.c_int32), _ptr(R, ctypes.c_float), _ptr(t, ctypes.c_float), mask,
+                posed_out.ctypes.data, unposed_out.ctypes.data, _ptr(idx, ctypes.c_int32), ctypes.byref(nu),
+                cp.ctypes.data, cu.ctypes.data, sp.ctypes.data, su.ctypes.data, stream or None,
+            )
+        )
+        k = nu.value
+        posed = posed_out.reshape((n, nsurf) + self.img_shape)
+        unposed = unposed_out.reshape(-1)[: k * nsurf * int(np.prod(self.img_shape))].reshape((k, nsurf) + self.img_shape)
+        return posed, unposed, idx, cp, cu[:k], sp, su[:k]
+
+    def render_hypotheses_compact_device(self, pano1, pano2, R, t, dev_posed, dev_unposed, dev_counts_posed=None, dev_counts_unposed=None,
+                                         dev_status_posed=None, dev_status_unposed=None, surfaces=("floor", "ceiling"), stream: int = 0):
+        """Device-output variant (asynchronous on `stream`).  Returns (unposed_of_hyp (n,) int32, n_unique)."""
+        n, p1, p2, R, t = self._hyp_args(pano1, pano2, R, t)
+        mask = self._surf_mask(surfaces)
+        idx = np.zeros(n, np.int32)
+        nu = ctypes.c_int32(0)
+        nat.check(
+            self._lib.salve_bev_render_hypotheses_compact(
+                self._h, n, _ptr(p1, ctypes.c_int32), _ptr(p2, ctypes.c_int32), _ptr(R, ctypes.c_float), _ptr(t, ctypes.c_float), mask,
+                _vp(dev_posed), _vp(dev_unposed), _ptr(idx, ctypes.c_int32), ctypes.byref(nu),
+                _vp(dev_counts_posed), _vp(dev_counts_unposed), _vp(dev_status_posed), _vp(dev_status_unposed), stream or None,
+            )
+        )
+        return idx, nu.value
+
+    def set_dedup_unposed(self, on: bool) -> None:
+        nat.check(self._lib.salve_bev_set_dedup_unposed(self._h, int(on)))
+
     def render_images(self, slots, surfaces: Sequence[str], posed, R, t, stream: int = 0):
         """Individual images.  Returns (images (n, gh, gw, 3), counts (n,8), status (n,))."""
         slots = np.ascontiguousarray(slots, np.int32).reshape(-1)

@@ -195,6 +195,55 @@ def test_device_output_path_equals_host_path():
     r.close(); r2.close()
 
 
+def test_dedup_of_unposed_renders_is_invisible():
+    """img2 does not depend on the hypothesis (reference bev_rendering_utils.py:451-455): rendering each distinct
+    (pano 2, surface) once must give the same bytes, counters and status as rendering all 4 images of every hypothesis,
+    through the full host layout, the full device layout and the compact layouts (odd chunk sizes on purpose)."""
+    import torch
+
+    from salve_b200.renderer import BevRenderer
+
+    n_p, n_h = 4, 13
+    rgbs, depths, p1, p2, Rm, t = synth.synth_building(n_p, n_h, 512, 1024, seed=6)
+    r = BevRenderer(max_panos=n_p, max_images=10)
+    for k in range(n_p):
+        r.upload_pano(k, rgbs[k], depths[k])
+    r.set_dedup_unposed(False)
+    ref, cref, sref = r.render_hypotheses(p1, p2, Rm, t)
+    n_launch_plain = r.launch_count()
+    r.set_dedup_unposed(True)
+    a, ca, sa = r.render_hypotheses(p1, p2, Rm, t)
+    assert np.array_equal(a, ref) and np.array_equal(ca[..., :6], cref[..., :6]) and np.array_equal(sa, sref)
+    # device, full layout
+    out = torch.zeros(n_h * 4 * 501 * 501 * 3, dtype=torch.uint8, device="cuda")
+    cnt = torch.zeros(n_h * 4 * 8, dtype=torch.int32, device="cuda")
+    st = torch.full((n_h * 4,), -1, dtype=torch.int32, device="cuda")
+    r.render_hypotheses_device(p1, p2, Rm, t, out, cnt, st)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy().reshape(ref.shape), ref)
+    assert np.array_equal(cnt.cpu().numpy().reshape(cref.shape)[..., :6], cref[..., :6])
+    assert np.array_equal(st.cpu().numpy().reshape(sref.shape), sref)
+    # host, compact layout
+    posed, unposed, idx, cp, cu, sp, su = r.render_hypotheses_compact(p1, p2, Rm, t)
+    assert unposed.shape[0] == len(set(p2.tolist())) < n_h
+    for h in range(n_h):
+        for si in range(2):
+            assert np.array_equal(posed[h, si], ref[h, si, 0]) and np.array_equal(unposed[idx[h], si], ref[h, si, 1])
+            assert np.array_equal(cp[h, si, :6], cref[h, si, 0, :6]) and np.array_equal(cu[idx[h], si, :6], cref[h, si, 1, :6])
+            assert sp[h, si] == sref[h, si, 0] and su[idx[h], si] == sref[h, si, 1]
+    # device, compact layout, one surface
+    dp = torch.zeros(n_h * 501 * 501 * 3, dtype=torch.uint8, device="cuda")
+    du = torch.zeros(n_p * 501 * 501 * 3, dtype=torch.uint8, device="cuda")
+    idx2, nu = r.render_hypotheses_compact_device(p1, p2, Rm, t, dp, du, surfaces=("ceiling",))
+    torch.cuda.synchronize()
+    dp = dp.cpu().numpy().reshape(n_h, 501, 501, 3)
+    du = du.cpu().numpy().reshape(n_p, 501, 501, 3)
+    assert nu == unposed.shape[0] and np.array_equal(idx2, idx)
+    for h in range(n_h):
+        assert np.array_equal(dp[h], ref[h, 1, 0]) and np.array_equal(du[idx2[h]], ref[h, 1, 1])
+    r.close()
+
+
 # ---- stream compaction / back-projection -----------------------------------------------------------------
 @pytest.mark.parametrize("surf", ["floor", "ceiling"])
 def test_backproject_compaction_bit_exact(R, surf):
