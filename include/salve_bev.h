@@ -225,8 +225,8 @@ int salve_bev_remove_hallucinated(salve_bev_ctx* ctx, const uint8_t* host_sparse
                                     mesh of the image, built on demand by the explicit-mesh path (zipper + parallel Lawson flips) */
 #define SALVE_BEV_TAP_INTERP 6   /* g*3 uint8: interpolated image before mask and flip */
 #define SALVE_BEV_TAP_HULL 7     /* g uint8: inside closed convex hull */
-#define SALVE_BEV_TAP_QTRI 8     /* g*3 int32: per interpolated pixel the vertex pixel ids of the Delaunay triangle its flip descent
-                                    ended in; -1 elsewhere */
+#define SALVE_BEV_TAP_QTRI 8     /* g*3 int32: per interpolated pixel the vertex pixel ids (ascending) of the Delaunay triangle its
+                                    flip descent ended in; -1 elsewhere */
 int salve_bev_tap(salve_bev_ctx* ctx, int32_t image, int32_t what, void* host_buf, int64_t host_buf_bytes, void* stream);
 
 /* Per-stage device time (ms, CUDA events) of the most recent render call, summed over its chunks:
@@ -235,9 +235,11 @@ int salve_bev_last_timings(salve_bev_ctx* ctx, float* host_ms);
 /* Enable/disable per-stage event timing (off by default: events add sync points at read time only). */
 int salve_bev_enable_timing(salve_bev_ctx* ctx, int32_t on);
 
-/* Diagnostics of image_kernel for the images of the most recent chunk: 16 int64 per image.  [0..11] SM clock at the phase
- * boundaries (start, sites, hull+masks, list, pass 1, shade, list, pass 1b, shade, list, pass 2, end); [12..14] number of
- * pixels entering pass 1, pass 1b, pass 2.  host_clk: n_img * 16 int64.  Synchronises the device. */
+/* Diagnostics of image_kernel for the images of the most recent chunk: 24 int64 per image.  [0..11] SM clock at the phase
+ * boundaries (start, sites, hull+masks, [3] start of pass 1, pass 1, shade, list, pass 1b, shade, list, pass 2, end); [12..14]
+ * number of pixels entering pass 1, pass 1b, pass 2; [15] pass 2: descents << 40 | row waves << 20 | flips; [18] edge rule +
+ * list done, [16] window pass done, [17] pixels entering the window pass; rest reserved.  host_clk: n_img * 24 int64.
+ * Synchronises the device. */
 int salve_bev_last_phase_clocks(salve_bev_ctx* ctx, int64_t* host_clk, int32_t n_img);
 
 /* Number of kernel launches issued by this context since creation (bench.py's gpu_launches). */

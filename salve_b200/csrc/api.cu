@@ -57,7 +57,7 @@ struct salve_bev_ctx {
     uint32_t *list0 = nullptr, *list1 = nullptr, *cand = nullptr;
     uint32_t* qlist = nullptr;  // per image work list of image_kernel (g entries)
     unsigned long long* qres = nullptr;  // per image, per list entry: the resolved triangle
-    long long* phase_clk = nullptr;      // diagnostics: 16 slots per image of the last chunk
+    long long* phase_clk = nullptr;      // diagnostics: 24 slots per image of the last chunk
     uint32_t* keepbits = nullptr;        // per CTA slot keep-mask bit rows of image_kernel
     int32_t* work_counter = nullptr;     // image_kernel's dynamic image counter
     int image_slots = 0;                 // persistent CTAs of image_kernel (scratch slots)
@@ -173,7 +173,7 @@ extern "C" int salve_bev_ctx_create(const salve_bev_config* cfg, salve_bev_ctx**
     }
     ALLOC(c->qlist, (size_t)c->image_slots * c->g_stride);
     ALLOC(c->qres, (size_t)c->image_slots * c->g_stride);
-    ALLOC(c->phase_clk, N * 16);
+    ALLOC(c->phase_clk, N * 24);
     ALLOC(c->keepbits, (size_t)c->image_slots * c->bits_stride);
     ALLOC(c->work_counter, 1);
     ALLOC(c->cache_out, 2 * P * c->img_bytes + 64);  // +64: replicate_images_kernel reads whole words
@@ -1152,7 +1152,7 @@ extern "C" int salve_bev_last_phase_clocks(salve_bev_ctx* c, int64_t* host_clk, 
     if (n_img < 0 || n_img > c->cfg.max_images) FAIL(SALVE_BEV_E_CAPACITY, "more images than a chunk holds");
     CU(cudaSetDevice(c->cfg.device));
     CU(cudaDeviceSynchronize());
-    CU(cudaMemcpy(host_clk, c->phase_clk, sizeof(long long) * 16 * (size_t)n_img, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(host_clk, c->phase_clk, sizeof(long long) * 24 * (size_t)n_img, cudaMemcpyDeviceToHost));
     return SALVE_BEV_OK;
 }
 

@@ -475,11 +475,188 @@ __device__ __forceinline__ void resolve_small(const ImageShared& S, int wpr, int
     }
 }
 
+// ---- pass 0: small triangles in a register window ---------------------------------------------------------------------------
+// 92 % of the queries that are left after the edge rule end in a triangle within 2 px of the pixel with a circumradius of
+// at most 2 px.  For them the whole Lawson descent runs on a (2*NR+1)-row x 32-column window of the occupancy bitmap held in
+// registers, in coordinates relative to the query q = (0, 0):
+//   * circle of (a, b, c): A2 = twice the area, (U, V) = 2*A2 * (centre - a); a lattice point p has
+//     |p - centre|^2 - R^2 = -inc(p) / A2 with inc an integer, so points off the circle miss it by at least 1/A2 in squared
+//     distance.  With |coordinates| <= 16 every float below is exact to ~1e-5, hence "strictly inside" (margin > 1/(2 A2)) and
+//     "on the circle" (|.| <= 1/(2 A2)) are decided EXACTLY by float interval arithmetic per row: no per-point test at all.
+//   * one trip = the strict-interior masks of all rows (unrolled; every lane executes the same code), then either a flip towards
+//     the violator nearest to q or, if the circle is empty, the on-circle sites and their symbolic-perturbation tests.
+// A query whose triangle or circle leaves the window is handed to the general passes.
+template <int NR>
+__device__ __forceinline__ void resolve_window(const ImageShared& S, int wpr, int W, int H, const uint32_t* __restrict__ qlist,
+                                               unsigned long long* __restrict__ qres, int n, int* s_next, uint32_t* defer, int lane,
+                                               int& my_flips, int& my_maxflips) {
+    constexpr int NROW = 2 * NR + 1;
+    constexpr int MAXGAP = 14, MAXFLIPS = 16;
+    const unsigned FULL = 0xffffffffu;
+    bool active = false, exhausted = false;
+    int x = 0, r = 0, idx = 0, flips = 0;
+    uint32_t wr[NROW];  // wr[dy + NR]: bit 16 + dx <-> pixel (x + dx, r + dy)
+#pragma unroll
+    for (int k = 0; k < NROW; k++) wr[k] = 0u;
+    int ax = 0, ay = 0, bx = 0, by = 0, cx = 0, cy = 0;
+
+    auto give_up = [&]() {
+        atomicOr(&defer[r * wpr + (x >> 5)], 1u << (x & 31));
+        qres[idx] = 0ull;
+        active = false;
+    };
+    // nearest set bit to dx = 0 in a window row (m != 0): returns dx
+    auto nearest = [](uint32_t m) -> int {
+        const uint32_t lo = m & 0x1FFFFu, hi = m >> 17;  // dx <= 0, dx >= 1
+        const int dl = lo ? 16 - (31 - __clz(lo)) : 64, dr = hi ? __ffs(hi) : 64;  // distances
+        return dl <= dr ? -dl : dr;
+    };
+    auto cross = [](int px, int py, int qx, int qy) { return px * qy - py * qx; };
+    auto contains0 = [&](int px, int py, int qx, int qy, int sx, int sy) {  // CCW (p, q, s) contains the origin (closed)
+        return (qx - px) * (sy - py) - (qy - py) * (sx - px) > 0 && cross(px, py, qx, qy) >= 0 && cross(qx, qy, sx, sy) >= 0 && cross(sx, sy, px, py) >= 0;
+    };
+
+    while (true) {
+        // ---- refill idle lanes
+        const unsigned idle = __ballot_sync(FULL, !active);
+        if (idle && !exhausted && (__popc(idle) >= 8 || idle == FULL)) {
+            const int leader = __ffs(idle) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(s_next, __popc(idle));
+            base = __shfl_sync(FULL, base, leader);
+            if (base + __popc(idle) >= n) exhausted = true;
+            if (!active) {
+                const int i = base + __popc(idle & ((1u << lane) - 1u));
+                if (i < n) {
+                    const uint32_t code = qlist[i];
+                    x = (int)(code & COL_MASK); r = (int)(code >> COL_BITS); idx = i;
+                    active = true; flips = 0;
+                    // window
+                    const int c0 = x - 16;
+                    const int w0 = c0 >> 5, sh = c0 & 31;  // c0 may be negative: arithmetic shift = floor
+#pragma unroll
+                    for (int k = 0; k < NROW; k++) {
+                        const int y = r + k - NR;
+                        uint32_t lo = 0u, hi = 0u;
+                        if (y >= 0 && y < H) {
+                            const uint32_t* row = S.occ + y * wpr;
+                            if (w0 >= 0) lo = row[w0];
+                            if (w0 + 1 < wpr) hi = row[w0 + 1];
+                        }
+                        wr[k] = __funnelshift_r(lo, hi, sh);
+                    }
+                    // initial triangle: nearest sites left and right on the row, nearest site of the closest non-empty window row
+                    const uint32_t ml = wr[NR] & 0xFFFFu, mr = wr[NR] >> 17;
+                    bool ok = ml != 0u && mr != 0u;
+                    int xl = 0, xr = 0;
+                    if (ok) { xl = (31 - __clz(ml)) - 16; xr = __ffs(mr); ok = xr - xl <= MAXGAP; }
+                    int px = 0, py = 0;
+                    bool found = false;
+#pragma unroll
+                    for (int k = 1; k <= NR; k++) {
+#pragma unroll
+                        for (int sgn = 1; sgn >= -1; sgn -= 2) {
+                            const uint32_t m = wr[NR + sgn * k] & 0x01FFFF00u;  // |dx| <= 8
+                            if (!found && m) { found = true; px = nearest(m); py = sgn * k; }
+                        }
+                    }
+                    ok = ok && found;
+                    if (ok) {
+                        if (py > 0) { ax = xl; bx = xr; } else { ax = xr; bx = xl; }
+                        ay = 0; by = 0; cx = px; cy = py;
+                    } else give_up();
+                }
+            }
+        }
+        if (!__any_sync(FULL, active)) { if (exhausted) break; continue; }
+        if (!active) continue;
+
+        // ---- circle of (a, b, c)
+        const int ux = bx - ax, uy = by - ay, vx = cx - ax, vy = cy - ay;
+        const int b2 = ux * ux + uy * uy, c2 = vx * vx + vy * vy;
+        const int A2 = ux * vy - uy * vx;  // > 0
+        const int U = b2 * vy - uy * c2, V = ux * c2 - b2 * vx;
+        const float inv = 0.5f / (float)A2;
+        const float fU = (float)U, fV = (float)V;
+        const float ccx = (float)ax + fU * inv, ccy = (float)ay + fV * inv;
+        const float R2 = (fU * fU + fV * fV) * inv * inv;
+        const float thr = inv;  // half the smallest possible |distance^2 - R^2| of a lattice point off the circle
+        // does the closed disc stay inside rows +-NR and columns +-15 (conservative, float)?  Only then can the window certify
+        // an empty circle; a larger circle can still be searched for violators inside the window (any violator is a valid flip)
+        const float Rr = sqrt_approx(R2) + 0.01f;
+        const bool fits = fabsf(ccy) + Rr < (float)NR + 0.99f && fabsf(ccx) + Rr < 15.0f;
+        // ---- strict interior, row by row (q's row first, then +-1, +-2, ...); the violator nearest to q wins
+        bool have = false;
+        int dx = 0, dy = 0;
+#pragma unroll
+        for (int k = 0; k < NROW; k++) {
+            const int yy = (k == 0) ? 0 : ((k & 1) ? (k + 1) / 2 : -(k / 2));
+            const float e = (float)yy - ccy;
+            const float t = R2 - e * e - thr;
+            if (t > 0.0f) {
+                const float hw = sqrt_approx(t);
+                const int i0 = max(__float2int_ru(ccx - hw) + 16, 0), i1 = min(__float2int_rd(ccx + hw) + 16, 31);
+                const uint32_t m = (i0 <= i1) ? (wr[yy + NR] & ((2u << i1) - 1u) & ~((1u << i0) - 1u)) : 0u;
+                if (m && !have) { have = true; dx = nearest(m); dy = yy; }
+            }
+        }
+        if (have && !fits) {
+            // large circle: float may misjudge points near it -- confirm the violator exactly (int32: |coordinates| <= 16)
+            const int ex = dx - ax, ey = dy - ay;
+            if (U * ex + V * ey - A2 * (ex * ex + ey * ey) <= 0) { give_up(); continue; }
+        }
+        if (!have && !fits) { give_up(); continue; }
+        if (!have) {
+            // ---- empty circle: sites ON it decide by the symbolic perturbation (same rule as incircle_pert())
+            const uint32_t va = vlabel(r + ay, x + ax), vb = vlabel(r + by, x + bx), vc = vlabel(r + cy, x + cx);
+            long long wa = -1, wb = 0, wc = 0;
+#pragma unroll
+            for (int k = 0; k < NROW; k++) {
+                const int yy = k - NR;
+                const float e = (float)yy - ccy;
+                const float to = R2 - e * e + thr;
+                if (to >= 0.0f && !have) {
+                    const float hwo = sqrt_approx(to);
+                    const int o0 = __float2int_ru(ccx - hwo) + 16, o1 = __float2int_rd(ccx + hwo) + 16;
+                    uint32_t m = wr[k] & ((2u << o1) - 1u) & ~((1u << o0) - 1u);
+                    const float ti = to - 2.0f * thr;
+                    if (ti > 0.0f) {
+                        const float hwi = sqrt_approx(ti);
+                        const int i0 = __float2int_ru(ccx - hwi) + 16, i1 = __float2int_rd(ccx + hwi) + 16;
+                        m &= ~(((2u << i1) - 1u) & ~((1u << i0) - 1u));
+                    }
+                    while (m) {
+                        const int b = __ffs(m) - 1; m &= m - 1;
+                        const int ddx = b - 16;
+                        const uint32_t vd = vlabel(r + yy, x + ddx);
+                        if (vd == va || vd == vb || vd == vc) continue;
+                        if (wa < 0) { wa = pert_weight(va, W); wb = pert_weight(vb, W); wc = pert_weight(vc, W); }
+                        const long long pert = wa * orient_v(vb, vc, vd) - wb * orient_v(va, vc, vd) + wc * orient_v(va, vb, vd) - pert_weight(vd, W) * (long long)A2;
+                        if (pert > 0) { have = true; dx = ddx; dy = yy; break; }
+                    }
+                }
+            }
+            if (!have) {  // t is the triangle of the canonical triangulation over q
+                qres[idx] = QRES_DONE | (unsigned long long)va | ((unsigned long long)vb << 21) | ((unsigned long long)vc << 42);
+                my_flips += flips; my_maxflips = max(my_maxflips, flips);
+                active = false;
+                continue;
+            }
+        }
+        // ---- Lawson flip inside {a, b, c, d}: keep the new triangle that contains q
+        if (contains0(dx, dy, bx, by, cx, cy)) { ax = dx; ay = dy; }
+        else if (contains0(ax, ay, dx, dy, cx, cy)) { bx = dx; by = dy; }
+        else if (contains0(ax, ay, bx, by, dx, dy)) { cx = dx; cy = dy; }
+        else { give_up(); continue; }  // cannot happen
+        if (++flips > MAXFLIPS) give_up();
+    }
+}
+
 // ---- warp-cooperative versions for queries whose triangles are large (wide gaps, hull pockets) -------------------------
 // One lane per row of each 32-row wave (row offsets 0, -1, +1, -2, ... from qy).  Returns, in every lane, the violator
 // nearest to q found in the first wave that has one (x | y << 16), or -1.
 __device__ __forceinline__ int coop_find_violator(const uint32_t* __restrict__ occ, const float* __restrict__ hlf, const float* __restrict__ hrf, int wpr,
-                                                  int W, int H, const Tri2& t, int qx, int qy, int grid_w, int lane) {
+                                                  int W, int H, const Tri2& t, int qx, int qy, int grid_w, int lane, int& waves) {
     const long long bx = t.bx - t.ax, by = t.by - t.ay, cx = t.cx - t.ax, cy = t.cy - t.ay;
     const long long b2 = bx * bx + by * by, c2 = cx * cx + cy * cy;
     const long long A2 = bx * cy - by * cx;
@@ -489,6 +666,7 @@ __device__ __forceinline__ int coop_find_violator(const uint32_t* __restrict__ o
     const uint32_t va = vlabel(t.ay, t.ax), vb = vlabel(t.by, t.bx), vc = vlabel(t.cy, t.cx);
     bool up_dead = false, dn_dead = false;
     for (int wave = 0;; wave++) {
+        waves++;
         const int o = wave * 32 + lane;
         const int k = (o + 1) >> 1;
         const bool down = (o & 1) != 0;
@@ -578,9 +756,10 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
     int32_t* counts_final = dst >= 0 ? (A.counts_out ? A.counts_out + (size_t)dst * 8 : nullptr) : A.cache_counts + (size_t)(-1 - dst) * 8;
     int32_t* status_final = dst >= 0 ? (A.status ? A.status + dst : nullptr) : A.cache_status + (-1 - dst);
     const bool raw = A.raw_mode != 0;
-    long long* pclk = A.phase_clk ? A.phase_clk + (size_t)img * 16 : nullptr;
+    long long* pclk = A.phase_clk ? A.phase_clk + (size_t)img * 24 : nullptr;
     auto mark = [&](int k) { if (pclk && tid == 0) pclk[k] = clock64(); };
     mark(0);
+    if (pclk && tid == 0) pclk[15] = 0;  // pass 2: descents << 40 | waves << 20 | flips
 
     if (tid == 0) {
         s_S = 0; s_M = 0; s_mincol = 1 << 30; s_maxcol = -1; s_ne_cnt = 0; s_keep_cnt = 0; s_nitems = 0; s_next = 0;
@@ -811,8 +990,12 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
         o[1] = (uint8_t)((ua * ((ca >> 8) & 0xFF) + ub * ((cb >> 8) & 0xFF) + uc * ((cc >> 8) & 0xFF)) / A2);
         o[2] = (uint8_t)((ua * ((ca >> 16) & 0xFF) + ub * ((cb >> 16) & 0xFF) + uc * ((cc >> 16) & 0xFF)) / A2);
         if (qtri) {
+            // ascending vertex ids: two warps of the cooperative pass may reach the same triangle with different rotations and
+            // write the same pixel concurrently; in canonical order their stores are identical word for word
             int32_t* q = qtri + ((size_t)r * w + x) * 3;
-            q[0] = t.ay * w + t.ax; q[1] = t.by * w + t.bx; q[2] = t.cy * w + t.cx;
+            const int i0 = t.ay * w + t.ax, i1 = t.by * w + t.bx, i2 = t.cy * w + t.cx;
+            const int lo = min(i0, min(i1, i2)), hi = max(i0, max(i1, i2));
+            q[0] = lo; q[1] = i0 + i1 + i2 - lo - hi; q[2] = hi;
         }
     };
     auto flip_to = [&](Tri2& t, int v, int x, int r) {
@@ -859,6 +1042,17 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
 
     // ---- G1. pass 1 (small circles) and pass 1b (any circle, bounded work): one query per lane ---------------------------
     for (int i = tid; i < nwords; i += IMAGE_NT) defer[i] = 0u;
+    __syncthreads();
+    mark(18);
+    if (pclk && tid == 0) pclk[17] = s_nitems;
+    if (status == 0) resolve_window<3>(S, wpr, w, h, qlist, qres, s_nitems, &s_next, defer, lane, my_flips, my_maxflips);
+    __syncthreads();
+    mark(16);
+    if (status == 0) shade(s_nitems);
+    __syncthreads();
+    if (tid == 0) { s_nitems = 0; s_next = 0; }
+    __syncthreads();
+    if (status == 0) build_list(defer, true);
     __syncthreads();
     mark(3);
     if (pclk && tid == 0) pclk[12] = s_nitems;
@@ -907,13 +1101,14 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
             Tri2 t;
             const bool in_row = S.cnt[r] > 1 && x > S.first[r] && x < S.last[r];
             if (!(in_row ? init_tri_row(S, wpr, w, x, r, t) : init_tri_hull(S, x, r, t))) continue;
-            int flips = 0;
+            int flips = 0, waves = 0;
             while (flips < IMAGE_MAX_FLIPS) {
-                const int v = coop_find_violator(S.occ, S.hlf, S.hrf, wpr, w, h, t, x, r, w, lane);
+                const int v = coop_find_violator(S.occ, S.hlf, S.hrf, wpr, w, h, t, x, r, w, lane, waves);
                 if (v < 0 || !flip_to(t, v, x, r)) break;
                 flips++;
             }
             if (lane == 0) { my_flips += flips; my_maxflips = max(my_maxflips, flips); }
+            if (pclk && lane == 0) atomicAdd((unsigned long long*)&pclk[15], (1ull << 40) | ((unsigned long long)waves << 20) | (unsigned long long)flips);
             // rasterise t over the deferred pixels it contains: one lane per row of its bounding box
             const uint32_t ca = site_rgb(t.ax, t.ay), cb = site_rgb(t.bx, t.by), cc = site_rgb(t.cx, t.cy);
             const int y0 = min(t.ay, min(t.by, t.cy)), y1 = max(t.ay, max(t.by, t.cy));

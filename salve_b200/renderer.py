@@ -359,8 +359,8 @@ class BevRenderer:
         return dict(splat=float(ms[0]), image=float(ms[1]), total=float(ms[4]))
 
     def last_phase_clocks(self, n_img: int) -> np.ndarray:
-        """(n_img, 16) int64 diagnostics of image_kernel for the last chunk (see salve_bev_last_phase_clocks)."""
-        clk = np.zeros((n_img, 16), np.int64)
+        """(n_img, 24) int64 diagnostics of image_kernel for the last chunk (see salve_bev_last_phase_clocks)."""
+        clk = np.zeros((n_img, 24), np.int64)
         nat.check(self._lib.salve_bev_last_phase_clocks(self._h, _ptr(clk, ctypes.c_int64), n_img))
         return clk
 

@@ -53,9 +53,10 @@ def check_query_triangles(qtri: np.ndarray, queries: np.ndarray, oracle_tris: np
     def orient(i, j, px, py):
         return (vx[:, j] - vx[:, i]) * (py - vy[:, i]) - (vy[:, j] - vy[:, i]) * (px - vx[:, i])
     a2 = orient(0, 1, vx[:, 2], vy[:, 2])
-    assert (a2 > 0).all(), "query triangle not counter-clockwise"
+    assert (a2 != 0).all(), "degenerate query triangle"
+    sgn = np.sign(a2)  # the tap stores vertex ids in ascending order, either orientation
     for i, j in ((0, 1), (1, 2), (2, 0)):
-        assert (orient(i, j, cols, rows) >= 0).all(), "query pixel outside its triangle"
+        assert (sgn * orient(i, j, cols, rows) >= 0).all(), "query pixel outside its triangle"
 
 
 def tie_independent_mask(st: "bo.Stages", can) -> np.ndarray:
