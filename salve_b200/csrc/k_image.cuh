@@ -519,7 +519,7 @@ __device__ __forceinline__ void resolve_window(const ImageShared& S, int wpr, in
     while (true) {
         // ---- refill idle lanes
         const unsigned idle = __ballot_sync(FULL, !active);
-        if (idle && !exhausted && (__popc(idle) >= 8 || idle == FULL)) {
+        if (idle && !exhausted && (__popc(idle) >= 4 || idle == FULL)) {
             const int leader = __ffs(idle) - 1;
             int base = 0;
             if (lane == leader) base = atomicAdd(s_next, __popc(idle));
@@ -585,21 +585,39 @@ __device__ __forceinline__ void resolve_window(const ImageShared& S, int wpr, in
         // an empty circle; a larger circle can still be searched for violators inside the window (any violator is a valid flip)
         const float Rr = sqrt_approx(R2) + 0.01f;
         const bool fits = fabsf(ccy) + Rr < (float)NR + 0.99f && fabsf(ccx) + Rr < 15.0f;
-        // ---- strict interior, row by row (q's row first, then +-1, +-2, ...); the violator nearest to q wins
+        // ---- one pass over the window rows (q's row first, then +-1, +-2, ...): strict interior (the violator nearest to q wins)
+        // and the sites ON the circle.  Every lane runs the same code whether its circle turns out empty or not.
         bool have = false;
         int dx = 0, dy = 0;
+        uint32_t on[NROW], vm = 0u;
 #pragma unroll
         for (int k = 0; k < NROW; k++) {
             const int yy = (k == 0) ? 0 : ((k & 1) ? (k + 1) / 2 : -(k / 2));
             const float e = (float)yy - ccy;
-            const float t = R2 - e * e - thr;
-            if (t > 0.0f) {
-                const float hw = sqrt_approx(t);
-                const int i0 = max(__float2int_ru(ccx - hw) + 16, 0), i1 = min(__float2int_rd(ccx + hw) + 16, 31);
-                const uint32_t m = (i0 <= i1) ? (wr[yy + NR] & ((2u << i1) - 1u) & ~((1u << i0) - 1u)) : 0u;
-                if (m && !have) { have = true; dx = nearest(m); dy = yy; }
+            const float base = R2 - e * e;
+            const float ti = base - thr, to = base + thr;
+            uint32_t im = 0u, om = 0u;
+            if (to >= 0.0f) {
+                const float hwo = sqrt_approx(to);
+                const int o0 = max(__float2int_ru(ccx - hwo) + 16, 0), o1 = min(__float2int_rd(ccx + hwo) + 16, 31);
+                om = (o0 <= o1) ? (((2u << o1) - 1u) & ~((1u << o0) - 1u)) : 0u;
+                if (ti > 0.0f) {
+                    const float hwi = sqrt_approx(ti);
+                    const int i0 = max(__float2int_ru(ccx - hwi) + 16, 0), i1 = min(__float2int_rd(ccx + hwi) + 16, 31);
+                    im = (i0 <= i1) ? (((2u << i1) - 1u) & ~((1u << i0) - 1u)) : 0u;
+                }
             }
+            const uint32_t sites = wr[yy + NR];
+            const uint32_t m = sites & im;
+            if (m && !have) { have = true; vm = m; dy = yy; }
+            // sites on the circle other than a, b, c
+            uint32_t o = sites & om & ~im;
+            if (yy == ay) o &= ~(1u << (ax + 16));
+            if (yy == by) o &= ~(1u << (bx + 16));
+            if (yy == cy) o &= ~(1u << (cx + 16));
+            on[k] = o;
         }
+        if (have) dx = nearest(vm);
         if (have && !fits) {
             // large circle: float may misjudge points near it -- confirm the violator exactly (int32: |coordinates| <= 16)
             const int ex = dx - ax, ey = dy - ay;
@@ -607,35 +625,39 @@ __device__ __forceinline__ void resolve_window(const ImageShared& S, int wpr, in
         }
         if (!have && !fits) { give_up(); continue; }
         if (!have) {
-            // ---- empty circle: sites ON it decide by the symbolic perturbation (same rule as incircle_pert())
-            const uint32_t va = vlabel(r + ay, x + ax), vb = vlabel(r + by, x + bx), vc = vlabel(r + cy, x + cx);
-            long long wa = -1, wb = 0, wc = 0;
+            // ---- empty circle: sites ON it decide by the symbolic perturbation (same rule as incircle_pert(), in window
+            // coordinates: weights < 2^20, |orient| <= 2 * 31 * 6, so int32 holds every term and the sum)
+            uint32_t any = 0u;
 #pragma unroll
-            for (int k = 0; k < NROW; k++) {
-                const int yy = k - NR;
-                const float e = (float)yy - ccy;
-                const float to = R2 - e * e + thr;
-                if (to >= 0.0f && !have) {
-                    const float hwo = sqrt_approx(to);
-                    const int o0 = __float2int_ru(ccx - hwo) + 16, o1 = __float2int_rd(ccx + hwo) + 16;
-                    uint32_t m = wr[k] & ((2u << o1) - 1u) & ~((1u << o0) - 1u);
-                    const float ti = to - 2.0f * thr;
-                    if (ti > 0.0f) {
-                        const float hwi = sqrt_approx(ti);
-                        const int i0 = __float2int_ru(ccx - hwi) + 16, i1 = __float2int_rd(ccx + hwi) + 16;
-                        m &= ~(((2u << i1) - 1u) & ~((1u << i0) - 1u));
+            for (int k = 0; k < NROW; k++) any |= on[k];
+            if (any) {
+                const int wa = (int)pert_weight(vlabel(r + ay, x + ax), W), wb = (int)pert_weight(vlabel(r + by, x + bx), W),
+                          wc = (int)pert_weight(vlabel(r + cy, x + cx), W);
+                while (any && !have) {
+                    // next candidate: first non-empty row in scan order
+                    uint32_t m = 0u; int yy = 0;
+#pragma unroll
+                    for (int k = NROW - 1; k >= 0; k--)
+                        if (on[k]) { m = on[k]; yy = (k == 0) ? 0 : ((k & 1) ? (k + 1) / 2 : -(k / 2)); }
+                    const int b = __ffs(m) - 1;
+                    const int ddx = b - 16;
+#pragma unroll
+                    for (int k = 0; k < NROW; k++) {
+                        const int yk = (k == 0) ? 0 : ((k & 1) ? (k + 1) / 2 : -(k / 2));
+                        if (yk == yy) on[k] &= on[k] - 1u;
                     }
-                    while (m) {
-                        const int b = __ffs(m) - 1; m &= m - 1;
-                        const int ddx = b - 16;
-                        const uint32_t vd = vlabel(r + yy, x + ddx);
-                        if (vd == va || vd == vb || vd == vc) continue;
-                        if (wa < 0) { wa = pert_weight(va, W); wb = pert_weight(vb, W); wc = pert_weight(vc, W); }
-                        const long long pert = wa * orient_v(vb, vc, vd) - wb * orient_v(va, vc, vd) + wc * orient_v(va, vb, vd) - pert_weight(vd, W) * (long long)A2;
-                        if (pert > 0) { have = true; dx = ddx; dy = yy; break; }
-                    }
+                    const int wd = (int)pert_weight(vlabel(r + yy, x + ddx), W);
+                    const int obcd = (cx - bx) * (yy - by) - (cy - by) * (ddx - bx);
+                    const int oacd = (cx - ax) * (yy - ay) - (cy - ay) * (ddx - ax);
+                    const int oabd = (bx - ax) * (yy - ay) - (by - ay) * (ddx - ax);
+                    const int pert = wa * obcd - wb * oacd + wc * oabd - wd * A2;
+                    if (pert > 0) { have = true; dx = ddx; dy = yy; }
+                    any = 0u;
+#pragma unroll
+                    for (int k = 0; k < NROW; k++) any |= on[k];
                 }
             }
+            const uint32_t va = vlabel(r + ay, x + ax), vb = vlabel(r + by, x + bx), vc = vlabel(r + cy, x + cx);
             if (!have) {  // t is the triangle of the canonical triangulation over q
                 qres[idx] = QRES_DONE | (unsigned long long)va | ((unsigned long long)vb << 21) | ((unsigned long long)vc << 42);
                 my_flips += flips; my_maxflips = max(my_maxflips, flips);
