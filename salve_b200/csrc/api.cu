@@ -442,8 +442,7 @@ static int render_chunk(salve_bev_ctx* c, int n_img, const std::vector<SplatJob>
     CU(cudaMemsetAsync(dev_counts, 0, sizeof(int32_t) * 8 * n_img, st));
     SplatParams P = make_splat_params(c);
     const int rows = P.H - 2 * P.crop_rows;
-    const int quads = rows * (P.W >> 2);
-    dim3 grid((quads + 255) / 256, (unsigned)jobs.size());
+    dim3 grid((unsigned)(((rows + SPLAT_ROWS - 1) / SPLAT_ROWS) * ((P.W + 1023) >> 10)), (unsigned)jobs.size());
     splat_pano_kernel<<<grid, 256, 0, st>>>(P, c->d_jobs, c->keygrid, c->g_stride, dev_counts);
     c->launches++;
     CU(cudaGetLastError());

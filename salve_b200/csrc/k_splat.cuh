@@ -68,50 +68,88 @@ __device__ __forceinline__ bool bbox_pixel(const SplatParams& P, double x, doubl
     return true;
 }
 
-// One thread = 4 consecutive pano columns of one row.  grid = (ceil(rows*W/4 / block), n_jobs).
-// Reads only the depth map (2 B/px, 8-byte vector loads); colours are gathered later for winners only.
-__global__ void __launch_bounds__(256) splat_pano_kernel(SplatParams P, const SplatJob* __restrict__ jobs,
+// One thread = 4 consecutive pano columns (one 8-byte depth load per row) x SPLAT_ROWS consecutive rows: the column factors
+// cos/sin theta stay in registers across the rows, and the depth loads of a batch of rows are issued together.
+// grid = (ceil(rows / SPLAT_ROWS) * ceil(W / 1024), n_jobs), block = 256.
+// Reads only the depth map (2 B/px); colours are gathered later for winners only.
+constexpr int SPLAT_ROWS = 8;
+constexpr int SPLAT_BATCH = 4;
+
+__global__ void __launch_bounds__(256, 3) splat_pano_kernel(SplatParams P, const SplatJob* __restrict__ jobs,
                                                          uint32_t* __restrict__ keygrid_base, size_t keygrid_stride,
                                                          int32_t* __restrict__ counts /* [n_img][8] */) {
     const SplatJob job = jobs[blockIdx.y];
     const int rows = P.H - 2 * P.crop_rows;
-    const int quads_per_row = P.W >> 2;
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ncg = (P.W + 1023) >> 10;  // column groups of 1024 columns
+    const int cg = blockIdx.x % ncg, rg = blockIdx.x / ncg;
+    const int u0 = ((cg << 8) + threadIdx.x) << 2;
     int n_crop_f = 0, n_crop_c = 0, n_box_f = 0, n_box_c = 0;
-    if (q < rows * quads_per_row) {
-        const int v = P.crop_rows + q / quads_per_row;
-        const int u0 = (q % quads_per_row) << 2;
-        const uint16_t* dp = P.depth[job.pano_slot] + (size_t)v * P.W + u0;
-        const uint2 raw = __ldg(reinterpret_cast<const uint2*>(dp));
-        const uint32_t d16[4] = {raw.x & 0xFFFFu, raw.x >> 16, raw.y & 0xFFFFu, raw.y >> 16};
-        const double cphi = __ldg(P.cos_phi + v), sz = __ldg(P.neg_sin_phi + v);
+    if (u0 < P.W) {
+        double ct[4], st[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { ct[k] = __ldg(P.cos_theta + u0 + k); st[k] = __ldg(P.sin_theta + u0 + k); }
         const double tx = (double)__fmul_rn(job.t[0], 1.5f), ty = (double)__fmul_rn(job.t[1], 1.5f);
         uint32_t* kg_f = job.img_floor >= 0 ? keygrid_base + (size_t)job.img_floor * keygrid_stride : nullptr;
         uint32_t* kg_c = job.img_ceil >= 0 ? keygrid_base + (size_t)job.img_ceil * keygrid_stride : nullptr;
+        const uint16_t* dbase = P.depth[job.pano_slot];
+        const int r0 = rg * SPLAT_ROWS;
+#pragma unroll 1
+        for (int rb = 0; rb < SPLAT_ROWS; rb += SPLAT_BATCH) {
+            uint2 raw[SPLAT_BATCH];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int u = u0 + k;
-            const double d = (double)__fmul_rn((float)d16[k], P.depth_scale);
-            const double z = __dmul_rn(d, sz);
-            const bool is_f = (z > P.a_lo && z <= P.a_hi);
-            const bool is_c = (z > P.b_lo && z <= P.b_hi);
-            if (is_f) n_crop_f++;
-            if (is_c) n_crop_c++;
-            const bool do_f = is_f && kg_f != nullptr, do_c = is_c && kg_c != nullptr;
-            if (!do_f && !do_c) continue;
-            const double x = __dmul_rn(d, __dmul_rn(cphi, __ldg(P.cos_theta + u)));
-            const double y = __dmul_rn(d, __dmul_rn(cphi, __ldg(P.sin_theta + u)));
-            double wx, wy;
-            rot_pose(x, y, job.posed != 0, job.R, tx, ty, wx, wy);
-            int row, col;
-            if (!bbox_pixel(P, wx, wy, row, col)) continue;
-            if (do_f) n_box_f++;
-            if (do_c) n_box_c++;
-            const int sl = z_slice4(z);
-            if (sl < 0) continue;
-            const uint32_t key = (((uint32_t)sl << KEY_IDX_BITS) | (uint32_t)(v * P.W + u)) + 1u;
-            if (do_f) atomicMax(kg_f + row * P.grid_w + col, key);
-            if (do_c) atomicMax(kg_c + row * P.grid_w + col, key);
+            for (int j = 0; j < SPLAT_BATCH; j++) {
+                const int rr = r0 + rb + j;
+                raw[j] = (rr < rows) ? __ldg(reinterpret_cast<const uint2*>(dbase + (size_t)(P.crop_rows + rr) * P.W + u0)) : make_uint2(0u, 0u);
+            }
+#pragma unroll
+            for (int j = 0; j < SPLAT_BATCH; j++) {
+                const int rr = r0 + rb + j;
+                if (rr >= rows) break;
+                const int v = P.crop_rows + rr;
+                const uint32_t d16[4] = {raw[j].x & 0xFFFFu, raw[j].x >> 16, raw[j].y & 0xFFFFu, raw[j].y >> 16};
+                const double cphi = __ldg(P.cos_phi + v), sz = __ldg(P.neg_sin_phi + v);
+                // targets of the 4 pixels; consecutive pano pixels often land on the same BEV pixel (near the camera up to 4 of
+                // them): merged here (max of the keys) they cost one atomic instead of several on the same address
+                int pix[4]; uint32_t key[4]; bool ff[4], cf[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    ff[k] = false; cf[k] = false; pix[k] = -1; key[k] = 0u;
+                    const double d = (double)__fmul_rn((float)d16[k], P.depth_scale);
+                    const double z = __dmul_rn(d, sz);
+                    const bool is_f = (z > P.a_lo && z <= P.a_hi);
+                    const bool is_c = (z > P.b_lo && z <= P.b_hi);
+                    if (is_f) n_crop_f++;
+                    if (is_c) n_crop_c++;
+                    const bool do_f = is_f && kg_f != nullptr, do_c = is_c && kg_c != nullptr;
+                    if (!do_f && !do_c) continue;
+                    const double x = __dmul_rn(d, __dmul_rn(cphi, ct[k]));
+                    const double y = __dmul_rn(d, __dmul_rn(cphi, st[k]));
+                    double wx, wy;
+                    rot_pose(x, y, job.posed != 0, job.R, tx, ty, wx, wy);
+                    int row, col;
+                    if (!bbox_pixel(P, wx, wy, row, col)) continue;
+                    if (do_f) n_box_f++;
+                    if (do_c) n_box_c++;
+                    const int sl = z_slice4(z);
+                    if (sl < 0) continue;
+                    key[k] = (((uint32_t)sl << KEY_IDX_BITS) | (uint32_t)(v * P.W + u0 + k)) + 1u;
+                    pix[k] = row * P.grid_w + col;
+                    ff[k] = do_f; cf[k] = do_c;
+                }
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    if (pix[k] >= 0 && pix[k] == pix[k + 1] && ff[k] == ff[k + 1] && cf[k] == cf[k + 1]) {
+                        key[k + 1] = max(key[k + 1], key[k]);
+                        pix[k] = -1;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (pix[k] < 0) continue;
+                    if (ff[k]) atomicMax(kg_f + pix[k], key[k]);
+                    if (cf[k]) atomicMax(kg_c + pix[k], key[k]);
+                }
+            }
         }
     }
     if (counts != nullptr) {
