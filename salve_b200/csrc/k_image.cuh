@@ -35,8 +35,6 @@ namespace bev {
 
 constexpr int IMAGE_NT = 512;
 constexpr int IMAGE_MAX_FLIPS = 100000;  // safety cap on one descent (never reached: the lift is strictly monotone)
-constexpr int IMAGE_MAX_GAP = 24;        // pass 1: row gap (nearest site left to nearest site right) at most this,
-constexpr int IMAGE_TRIP_BUDGET = 24;    //   and at most this many five-row trips + flips per query
 constexpr int IMAGE_MAX_GAP_B = 64;      // pass 1b: the same for the int64 / float64 state machine;
 constexpr int IMAGE_ROW_BUDGET_B = 160;  //   what is left goes to the cooperative pass
 constexpr double IMAGE_MAX_R_B = 12.0;   // pass 1b: largest circumradius (px)
@@ -318,162 +316,7 @@ __device__ __forceinline__ void resolve_pass(const ImageShared& S, int wpr, int 
     }
 }
 
-// ---- pass 1: small circles, FIVE rows of the scan per trip ----------------------------------------------------------------
-// Same state machine, specialised for the bulk of the queries (holes of a few pixels): triangles within 32 px of vertex a
-// and circumradius <= 14 px.  Then the exact in-circle determinant fits int32, the chord of a row fits a 32-bit window of the
-// occupancy row (one funnel shift), and float32 locates the chord to < 0.02 px: bits further than 0.05 px inside the chord are
-// violators without any test, only bits within 0.05 px of its ends (lattice points on the circle: ties) take the exact test.
-// A trip scans the next five rows (r, r+1, r-1, r+2, r-2, then r+3, ...), keeps the deepest violator (largest determinant)
-// and flips once, so the flip / circle-setup code runs converged instead of for two or three lanes at a time.
 __device__ __forceinline__ float sqrt_approx(float v) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
-
-__device__ __forceinline__ void resolve_small(const ImageShared& S, int wpr, int W, int H, const uint32_t* __restrict__ qlist,
-                                              unsigned long long* __restrict__ qres, int n, int* s_next, uint32_t* defer, int max_gap,
-                                              int trip_budget, int lane, int& my_flips, int& my_maxflips) {
-    const unsigned FULL = 0xffffffffu;
-    bool active = false, exhausted = false, need_setup = false;
-    int x = 0, r = 0, idx = 0, obase = 0, budget = 0, flips = 0;
-    bool up_ok = true, dn_ok = true;
-    Tri2 t = {0, 0, 0, 0, 0, 0};
-    float ux2 = 0.f, uy2 = 0.f, cxa = 0.f;
-    int eA2 = 1, eU = 0, eV = 0;
-    uint32_t va = 0, vb = 0, vc = 0;
-    int wa = 0, wb = 0, wc = 0;
-
-    auto give_up = [&]() {  // hand the query to the next pass
-        atomicOr(&defer[r * wpr + (x >> 5)], 1u << (x & 31));
-        qres[idx] = 0ull;
-        active = false;
-    };
-
-    while (true) {
-        // ---- refill idle lanes
-        const unsigned idle = __ballot_sync(FULL, !active);
-        if (idle && !exhausted && (__popc(idle) >= 8 || idle == FULL)) {
-            const int leader = __ffs(idle) - 1;
-            int base = 0;
-            if (lane == leader) base = atomicAdd(s_next, __popc(idle));
-            base = __shfl_sync(FULL, base, leader);
-            if (base + __popc(idle) >= n) exhausted = true;
-            if (!active) {
-                const int i = base + __popc(idle & ((1u << lane) - 1u));
-                if (i < n) {
-                    const uint32_t code = qlist[i];
-                    x = (int)(code & COL_MASK); r = (int)(code >> COL_BITS); idx = i;
-                    active = true; budget = trip_budget; flips = 0; need_setup = true;
-                    bool ok = S.cnt[r] > 1 && x > S.first[r] && x < S.last[r] && init_tri_row(S, wpr, W, x, r, t);
-                    if (ok) ok = abs(t.bx - t.ax) <= max_gap;
-                    if (!ok) give_up();
-                }
-            }
-        }
-        if (!__any_sync(FULL, active)) { if (exhausted) break; continue; }
-
-        // ---- circle of a new triangle
-        if (active && need_setup) {
-            need_setup = false;
-            const int bx = t.bx - t.ax, by = t.by - t.ay, cx = t.cx - t.ax, cy = t.cy - t.ay;
-            bool ok = max(max(abs(bx), abs(by)), max(abs(cx), abs(cy))) <= 32;
-            if (ok) {
-                const int b2 = bx * bx + by * by, c2 = cx * cx + cy * cy;
-                eA2 = bx * cy - by * cx;  // > 0
-                // in-circle determinant of d = a + (dx, dy):  inc = eU*dx + eV*dy - eA2*(dx^2+dy^2)   (> 0: strictly inside)
-                eU = b2 * cy - by * c2; eV = bx * c2 - b2 * cx;
-                const float fu = (float)eU, fv = (float)eV, fa = (float)eA2;
-                ok = fu * fu + fv * fv <= 784.0f * fa * fa;  // circumradius^2 = (U^2+V^2) / (4 A2^2) <= 14^2
-                const float inv = 1.0f / fa;
-                const float ux = 0.5f * fu * inv;
-                uy2 = fv * inv; ux2 = ux * ux; cxa = (float)t.ax + ux;
-                va = vlabel(t.ay, t.ax); vb = vlabel(t.by, t.bx); vc = vlabel(t.cy, t.cx);
-                wa = (int)pert_weight(va, W); wb = (int)pert_weight(vb, W); wc = (int)pert_weight(vc, W);
-                obase = 0; up_ok = true; dn_ok = true;
-            }
-            if (!ok) give_up();
-        }
-
-        // ---- five rows of the scan
-        int best_inc = -1, best_x = 0, best_y = 0;
-#pragma unroll
-        for (int j = 0; j < 5; j++) {
-            const int o = obase + j;
-            const int k = (o + 1) >> 1;
-            const bool down = (o & 1) != 0;
-            const bool on = active && (down ? dn_ok : up_ok);
-            if (!__any_sync(FULL, on)) continue;
-            if (!on) continue;
-            const int y = down ? r - k : r + k;
-            bool dead = (y < 0 || y >= H);
-            if (!dead) {
-                const float dyr = (float)(y - t.ay);
-                const float tt = fmaf(dyr, uy2 - dyr, ux2);  // squared half chord of the circle on this row
-                if (tt < -0.5f) dead = true;
-                else {
-                    const float hw = sqrt_approx(fmaxf(tt, 0.0f));
-                    const float lo = cxa - hw, hi = cxa + hw;
-                    // circle and hull are convex and both contain q: a row that misses their intersection ends its direction
-                    if (!(fmaxf(lo - 0.05f, S.hlf[y] - 0.01f) <= fminf(hi + 0.05f, S.hrf[y] + 0.01f))) dead = true;
-                    else {
-                        const int xo0 = max((int)ceilf(lo - 0.05f), 0), xo1 = min((int)floorf(hi + 0.05f), W - 1);
-                        if (xo0 <= xo1) {
-                            const uint32_t* row = S.occ + y * wpr;
-                            const int w0 = xo0 >> 5;
-                            const uint32_t lo32 = row[w0], hi32 = (w0 + 1 < wpr) ? row[w0 + 1] : 0u;
-                            const int nb = xo1 - xo0 + 1;  // <= 30: the chord is at most 2 * 14.05 + 1 wide
-                            uint32_t win = __funnelshift_r(lo32, hi32, xo0 & 31) & ((1u << nb) - 1u);  // bit i <-> column xo0 + i
-                            if (win) {
-                                const int i0 = max((int)ceilf(lo + 0.05f) - xo0, 0), i1 = min((int)floorf(hi - 0.05f) - xo0, nb - 1);  // certainly inside
-                                const uint32_t inner = (i0 <= i1) ? (((2u << i1) - 1u) & ~((1u << i0) - 1u)) : 0u;  // i0 >= 0, i1 <= nb - 1 <= 29
-                                const uint32_t sure = win & inner;
-                                uint32_t amb = win & ~inner;  // within 0.05 px of the chord ends: at most one lattice point per end
-                                if (sure) {
-                                    // the determinant is a concave parabola along the row: deepest at the bit nearest the centre
-                                    const int cpos = min(max(__float2int_rn(cxa) - xo0, 0), nb - 1);
-                                    const uint32_t below = sure & ((2u << cpos) - 1u), above = sure & ~((2u << cpos) - 1u);
-                                    const int pb = below ? 31 - __clz(below) : -64, pa = above ? __ffs(above) - 1 : 128;
-                                    const int pos = (cpos - pb <= pa - cpos) ? pb : pa;
-                                    const int dx = xo0 + pos - t.ax, dy = y - t.ay;
-                                    const int inc = eU * dx + eV * dy - eA2 * (dx * dx + dy * dy);
-                                    if (inc > best_inc) { best_inc = inc; best_x = xo0 + pos; best_y = y; }
-                                }
-                                while (amb) {
-                                    const int b = __ffs(amb) - 1; amb &= amb - 1;
-                                    const int cxx = xo0 + b;
-                                    const uint32_t vd = vlabel(y, cxx);
-                                    if (vd == va || vd == vb || vd == vc) continue;
-                                    const int dx = cxx - t.ax, dy = y - t.ay;
-                                    const int inc = eU * dx + eV * dy - eA2 * (dx * dx + dy * dy);
-                                    if (inc > 0) { if (inc > best_inc) { best_inc = inc; best_x = cxx; best_y = y; } }
-                                    else if (inc == 0 && best_inc < 0) {  // co-circular: symbolic perturbation, same rule as incircle_pert()
-                                        const long long pert = (long long)wa * orient_v(vb, vc, vd) - (long long)wb * orient_v(va, vc, vd) +
-                                                               (long long)wc * orient_v(va, vb, vd) - pert_weight(vd, W) * (long long)eA2;
-                                        if (pert > 0) { best_inc = 0; best_x = cxx; best_y = y; }
-                                    }
-                                }
-                            }
-                        }
-                    }
-                }
-            }
-            if (dead) { if (down) dn_ok = false; else up_ok = false; }
-        }
-        if (!active) continue;
-        obase += 5;
-        if (best_inc >= 0) {
-            // Lawson flip inside {a,b,c,d}: keep the new triangle that contains q
-            bool ok = true;
-            if (ccw_contains(best_x, best_y, t.bx, t.by, t.cx, t.cy, x, r)) { t.ax = best_x; t.ay = best_y; }
-            else if (ccw_contains(t.ax, t.ay, best_x, best_y, t.cx, t.cy, x, r)) { t.bx = best_x; t.by = best_y; }
-            else if (ccw_contains(t.ax, t.ay, t.bx, t.by, best_x, best_y, x, r)) { t.cx = best_x; t.cy = best_y; }
-            else ok = false;  // cannot happen (d is inside the triangle or across exactly one edge)
-            flips++; need_setup = true;
-            if (!ok || --budget < 0) give_up();
-        } else if (!up_ok && !dn_ok) {  // scan complete: t is the triangle of the canonical triangulation over q
-            qres[idx] = QRES_DONE | (unsigned long long)va | ((unsigned long long)vb << 21) | ((unsigned long long)vc << 42);
-            my_flips += flips; my_maxflips = max(my_maxflips, flips);
-            active = false;
-        } else if (--budget < 0) give_up();
-    }
-}
 
 // ---- pass 0: small triangles in a register window ---------------------------------------------------------------------------
 // 92 % of the queries that are left after the edge rule end in a triangle within 2 px of the pixel with a circumradius of
@@ -1076,18 +919,8 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
     __syncthreads();
     if (status == 0) build_list(defer, true);
     __syncthreads();
-    mark(3);
-    if (pclk && tid == 0) pclk[12] = s_nitems;
-    if (status == 0) resolve_small(S, wpr, w, h, qlist, qres, s_nitems, &s_next, defer, IMAGE_MAX_GAP, IMAGE_TRIP_BUDGET, lane, my_flips, my_maxflips);
-    __syncthreads();
-    mark(4);
-    if (status == 0) shade(s_nitems);
-    __syncthreads();
-    mark(5);
-    if (tid == 0) { s_nitems = 0; s_next = 0; }
-    __syncthreads();
-    if (status == 0) build_list(defer, true);
-    __syncthreads();
+    mark(3); mark(4); mark(5);
+    if (pclk && tid == 0) pclk[12] = 0;
     mark(6);
     if (pclk && tid == 0) pclk[13] = s_nitems;
     if (status == 0) resolve_pass<false>(S, wpr, w, h, qlist, qres, s_nitems, &s_next, defer, IMAGE_MAX_GAP_B, IMAGE_ROW_BUDGET_B, lane, my_flips, my_maxflips);
