@@ -157,6 +157,19 @@ int salve_bev_render_hypotheses_compact_host(salve_bev_ctx* ctx, int32_t n_hyp, 
 int salve_bev_set_dedup_unposed(salve_bev_ctx* ctx, int32_t on);
 
 /*
+ * Verifier pre-processing, fused: replaces, for a batch of hypotheses kept on the device, the JPEG round trip +
+ * ZindData + the val/test transform of the reference: ResizeQuadruplet (cv2.resize INTER_LINEAR, salve/utils/transform.py:256-272) ->
+ * CropQuadruplet centre (transform.py:386-420) -> ToTensorQuadruplet (transform.py:105-123) -> NormalizeQuadruplet with the ImageNet
+ * mean/std * 255 (transform.py:177-202, normalization_utils.py:13-26) -> torch.cat along channels (models/early_fusion.py:60-61).
+ *   host_src : n * 4 DEVICE pointers (host array) to grid_h x grid_w x 3 uint8 renders, per hypothesis in the order the model takes them:
+ *              x1c, x2c, x1f, x2f = ceiling img1, ceiling img2, floor img1, floor img2 (dataset/zind_data.py:306-315)
+ *   dev_out  : n x 12 x crop_hw x crop_hw float32, bit-identical to the reference chain (cv2's 8-bit bilinear is fixed point)
+ * resize_hw <= grid size (down-scaling, the released configs use 234), crop_hw <= min(resize_hw, 256) (224).  Asynchronous on `stream`.
+ */
+int salve_bev_verifier_preprocess(salve_bev_ctx* ctx, int32_t n, const uint8_t* const* host_src, int32_t resize_hw, int32_t crop_hw,
+                                  float* dev_out, void* stream);
+
+/*
  * Render individual images: image k = pano slot[k], surface[k] (SALVE_BEV_SURF_*), posed[k] != 0 ->
  * apply (R[k], t[k]) as for pano 1 of a pair.  Replaces get_xyzrgb_from_depth + the frame change of
  * render_bev_pair + render_bev_image (bev_rendering_utils.py:347-414, 443-451, 254-328).

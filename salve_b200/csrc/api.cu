@@ -11,6 +11,7 @@
 #include "bev_common.cuh"
 #include "k_flip.cuh"
 #include "k_image.cuh"
+#include "k_preprocess.cuh"
 #include "k_raster.cuh"
 #include "k_sites.cuh"
 #include "k_splat.cuh"
@@ -66,6 +67,9 @@ struct salve_bev_ctx {
     int32_t* d_dest = nullptr;           // per image of the chunk: destination (see ImageArgs::dest)
     int32_t* h_dest[2] = {nullptr, nullptr};
     bool dedup_unposed = true;
+    // verifier pre-processing: resize taps of the last (src, resize, crop) combination, pinned staging of the pointer table
+    ResizeTap* d_taps = nullptr; int taps_key[4] = {0, 0, 0, 0};
+    const uint8_t** h_pp_src = nullptr; const uint8_t** d_pp_src = nullptr; size_t pp_cap = 0; cudaEvent_t ev_pp = nullptr;
     size_t g_stride = 0, bits_stride = 0, tris_stride = 0, cand_stride = 0;
     ImgHeader* headers = nullptr;
     int32_t* counts = nullptr;
@@ -251,6 +255,10 @@ extern "C" void salve_bev_ctx_destroy(salve_bev_ctx* c) {
         if (c->h_dest[k]) cudaFreeHost(c->h_dest[k]);
     }
     if (c->ev_cache) cudaEventDestroy(c->ev_cache);
+    if (c->ev_pp) cudaEventDestroy(c->ev_pp);
+    if (c->h_pp_src) cudaFreeHost(c->h_pp_src);
+    if (c->d_pp_src) cudaFree(c->d_pp_src);
+    if (c->d_taps) cudaFree(c->d_taps);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->h_meta) cudaFreeHost(c->h_meta);
     delete c;
@@ -778,6 +786,72 @@ extern "C" int salve_bev_render_hypotheses_compact_host(salve_bev_ctx* c, int32_
     return render_compact(c, n_hyp, p1, p2, R, t, surfaces, true, host_posed, host_unposed, host_unposed_of_hyp, host_n_unique, host_counts_posed,
                           host_counts_unposed, host_status_posed, host_status_unposed, (cudaStream_t)stream);
 }
+// cv2's recipe for the taps of one axis (imgproc/src/resize.cpp): scale in double, position in float, 11-bit weights
+static void linear_taps(int src, int dst, int off, int n, std::vector<ResizeTap>& out) {
+    const double scale = (double)src / (double)dst;
+    out.resize(n);
+    for (int i = 0; i < n; i++) {
+        const int d = i + off;
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int s = (int)floorf(f);
+        f -= (float)s;
+        if (s < 0) { f = 0.f; s = 0; }
+        if (s >= src - 1) { f = 0.f; s = src - 1; }
+        ResizeTap t;
+        t.s0 = s; t.s1 = std::min(s + 1, src - 1);
+        t.w0 = (int)lrintf((1.f - f) * 2048.f); t.w1 = (int)lrintf(f * 2048.f);
+        out[i] = t;
+    }
+}
+
+extern "C" int salve_bev_verifier_preprocess(salve_bev_ctx* c, int32_t n, const uint8_t* const* host_src, int32_t resize_hw, int32_t crop_hw,
+                                             float* dev_out, void* stream) {
+    if (!c || (n > 0 && (!host_src || !dev_out))) FAIL(SALVE_BEV_E_INVALID, "null argument");
+    if (n < 0 || resize_hw < 1 || crop_hw < 1 || crop_hw > resize_hw || crop_hw > 256) FAIL(SALVE_BEV_E_INVALID, "need 1 <= crop <= resize, crop <= 256");
+    if (resize_hw > c->G.grid_h || resize_hw > c->G.grid_w) FAIL(SALVE_BEV_E_INVALID, "only down-scaling is pinned against cv2");
+    if (n == 0) return SALVE_BEV_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(c->cfg.device));
+    if (!c->ev_pp) CU(cudaEventCreateWithFlags(&c->ev_pp, cudaEventDisableTiming));
+    const int key[4] = {c->G.grid_h, c->G.grid_w, resize_hw, crop_hw};
+    if (!c->d_taps || memcmp(key, c->taps_key, sizeof(key)) != 0) {
+        const int off = (int)((resize_hw - crop_hw) / 2);  // int((h - crop_h) / 2), transform.py:412-413
+        std::vector<ResizeTap> tx, ty;
+        linear_taps(c->G.grid_w, resize_hw, off, crop_hw, tx);
+        linear_taps(c->G.grid_h, resize_hw, off, crop_hw, ty);
+        if (!c->d_taps) CU(cudaMalloc((void**)&c->d_taps, sizeof(ResizeTap) * 512));
+        CU(cudaStreamSynchronize(st));
+        CU(cudaMemcpy(c->d_taps, tx.data(), sizeof(ResizeTap) * crop_hw, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(c->d_taps + 256, ty.data(), sizeof(ResizeTap) * crop_hw, cudaMemcpyHostToDevice));
+        memcpy(c->taps_key, key, sizeof(key));
+    }
+    const size_t np = (size_t)n * 4;
+    if (c->pp_cap < np) {
+        CU(cudaEventSynchronize(c->ev_pp));
+        if (c->h_pp_src) CU(cudaFreeHost(c->h_pp_src));
+        if (c->d_pp_src) CU(cudaFree(c->d_pp_src));
+        c->h_pp_src = nullptr; c->d_pp_src = nullptr; c->pp_cap = 0;
+        CU(cudaMallocHost((void**)&c->h_pp_src, sizeof(void*) * np));
+        CU(cudaMalloc((void**)&c->d_pp_src, sizeof(void*) * np));
+        c->pp_cap = np;
+    }
+    CU(cudaEventSynchronize(c->ev_pp));  // the previous call's copy out of the pinned table is done
+    memcpy(c->h_pp_src, host_src, sizeof(void*) * np);
+    CU(cudaMemcpyAsync(c->d_pp_src, c->h_pp_src, sizeof(void*) * np, cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(c->ev_pp, st));
+    PreprocArgs A;
+    A.src = c->d_pp_src; A.xtap = c->d_taps; A.ytap = c->d_taps + 256;
+    A.src_w = c->G.grid_w; A.crop_h = crop_hw; A.crop_w = crop_hw;
+    const double mean[3] = {0.485, 0.456, 0.406}, stdv[3] = {0.229, 0.224, 0.225};  // normalization_utils.py:21-25
+    for (int k = 0; k < 3; k++) { A.mean[k] = (float)(mean[k] * 255); A.stdv[k] = (float)(stdv[k] * 255); }
+    A.out = dev_out;
+    dim3 grid((crop_hw + PREPROC_ROWS - 1) / PREPROC_ROWS, 4, (unsigned)n);
+    verifier_preprocess_kernel<<<grid, 256, 0, st>>>(A);
+    c->launches++;
+    CU(cudaGetLastError());
+    return SALVE_BEV_OK;
+}
+
 extern "C" int salve_bev_set_dedup_unposed(salve_bev_ctx* c, int32_t on) {
     if (!c) FAIL(SALVE_BEV_E_INVALID, "null argument");
     c->dedup_unposed = on != 0;

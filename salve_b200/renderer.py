@@ -227,6 +227,31 @@ class BevRenderer:
         )
         return idx, nu.value
 
+    # -- verifier pre-processing ---------------------------------------------------------------------
+    def quadruplet_pointers_full(self, dev_out, n: int) -> np.ndarray:
+        """(n, 4) device addresses x1c, x2c, x1f, x2f into a full-layout device buffer of render_hypotheses_device
+        (floor + ceiling): per hypothesis the images are [floor img1, floor img2, ceiling img1, ceiling img2]."""
+        ib = int(np.prod(self.img_shape))
+        base = np.uint64(_vp(dev_out)) + np.arange(n, dtype=np.uint64)[:, None] * np.uint64(4 * ib)
+        return base + np.array([2, 3, 0, 1], np.uint64)[None, :] * np.uint64(ib)
+
+    def quadruplet_pointers_compact(self, dev_posed, dev_unposed, unposed_of_hyp: np.ndarray) -> np.ndarray:
+        """Same for the compact layout of render_hypotheses_compact_device (floor + ceiling)."""
+        ib = int(np.prod(self.img_shape))
+        n = len(unposed_of_hyp)
+        h = np.arange(n, dtype=np.uint64)
+        u = np.asarray(unposed_of_hyp, np.uint64)
+        p, q = np.uint64(_vp(dev_posed)), np.uint64(_vp(dev_unposed))
+        two = np.uint64(2)
+        return np.stack([p + (h * two + 1) * np.uint64(ib), q + (u * two + 1) * np.uint64(ib), p + (h * two) * np.uint64(ib), q + (u * two) * np.uint64(ib)], 1)
+
+    def verifier_preprocess(self, src_ptrs: np.ndarray, dev_out, resize_hw: int = 234, crop_hw: int = 224, stream: int = 0) -> None:
+        """Fused val/test transform of the reference (resize 234 -> centre crop 224 -> CHW float32 -> ImageNet normalise -> channel
+        concatenation; salve/train_utils.py:126-159).  src_ptrs: (n, 4) uint64 device addresses of 501x501x3 uint8 renders in the
+        model's order x1c, x2c, x1f, x2f; dev_out: device float32 (n, 12, crop, crop).  Asynchronous on `stream`."""
+        src = np.ascontiguousarray(src_ptrs, np.uint64).reshape(-1, 4)
+        nat.check(self._lib.salve_bev_verifier_preprocess(self._h, src.shape[0], src.ctypes.data, int(resize_hw), int(crop_hw), _vp(dev_out), stream or None))
+
     def set_dedup_unposed(self, on: bool) -> None:
         nat.check(self._lib.salve_bev_set_dedup_unposed(self._h, int(on)))
 

@@ -244,6 +244,55 @@ def test_dedup_of_unposed_renders_is_invisible():
     r.close()
 
 
+def test_verifier_preprocess_bit_exact():
+    """Fused resize 234 / crop 224 / CHW / normalise / concat kernel == the reference transform chain (oracle restatement pinned by
+    tests/golden/preprocess_c1.npz), on the golden inputs and on real renders through both output layouts."""
+    import hashlib
+    import importlib.util
+
+    import torch
+
+    from oracle import preprocess_oracle as po
+    from salve_b200.renderer import BevRenderer
+
+    spec = importlib.util.spec_from_file_location("mgp", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "make_golden_preprocess.py"))
+    mgp = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mgp)
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "preprocess_c1.npz"))
+    imgs = mgp.golden_inputs()
+    r = BevRenderer(max_panos=3, max_images=12)
+    d_in = [torch.from_numpy(a).cuda() for a in imgs]
+    out = torch.zeros((1, 12, 224, 224), dtype=torch.float32, device="cuda")
+    r.verifier_preprocess(np.array([[t.data_ptr() for t in d_in]], np.uint64), out)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()[0]
+    assert np.array_equal(got, po.preprocess_quadruplet(*imgs))
+    assert np.array_equal(np.frombuffer(hashlib.sha256(np.ascontiguousarray(got).tobytes()).digest(), np.uint8), g["sha256"])
+    # real renders, full and compact layouts, other sizes
+    rgbs, depths, p1, p2, Rm, t = synth.synth_building(3, 4, 512, 1024, seed=8)
+    for k in range(3):
+        r.upload_pano(k, rgbs[k], depths[k])
+    full = torch.zeros(4 * 4 * 501 * 501 * 3, dtype=torch.uint8, device="cuda")
+    r.render_hypotheses_device(p1, p2, Rm, t, full)
+    o_full = torch.zeros((4, 12, 224, 224), dtype=torch.float32, device="cuda")
+    r.verifier_preprocess(r.quadruplet_pointers_full(full, 4), o_full)
+    dp = torch.zeros(4 * 2 * 501 * 501 * 3, dtype=torch.uint8, device="cuda")
+    du = torch.zeros(3 * 2 * 501 * 501 * 3, dtype=torch.uint8, device="cuda")
+    idx, nu = r.render_hypotheses_compact_device(p1, p2, Rm, t, dp, du)
+    o_comp = torch.zeros((4, 12, 224, 224), dtype=torch.float32, device="cuda")
+    r.verifier_preprocess(r.quadruplet_pointers_compact(dp, du, idx), o_comp)
+    o_small = torch.zeros((4, 12, 96, 96), dtype=torch.float32, device="cuda")
+    r.verifier_preprocess(r.quadruplet_pointers_full(full, 4), o_small, resize_hw=101, crop_hw=96)
+    torch.cuda.synchronize()
+    host = full.cpu().numpy().reshape(4, 2, 2, 501, 501, 3)
+    for h in range(4):
+        want = po.preprocess_quadruplet(host[h, 1, 0], host[h, 1, 1], host[h, 0, 0], host[h, 0, 1])
+        assert np.array_equal(o_full[h].cpu().numpy(), want) and np.array_equal(o_comp[h].cpu().numpy(), want)
+        want_s = po.preprocess_quadruplet(host[h, 1, 0], host[h, 1, 1], host[h, 0, 0], host[h, 0, 1], 101, 96)
+        assert np.array_equal(o_small[h].cpu().numpy(), want_s)
+    r.close()
+
+
 # ---- stream compaction / back-projection -----------------------------------------------------------------
 @pytest.mark.parametrize("surf", ["floor", "ceiling"])
 def test_backproject_compaction_bit_exact(R, surf):

@@ -4,6 +4,8 @@ imported reference itself."""
 
 import hashlib
 
+import os
+
 import numpy as np
 import pytest
 
@@ -178,3 +180,37 @@ def test_single_point_rows_and_collinear():
     cols = rows.copy()  # oblique line: no real triangle
     tri_v, stats = cdt.triangulate(rows, cols, 12)
     assert (tri_v >= 0).all(1).sum() == 0
+
+
+# ---- verifier pre-processing ---------------------------------------------------------------------
+def _golden_preprocess_inputs():
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("mgp", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "make_golden_preprocess.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m.golden_inputs()
+
+
+def test_preprocess_oracle_equals_reference_golden():
+    """tests/golden/preprocess_c1.npz was produced by the reference's own transform classes (scripts/make_golden_preprocess.py)."""
+    import hashlib
+
+    from oracle import preprocess_oracle as po
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "preprocess_c1.npz"))
+    out = po.preprocess_quadruplet(*_golden_preprocess_inputs())
+    assert out.shape == (12, 224, 224) and out.dtype == np.float32
+    assert np.array_equal(out[:, g["rows"], :], g["values"])
+    assert np.array_equal(np.frombuffer(hashlib.sha256(np.ascontiguousarray(out).tobytes()).digest(), np.uint8), g["sha256"])
+
+
+def test_preprocess_oracle_resize_equals_cv2():
+    """The restated fixed-point bilinear against OpenCV itself (third-party arithmetic of the chain), down-scaling sizes."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import preprocess_oracle as po
+
+    rng = np.random.default_rng(3)
+    for shape, out in (((501, 501, 3), (234, 234)), ((501, 501, 3), (224, 224)), ((64, 37, 3), (50, 29)), ((300, 200, 3), (299, 101))):
+        img = rng.integers(0, 256, size=shape, dtype=np.int64).astype(np.uint8)
+        assert np.array_equal(cv2.resize(img, (out[1], out[0]), interpolation=cv2.INTER_LINEAR), po.resize_linear_u8(img, out[0], out[1]))
