@@ -96,8 +96,17 @@ int salve_bev_get_uni_sphere_xyz(salve_bev_ctx* ctx, double* host_out);
  * what imageio.imread returns at bev_rendering_utils.py:367,370.
  */
 int salve_bev_upload_pano(salve_bev_ctx* ctx, int32_t slot, const uint8_t* host_rgb, const uint16_t* host_depth, void* stream);
-/* Alias device memory owned by the caller instead of copying (must stay valid while used). */
+/* Alias device memory owned by the caller instead of copying (must stay valid while used).  rgb 2-byte, depth 8-byte aligned. */
 int salve_bev_bind_pano(salve_bev_ctx* ctx, int32_t slot, const uint8_t* dev_rgb, const uint16_t* dev_depth);
+/*
+ * Full-resolution colour.  ZInD panos are 2048x1024; get_xyzrgb_from_depth brings them to the depth map's
+ * 1024x512 with cv2.resize(rgb, (1024, 512), INTER_LINEAR) (bev_rendering_utils.py:373-375), which at a scale of exactly 2 is the
+ * rounded 2x2 box mean (sum + 2) >> 2.  rgb_2x: (2*pano_h, 2*pano_w, 3) uint8; depth: (pano_h, pano_w) uint16 as before.  The
+ * down-sampled pano is never materialised: the 2x2 mean is taken when a winner's colour is gathered (50 k gathers per image
+ * instead of a 6 MB pass per pano).
+ */
+int salve_bev_upload_pano_fullres(salve_bev_ctx* ctx, int32_t slot, const uint8_t* host_rgb_2x, const uint16_t* host_depth, void* stream);
+int salve_bev_bind_pano_fullres(salve_bev_ctx* ctx, int32_t slot, const uint8_t* dev_rgb_2x, const uint16_t* dev_depth);
 
 /*
  * Height bands of the two surfaces, each keeps lo < z <= hi.  Defaults are the reference's

@@ -52,6 +52,8 @@ SYMBOLS = {
     "salve_bev_get_uni_sphere_xyz": (ctypes.c_int, [c_vp, c_f64p]),
     "salve_bev_upload_pano": (ctypes.c_int, [c_vp, ctypes.c_int32, c_vp, c_vp, c_vp]),
     "salve_bev_bind_pano": (ctypes.c_int, [c_vp, ctypes.c_int32, c_vp, c_vp]),
+    "salve_bev_upload_pano_fullres": (ctypes.c_int, [c_vp, ctypes.c_int32, c_vp, c_vp, c_vp]),
+    "salve_bev_bind_pano_fullres": (ctypes.c_int, [c_vp, ctypes.c_int32, c_vp, c_vp]),
     "salve_bev_render_hypotheses": (ctypes.c_int, [c_vp, ctypes.c_int32, c_i32p, c_i32p, c_f32p, c_f32p, ctypes.c_uint32, c_vp, c_vp, c_vp, c_vp]),
     "salve_bev_render_hypotheses_host": (ctypes.c_int, [c_vp, ctypes.c_int32, c_i32p, c_i32p, c_f32p, c_f32p, ctypes.c_uint32, c_vp, c_vp, c_vp, c_vp]),
     "salve_bev_render_hypotheses_compact": (ctypes.c_int, [c_vp, ctypes.c_int32, c_i32p, c_i32p, c_f32p, c_f32p, ctypes.c_uint32, c_vp, c_vp, c_i32p, c_i32p, c_vp, c_vp, c_vp, c_vp, c_vp]),

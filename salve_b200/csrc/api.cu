@@ -44,6 +44,7 @@ struct salve_bev_ctx {
     // pano slots
     uint8_t* pano_rgb_store = nullptr;
     uint16_t* pano_depth_store = nullptr;
+    uint8_t* pano_rgb2x_store = nullptr;  // lazily allocated: full-resolution (2H, 2W) rgb of the slots uploaded that way
     std::vector<const uint8_t*> h_rgb_ptr;
     std::vector<const uint16_t*> h_depth_ptr;
     const uint16_t** d_depth_ptr = nullptr;
@@ -240,7 +241,7 @@ extern "C" void salve_bev_ctx_destroy(salve_bev_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->cfg.device);
     cudaDeviceSynchronize();
-    void* ptrs[] = {c->pano_rgb_store, c->pano_depth_store, c->d_depth_ptr, c->d_tables, c->keygrid, c->color, c->occ, c->nonempty,
+    void* ptrs[] = {c->pano_rgb_store, c->pano_rgb2x_store, c->pano_depth_store, c->d_depth_ptr, c->d_tables, c->keygrid, c->color, c->occ, c->nonempty,
                     c->keep, c->tmpbits, c->wprefix, c->tris, c->owner, c->list0, c->list1, c->cand, c->qlist, c->qres, c->phase_clk, c->keepbits, c->work_counter, c->cache_out, c->cache_counts, c->cache_status, c->d_dest, c->headers, c->counts,
                     c->status, c->d_jobs, c->d_color_src, c->out_store};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -308,16 +309,37 @@ extern "C" int salve_bev_upload_pano(salve_bev_ctx* c, int32_t slot, const uint8
     uint16_t* dd = c->pano_depth_store + (size_t)slot * H * W;
     CU(cudaMemcpyAsync(drgb, host_rgb, H * W * 3, cudaMemcpyHostToDevice, (cudaStream_t)stream));
     CU(cudaMemcpyAsync(dd, host_depth, H * W * 2, cudaMemcpyHostToDevice, (cudaStream_t)stream));
-    if (c->h_rgb_ptr[slot] != drgb || c->h_depth_ptr[slot] != dd) { c->h_rgb_ptr[slot] = drgb; c->h_depth_ptr[slot] = dd; c->ptr_dirty = true; }
+    if (c->h_rgb_ptr[slot] != drgb || c->h_depth_ptr[slot] != dd) { c->h_rgb_ptr[slot] = drgb; c->h_depth_ptr[slot] = dd; c->ptr_dirty = true; }  // untagged: 1x
     return SALVE_BEV_OK;
 }
 
-extern "C" int salve_bev_bind_pano(salve_bev_ctx* c, int32_t slot, const uint8_t* dev_rgb, const uint16_t* dev_depth) {
+static int bind_pano_impl(salve_bev_ctx* c, int32_t slot, const uint8_t* dev_rgb, const uint16_t* dev_depth, bool fullres) {
     if (!c || !dev_rgb || !dev_depth) FAIL(SALVE_BEV_E_INVALID, "null argument");
     if (slot < 0 || slot >= c->cfg.max_panos) FAIL(SALVE_BEV_E_CAPACITY, "pano slot out of range");
     if (((uintptr_t)dev_depth & 7) != 0) FAIL(SALVE_BEV_E_INVALID, "depth pointer must be 8-byte aligned");
-    c->h_rgb_ptr[slot] = dev_rgb; c->h_depth_ptr[slot] = dev_depth; c->ptr_dirty = true;
+    if (((uintptr_t)dev_rgb & 1) != 0) FAIL(SALVE_BEV_E_INVALID, "rgb pointer must be 2-byte aligned");
+    // bit 0 of a colour source tags a full-resolution pano (gather_rgb)
+    c->h_rgb_ptr[slot] = reinterpret_cast<const uint8_t*>((uintptr_t)dev_rgb | (fullres ? 1u : 0u));
+    c->h_depth_ptr[slot] = dev_depth; c->ptr_dirty = true;
     return SALVE_BEV_OK;
+}
+extern "C" int salve_bev_bind_pano(salve_bev_ctx* c, int32_t slot, const uint8_t* dev_rgb, const uint16_t* dev_depth) {
+    return bind_pano_impl(c, slot, dev_rgb, dev_depth, false);
+}
+extern "C" int salve_bev_bind_pano_fullres(salve_bev_ctx* c, int32_t slot, const uint8_t* dev_rgb_2x, const uint16_t* dev_depth) {
+    return bind_pano_impl(c, slot, dev_rgb_2x, dev_depth, true);
+}
+extern "C" int salve_bev_upload_pano_fullres(salve_bev_ctx* c, int32_t slot, const uint8_t* host_rgb_2x, const uint16_t* host_depth, void* stream) {
+    if (!c || !host_rgb_2x || !host_depth) FAIL(SALVE_BEV_E_INVALID, "null argument");
+    if (slot < 0 || slot >= c->cfg.max_panos) FAIL(SALVE_BEV_E_CAPACITY, "pano slot out of range");
+    CU(cudaSetDevice(c->cfg.device));
+    const size_t H = c->cfg.pano_h, W = c->cfg.pano_w, P = c->cfg.max_panos;
+    if (!c->pano_rgb2x_store) CU(cudaMalloc((void**)&c->pano_rgb2x_store, P * H * W * 12));
+    uint8_t* drgb = c->pano_rgb2x_store + (size_t)slot * H * W * 12;
+    uint16_t* dd = c->pano_depth_store + (size_t)slot * H * W;
+    CU(cudaMemcpyAsync(drgb, host_rgb_2x, H * W * 12, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    CU(cudaMemcpyAsync(dd, host_depth, H * W * 2, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return bind_pano_impl(c, slot, drgb, dd, true);
 }
 
 static SplatParams make_splat_params(salve_bev_ctx* c) {
@@ -358,7 +380,7 @@ static int run_image_stage(salve_bev_ctx* c, int n_img, const GridParams& G, con
     IA.n_img = n_img; IA.work_counter = c->work_counter;
     CU(cudaMemsetAsync(c->work_counter, 0, sizeof(int32_t), st));
     IA.keygrid = keygrid; IA.keygrid_stride = c->g_stride;
-    IA.color_src = color_src;
+    IA.color_src = color_src; IA.pano_w = c->cfg.pano_w;
     IA.counts = dev_counts; IA.status = dev_status;
     IA.out = dev_out; IA.out_stride = (size_t)G.g * 3;
     IA.dest = dest; IA.counts_out = counts_out;
@@ -386,7 +408,7 @@ static int run_mesh_stages(salve_bev_ctx* c, const GridParams& G, const uint32_t
     SA.wprefix = c->wprefix;
     SA.tris = c->tris; SA.tris_stride = c->tris_stride;
     SA.headers = c->headers; SA.counts = dev_counts; SA.status = dev_status;
-    SA.color_src = color_src;
+    SA.color_src = color_src; SA.pano_w = c->cfg.pano_w;
     SA.out = dev_out; SA.out_stride = (size_t)G.g * 3;
     SA.raw_mode = raw_mode; SA.skip_empty_check = skip_empty;
     sites_kernel<<<1, SITES_NT, 0, st>>>(SA);
@@ -1131,7 +1153,7 @@ extern "C" int salve_bev_tap(salve_bev_ctx* c, int32_t image, int32_t what, void
             const uint8_t* src1 = nullptr;
             CU(cudaMemcpyAsync(&src1, csrc, sizeof(void*), cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
-            tap_color_kernel<<<(unsigned)((g + 255) / 256), 256, 0, st>>>(kg, src1, (int)g, (uint32_t*)d);
+            tap_color_kernel<<<(unsigned)((g + 255) / 256), 256, 0, st>>>(kg, src1, (int)g, c->cfg.pano_w, (uint32_t*)d);
             c->launches++;
             CU(cudaGetLastError());
             CU(cudaMemcpyAsync(host_buf, d, bytes, cudaMemcpyDeviceToHost, st));

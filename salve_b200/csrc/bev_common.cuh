@@ -79,6 +79,26 @@ __host__ __device__ __forceinline__ uint32_t hash32(uint32_t h) {
     return h;
 }
 
+// ---- colour gather ---------------------------------------------------------------------------
+// A colour source is a u8 rgb array indexed by the key's source index.  Bit 0 of the pointer (sources are 2-byte aligned)
+// tags a FULL-RESOLUTION pano of (2H, 2W): the colour of pano pixel (v, u) is then the rounded mean of its 2x2 block,
+// (sum + 2) >> 2 -- exactly what cv2.resize(rgb, (W, H), INTER_LINEAR) gives at a scale of 2, which is how the reference
+// brings a 2048x1024 ZInD pano to 1024x512 (bev_rendering_utils.py:373-375).  No down-sampled copy is ever materialised.
+__device__ __forceinline__ uint32_t load_rgb(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16); }
+__device__ __forceinline__ uint32_t gather_rgb(const uint8_t* tagged, uint32_t idx, int pano_w) {
+    const uintptr_t a = (uintptr_t)tagged;
+    const uint8_t* base = reinterpret_cast<const uint8_t*>(a & ~(uintptr_t)1);
+    if (!(a & 1)) return load_rgb(base + (size_t)idx * 3);
+    const uint32_t v = idx / (uint32_t)pano_w, u = idx - v * (uint32_t)pano_w;
+    const size_t pitch = (size_t)pano_w * 6;
+    const uint8_t* p = base + (size_t)(2 * v) * pitch + (size_t)u * 6;
+    const uint8_t* q = p + pitch;
+    const uint32_t r = ((uint32_t)p[0] + p[3] + q[0] + q[3] + 2u) >> 2;
+    const uint32_t g = ((uint32_t)p[1] + p[4] + q[1] + q[4] + 2u) >> 2;
+    const uint32_t b = ((uint32_t)p[2] + p[5] + q[2] + q[5] + 2u) >> 2;
+    return r | (g << 8) | (b << 16);
+}
+
 // ---- splat key -----------------------------------------------------------------------------
 // key = (z-slice << 29 | source index) + 1; 0 = empty.  max over keys == the reference's rule
 // "later z-slice wins, then later point index wins" (salve/utils/zorder_utils.py:49-65).

@@ -44,7 +44,8 @@ struct ImageArgs {
     int32_t n_img;                    // images of this launch; CTAs are persistent and take images from *work_counter
     int32_t* work_counter;            // zeroed by the host before the launch
     const uint32_t* keygrid; size_t keygrid_stride;
-    const uint8_t* const* color_src;  // per image: u8 rgb triples indexed by the key's source index
+    const uint8_t* const* color_src;  // per image: u8 rgb triples indexed by the key's source index (tagged, see gather_rgb)
+    int32_t pano_w;                   // width of the key's index space (for tagged full-resolution sources)
     int32_t* counts;                  // [n_img][8] working counters, indexed like the key grids ([0], [1] come from the splat)
     int32_t* status;                  // by destination, or null
     uint8_t* out; size_t out_stride;  // final images by destination (bytes per image)
@@ -117,7 +118,6 @@ __device__ __forceinline__ int next_bit(const uint32_t* row, int x, int xmax) {
     }
 }
 
-__device__ __forceinline__ uint32_t load_rgb(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16); }
 
 struct ImageShared {
     uint32_t* occ; uint32_t* keep; uint32_t* tmp;
@@ -649,7 +649,7 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 col[j] = 0u;
-                if (key[j]) col[j] = load_rgb(csrc + (size_t)((key[j] - 1u) & KEY_IDX_MASK) * 3);
+                if (key[j]) col[j] = gather_rgb(csrc, (key[j] - 1u) & KEY_IDX_MASK, A.pano_w);
             }
 #pragma unroll
             for (int j = 0; j < 8; j++) {
@@ -1032,14 +1032,13 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
 }
 
 // colour word tap: r | g<<8 | b<<16 | 0xFF<<24 at sites, 0 elsewhere
-__global__ void tap_color_kernel(const uint32_t* __restrict__ keygrid, const uint8_t* __restrict__ csrc, int g, uint32_t* __restrict__ outc) {
+__global__ void tap_color_kernel(const uint32_t* __restrict__ keygrid, const uint8_t* __restrict__ csrc, int g, int pano_w, uint32_t* __restrict__ outc) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= g) return;
     const uint32_t key = keygrid[p];
     uint32_t cw = 0;
     if (key) {
-        const uint8_t* s = csrc + (size_t)((key - 1u) & KEY_IDX_MASK) * 3;
-        cw = (uint32_t)s[0] | ((uint32_t)s[1] << 8) | ((uint32_t)s[2] << 16) | 0xFF000000u;
+        cw = gather_rgb(csrc, (key - 1u) & KEY_IDX_MASK, pano_w) | 0xFF000000u;
     }
     outc[p] = cw;
 }

@@ -33,7 +33,8 @@ struct SitesArgs {
     ImgHeader* headers;
     int32_t* counts;                 // [n_img][8]
     int32_t* status;                 // [n_img] or null
-    const uint8_t* const* color_src; // per image: u8 rgb triples indexed by the key's source index
+    const uint8_t* const* color_src; // per image: u8 rgb triples indexed by the key's source index (tagged, see gather_rgb)
+    int32_t pano_w;
     uint8_t* out; size_t out_stride; // final images (bytes per image)
     int32_t raw_mode;                // 1: no keep mask, no flip (interp_dense_grid_from_sparse semantics)
     int32_t skip_empty_check;        // 1: generic interp path (no EMPTY status)
@@ -116,8 +117,8 @@ __global__ void __launch_bounds__(SITES_NT) sites_kernel(SitesArgs A) {
             uint32_t key = (c < w) ? keygrid[r * w + c] : 0u;
             uint32_t cw = 0; bool ne = false;
             if (key) {
-                const uint8_t* p = csrc + (size_t)((key - 1u) & KEY_IDX_MASK) * 3;
-                const uint32_t cr = p[0], cg = p[1], cb = p[2];
+                const uint32_t c3 = gather_rgb(csrc, (key - 1u) & KEY_IDX_MASK, A.pano_w);
+                const uint32_t cr = c3 & 0xFF, cg = (c3 >> 8) & 0xFF, cb = c3 >> 16;
                 cw = cr | (cg << 8) | (cb << 16) | 0xFF000000u;
                 ne = ((cr * cg * cb) & 0xFFu) != 0u;  // uint8 product wraps (interpolation_utils.py:95)
             }

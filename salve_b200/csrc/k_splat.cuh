@@ -301,9 +301,10 @@ __global__ void __launch_bounds__(COMPACT_BLOCK) crop_write_kernel(SplatParams P
         x = wx; y = wy;
     }
     o[0] = x; o[1] = y; o[2] = z;
-    o[3] = __ddiv_rn((double)rgb[src * 3 + 0], 255.0);  // rgb / 255.0, bev_rendering_utils.py:394
-    o[4] = __ddiv_rn((double)rgb[src * 3 + 1], 255.0);
-    o[5] = __ddiv_rn((double)rgb[src * 3 + 2], 255.0);
+    const uint32_t c3 = gather_rgb(rgb, (uint32_t)src, P.W);
+    o[3] = __ddiv_rn((double)(c3 & 0xFF), 255.0);  // rgb / 255.0, bev_rendering_utils.py:394
+    o[4] = __ddiv_rn((double)((c3 >> 8) & 0xFF), 255.0);
+    o[5] = __ddiv_rn((double)(c3 >> 16), 255.0);
 }
 
 // ---- z-order rule on explicit arrays (choose_elevated_repeated_vals) ----------------------------

@@ -125,6 +125,18 @@ class BevRenderer:
         """Host pointers (e.g. pinned torch tensors): asynchronous H2D on `stream`."""
         nat.check(self._lib.salve_bev_upload_pano(self._h, slot, rgb_ptr, depth_ptr, stream or None))
 
+    def upload_pano_fullres(self, slot: int, rgb_2x: np.ndarray, depth: np.ndarray, stream: int = 0) -> None:
+        """Full-resolution colour: rgb_2x (2H, 2W, 3) uint8 with the (H, W) depth map.  Equivalent to uploading
+        cv2.resize(rgb_2x, (W, H), INTER_LINEAR) (reference bev_rendering_utils.py:373-375); the 2x2 mean is fused into the colour gather."""
+        rgb_2x = np.ascontiguousarray(rgb_2x, np.uint8)
+        depth = np.ascontiguousarray(depth, np.uint16)
+        if rgb_2x.shape != (2 * self.pano_h, 2 * self.pano_w, 3) or depth.shape != (self.pano_h, self.pano_w):
+            raise ValueError(f"need rgb ({2 * self.pano_h},{2 * self.pano_w},3) uint8 + depth ({self.pano_h},{self.pano_w}) uint16")
+        nat.check(self._lib.salve_bev_upload_pano_fullres(self._h, slot, rgb_2x.ctypes.data, depth.ctypes.data, stream or None))
+
+    def bind_pano_fullres(self, slot: int, dev_rgb_2x, dev_depth) -> None:
+        nat.check(self._lib.salve_bev_bind_pano_fullres(self._h, slot, _vp(dev_rgb_2x), _vp(dev_depth)))
+
     def bind_pano(self, slot: int, dev_rgb, dev_depth) -> None:
         nat.check(self._lib.salve_bev_bind_pano(self._h, slot, _vp(dev_rgb), _vp(dev_depth)))
 

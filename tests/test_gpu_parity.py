@@ -293,6 +293,31 @@ def test_verifier_preprocess_bit_exact():
     r.close()
 
 
+def test_fullres_pano_colour_gather_equals_downsampled_upload():
+    """a 2048x1024 pano uploaded at full resolution (2x2 mean fused into the colour gather) renders the same
+    bytes as uploading cv2.resize(rgb, (1024, 512), INTER_LINEAR) -- what get_xyzrgb_from_depth does (bev_rendering_utils.py:373-375)."""
+    from oracle import preprocess_oracle as po
+    from salve_b200.renderer import BevRenderer
+
+    H, W = 512, 1024
+    rng = np.random.default_rng(11)
+    big = [rng.integers(0, 256, size=(2 * H, 2 * W, 3), dtype=np.int64).astype(np.uint8) for _ in range(2)]
+    small = [po.resize_linear_u8(b, H, W) for b in big]  # == cv2.resize (tests/test_oracle_cpu.py)
+    depth = [synth.synth_depth(H, W, 40 + k, jitter=0.2) for k in range(2)]
+    Rm, t = synth.synth_pose(12)
+    ra = BevRenderer(max_panos=2, max_images=8)
+    rb = BevRenderer(max_panos=2, max_images=8)
+    for k in range(2):
+        ra.upload_pano(k, small[k], depth[k])
+        rb.upload_pano_fullres(k, big[k], depth[k])
+    a, ca, sa = ra.render_hypotheses([0], [1], Rm[None], t[None])
+    b, cb, sb = rb.render_hypotheses([0], [1], Rm[None], t[None])
+    assert np.array_equal(a, b) and np.array_equal(ca[..., :6], cb[..., :6]) and np.array_equal(sa, sb)
+    assert np.array_equal(ra.tap(1, "color"), rb.tap(1, "color"))
+    assert np.array_equal(ra.backproject(0, -np.inf, -1.0), rb.backproject(0, -np.inf, -1.0))
+    ra.close(); rb.close()
+
+
 # ---- stream compaction / back-projection -----------------------------------------------------------------
 @pytest.mark.parametrize("surf", ["floor", "ceiling"])
 def test_backproject_compaction_bit_exact(R, surf):

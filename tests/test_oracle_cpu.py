@@ -214,3 +214,16 @@ def test_preprocess_oracle_resize_equals_cv2():
     for shape, out in (((501, 501, 3), (234, 234)), ((501, 501, 3), (224, 224)), ((64, 37, 3), (50, 29)), ((300, 200, 3), (299, 101))):
         img = rng.integers(0, 256, size=shape, dtype=np.int64).astype(np.uint8)
         assert np.array_equal(cv2.resize(img, (out[1], out[0]), interpolation=cv2.INTER_LINEAR), po.resize_linear_u8(img, out[0], out[1]))
+
+
+def test_resize_at_scale_two_is_the_rounded_box_mean():
+    """cv2.resize(INTER_LINEAR) at a scale of exactly 2 == (sum of the 2x2 block + 2) >> 2: the identity the
+    fused full-resolution colour gather relies on."""
+    from oracle import preprocess_oracle as po
+
+    rng = np.random.default_rng(4)
+    big = rng.integers(0, 256, size=(64, 96, 3), dtype=np.int64).astype(np.uint8)
+    box = (big[0::2, 0::2].astype(np.int32) + big[0::2, 1::2] + big[1::2, 0::2] + big[1::2, 1::2] + 2) >> 2
+    assert np.array_equal(po.resize_linear_u8(big, 32, 48), box.astype(np.uint8))
+    cv2 = pytest.importorskip("cv2")
+    assert np.array_equal(cv2.resize(big, (48, 32), interpolation=cv2.INTER_LINEAR), box.astype(np.uint8))
