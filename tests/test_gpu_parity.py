@@ -552,3 +552,47 @@ def test_file_driver_roundtrip(tmp_path):
     bad = type("A", (), {})(); bad.__dict__.update(scale=0.001, crop_z_range=[0, 1])
     with pytest.raises(ValueError):
         bru.get_xyzrgb_from_depth(bad, "x", "y", False)
+
+
+def test_batched_floor_driver_writes_the_reference_tree(tmp_path):
+    """salve_b200.driver.render_building_floor_pairs (batched, de-duplicated, full-resolution panos) writes the same files with the
+    same pixels as the per-pair generate_texture_maps_for_pair loop of scripts/render_dataset_bev.py:87-117."""
+    import cv2
+
+    from salve_b200 import driver
+    from salve_b200.common.sim2 import Sim2
+    from salve_b200.utils import bev_rendering_utils as bru
+
+    b, floor = "0002", "floor_01"
+    raw, dep, hyp = tmp_path / "raw", tmp_path / "depth", tmp_path / "hyp"
+    (raw / b / "panos").mkdir(parents=True); (dep / b).mkdir(parents=True)
+    paths = {}
+    for k in (2, 5, 9):
+        rgb, d = synth.synth_pano(512, 1024, 60 + k, "smooth", jitter=0.2)
+        if k == 5:  # one pano at ZInD's native 2048x1024
+            rgb = cv2.resize(rgb, (2048, 1024), interpolation=cv2.INTER_CUBIC)
+        p = raw / b / "panos" / f"floor_01_partial_room_0{k}_pano_{k}.jpg"
+        cv2.imwrite(str(p), rgb[:, :, ::-1], [cv2.IMWRITE_JPEG_QUALITY, 95])
+        cv2.imwrite(str(dep / b / f"{p.stem}.depth.png"), d)
+        paths[k] = str(p)
+    pairs = {"gt_alignment_approx": [(2, 5, "door_0_0_identity"), (2, 9, "window_1_0_rotated")], "incorrect_alignment": [(5, 9, "door_1_1_identity"), (2, 5, "opening_0_1_rotated")]}
+    j = 0
+    for lt, lst in pairs.items():
+        (hyp / b / floor / lt).mkdir(parents=True)
+        for i1, i2, uuid in lst:
+            Rm, t = synth.synth_pose(30 + j); j += 1
+            Sim2(Rm.astype(np.float64), t.astype(np.float64), 1.0).save_as_json(str(hyp / b / floor / lt / f"{i1}_{i2}__{uuid}.json"))
+    # reference-style loop
+    for lt in driver.LABEL_TYPES:
+        for pair_idx, pf in enumerate(sorted((hyp / b / floor / lt).glob("*.json"))):
+            for s in ("floor", "ceiling"):
+                bru.generate_texture_maps_for_pair(paths, s, str(pf), pair_idx, lt, str(tmp_path / "bev_ref"), b, floor, str(dep), ["rgb_texture"], None, None)
+    st = driver.render_building_floor_pairs(str(dep), str(tmp_path / "bev"), str(hyp), str(raw), b, floor)
+    assert st["hypotheses"] == 4 and st["rendered"] == 8 and st["files_written"] == 16
+    for lt in driver.LABEL_TYPES:
+        ref_files = sorted(os.listdir(tmp_path / "bev_ref" / lt / b))
+        assert sorted(os.listdir(tmp_path / "bev" / lt / b)) == ref_files and len(ref_files) == 8
+        for f in ref_files:
+            assert np.array_equal(cv2.imread(str(tmp_path / "bev" / lt / b / f)), cv2.imread(str(tmp_path / "bev_ref" / lt / b / f))), f
+    st2 = driver.render_building_floor_pairs(str(dep), str(tmp_path / "bev"), str(hyp), str(raw), b, floor)
+    assert st2["skipped_existing"] == 4 and st2["files_written"] == 0

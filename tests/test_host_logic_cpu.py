@@ -107,3 +107,19 @@ def test_gloo_world_size_2_shards_without_data_collective():
     assert sorted(b0 + b1) == [0, 1, 2, 3, 4, 5] and not set(b0) & set(b1)
     assert tot0 == tot1 == dict(units=28, max_elapsed_s=1.5)
     assert pr0 == pr1 and sum(pr0) == 28
+
+
+def test_driver_enumeration_follows_the_reference_order(tmp_path):
+    """scripts/render_dataset_bev.py:29-31, 87-91: pano id from the file name; label types in the reference's order,
+    JSONs sorted, pair_idx restarting per label type."""
+    from salve_b200 import driver
+
+    assert driver.panoid_from_fpath("/x/panos/floor_01_partial_room_07_pano_19.jpg") == 19
+    for lt, names in (("incorrect_alignment", ["5_9__b.json", "2_5__a.json"]), ("gt_alignment_approx", ["2_9__z.json", "2_5__y.json"])):
+        d = tmp_path / "0007" / "floor_02" / lt
+        d.mkdir(parents=True)
+        for n in names:
+            (d / n).write_text("{}")
+    got = [(lt, k, os.path.basename(p)) for lt, k, p in driver.enumerate_floor_hypotheses(str(tmp_path), "0007", "floor_02")]
+    assert got == [("gt_alignment_approx", 0, "2_5__y.json"), ("gt_alignment_approx", 1, "2_9__z.json"),
+                   ("incorrect_alignment", 0, "2_5__a.json"), ("incorrect_alignment", 1, "5_9__b.json")]
