@@ -383,6 +383,19 @@ def run_ours(args):
         kernels[name] = {"ms_per_step": ms, "alg_bytes_per_step": alg[name], "achieved_gbs": gbs, "frac": gbs / peak,
                          "share_of_step": stage_ms[name] / max(stage_ms["total"], 1e-9)}
     dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
+    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this same step
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        kname = {"splat": "splat_pano_kernel", "image": "image_kernel"}[dom]
+        if kname in tj:
+            e = tj[kname]
+            per_unit = (e["dram_bytes_read"] + e["dram_bytes_write"]) / e.get("images_in_launch", e.get("pano_passes_in_launch", 1))
+            units = (n_rendered if dom == "image" else n_jobs) / chunks_per_step
+            traffic = per_unit * units
+            traffic_src = "profiles/r01_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, scaled to this launch's unit count)"
     roofline = {
         "kernel": {"splat": "splat_pano_kernel", "image": "image_kernel"}[dom],
         "bound": "hbm",
@@ -390,7 +403,8 @@ def run_ours(args):
         "peak": peak,
         "unit": "GB/s",
         "frac": kernels[dom]["frac"],
-        "traffic": None,
+        "traffic": traffic,
+        "traffic_source": traffic_src,
         "peak_source": peak_src,
         "alg_bytes_per_launch": alg[dom] / chunks_per_step,
         "avg_launch_ms": kernels[dom]["ms_per_step"] / chunks_per_step,
@@ -420,7 +434,8 @@ def run_ours(args):
         "higher_is_better": True,
         "scaling": "weak",
         "vs_baseline": None,
-        "dtype": "f64 geometry, int64 predicates, u8 colour",
+        "dtype": "f64",
+        "dtype_detail": "f64 geometry (f32 pose parameters), exact int32/int64 predicates, u8 colour, exact u32 barycentrics",
         "data": "synthetic",
         "config": workload_config(world),
         "clocks": clocks,

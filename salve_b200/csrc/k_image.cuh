@@ -34,6 +34,7 @@
 namespace bev {
 
 constexpr int IMAGE_NT = 512;
+constexpr int SITES_BATCH = 8;
 constexpr int IMAGE_MAX_FLIPS = 100000;  // safety cap on one descent (never reached: the lift is strictly monotone)
 constexpr int IMAGE_MAX_GAP_B = 64;      // pass 1b: the same for the int64 / float64 state machine;
 constexpr int IMAGE_ROW_BUDGET_B = 160;  //   what is left goes to the cooperative pass
@@ -633,26 +634,26 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
     __syncthreads();
 
     // ---- A. winners -> occupancy / non-empty bit rows, sparse image (site colours, rest zero) --------
-    // Loads are issued in batches of 8 words per lane (keys, then the colour gathers) so that a warp keeps 8 independent
-    // requests in flight instead of one dependent pair.
+    // Loads are issued in batches of SITES_BATCH words per lane (keys, then the colour gathers) so that a warp keeps that many
+    // independent requests in flight instead of one dependent pair (16 = a whole row of the 501-px grid).
     for (int r = warp; r < h; r += NW) {
         int running = 0, first = -1, last = -1, ne_cnt = 0;
         uint8_t* orow = out + (size_t)(raw ? r : (h - 1 - r)) * w * 3;
         const uint32_t* krow = keygrid + (size_t)r * w;
-        for (int wi0 = 0; wi0 < wpr; wi0 += 8) {
-            uint32_t key[8], col[8];
+        for (int wi0 = 0; wi0 < wpr; wi0 += SITES_BATCH) {
+            uint32_t key[SITES_BATCH], col[SITES_BATCH];
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
+            for (int j = 0; j < SITES_BATCH; j++) {
                 const int c = (wi0 + j) * 32 + lane;
                 key[j] = (wi0 + j < wpr && c < w) ? __ldg(krow + c) : 0u;
             }
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
+            for (int j = 0; j < SITES_BATCH; j++) {
                 col[j] = 0u;
                 if (key[j]) col[j] = gather_rgb(csrc, (key[j] - 1u) & KEY_IDX_MASK, A.pano_w);
             }
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
+            for (int j = 0; j < SITES_BATCH; j++) {
                 const int wi = wi0 + j;
                 if (wi >= wpr) break;
                 const int c = wi * 32 + lane;
@@ -694,39 +695,46 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
         S.hlf[r] = __int_as_float(0x7f800000); S.hrf[r] = __int_as_float(0xff800000);
     }
 
-    // ---- C. exact convex hull from the per-row first / last sites: two monotone chains (threads 0 and 32) ------------
+    // ---- C. exact convex hull from the per-row first / last sites: two monotone chains (warps 0 and 1) ---------------
+    // Lane 0 builds the chain (serial, one step per non-empty row); the whole warp then fills the per-row bounds edge by edge.
     __syncthreads();
-    if (status == 0 && (tid == 0 || tid == 32)) {
-        const bool left = tid == 0;
+    if (status == 0 && warp < 2) {
+        const bool left = warp == 0;
         const int16_t* xs = left ? S.first : S.last;
         int16_t* e0 = left ? S.hl0 : S.hr0;   // per row: rows of the two end points of the hull edge crossing it
         int16_t* e1 = left ? S.hl1 : S.hr1;
         int16_t* stk = left ? S.stk_l : S.stk_r;
         int16_t* bound = left ? S.hlo : S.hhi;
+        float* bf = left ? S.hlf : S.hrf;
         int top = 0;
-        int r = S.cnt[0] > 0 ? 0 : S.up[0];
-        while (r >= 0) {
-            const int x = xs[r];
-            while (top >= 2) {
-                const int r1 = stk[top - 1], r0 = stk[top - 2];
-                const int o = orient_i(xs[r0], r0, xs[r1], r1, x, r);
-                // going up, the left chain turns clockwise at every vertex and the right chain counter-clockwise
-                if (left ? (o >= 0) : (o <= 0)) top--; else break;
+        if (lane == 0) {
+            int r = S.cnt[0] > 0 ? 0 : S.up[0];
+            while (r >= 0) {
+                const int x = xs[r];
+                while (top >= 2) {
+                    const int r1 = stk[top - 1], r0 = stk[top - 2];
+                    const int o = orient_i(xs[r0], r0, xs[r1], r1, x, r);
+                    // going up, the left chain turns clockwise at every vertex and the right chain counter-clockwise
+                    if (left ? (o >= 0) : (o <= 0)) top--; else break;
+                }
+                stk[top++] = (int16_t)r;
+                r = S.up[r];
             }
-            stk[top++] = (int16_t)r;
-            r = S.up[r];
+            if (top <= 2) atomicAdd(&s_hull_ok, left ? 1 : 2);  // this chain has no interior vertex
         }
+        top = __shfl_sync(0xffffffffu, top, 0);
+        __syncwarp();
         for (int k = 1; k < top; k++) {
             const int r0 = stk[k - 1], r1 = stk[k];
             const int x0 = xs[r0], x1 = xs[r1], dy = r1 - r0;
-            for (int rr = r0; rr <= r1; rr++) {
+            for (int rr = r0 + lane; rr <= r1; rr += 32) {
                 const int num = x0 * dy + (x1 - x0) * (rr - r0);  // >= 0: a convex combination scaled by dy
                 bound[rr] = (int16_t)(left ? (num + dy - 1) / dy : num / dy);  // ceil on the left, floor on the right
                 e0[rr] = (int16_t)r0; e1[rr] = (int16_t)r1;
-                (left ? S.hlf : S.hrf)[rr] = (float)num / (float)dy;
+                bf[rr] = (float)num / (float)dy;
             }
+            __syncwarp();  // the shared end row of consecutive edges is written by both: keep their order
         }
-        if (top <= 2) atomicAdd(&s_hull_ok, left ? 1 : 2);  // this chain has no interior vertex
     }
 
     // ---- D. keep mask = Chebyshev dilation of `nonempty` by K/2, zero padded ---------------------------

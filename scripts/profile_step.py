@@ -1,5 +1,7 @@
-"""Small fixed workload for ncu: N hypotheses of one synthetic building, W warm-up passes + 1 profiled pass.
-    python scripts/profile_step.py [n_hyp] [n_panos]
+"""Fixed workload for ncu: the bench step (or a smaller one), W warm-up passes + 1 profiled pass.
+    python scripts/profile_step.py [n_hyp=640] [n_panos=40] [passes=2] [max_images=1480]
+With the defaults one pass is exactly one bench.py step: 1 splat_pano_kernel + 1 image_kernel launch over 1 360 images
+(1 280 posed + 80 un-posed) + 1 replicate_images_kernel launch.
 """
 import os
 import sys
@@ -11,11 +13,12 @@ import torch
 from oracle import synth
 from salve_b200.renderer import BevRenderer
 
-n_hyp = int(sys.argv[1]) if len(sys.argv) > 1 else 148
-n_panos = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+n_hyp = int(sys.argv[1]) if len(sys.argv) > 1 else 640
+n_panos = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 passes = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+max_images = int(sys.argv[4]) if len(sys.argv) > 4 else 1480
 rgbs, depths, p1, p2, R, t = synth.synth_building(n_panos, n_hyp, 512, 1024, seed=0)
-r = BevRenderer(max_panos=n_panos, max_images=592)
+r = BevRenderer(max_panos=n_panos, max_images=max_images)
 for k in range(n_panos):
     r.upload_pano(k, rgbs[k], depths[k])
 out = torch.empty(n_hyp * 4 * 501 * 501 * 3, dtype=torch.uint8, device="cuda")
