@@ -13,19 +13,21 @@
 // Densification = "query-driven Lawson flips".  The value of linear interpolation at a non-site pixel q
 // is fixed by the Delaunay triangle that contains q.  For each such pixel a thread holds ONE triangle
 // (a,b,c) of sites with q inside it and repeats the Lawson step restricted to q: find a site d that
-// violates the empty-circumcircle property of (a,b,c) (exact int64 in-circle test; co-circular ties
+// violates the empty-circumcircle property of (a,b,c) (exact in-circle test; co-circular ties
 // by the same symbolic perturbation as the mesh path and the CPU checker), flip inside the 4-point
 // configuration {a,b,c,d} and keep the one new triangle that still contains q.  The lifted plane over
 // q rises strictly with every flip, so the descent ends at the unique triangle of the canonical
 // (perturbed) Delaunay triangulation over q -- bit-identical to rasterising the full mesh, but the
 // only state is the 32 KB occupancy bitmap in shared memory: no mesh, no atomics, no rounds.
-// Violators are searched row by row outward from q inside the circumcircle's per-row chord; the
-// chord is estimated in float64 (with a margin) and every candidate is confirmed exactly.
-// Consecutive query pixels of a row reuse the previous triangle while they stay inside it.
 //
-// The closed convex hull (pixels outside get 0, like griddata's NaN) is computed exactly from the
-// per-row first/last sites (two monotone chains) concurrently with the first phase of queries, which
-// only handles pixels between the first and last site of their own row and therefore needs no hull.
+// Order of work per image (persistent CTAs take images from an atomic counter):
+//   A  winners -> colours, bit rows          B  guards          C  exact convex hull (two monotone chains)
+//   D  keep mask (separable dilation)         F  EDGE RULE (queries between two opposite 4-neighbour sites: mean of two
+//      colours, bit-parallel) + query list    G0 WINDOW PASS (small triangles, 7 x 32 window in registers, exact float
+//      interval classification)               G1 per-lane int64/float64 row scan, circumradius <= 12 px
+//   G2 warp-cooperative pass (32 rows per trip), final triangle shared by all deferred pixels inside it
+//   H  masked-out sites, counters.
+// The closed convex hull decides which pixels are queries at all (outside it griddata gives NaN -> 0).
 #pragma once
 #include <type_traits>
 
@@ -36,9 +38,9 @@ namespace bev {
 constexpr int IMAGE_NT = 512;
 constexpr int SITES_BATCH = 8;
 constexpr int IMAGE_MAX_FLIPS = 100000;  // safety cap on one descent (never reached: the lift is strictly monotone)
-constexpr int IMAGE_MAX_GAP_B = 64;      // pass 1b: the same for the int64 / float64 state machine;
-constexpr int IMAGE_ROW_BUDGET_B = 160;  //   what is left goes to the cooperative pass
-constexpr double IMAGE_MAX_R_B = 12.0;   // pass 1b: largest circumradius (px)
+constexpr int IMAGE_MAX_GAP_B = 64;      // pass G1: widest row gap (nearest site left to nearest site right),
+constexpr int IMAGE_ROW_BUDGET_B = 160;  //   rows + flips per query,
+constexpr double IMAGE_MAX_R_B = 12.0;   //   largest circumradius (px); what is left goes to the cooperative pass
 
 struct ImageArgs {
     GridParams G;
@@ -165,14 +167,14 @@ __device__ __forceinline__ bool init_tri_hull(const ImageShared& S, int x, int r
     return false;
 }
 
-// ---- pass 1 / 1b: one query pixel per LANE, as a state machine -----------------------------------------------------------
+// ---- pass G1: one query pixel per LANE, as a state machine ----------------------------------------------------------------
 // Every trip of the loop, each active lane examines ONE row of its current circumcircle scan (rows outward from the query:
 // r, r+1, r-1, r+2, ...).  A lane that finds a violator flips and restarts its scan; a lane whose scan ends has resolved its
 // query and stores the triangle; idle lanes are refilled from the work list.  Lanes therefore stay converged on the row step
 // whatever the length of their own descent.
-// SMALL (pass 1): only triangles that stay within 32 px of vertex a with circumradius <= 30 px -- the exact in-circle test
-// fits int32 and the chord estimate float32 (margin 0.05 px); everything else is deferred.  !SMALL (pass 1b): int64 / float64
-// (margin 1e-3 px), bounded by a row budget.  The estimate only proposes candidates; each is confirmed exactly.
+// Instantiated with SMALL = false only: int64 determinant, float64 chord estimate (margin 1e-3 px), bounded by a row budget
+// and a largest circumradius.  The estimate only proposes candidates; each is confirmed exactly.  (SMALL = true, an int32 /
+// float32 variant for circles of <= 30 px, is superseded by the window pass.)
 constexpr unsigned long long QRES_DONE = 1ull << 63;
 
 template <bool SMALL>
@@ -913,7 +915,7 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
         }
     };
 
-    // ---- G1. pass 1 (small circles) and pass 1b (any circle, bounded work): one query per lane ---------------------------
+    // ---- G0 / G1. window pass (small triangles), then the per-lane row scan (bounded work): one query per lane -------------
     for (int i = tid; i < nwords; i += IMAGE_NT) defer[i] = 0u;
     __syncthreads();
     mark(18);

@@ -421,6 +421,41 @@ def test_edge_empty_cloud_returns_none():
     assert render_bev_image(BEVParams(), np.zeros((0, 6)), False) is None
 
 
+def test_edge_batch_with_empty_and_degenerate_panos_through_every_layout():
+    """A batch never aborts: a pano whose points all fall outside the BEV box gives status EMPTY (the reference returns None,
+    bev_rendering_utils.py:279-280 / (None, None) :457-458), one with < 4 sites gives DEGENERATE (all-zero image,
+    interpolation_utils.py:37-42); both survive the de-duplicated, the plain and the compact layouts identically."""
+    from salve_b200.renderer import IMG_DEGENERATE, IMG_EMPTY, BevRenderer
+
+    H, W = 512, 1024
+    rgb0, d0 = synth.synth_pano(H, W, 70, "iid")
+    far = np.full((H, W), 60000, np.uint16)  # 60 m: every point is outside the 10 m box
+    few = np.full((H, W), 60000, np.uint16)
+    few[420:423, 100] = 1800  # three floor points only (rows 432.. are cropped)
+    r = BevRenderer(max_panos=3, max_images=6)
+    r.upload_pano(0, rgb0, d0); r.upload_pano(1, rgb0, far); r.upload_pano(2, rgb0, few)
+    Rm = np.stack([synth.synth_pose(k)[0] for k in range(4)]); t = np.stack([synth.synth_pose(k)[1] * 0 for k in range(4)])
+    p1, p2 = [0, 0, 1, 2], [1, 2, 0, 0]
+    r.set_dedup_unposed(False)
+    ref, cref, sref = r.render_hypotheses(p1, p2, Rm, t)
+    assert (sref[0, :, 1] == IMG_EMPTY).all() and (sref[2, :, 0] == IMG_EMPTY).all() and sref[0, 0, 0] == 0
+    assert sref[1, 0, 1] == IMG_DEGENERATE and not ref[1, 0, 1].any() and cref[1, 0, 1, 2] == 3
+    assert not ref[0, 0, 1].any()
+    r.set_dedup_unposed(True)
+    a, ca, sa = r.render_hypotheses(p1, p2, Rm, t)
+    assert np.array_equal(a, ref) and np.array_equal(sa, sref) and np.array_equal(ca[..., :6], cref[..., :6])
+    posed, unposed, idx, cp, cu, sp, su = r.render_hypotheses_compact(p1, p2, Rm, t, surfaces=("floor",))
+    for h in range(4):
+        assert np.array_equal(posed[h, 0], ref[h, 0, 0]) and np.array_equal(unposed[idx[h], 0], ref[h, 0, 1])
+        assert sp[h, 0] == sref[h, 0, 0] and su[idx[h], 0] == sref[h, 0, 1]
+    # nothing to do is not an error
+    e, ce, se = r.render_hypotheses([], [], np.zeros((0, 2, 2), np.float32), np.zeros((0, 2), np.float32))
+    assert e.shape[0] == 0
+    pe = r.render_hypotheses_compact([], [], np.zeros((0, 2, 2), np.float32), np.zeros((0, 2), np.float32))
+    assert pe[0].shape[0] == 0 and pe[1].shape[0] == 0
+    r.close()
+
+
 def test_edge_degenerate_clouds_render_zero():
     from salve_b200.common.bevparams import BEVParams
     from salve_b200.utils.bev_rendering_utils import render_bev_image
