@@ -237,7 +237,7 @@ def run_ours(args):
     rgbs, depths, p1, p2, R, t = synth.synth_building(N_PANOS, N_HYP, PANO_H, PANO_W, seed=rank)
     n_img = N_HYP * 4
     dev_chunk = int(os.environ.get("BENCH_DEV_CHUNK", "1480"))  # images per internal chunk (10 per SM): one launch per step
-    e2e_chunk = int(os.environ.get("BENCH_E2E_CHUNK", "296"))   # host path: smaller chunks so that D2H overlaps rendering
+    e2e_chunk = int(os.environ.get("BENCH_E2E_CHUNK", "444"))   # host path: smaller chunks so that D2H overlaps rendering
     r = BevRenderer(pano_h=PANO_H, pano_w=PANO_W, max_panos=N_PANOS, max_images=dev_chunk, device=local)
     stream = torch.cuda.current_stream(dev)
     sh = stream.cuda_stream
