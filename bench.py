@@ -159,31 +159,79 @@ def workload_config(n_gpus: int):
 # clocks sampler
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md "clocks" line).
+
+    Samples NVML in-process every few ms (`nvidia-smi -lms` needs ~1 s to produce its first row, longer than a
+    default timed region); falls back to the nvidia-smi loop of the recipe if NVML cannot be loaded."""
+
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index: int):
-        self.index = index
-        self.rows = []
-        self.proc = None
+    def __init__(self, index: int, uuid: str | None = None, period_s: float = 0.004):
+        self.index, self.uuid, self.period = index, uuid, period_s
+        self.sm, self.reasons, self.mx = [], set(), None
+        self.rows, self.proc, self.th, self.nv, self.h = [], None, None, None, None
+        self._stop = threading.Event()
+        self.source = None
 
     def start(self):
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = None
+            if self.uuid:
+                try:
+                    h = nv.nvmlDeviceGetHandleByUUID(self.uuid if self.uuid.startswith("GPU-") else "GPU-" + self.uuid)
+                except Exception:
+                    h = None
+            if h is None:
+                h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.nv, self.h = nv, h
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.source = "nvml"
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nv = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
             )
+            self.source = "nvidia-smi"
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        nv, h = self.nv, self.h
+        names = [("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap)]
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                for n, b in names:
+                    if bits & b:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self.nv is not None:
+            self._stop.set()
+            self.th.join(timeout=2)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_min_mhz": min(self.sm) if self.sm else None,
+                    "sm_max_mhz": self.mx, "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml"}
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -207,6 +255,7 @@ class ClockSampler:
             "sm_max_mhz": max(mx) if mx else None,
             "reasons": sorted(reasons),
             "samples": len(sm),
+            "source": "nvidia-smi",
         }
 
 
@@ -266,7 +315,7 @@ def run_ours(args):
 
     # ---- `value`: K timed steps, CUDA events on the launching stream, L2 flush between ------------
     r.enable_timing(True)
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, uuid=str(torch.cuda.get_device_properties(local).uuid))
     if rank == 0:
         sampler.start()
     launches0 = r.launch_count()
@@ -457,7 +506,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -82,7 +82,8 @@ class SalveBevError(RuntimeError):
 
 
 def lib_path() -> str:
-    return _build.LIB_PATH
+    # SALVE_BEV_LIB: developer override used by scripts/variant_bench.py to time differently compiled builds of the same sources
+    return os.environ.get("SALVE_BEV_LIB") or _build.LIB_PATH
 
 
 def load():

@@ -33,20 +33,22 @@ def needs_build() -> bool:
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str | None = None) -> str:
+    """`defines` / `out`: developer variants (e.g. -DIMAGE_NT=256 into scratch/lib_nt256.so) for scripts/variant_bench.py."""
+    out = out or LIB_PATH
+    if out == LIB_PATH and not force and not needs_build():
         return LIB_PATH
-    cmd = [_nvcc(), *NVCC_FLAGS]
+    cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines]]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB_PATH]
+    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-o", out]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
         raise RuntimeError("nvcc failed building libsalve_bev.so")
     if verbose:
         sys.stderr.write(res.stdout + res.stderr)
-    return LIB_PATH
+    return out
 
 
 if __name__ == "__main__":

@@ -62,6 +62,7 @@ struct salve_bev_ctx {
     long long* phase_clk = nullptr;      // diagnostics: 24 slots per image of the last chunk
     uint32_t* keepbits = nullptr;        // per CTA slot keep-mask bit rows of image_kernel
     int32_t* work_counter = nullptr;     // image_kernel's dynamic image counter
+    int32_t* d_order = nullptr;          // image_kernel's hand-out order (image_order_kernel)
     int image_slots = 0;                 // persistent CTAs of image_kernel (scratch slots)
     // hypothesis-independent (un-posed pano 2) renders of the current call: max_panos x 2 surfaces
     uint8_t* cache_out = nullptr; int32_t* cache_counts = nullptr; int32_t* cache_status = nullptr;
@@ -181,6 +182,7 @@ extern "C" int salve_bev_ctx_create(const salve_bev_config* cfg, salve_bev_ctx**
     ALLOC(c->phase_clk, N * 24);
     ALLOC(c->keepbits, (size_t)c->image_slots * c->bits_stride);
     ALLOC(c->work_counter, 1);
+    ALLOC(c->d_order, N);
     ALLOC(c->cache_out, 2 * P * c->img_bytes + 64);  // +64: replicate_images_kernel reads whole words
     ALLOC(c->cache_counts, 2 * P * 8);
     ALLOC(c->cache_status, 2 * P);
@@ -242,7 +244,7 @@ extern "C" void salve_bev_ctx_destroy(salve_bev_ctx* c) {
     cudaSetDevice(c->cfg.device);
     cudaDeviceSynchronize();
     void* ptrs[] = {c->pano_rgb_store, c->pano_rgb2x_store, c->pano_depth_store, c->d_depth_ptr, c->d_tables, c->keygrid, c->color, c->occ, c->nonempty,
-                    c->keep, c->tmpbits, c->wprefix, c->tris, c->owner, c->list0, c->list1, c->cand, c->qlist, c->qres, c->phase_clk, c->keepbits, c->work_counter, c->cache_out, c->cache_counts, c->cache_status, c->d_dest, c->headers, c->counts,
+                    c->keep, c->tmpbits, c->wprefix, c->tris, c->owner, c->list0, c->list1, c->cand, c->qlist, c->qres, c->phase_clk, c->keepbits, c->work_counter, c->d_order, c->cache_out, c->cache_counts, c->cache_status, c->d_dest, c->headers, c->counts,
                     c->status, c->d_jobs, c->d_color_src, c->out_store};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < N_TMP; i++) if (c->tmp[i]) cudaFree(c->tmp[i]);
@@ -379,6 +381,13 @@ static int run_image_stage(salve_bev_ctx* c, int n_img, const GridParams& G, con
     IA.G = G;
     IA.n_img = n_img; IA.work_counter = c->work_counter;
     CU(cudaMemsetAsync(c->work_counter, 0, sizeof(int32_t), st));
+    IA.order = nullptr;
+    if (n_img > c->image_slots && n_img <= c->cfg.max_images && n_img <= 16384) {  // more images than CTAs: longest expected first
+        image_order_kernel<<<(n_img + 255) / 256, 256, 0, st>>>(dev_counts, n_img, c->d_order);
+        c->launches++;
+        CU(cudaGetLastError());
+        IA.order = c->d_order;
+    }
     IA.keygrid = keygrid; IA.keygrid_stride = c->g_stride;
     IA.color_src = color_src; IA.pano_w = c->cfg.pano_w;
     IA.counts = dev_counts; IA.status = dev_status;

@@ -35,17 +35,27 @@
 
 namespace bev {
 
-constexpr int IMAGE_NT = 512;
+#ifndef IMAGE_NT
+#define IMAGE_NT_DEF 512
+#else
+#define IMAGE_NT_DEF IMAGE_NT
+#undef IMAGE_NT
+#endif
+constexpr int IMAGE_NT = IMAGE_NT_DEF;
+#ifndef IMAGE_COOP_MIN_BAND
+#define IMAGE_COOP_MIN_BAND 4
+#endif
+#ifndef IMAGE_COOP_BAND_DIV
+#define IMAGE_COOP_BAND_DIV 2
+#endif
 constexpr int SITES_BATCH = 8;
 constexpr int IMAGE_MAX_FLIPS = 100000;  // safety cap on one descent (never reached: the lift is strictly monotone)
-constexpr int IMAGE_MAX_GAP_B = 64;      // pass G1: widest row gap (nearest site left to nearest site right),
-constexpr int IMAGE_ROW_BUDGET_B = 160;  //   rows + flips per query,
-constexpr double IMAGE_MAX_R_B = 12.0;   //   largest circumradius (px); what is left goes to the cooperative pass
 
 struct ImageArgs {
     GridParams G;
     int32_t n_img;                    // images of this launch; CTAs are persistent and take images from *work_counter
     int32_t* work_counter;            // zeroed by the host before the launch
+    const int32_t* order;             // k-th image to hand out (longest expected first), or null: k
     const uint32_t* keygrid; size_t keygrid_stride;
     const uint8_t* const* color_src;  // per image: u8 rgb triples indexed by the key's source index (tagged, see gather_rgb)
     int32_t pano_w;                   // width of the key's index space (for tagged full-resolution sources)
@@ -167,157 +177,7 @@ __device__ __forceinline__ bool init_tri_hull(const ImageShared& S, int x, int r
     return false;
 }
 
-// ---- pass G1: one query pixel per LANE, as a state machine ----------------------------------------------------------------
-// Every trip of the loop, each active lane examines ONE row of its current circumcircle scan (rows outward from the query:
-// r, r+1, r-1, r+2, ...).  A lane that finds a violator flips and restarts its scan; a lane whose scan ends has resolved its
-// query and stores the triangle; idle lanes are refilled from the work list.  Lanes therefore stay converged on the row step
-// whatever the length of their own descent.
-// Instantiated with SMALL = false only: int64 determinant, float64 chord estimate (margin 1e-3 px), bounded by a row budget
-// and a largest circumradius.  The estimate only proposes candidates; each is confirmed exactly.  (SMALL = true, an int32 /
-// float32 variant for circles of <= 30 px, is superseded by the window pass.)
 constexpr unsigned long long QRES_DONE = 1ull << 63;
-
-template <bool SMALL>
-__device__ __forceinline__ void resolve_pass(const ImageShared& S, int wpr, int W, int H, const uint32_t* __restrict__ qlist,
-                                             unsigned long long* __restrict__ qres, int n, int* s_next, uint32_t* defer, int max_gap,
-                                             int row_budget, int lane, int& my_flips, int& my_maxflips) {
-    typedef typename std::conditional<SMALL, float, double>::type real;
-    typedef typename std::conditional<SMALL, int, long long>::type exact;
-    const unsigned FULL = 0xffffffffu;
-    const real margin = SMALL ? (real)0.05 : (real)1e-3, neg_tol = SMALL ? (real)-0.5 : (real)-1e-6;
-    bool active = false, exhausted = false;
-    int x = 0, r = 0, idx = 0, k = 0, budget = 0, flips = 0;
-    bool down = false, up_ok = true, dn_ok = true;
-    Tri2 t = {0, 0, 0, 0, 0, 0};
-    real ux2 = 0, uy2 = 0, cxa = 0;
-    exact eA2 = 1, eU = 0, eV = 0;
-    uint32_t va = 0, vb = 0, vc = 0;
-    int wa = 0, wb = 0, wc = 0;
-
-    // circle of the current triangle; false: not a triangle this pass handles
-    auto setup = [&]() -> bool {
-        const int bx = t.bx - t.ax, by = t.by - t.ay, cx = t.cx - t.ax, cy = t.cy - t.ay;
-        if (SMALL && max(max(abs(bx), abs(by)), max(abs(cx), abs(cy))) > 32) return false;
-        const exact b2 = (exact)bx * bx + (exact)by * by, c2 = (exact)cx * cx + (exact)cy * cy;
-        eA2 = (exact)bx * cy - (exact)by * cx;  // > 0
-        // in-circle determinant of d = a + (dx, dy):  inc = eU*dx + eV*dy - eA2*(dx^2+dy^2)   (> 0: strictly inside)
-        eU = b2 * cy - by * c2; eV = bx * c2 - b2 * cx;
-        if (SMALL) {
-            const float fu = (float)eU, fv = (float)eV, fa = (float)eA2;
-            if (fu * fu + fv * fv > 3600.0f * fa * fa) return false;  // circumradius^2 = (U^2+V^2) / (4 A2^2) > 30^2
-        } else {
-            // a lane walks one row per trip: circles taller than ~one warp of rows are cheaper in the cooperative pass,
-            // which scans 32 rows per trip and shares the triangle it ends in among all the pixels inside it
-            const double fu = (double)eU, fv = (double)eV, fa = (double)eA2;
-            if (fu * fu + fv * fv > (4.0 * IMAGE_MAX_R_B * IMAGE_MAX_R_B) * fa * fa) return false;
-        }
-        const real inv = (real)1 / (real)eA2;
-        const real ux = (real)0.5 * (real)eU * inv;
-        uy2 = (real)eV * inv; ux2 = ux * ux; cxa = (real)t.ax + ux;
-        va = vlabel(t.ay, t.ax); vb = vlabel(t.by, t.bx); vc = vlabel(t.cy, t.cx);
-        wa = (int)pert_weight(va, W); wb = (int)pert_weight(vb, W); wc = (int)pert_weight(vc, W);
-        k = 0; down = false; up_ok = true; dn_ok = true;
-        return true;
-    };
-    auto give_up = [&]() {  // hand the query to the next pass
-        atomicOr(&defer[r * wpr + (x >> 5)], 1u << (x & 31));
-        qres[idx] = 0ull;
-        active = false;
-    };
-
-    while (true) {
-        // ---- refill idle lanes
-        const unsigned idle = __ballot_sync(FULL, !active);
-        if (idle && !exhausted && (__popc(idle) >= 8 || idle == FULL)) {
-            const int leader = __ffs(idle) - 1;
-            int base = 0;
-            if (lane == leader) base = atomicAdd(s_next, __popc(idle));
-            base = __shfl_sync(FULL, base, leader);
-            if (base + __popc(idle) >= n) exhausted = true;
-            if (!active) {
-                const int i = base + __popc(idle & ((1u << lane) - 1u));
-                if (i < n) {
-                    const uint32_t code = qlist[i];
-                    x = (int)(code & COL_MASK); r = (int)(code >> COL_BITS); idx = i;
-                    active = true; budget = row_budget; flips = 0;
-                    bool ok = S.cnt[r] > 1 && x > S.first[r] && x < S.last[r] && init_tri_row(S, wpr, W, x, r, t);
-                    if (ok) ok = abs(t.bx - t.ax) <= max_gap;
-                    if (ok) ok = setup();
-                    if (!ok) give_up();
-                }
-            }
-        }
-        if (!__any_sync(FULL, active)) { if (exhausted) break; continue; }
-        if (!active) continue;
-
-        // ---- one row of the scan
-        const int y = down ? r - k : r + k;
-        bool dead = false;
-        int vx = -1;
-        if (y < 0 || y >= H) dead = true;
-        else {
-            const real dyr = (real)(y - t.ay);
-            const real tt = ux2 + dyr * (uy2 - dyr);  // squared half chord of the circle on this row
-            if (tt < neg_tol) dead = true;
-            else {
-                const real hw = sqrt(max(tt, (real)0)) + margin;
-                // circle (with margin) and hull are convex and both contain q: once a row misses their intersection, so do
-                // all rows beyond it.  This bounds the scan of the huge circumcircles of flat triangles along the hull.
-                const real lo = max(cxa - hw, (real)S.hlf[y] - (real)1e-2), hi = min(cxa + hw, (real)S.hrf[y] + (real)1e-2);
-                if (!(lo <= hi)) dead = true;
-                else {
-                    const int x0 = (int)ceil(lo), x1 = (int)floor(hi);
-                    if (x0 <= x1) {
-                        const uint32_t* row = S.occ + y * wpr;
-                        int pl = prev_bit(row, min(x, x1), x0);
-                        int pr = next_bit(row, max(x + 1, x0), x1);
-                        while (pl >= 0 || pr >= 0) {
-                            const bool take_l = pr < 0 || (pl >= 0 && x - pl <= pr - x);
-                            const int cxx = take_l ? pl : pr;
-                            const uint32_t vd = vlabel(y, cxx);
-                            if (vd != va && vd != vb && vd != vc) {
-                                const exact dx = cxx - t.ax, dy = y - t.ay;
-                                const exact inc = eU * dx + eV * dy - eA2 * (dx * dx + dy * dy);
-                                if (inc > 0) { vx = cxx; break; }
-                                if (inc == 0) {  // co-circular: symbolic perturbation, same rule as incircle_pert()
-                                    const long long pert = (long long)wa * orient_v(vb, vc, vd) - (long long)wb * orient_v(va, vc, vd) +
-                                                           (long long)wc * orient_v(va, vb, vd) - pert_weight(vd, W) * (long long)eA2;
-                                    if (pert > 0) { vx = cxx; break; }
-                                }
-                            }
-                            if (take_l) pl = prev_bit(row, cxx - 1, x0); else pr = next_bit(row, cxx + 1, x1);
-                        }
-                    }
-                }
-            }
-        }
-        if (vx >= 0) {
-            // Lawson flip inside {a,b,c,d}: keep the new triangle that contains q
-            bool ok = true;
-            if (ccw_contains(vx, y, t.bx, t.by, t.cx, t.cy, x, r)) { t.ax = vx; t.ay = y; }
-            else if (ccw_contains(t.ax, t.ay, vx, y, t.cx, t.cy, x, r)) { t.bx = vx; t.by = y; }
-            else if (ccw_contains(t.ax, t.ay, t.bx, t.by, vx, y, x, r)) { t.cx = vx; t.cy = y; }
-            else ok = false;  // cannot happen (d is inside the triangle or across exactly one edge)
-            flips++;
-            if (!ok || !setup() || --budget < 0) give_up();
-            continue;
-        }
-        if (dead) { if (down) dn_ok = false; else up_ok = false; }
-        if (!up_ok && !dn_ok) {  // scan complete: t is the triangle of the canonical triangulation over q
-            qres[idx] = QRES_DONE | (unsigned long long)va | ((unsigned long long)vb << 21) | ((unsigned long long)vc << 42);
-            my_flips += flips; my_maxflips = max(my_maxflips, flips);
-            active = false;
-            continue;
-        }
-        if (--budget < 0) { give_up(); continue; }
-        // next row: r, r+1, r-1, r+2, r-2, ... skipping finished directions
-        do {
-            if (k == 0) { k = 1; down = false; }
-            else if (!down) down = true;
-            else { k++; down = false; }
-        } while (down ? !dn_ok : !up_ok);
-    }
-}
 
 __device__ __forceinline__ float sqrt_approx(float v) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
 
@@ -587,6 +447,22 @@ __device__ __forceinline__ int coop_find_violator(const uint32_t* __restrict__ o
     }
 }
 
+// Hand-out order of a chunk's images: longest expected first, so that the launch does not end with a few CTAs working on long
+// images while the rest of the GPU idles (durations vary 6x; measured makespan 10.2 -> 8.4 ms on 1 358 images / 296 CTAs).
+// The predictor is the crop count the splat has already produced (points inside the height band): panos that see more floor or
+// ceiling give larger, sparser footprints, hence more queries.  rank = number of images that come first (ties by index).
+__global__ void __launch_bounds__(256) image_order_kernel(const int32_t* __restrict__ counts, int n, int32_t* __restrict__ order) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int key = counts[i * 8];
+    int rank = 0;
+    for (int j = 0; j < n; j++) {
+        const int kj = __ldg(counts + j * 8);
+        rank += (kj > key || (kj == key && j < i)) ? 1 : 0;
+    }
+    order[rank] = i;
+}
+
 __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
     const int slot = blockIdx.x;  // scratch slot of this (persistent) CTA
     const int h = A.G.grid_h, w = A.G.grid_w, wpr = A.G.wpr;
@@ -610,12 +486,16 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
     }
     __shared__ int s_S, s_M, s_mincol, s_maxcol, s_ne_cnt, s_keep_cnt, s_nitems, s_next, s_filled, s_flips, s_maxflips, s_hull_ok, s_img;
 
-  for (;;) {  // images are handed out dynamically: their cost varies by 3x
+  // Images are handed out dynamically (their cost varies by 3x).  Thread 0 claims the next index while the CTA finishes the
+  // current image (stage H), so that the round trip of the atomic is not paid at the hand-over barrier.
+  int next_img = 0;
+  if (tid == 0) next_img = atomicAdd(A.work_counter, 1);
+  for (;;) {
     __syncthreads();  // the previous image is finished by every thread (shared state is reused)
-    if (tid == 0) s_img = atomicAdd(A.work_counter, 1);
+    if (tid == 0) s_img = next_img;
     __syncthreads();
-    const int img = s_img;
-    if (img >= A.n_img) break;
+    if (s_img >= A.n_img) break;
+    const int img = A.order ? A.order[s_img] : s_img;
     const uint32_t* keygrid = A.keygrid + (size_t)img * A.keygrid_stride;
     const uint8_t* csrc = A.color_src[img];
     const int dst = A.dest ? A.dest[img] : img;
@@ -627,7 +507,11 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
     long long* pclk = A.phase_clk ? A.phase_clk + (size_t)img * 24 : nullptr;
     auto mark = [&](int k) { if (pclk && tid == 0) pclk[k] = clock64(); };
     mark(0);
-    if (pclk && tid == 0) pclk[15] = 0;  // pass 2: descents << 40 | waves << 20 | flips
+    if (pclk && tid == 0) {
+        pclk[15] = 0;  // cooperative pass: descents << 40 | waves << 20 | flips
+        unsigned long long ns; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+        pclk[19] = (long long)ns; pclk[21] = slot; pclk[23] = dst; pclk[4] = counts[0]; pclk[5] = counts[1];
+    }
 
     if (tid == 0) {
         s_S = 0; s_M = 0; s_mincol = 1 << 30; s_maxcol = -1; s_ne_cnt = 0; s_keep_cnt = 0; s_nitems = 0; s_next = 0;
@@ -698,7 +582,7 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
     }
 
     // ---- C. exact convex hull from the per-row first / last sites: two monotone chains (warps 0 and 1) ---------------
-    // Lane 0 builds the chain (serial, one step per non-empty row); the whole warp then fills the per-row bounds edge by edge.
+    // The warp pre-filters the rows, lane 0 builds the chain from the survivors; the whole warp then fills the per-row bounds edge by edge.
     __syncthreads();
     if (status == 0 && warp < 2) {
         const bool left = warp == 0;
@@ -708,10 +592,34 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
         int16_t* stk = left ? S.stk_l : S.stk_r;
         int16_t* bound = left ? S.hlo : S.hhi;
         float* bf = left ? S.hlf : S.hrf;
+        // Parallel pre-filter: a row's extreme site that lies on or inside the segment between the extreme sites of two other
+        // rows (here: the rows at distance 1, 2, 4, ... on either side) is not a strict vertex of this chain.  What survives
+        // (the corners and a few dozen rows of a ragged wall) goes to the serial monotone-chain scan in row order.
+        int16_t* cand = e0;  // free until the fill below
+        int ncand = 0;
+        for (int r0 = 0; r0 < h; r0 += 32) {
+            const int r = r0 + lane;
+            bool alive = r < h && S.cnt[r] > 0;
+            if (alive) {
+                const int x = xs[r];
+                for (int d = 1; d < h && alive; d <<= 1) {
+                    const int ra = r - d, rb = r + d;
+                    if (ra < 0 || rb >= h) break;
+                    if (S.cnt[ra] > 0 && S.cnt[rb] > 0) {
+                        const int o = orient_i(xs[ra], ra, x, r, xs[rb], rb);
+                        if (left ? (o >= 0) : (o <= 0)) alive = false;
+                    }
+                }
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, alive);
+            if (alive) cand[ncand + __popc(m & ((1u << lane) - 1u))] = (int16_t)r;
+            ncand += __popc(m);
+        }
+        __syncwarp();
         int top = 0;
         if (lane == 0) {
-            int r = S.cnt[0] > 0 ? 0 : S.up[0];
-            while (r >= 0) {
+            for (int i = 0; i < ncand; i++) {
+                const int r = cand[i];
                 const int x = xs[r];
                 while (top >= 2) {
                     const int r1 = stk[top - 1], r0 = stk[top - 2];
@@ -720,7 +628,6 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
                     if (left ? (o >= 0) : (o <= 0)) top--; else break;
                 }
                 stk[top++] = (int16_t)r;
-                r = S.up[r];
             }
             if (top <= 2) atomicAdd(&s_hull_ok, left ? 1 : 2);  // this chain has no interior vertex
         }
@@ -780,6 +687,7 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
     }
     if (tid == 0) {
         counts[2] = nS; counts[3] = s_ne_cnt; counts[4] = raw ? 0 : s_keep_cnt;
+        if (pclk) pclk[22] = nS;
     }
 
     mark(2);
@@ -925,22 +833,9 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
     mark(16);
     if (status == 0) shade(s_nitems);
     __syncthreads();
-    if (tid == 0) { s_nitems = 0; s_next = 0; }
-    __syncthreads();
-    if (status == 0) build_list(defer, true);
-    __syncthreads();
-    mark(3); mark(4); mark(5);
-    if (pclk && tid == 0) pclk[12] = 0;
-    mark(6);
-    if (pclk && tid == 0) pclk[13] = s_nitems;
-    if (status == 0) resolve_pass<false>(S, wpr, w, h, qlist, qres, s_nitems, &s_next, defer, IMAGE_MAX_GAP_B, IMAGE_ROW_BUDGET_B, lane, my_flips, my_maxflips);
-    __syncthreads();
-    mark(7);
-    if (status == 0) shade(s_nitems);
-    __syncthreads();
-    mark(8);
-
-    // ---- G2. pass 2: what is left (hull pockets, wide gaps, long descents), one warp per query ---------------------------
+    mark(3);
+    // ---- G2. cooperative pass: what the window pass handed on (hull pockets, wide gaps, the hole under the camera), one warp
+    // per query ----------------------------------------------------------------------------------------------------------
     // The final triangle of a descent is rasterised over ALL deferred pixels it contains (they share it), which are then
     // taken off the list: a big triangle across a hole is found about once instead of once per pixel.  Warps take
     // row-major bands of the list, so that the pixels of one triangle mostly meet the same warp.
@@ -952,11 +847,16 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
     if (pclk && tid == 0) pclk[14] = s_nitems;
     if (status == 0) {
         const int n = s_nitems;
-        const int band = max(16, (n + 4 * NW - 1) / (4 * NW));
+        // guided self-scheduling: bands shrink with what is left (long row-major bands first, so that the pixels of one
+        // triangle mostly meet the same warp; short ones at the end, so that no warp is left alone with a long band)
         while (true) {
-            int i0 = 0;
-            if (lane == 0) i0 = atomicAdd(&s_next, band);
-            i0 = __shfl_sync(0xffffffffu, i0, 0);
+            int i0 = 0, band = 0;
+            if (lane == 0) {
+                const int seen = *(volatile int*)&s_next;
+                band = min(max(IMAGE_COOP_MIN_BAND, (n - seen) / (IMAGE_COOP_BAND_DIV * NW)), max(n - seen, 1));
+                i0 = atomicAdd(&s_next, band);
+            }
+            i0 = __shfl_sync(0xffffffffu, i0, 0); band = __shfl_sync(0xffffffffu, band, 0);
             if (i0 >= n) break;
             const int i_end = min(n, i0 + band);
           for (int i = i0; i < i_end; i++) {
@@ -998,6 +898,7 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
     __syncthreads();
 
     mark(10);
+    if (tid == 0) next_img = atomicAdd(A.work_counter, 1);  // consumed at the hand-over
     // ---- H. masked-out sites, degenerate images, counters ------------------------------------------------------------
     if (status == 1 || status == 2) {
         // the reference returns None (empty) or an all-zero interpolation (degenerate): clear the site colours
@@ -1031,7 +932,11 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
     __syncthreads();
     if (tid == 0) {
         counts[5] = s_filled; counts[6] = s_maxflips; counts[7] = s_flips;
-        if (pclk) pclk[11] = clock64();
+        if (pclk) {
+            pclk[11] = clock64();
+            unsigned long long ns; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+            pclk[20] = (long long)ns;
+        }
         if (status_final) *status_final = status;
         if (counts_final) {
 #pragma unroll
