@@ -230,10 +230,12 @@ extern "C" int salve_bev_ctx_create(const salve_bev_config* cfg, salve_bev_ctx**
     CU(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
     c->image_smem = image_smem_bytes(c->G.grid_h, c->G.wpr);
     {
-        cudaFuncAttributes fa;
-        CU(cudaFuncGetAttributes(&fa, image_kernel));
-        c->max_smem_optin -= (int)fa.sharedSizeBytes;  // what is left for dynamic shared memory
-        CU(cudaFuncSetAttribute(image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
+        cudaFuncAttributes fa, fb;
+        CU(cudaFuncGetAttributes(&fa, image_kernel<true>));
+        CU(cudaFuncGetAttributes(&fb, image_kernel<false>));
+        c->max_smem_optin -= (int)std::max(fa.sharedSizeBytes, fb.sharedSizeBytes);  // what is left for dynamic shared memory
+        CU(cudaFuncSetAttribute(image_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
+        CU(cudaFuncSetAttribute(image_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
     }
     *out = c;
     return SALVE_BEV_OK;
@@ -399,7 +401,9 @@ static int run_image_stage(salve_bev_ctx* c, int n_img, const GridParams& G, con
     IA.bits = bits; IA.bits_stride = 3 * (size_t)G.grid_h * G.wpr;
     IA.qlist = c->qlist; IA.qlist_stride = c->g_stride; IA.qres = c->qres; IA.keepbits = c->keepbits; IA.keepbits_stride = c->bits_stride; IA.phase_clk = (n_img <= c->cfg.max_images && keygrid == c->keygrid) ? c->phase_clk : nullptr;
     IA.raw_mode = raw_mode; IA.skip_empty_check = skip_empty;
-    image_kernel<<<std::min(n_img, c->image_slots), IMAGE_NT, smem, st>>>(IA);
+    // grids of up to 512 x 512 pixels (the reference's 501 x 501 included) take the instantiation with int32 circle parameters
+    if (G.grid_h <= 512 && G.grid_w <= 512) image_kernel<true><<<std::min(n_img, c->image_slots), IMAGE_NT, smem, st>>>(IA);
+    else image_kernel<false><<<std::min(n_img, c->image_slots), IMAGE_NT, smem, st>>>(IA);
     c->launches++;
     CU(cudaGetLastError());
     return stage_event(c, st);

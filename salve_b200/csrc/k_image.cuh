@@ -197,6 +197,7 @@ __device__ __forceinline__ void resolve_window(const ImageShared& S, int wpr, in
                                                unsigned long long* __restrict__ qres, int n, int* s_next, uint32_t* defer, int lane,
                                                int& my_flips, int& my_maxflips) {
     constexpr int NROW = 2 * NR + 1;
+    static_assert(NROW * 9 <= 64, "on-circle candidates are packed 9 bits per row into one 64-bit word");
     constexpr int MAXGAP = 14, MAXFLIPS = 16;
     const unsigned FULL = 0xffffffffu;
     bool active = false, exhausted = false;
@@ -333,34 +334,27 @@ __device__ __forceinline__ void resolve_window(const ImageShared& S, int wpr, in
         if (!have) {
             // ---- empty circle: sites ON it decide by the symbolic perturbation (same rule as incircle_pert(), in window
             // coordinates: weights < 2^20, |orient| <= 2 * 31 * 6, so int32 holds every term and the sum)
-            uint32_t any = 0u;
+            // The circle fits (R < 4), so an on-circle site has |dx - rint(ccx)| <= 4: 9 bits per row, NROW rows in one 64-bit
+            // word, rows in scan order.
+            const int icx = __float2int_rn(ccx);
+            unsigned long long cand = 0ull;
 #pragma unroll
-            for (int k = 0; k < NROW; k++) any |= on[k];
-            if (any) {
+            for (int k = 0; k < NROW; k++) cand |= (unsigned long long)((uint32_t)(((unsigned long long)on[k] << 4) >> (icx + 16)) & 0x1FFu) << (9 * k);
+            if (cand) {
                 const int wa = (int)pert_weight(vlabel(r + ay, x + ax), W), wb = (int)pert_weight(vlabel(r + by, x + bx), W),
                           wc = (int)pert_weight(vlabel(r + cy, x + cx), W);
-                while (any && !have) {
-                    // next candidate: first non-empty row in scan order
-                    uint32_t m = 0u; int yy = 0;
-#pragma unroll
-                    for (int k = NROW - 1; k >= 0; k--)
-                        if (on[k]) { m = on[k]; yy = (k == 0) ? 0 : ((k & 1) ? (k + 1) / 2 : -(k / 2)); }
-                    const int b = __ffs(m) - 1;
-                    const int ddx = b - 16;
-#pragma unroll
-                    for (int k = 0; k < NROW; k++) {
-                        const int yk = (k == 0) ? 0 : ((k & 1) ? (k + 1) / 2 : -(k / 2));
-                        if (yk == yy) on[k] &= on[k] - 1u;
-                    }
+                while (cand && !have) {
+                    const int b = __ffsll((long long)cand) - 1;
+                    cand &= cand - 1ull;
+                    const int k = (b * 57) >> 9;  // b / 9 for b < 63
+                    const int ddx = b - 9 * k - 4 + icx;
+                    const int yy = (k & 1) ? (k + 1) >> 1 : -(k >> 1);
                     const int wd = (int)pert_weight(vlabel(r + yy, x + ddx), W);
                     const int obcd = (cx - bx) * (yy - by) - (cy - by) * (ddx - bx);
                     const int oacd = (cx - ax) * (yy - ay) - (cy - ay) * (ddx - ax);
                     const int oabd = (bx - ax) * (yy - ay) - (by - ay) * (ddx - ax);
                     const int pert = wa * obcd - wb * oacd + wc * oabd - wd * A2;
                     if (pert > 0) { have = true; dx = ddx; dy = yy; }
-                    any = 0u;
-#pragma unroll
-                    for (int k = 0; k < NROW; k++) any |= on[k];
                 }
             }
             const uint32_t va = vlabel(r + ay, x + ax), vb = vlabel(r + by, x + bx), vc = vlabel(r + cy, x + cx);
@@ -371,11 +365,19 @@ __device__ __forceinline__ void resolve_window(const ImageShared& S, int wpr, in
                 continue;
             }
         }
-        // ---- Lawson flip inside {a, b, c, d}: keep the new triangle that contains q
-        if (contains0(dx, dy, bx, by, cx, cy)) { ax = dx; ay = dy; }
-        else if (contains0(ax, ay, dx, dy, cx, cy)) { bx = dx; by = dy; }
-        else if (contains0(ax, ay, bx, by, dx, dy)) { cx = dx; cy = dy; }
-        else { give_up(); continue; }  // cannot happen
+        // ---- Lawson flip inside {a, b, c, d}: keep the new triangle that contains q (the origin).  The three candidates
+        // (d,b,c), (a,d,c), (a,b,d) share six cross products; orient(p,q,s) = p x q + q x s + s x p.  No branches.
+        {
+            const int Xab = cross(ax, ay, bx, by), Xbc = cross(bx, by, cx, cy), Xca = cross(cx, cy, ax, ay);
+            const int Xad = cross(ax, ay, dx, dy), Xbd = cross(bx, by, dx, dy), Xcd = cross(cx, cy, dx, dy);
+            const bool fa = (-Xbd >= 0) & (Xbc >= 0) & (Xcd >= 0) & (Xbc + Xcd - Xbd > 0);
+            const bool fb = (Xad >= 0) & (-Xcd >= 0) & (Xca >= 0) & (Xad - Xcd + Xca > 0);
+            const bool fc = (Xab >= 0) & (Xbd >= 0) & (-Xad >= 0) & (Xab + Xbd - Xad > 0);
+            if (fa) { ax = dx; ay = dy; }
+            else if (fb) { bx = dx; by = dy; }
+            else if (fc) { cx = dx; cy = dy; }
+            else { give_up(); continue; }  // cannot happen
+        }
         if (++flips > MAXFLIPS) give_up();
     }
 }
@@ -383,12 +385,16 @@ __device__ __forceinline__ void resolve_window(const ImageShared& S, int wpr, in
 // ---- warp-cooperative versions for queries whose triangles are large (wide gaps, hull pockets) -------------------------
 // One lane per row of each 32-row wave (row offsets 0, -1, +1, -2, ... from qy).  Returns, in every lane, the violator
 // nearest to q found in the first wave that has one (x | y << 16), or -1.
+// SG (grid_h, grid_w <= 512): |U|, |V| <= 2 * (2 * 511^2) * 511 < 2^31, so the circle's integers are int32 and only the in-circle
+// determinant itself is widened (32 x 32 -> 64 bit multiplies); larger grids keep everything in int64.
+template <bool SG>
 __device__ __forceinline__ int coop_find_violator(const uint32_t* __restrict__ occ, const float* __restrict__ hlf, const float* __restrict__ hrf, int wpr,
                                                   int W, int H, const Tri2& t, int qx, int qy, int grid_w, int lane, int& waves) {
-    const long long bx = t.bx - t.ax, by = t.by - t.ay, cx = t.cx - t.ax, cy = t.cy - t.ay;
-    const long long b2 = bx * bx + by * by, c2 = cx * cx + cy * cy;
-    const long long A2 = bx * cy - by * cx;
-    const long long U = b2 * cy - by * c2, V = bx * c2 - b2 * cx;
+    typedef typename std::conditional<SG, int, long long>::type I;
+    const I bx = t.bx - t.ax, by = t.by - t.ay, cx = t.cx - t.ax, cy = t.cy - t.ay;
+    const I b2 = bx * bx + by * by, c2 = cx * cx + cy * cy;
+    const I A2 = bx * cy - by * cx;
+    const I U = b2 * cy - by * c2, V = bx * c2 - b2 * cx;
     const double inv = 1.0 / (double)A2;
     const double ux = 0.5 * (double)U * inv, uy2 = (double)V * inv, ux2 = ux * ux, cxa = (double)t.ax + ux;
     const uint32_t va = vlabel(t.ay, t.ax), vb = vlabel(t.by, t.bx), vc = vlabel(t.cy, t.cx);
@@ -422,11 +428,11 @@ __device__ __forceinline__ int coop_find_violator(const uint32_t* __restrict__ o
                                 const int x = take_l ? pl : pr;
                                 const uint32_t vd = vlabel(y, x);
                                 if (vd != va && vd != vb && vd != vc) {
-                                    const long long dx = x - t.ax, dy = y - t.ay;
-                                    const long long inc = U * dx + V * dy - A2 * (dx * dx + dy * dy);
+                                    const int dx = x - t.ax, dy = y - t.ay;
+                                    const long long inc = (long long)U * dx + (long long)V * dy - (long long)A2 * (long long)(dx * dx + dy * dy);
                                     if (inc > 0 || (inc == 0 && incircle_pert(va, vb, vc, vd, grid_w) > 0)) {
-                                        const long long ddx = x - qx, ddy = y - qy;
-                                        best = ((unsigned long long)(ddx * ddx + ddy * ddy) << 32) | (uint32_t)(x | (y << 16));
+                                        const int ddx = x - qx, ddy = y - qy;
+                                        best = ((unsigned long long)(uint32_t)(ddx * ddx + ddy * ddy) << 32) | (uint32_t)(x | (y << 16));
                                         break;
                                     }
                                 }
@@ -463,6 +469,7 @@ __global__ void __launch_bounds__(256) image_order_kernel(const int32_t* __restr
     order[rank] = i;
 }
 
+template <bool SG>
 __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
     const int slot = blockIdx.x;  // scratch slot of this (persistent) CTA
     const int h = A.G.grid_h, w = A.G.grid_w, wpr = A.G.wpr;
@@ -868,7 +875,7 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
             if (!(in_row ? init_tri_row(S, wpr, w, x, r, t) : init_tri_hull(S, x, r, t))) continue;
             int flips = 0, waves = 0;
             while (flips < IMAGE_MAX_FLIPS) {
-                const int v = coop_find_violator(S.occ, S.hlf, S.hrf, wpr, w, h, t, x, r, w, lane, waves);
+                const int v = coop_find_violator<SG>(S.occ, S.hlf, S.hrf, wpr, w, h, t, x, r, w, lane, waves);
                 if (v < 0 || !flip_to(t, v, x, r)) break;
                 flips++;
             }
