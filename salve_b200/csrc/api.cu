@@ -58,6 +58,7 @@ struct salve_bev_ctx {
     unsigned long long* owner = nullptr;
     uint32_t *list0 = nullptr, *list1 = nullptr, *cand = nullptr;
     uint32_t* qlist = nullptr;  // per image work list of image_kernel (g entries)
+    uint32_t* clist = nullptr;  // per CTA slot: entries handed from the window pass to the cooperative pass
     unsigned long long* qres = nullptr;  // per image, per list entry: the resolved triangle
     long long* phase_clk = nullptr;      // diagnostics: 24 slots per image of the last chunk
     uint32_t* keepbits = nullptr;        // per CTA slot keep-mask bit rows of image_kernel
@@ -178,6 +179,7 @@ extern "C" int salve_bev_ctx_create(const salve_bev_config* cfg, salve_bev_ctx**
         c->image_slots = (int)std::min<size_t>(N, (size_t)2 * n_sm);  // persistent CTAs of image_kernel: 2 per SM
     }
     ALLOC(c->qlist, (size_t)c->image_slots * c->g_stride);
+    ALLOC(c->clist, (size_t)c->image_slots * c->g_stride);
     ALLOC(c->qres, (size_t)c->image_slots * c->g_stride);
     ALLOC(c->phase_clk, N * 24);
     ALLOC(c->keepbits, (size_t)c->image_slots * c->bits_stride);
@@ -246,7 +248,7 @@ extern "C" void salve_bev_ctx_destroy(salve_bev_ctx* c) {
     cudaSetDevice(c->cfg.device);
     cudaDeviceSynchronize();
     void* ptrs[] = {c->pano_rgb_store, c->pano_rgb2x_store, c->pano_depth_store, c->d_depth_ptr, c->d_tables, c->keygrid, c->color, c->occ, c->nonempty,
-                    c->keep, c->tmpbits, c->wprefix, c->tris, c->owner, c->list0, c->list1, c->cand, c->qlist, c->qres, c->phase_clk, c->keepbits, c->work_counter, c->d_order, c->cache_out, c->cache_counts, c->cache_status, c->d_dest, c->headers, c->counts,
+                    c->keep, c->tmpbits, c->wprefix, c->tris, c->owner, c->list0, c->list1, c->cand, c->qlist, c->clist, c->qres, c->phase_clk, c->keepbits, c->work_counter, c->d_order, c->cache_out, c->cache_counts, c->cache_status, c->d_dest, c->headers, c->counts,
                     c->status, c->d_jobs, c->d_color_src, c->out_store};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < N_TMP; i++) if (c->tmp[i]) cudaFree(c->tmp[i]);
@@ -399,7 +401,7 @@ static int run_image_stage(salve_bev_ctx* c, int n_img, const GridParams& G, con
     IA.hull = hull; IA.hull_stride = (size_t)G.g;
     IA.qtri = qtri; IA.qtri_stride = (size_t)G.g * 3;
     IA.bits = bits; IA.bits_stride = 3 * (size_t)G.grid_h * G.wpr;
-    IA.qlist = c->qlist; IA.qlist_stride = c->g_stride; IA.qres = c->qres; IA.keepbits = c->keepbits; IA.keepbits_stride = c->bits_stride; IA.phase_clk = (n_img <= c->cfg.max_images && keygrid == c->keygrid) ? c->phase_clk : nullptr;
+    IA.qlist = c->qlist; IA.qlist_stride = c->g_stride; IA.qres = c->qres; IA.clist = c->clist; IA.keepbits = c->keepbits; IA.keepbits_stride = c->bits_stride; IA.phase_clk = (n_img <= c->cfg.max_images && keygrid == c->keygrid) ? c->phase_clk : nullptr;
     IA.raw_mode = raw_mode; IA.skip_empty_check = skip_empty;
     // grids of up to 512 x 512 pixels (the reference's 501 x 501 included) take the instantiation with int32 circle parameters
     if (G.grid_h <= 512 && G.grid_w <= 512) image_kernel<true><<<std::min(n_img, c->image_slots), IMAGE_NT, smem, st>>>(IA);

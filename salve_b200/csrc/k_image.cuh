@@ -71,7 +71,8 @@ struct ImageArgs {
     int32_t* qtri; size_t qtri_stride;        // optional tap: per pixel the 3 vertex pixel ids of its triangle (pre-filled with -1)
     uint32_t* bits; size_t bits_stride;       // optional tap: occ, nonempty, keep bit planes (3 * grid_h * wpr words per image)
     uint32_t* qlist; size_t qlist_stride;     // per CTA work list of query pixels (row << 11 | col), capacity g
-    unsigned long long* qres;                 // per CTA, per list entry: resolved triangle (3 x 21-bit vertex labels | bit 63)
+    unsigned long long* qres;                 // per CTA, per list entry: triangle (3 x 21-bit vertex labels), final if | QRES_DONE
+    uint32_t* clist;                          // per CTA: list entries the window pass handed on (capacity g)
     uint32_t* keepbits; size_t keepbits_stride;  // per CTA scratch: non-empty, then keep bit rows (grid_h * wpr words)
     long long* phase_clk;                     // optional diagnostics: per image 16 slots, SM clock at the phase boundaries + list sizes
     int32_t raw_mode;                 // 1: no keep mask, no flip (interp_dense_grid_from_sparse semantics)
@@ -177,7 +178,9 @@ __device__ __forceinline__ bool init_tri_hull(const ImageShared& S, int x, int r
     return false;
 }
 
-constexpr unsigned long long QRES_DONE = 1ull << 63;
+constexpr unsigned long long QRES_DONE = 1ull << 63;     // the entry holds the query's final triangle
+// an entry without QRES_DONE is either 0 (no triangle) or a valid triangle around the query that is not final yet: three distinct
+// 21-bit labels fill bits 0..62, so a triangle never encodes to 0
 
 __device__ __forceinline__ float sqrt_approx(float v) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
 
@@ -207,9 +210,14 @@ __device__ __forceinline__ void resolve_window(const ImageShared& S, int wpr, in
     for (int k = 0; k < NROW; k++) wr[k] = 0u;
     int ax = 0, ay = 0, bx = 0, by = 0, cx = 0, cy = 0;
 
-    auto give_up = [&]() {
+    // hand the query to the cooperative pass, with the triangle the descent has reached so far (if there is one)
+    auto give_up = [&](bool with_tri) {
         atomicOr(&defer[r * wpr + (x >> 5)], 1u << (x & 31));
-        qres[idx] = 0ull;
+        unsigned long long v = 0ull;
+        if (with_tri)
+            v = (unsigned long long)vlabel(r + ay, x + ax) | ((unsigned long long)vlabel(r + by, x + bx) << 21) |
+                ((unsigned long long)vlabel(r + cy, x + cx) << 42);
+        qres[idx] = v;
         active = false;
     };
     // nearest set bit to dx = 0 in a window row (m != 0): returns dx
@@ -271,7 +279,7 @@ __device__ __forceinline__ void resolve_window(const ImageShared& S, int wpr, in
                     if (ok) {
                         if (py > 0) { ax = xl; bx = xr; } else { ax = xr; bx = xl; }
                         ay = 0; by = 0; cx = px; cy = py;
-                    } else give_up();
+                    } else give_up(false);
                 }
             }
         }
@@ -328,9 +336,9 @@ __device__ __forceinline__ void resolve_window(const ImageShared& S, int wpr, in
         if (have && !fits) {
             // large circle: float may misjudge points near it -- confirm the violator exactly (int32: |coordinates| <= 16)
             const int ex = dx - ax, ey = dy - ay;
-            if (U * ex + V * ey - A2 * (ex * ex + ey * ey) <= 0) { give_up(); continue; }
+            if (U * ex + V * ey - A2 * (ex * ex + ey * ey) <= 0) { give_up(true); continue; }
         }
-        if (!have && !fits) { give_up(); continue; }
+        if (!have && !fits) { give_up(true); continue; }
         if (!have) {
             // ---- empty circle: sites ON it decide by the symbolic perturbation (same rule as incircle_pert(), in window
             // coordinates: weights < 2^20, |orient| <= 2 * 31 * 6, so int32 holds every term and the sum)
@@ -376,9 +384,9 @@ __device__ __forceinline__ void resolve_window(const ImageShared& S, int wpr, in
             if (fa) { ax = dx; ay = dy; }
             else if (fb) { bx = dx; by = dy; }
             else if (fc) { cx = dx; cy = dy; }
-            else { give_up(); continue; }  // cannot happen
+            else { give_up(false); continue; }  // cannot happen
         }
-        if (++flips > MAXFLIPS) give_up();
+        if (++flips > MAXFLIPS) give_up(true);
     }
 }
 
@@ -799,24 +807,6 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
     uint32_t* defer = S.tmp;  // bit plane: queries handed to the next pass (the row-dilated plane is dead now)
     unsigned long long* qres = A.qres + (size_t)slot * A.qlist_stride;
 
-    // list of the pixels whose bit is set in `plane` (row-major, one warp per row); `plane` is cleared
-    auto build_list = [&](uint32_t* plane, bool clear) {
-        const int nw_pad = (nwords + 31) & ~31;
-        for (int item = tid; item < nw_pad; item += IMAGE_NT) {
-            uint32_t q = item < nwords ? plane[item] : 0u;
-            if (clear && q) plane[item] = 0u;
-            int n = __popc(q), incl = n;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-            const int total = __shfl_sync(0xffffffffu, incl, 31);
-            if (total == 0) continue;
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&s_nitems, total);
-            base = __shfl_sync(0xffffffffu, base, 0) + incl - n;
-            const int r = item / wpr, wi = item - r * wpr;
-            while (q) { const int b = __ffs(q) - 1; q &= q - 1; qlist[base++] = ((uint32_t)r << COL_BITS) | (uint32_t)(wi * 32 + b); }
-        }
-    };
     // interpolate the pixels a pass resolved: gathers, exact barycentrics and stores with every lane busy
     auto shade = [&](int n) {
         for (int i = tid; i < n; i += IMAGE_NT) {
@@ -846,9 +836,23 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
     // The final triangle of a descent is rasterised over ALL deferred pixels it contains (they share it), which are then
     // taken off the list: a big triangle across a hole is found about once instead of once per pixel.  Warps take
     // row-major bands of the list, so that the pixels of one triangle mostly meet the same warp.
+    const int n_win = s_nitems;
+    __syncthreads();
     if (tid == 0) { s_nitems = 0; s_next = 0; }
     __syncthreads();
-    if (status == 0) build_list(defer, false);
+    uint32_t* clist = A.clist + (size_t)slot * A.qlist_stride;
+    if (status == 0) {  // compact the entries the window pass did not finish (list order is kept within 32 entries)
+        const int n_pad = (n_win + 31) & ~31;
+        for (int i = tid; i < n_pad; i += IMAGE_NT) {
+            const bool pend = i < n_win && !(qres[i] & QRES_DONE);
+            const uint32_t m = __ballot_sync(0xffffffffu, pend);
+            if (!m) continue;
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_nitems, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (pend) clist[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)i;
+        }
+    }
     __syncthreads();
     mark(9);
     if (pclk && tid == 0) pclk[14] = s_nitems;
@@ -867,12 +871,19 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
             if (i0 >= n) break;
             const int i_end = min(n, i0 + band);
           for (int i = i0; i < i_end; i++) {
-            const uint32_t code = qlist[i];
+            const uint32_t idx = clist[i];
+            const uint32_t code = qlist[idx];
             const int x = (int)(code & COL_MASK), r = (int)(code >> COL_BITS);
             if (!((defer[r * wpr + (x >> 5)] >> (x & 31)) & 1u)) continue;  // already filled by another descent's triangle
             Tri2 t;
-            const bool in_row = S.cnt[r] > 1 && x > S.first[r] && x < S.last[r];
-            if (!(in_row ? init_tri_row(S, wpr, w, x, r, t) : init_tri_hull(S, x, r, t))) continue;
+            const unsigned long long part = qres[idx];
+            if (part != 0ull) {  // continue the window pass's descent (the entry is not QRES_DONE: it is on this list)
+                const uint32_t a = (uint32_t)part & M21, b = (uint32_t)(part >> 21) & M21, c = (uint32_t)(part >> 42) & M21;
+                t = {vcol(a), vrow(a), vcol(b), vrow(b), vcol(c), vrow(c)};
+            } else {
+                const bool in_row = S.cnt[r] > 1 && x > S.first[r] && x < S.last[r];
+                if (!(in_row ? init_tri_row(S, wpr, w, x, r, t) : init_tri_hull(S, x, r, t))) continue;
+            }
             int flips = 0, waves = 0;
             while (flips < IMAGE_MAX_FLIPS) {
                 const int v = coop_find_violator<SG>(S.occ, S.hlf, S.hrf, wpr, w, h, t, x, r, w, lane, waves);
