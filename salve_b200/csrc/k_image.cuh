@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
         const size_t frows = ((size_t)h * 4 + 15) & ~(size_t)15;
         S.hlf = (float*)p; p += frows; S.hrf = (float*)p; p += frows;
     }
-    __shared__ int s_S, s_M, s_mincol, s_maxcol, s_ne_cnt, s_keep_cnt, s_nitems, s_next, s_filled, s_flips, s_maxflips, s_hull_ok, s_img;
+    __shared__ int s_S, s_M, s_mincol, s_maxcol, s_ne_cnt, s_keep_cnt, s_nitems, s_next, s_filled, s_flips, s_maxflips, s_hull_ok, s_img, s_nedge, s_masked;
 
   // Images are handed out dynamically (their cost varies by 3x).  Thread 0 claims the next index while the CTA finishes the
   // current image (stage H), so that the round trip of the atomic is not paid at the hand-over barrier.
@@ -530,7 +530,7 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
 
     if (tid == 0) {
         s_S = 0; s_M = 0; s_mincol = 1 << 30; s_maxcol = -1; s_ne_cnt = 0; s_keep_cnt = 0; s_nitems = 0; s_next = 0;
-        s_filled = 0; s_flips = 0; s_maxflips = 0; s_hull_ok = 0;
+        s_filled = 0; s_flips = 0; s_maxflips = 0; s_hull_ok = 0; s_nedge = 0; s_masked = 0;
     }
     __syncthreads();
 
@@ -719,16 +719,18 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
     int my_filled = 0, my_flips = 0, my_maxflips = 0;
     uint32_t* qlist = A.qlist + (size_t)slot * A.qlist_stride;
     const bool edge_rule = A.qtri == nullptr;  // the triangle tap wants every query resolved to a triangle
+    uint32_t* elist = A.clist + (size_t)slot * A.qlist_stride;  // edge-rule pixels (the cooperative pass's list is built later)
     if (status == 0) {
         const int nw_pad = (nwords + 31) & ~31;
-        const ptrdiff_t dn = raw ? (ptrdiff_t)w * 3 : -(ptrdiff_t)w * 3;  // address step to row r + 1 in the (flipped) output
         for (int item = tid; item < nw_pad; item += IMAGE_NT) {  // a warp takes 32 consecutive words
-            uint32_t q = 0;
+            uint32_t q = 0, he = 0, ve = 0;
             if (item < nwords) {
                 const int r = item / wpr, wi = item - r * wpr;
                 const uint32_t hm = range_mask(wi, S.hlo[r], S.hhi[r]);
                 const uint32_t oc = S.occ[item];
-                q = S.keep[item] & ~oc & hm;
+                const uint32_t kp = S.keep[item];
+                q = kp & ~oc & hm;
+                if (oc & ~kp) s_masked = 1;  // a site the hallucination mask removes: stage H has work (rare)
                 if (A.hull && hm) {
                     uint8_t* hp = A.hull + (size_t)img * A.hull_stride + (size_t)r * w + wi * 32;
                     uint32_t m = hm;
@@ -736,41 +738,63 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
                 }
                 if (q && edge_rule) {
                     const uint32_t ol = wi > 0 ? S.occ[item - 1] : 0u, orr = wi + 1 < wpr ? S.occ[item + 1] : 0u;
-                    const uint32_t he = q & ((oc << 1) | (ol >> 31)) & ((oc >> 1) | (orr << 31));
-                    const uint32_t ve = q & (r + 1 < h ? S.occ[item + wpr] : 0u) & (r > 0 ? S.occ[item - wpr] : 0u);
-                    uint32_t e = he | ve;
-                    uint8_t* orow = out + (size_t)(raw ? r : h - 1 - r) * w * 3;
-                    while (e) {
-                        const int b = __ffs(e) - 1; e &= e - 1;
-                        const int x = wi * 32 + b;
-                        bool horiz = (he >> b) & 1u;
-                        if (horiz && ((ve >> b) & 1u)) {
-                            const long long wh = pert_weight(vlabel(r, x - 1), w) + pert_weight(vlabel(r, x + 1), w);
-                            const long long wv = pert_weight(vlabel(r - 1, x), w) + pert_weight(vlabel(r + 1, x), w);
-                            if (wh == wv) continue;  // residual tie of the perturbation: the general path decides
-                            horiz = wh < wv;
-                        }
-                        uint8_t* p = orow + x * 3;
-                        const uint8_t* pa = horiz ? p - 3 : p + dn;
-                        const uint8_t* pb = horiz ? p + 3 : p - dn;
-                        p[0] = (uint8_t)(((uint32_t)pa[0] + pb[0]) >> 1);
-                        p[1] = (uint8_t)(((uint32_t)pa[1] + pb[1]) >> 1);
-                        p[2] = (uint8_t)(((uint32_t)pa[2] + pb[2]) >> 1);
-                        q &= ~(1u << b);
-                        my_filled++;
-                    }
+                    he = q & ((oc << 1) | (ol >> 31)) & ((oc >> 1) | (orr << 31));
+                    ve = q & (r + 1 < h ? S.occ[item + wpr] : 0u) & (r > 0 ? S.occ[item - wpr] : 0u);
+                    q &= ~(he | ve);
                 }
             }
-            int n = __popc(q), incl = n;
+            // one warp scan for both lists: queries in the low half, edge-rule pixels in the high half (<= 1024 each per warp)
+            const uint32_t e = he | ve;
+            const int n = __popc(q) | (__popc(e) << 16);
+            int incl = n;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
             const int total = __shfl_sync(0xffffffffu, incl, 31);
             if (total == 0) continue;
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&s_nitems, total);
-            base = __shfl_sync(0xffffffffu, base, 0) + incl - n;
+            int base_q = 0, base_e = 0;
+            if (lane == 0) {
+                if (total & 0xFFFF) base_q = atomicAdd(&s_nitems, total & 0xFFFF);
+                if (total >> 16) base_e = atomicAdd(&s_nedge, total >> 16);
+            }
+            const int excl = incl - n;
+            base_q = __shfl_sync(0xffffffffu, base_q, 0) + (excl & 0xFFFF);
+            base_e = __shfl_sync(0xffffffffu, base_e, 0) + (excl >> 16);
             const int r = item / wpr, wi = item - r * wpr;
-            while (q) { const int b = __ffs(q) - 1; q &= q - 1; qlist[base++] = ((uint32_t)r << COL_BITS) | (uint32_t)(wi * 32 + b); }
+            const uint32_t code0 = ((uint32_t)r << COL_BITS) | (uint32_t)(wi * 32);
+            while (q) { const int b = __ffs(q) - 1; q &= q - 1; qlist[base_q++] = code0 + b; }
+            uint32_t m = e;
+            while (m) {  // bit 31: W-E pair present, bit 30: N-S pair present
+                const int b = __ffs(m) - 1; m &= m - 1;
+                elist[base_e++] = (code0 + b) | (((he >> b) & 1u) << 31) | (((ve >> b) & 1u) << 30);
+            }
+        }
+    }
+    __syncthreads();
+    // edge-rule pixels, one per thread: the exact mean of the two site colours
+    if (status == 0) {
+        const ptrdiff_t dn = raw ? (ptrdiff_t)w * 3 : -(ptrdiff_t)w * 3;  // address step to row r + 1 in the (flipped) output
+        const int ne = s_nedge;
+        for (int i = tid; i < ne; i += IMAGE_NT) {
+            const uint32_t code = elist[i];
+            const int x = (int)(code & COL_MASK), r = (int)((code >> COL_BITS) & 0x3FFu);
+            bool horiz = (code >> 31) != 0u;
+            if (horiz && ((code >> 30) & 1u)) {
+                const long long wh = pert_weight(vlabel(r, x - 1), w) + pert_weight(vlabel(r, x + 1), w);
+                const long long wv = pert_weight(vlabel(r - 1, x), w) + pert_weight(vlabel(r + 1, x), w);
+                if (wh == wv) {  // residual tie of the perturbation: the general path decides
+                    qlist[atomicAdd(&s_nitems, 1)] = code & ((1u << 21) - 1u);
+                    continue;
+                }
+                horiz = wh < wv;
+            }
+            uint8_t* p = out + ((size_t)(raw ? r : h - 1 - r) * w + x) * 3;
+            const uint8_t* pa = horiz ? p - 3 : p + dn;
+            const uint8_t* pb = horiz ? p + 3 : p - dn;
+            const uint32_t a0 = pa[0], a1 = pa[1], a2 = pa[2], b0 = pb[0], b1 = pb[1], b2 = pb[2];
+            p[0] = (uint8_t)((a0 + b0) >> 1);
+            p[1] = (uint8_t)((a1 + b1) >> 1);
+            p[2] = (uint8_t)((a2 + b2) >> 1);
+            my_filled++;
         }
     }
     __syncthreads();
@@ -929,7 +953,7 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
                 o[0] = 0; o[1] = 0; o[2] = 0;
             }
         }
-    } else if (!raw) {
+    } else if (!raw && (s_masked || status != 0)) {
         for (int item = tid; item < nwords; item += IMAGE_NT) {
             uint32_t m = S.occ[item] & ~S.keep[item];  // sites the hallucination mask removes
             const int r = item / wpr, wi = item - r * wpr;
