@@ -42,6 +42,9 @@ namespace bev {
 #undef IMAGE_NT
 #endif
 constexpr int IMAGE_NT = IMAGE_NT_DEF;
+#ifndef IMAGE_COOP_CHAIN
+#define IMAGE_COOP_CHAIN 1
+#endif
 #ifndef IMAGE_COOP_MIN_BAND
 #define IMAGE_COOP_MIN_BAND 4
 #endif
@@ -451,9 +454,13 @@ __device__ __forceinline__ int coop_find_violator(const uint32_t* __restrict__ o
                 }
             }
         }
-#pragma unroll
-        for (int sft = 16; sft > 0; sft >>= 1) { const unsigned long long ob = __shfl_xor_sync(0xffffffffu, best, sft); best = ob < best ? ob : best; }
-        if (best != ~0ull) return (int)(uint32_t)best;
+        // nearest violator of the wave: one 32-bit min reduction on the squared distance, first lane that holds it
+        const uint32_t d2 = (uint32_t)(best >> 32);  // 0xFFFFFFFF: none in this lane's row
+        const uint32_t dmin = __reduce_min_sync(0xffffffffu, d2);
+        if (dmin != 0xFFFFFFFFu) {
+            const int src = __ffs(__ballot_sync(0xffffffffu, d2 == dmin)) - 1;
+            return __shfl_sync(0xffffffffu, (int)(uint32_t)best, src);
+        }
         // convexity of circle /\ hull: a dead row kills every row beyond it in its direction
         if (__ballot_sync(0xffffffffu, row_dead && !down)) up_dead = true;
         if (__ballot_sync(0xffffffffu, row_dead && down)) dn_dead = true;
@@ -884,6 +891,8 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
         const int n = s_nitems;
         // guided self-scheduling: bands shrink with what is left (long row-major bands first, so that the pixels of one
         // triangle mostly meet the same warp; short ones at the end, so that no warp is left alone with a long band)
+        Tri2 tp = {0, 0, 0, 0, 0, 0};  // final triangle of this warp's previous descent
+        bool have_prev = false;
         while (true) {
             int i0 = 0, band = 0;
             if (lane == 0) {
@@ -908,6 +917,25 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
                 const bool in_row = S.cnt[r] > 1 && x > S.first[r] && x < S.last[r];
                 if (!(in_row ? init_tri_row(S, wpr, w, x, r, t) : init_tri_hull(S, x, r, t))) continue;
             }
+#if IMAGE_COOP_CHAIN
+            if (have_prev) {
+                // The previous query of this warp is usually a neighbour, and its final triangle tp a neighbour of the triangle
+                // wanted now.  If q lies beyond exactly one edge (u, v) of tp -- a Delaunay edge -- start from (v, u, s) with s a
+                // vertex of the triangle found above: two of the three vertices are then final more often than not.
+                const int o0 = orient_i(tp.ax, tp.ay, tp.bx, tp.by, x, r), o1 = orient_i(tp.bx, tp.by, tp.cx, tp.cy, x, r),
+                          o2 = orient_i(tp.cx, tp.cy, tp.ax, tp.ay, x, r);
+                if ((o0 < 0) + (o1 < 0) + (o2 < 0) == 1) {
+                    int ux, uy, vx, vy;
+                    if (o0 < 0) { ux = tp.ax; uy = tp.ay; vx = tp.bx; vy = tp.by; }
+                    else if (o1 < 0) { ux = tp.bx; uy = tp.by; vx = tp.cx; vy = tp.cy; }
+                    else { ux = tp.cx; uy = tp.cy; vx = tp.ax; vy = tp.ay; }
+                    const int sx[3] = {t.ax, t.bx, t.cx}, sy[3] = {t.ay, t.by, t.cy};
+#pragma unroll
+                    for (int k = 2; k >= 0; k--)
+                        if (ccw_contains(vx, vy, ux, uy, sx[k], sy[k], x, r)) t = {vx, vy, ux, uy, sx[k], sy[k]};
+                }
+            }
+#endif
             int flips = 0, waves = 0;
             while (flips < IMAGE_MAX_FLIPS) {
                 const int v = coop_find_violator<SG>(S.occ, S.hlf, S.hrf, wpr, w, h, t, x, r, w, lane, waves);
@@ -916,6 +944,7 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
             }
             if (lane == 0) { my_flips += flips; my_maxflips = max(my_maxflips, flips); }
             if (pclk && lane == 0) atomicAdd((unsigned long long*)&pclk[15], (1ull << 40) | ((unsigned long long)waves << 20) | (unsigned long long)flips);
+            tp = t; have_prev = true;
             // rasterise t over the deferred pixels it contains: one lane per row of its bounding box
             const uint32_t ca = site_rgb(t.ax, t.ay), cb = site_rgb(t.bx, t.by), cc = site_rgb(t.cx, t.cy);
             const int y0 = min(t.ay, min(t.by, t.cy)), y1 = max(t.ay, max(t.by, t.cy));
