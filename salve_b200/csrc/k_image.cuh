@@ -45,6 +45,9 @@ constexpr int IMAGE_NT = IMAGE_NT_DEF;
 #ifndef IMAGE_COOP_CHAIN
 #define IMAGE_COOP_CHAIN 1
 #endif
+#ifndef IMAGE_WIN_VINIT
+#define IMAGE_WIN_VINIT 1
+#endif
 #ifndef IMAGE_COOP_MIN_BAND
 #define IMAGE_COOP_MIN_BAND 4
 #endif
@@ -279,10 +282,30 @@ __device__ __forceinline__ void resolve_window(const ImageShared& S, int wpr, in
                         }
                     }
                     ok = ok && found;
+#if IMAGE_WIN_VINIT
+                    // nearest sites above and below in q's own column: q lies on the segment D-U as it lies on L-R.  The shorter
+                    // of the two is the likelier Delaunay edge (fewer flips to come), and D-U serves when L or R is missing.
+                    int yu = 0, yd = 0;
+#pragma unroll
+                    for (int k = NR; k >= 1; k--) {
+                        if (wr[NR + k] & 0x10000u) yu = k;
+                        if (wr[NR - k] & 0x10000u) yd = k;
+                    }
+                    if (yu != 0 && yd != 0 && (!ok || yu + yd < xr - xl)) {
+                        int qx = 0, qy = 0;  // apex: the nearer of L and R, else the site found in a neighbouring row
+                        if (ml != 0u && (mr == 0u || (16 - (31 - __clz(ml))) <= __ffs(mr))) qx = (31 - __clz(ml)) - 16;
+                        else if (mr != 0u) qx = __ffs(mr);
+                        else if (found && px != 0) { qx = px; qy = py; }
+                        if (qx < 0) { ax = 0; ay = -yd; bx = 0; by = yu; cx = qx; cy = qy; ok = true; }       // (D, U, P): P on the left
+                        else if (qx > 0) { ax = 0; ay = yu; bx = 0; by = -yd; cx = qx; cy = qy; ok = true; }  // (U, D, P): P on the right
+                        else if (ok) { if (py > 0) { ax = xl; bx = xr; } else { ax = xr; bx = xl; } ay = 0; by = 0; cx = px; cy = py; }
+                    } else
+#endif
                     if (ok) {
                         if (py > 0) { ax = xl; bx = xr; } else { ax = xr; bx = xl; }
                         ay = 0; by = 0; cx = px; cy = py;
-                    } else give_up(false);
+                    }
+                    if (!ok) give_up(false);
                 }
             }
         }
@@ -307,7 +330,7 @@ __device__ __forceinline__ void resolve_window(const ImageShared& S, int wpr, in
         // and the sites ON the circle.  Every lane runs the same code whether its circle turns out empty or not.
         bool have = false;
         int dx = 0, dy = 0;
-        uint32_t on[NROW], vm = 0u;
+        uint32_t on[NROW], vm = 0u, anyon = 0u;
 #pragma unroll
         for (int k = 0; k < NROW; k++) {
             const int yy = (k == 0) ? 0 : ((k & 1) ? (k + 1) / 2 : -(k / 2));
@@ -333,7 +356,7 @@ __device__ __forceinline__ void resolve_window(const ImageShared& S, int wpr, in
             if (yy == ay) o &= ~(1u << (ax + 16));
             if (yy == by) o &= ~(1u << (bx + 16));
             if (yy == cy) o &= ~(1u << (cx + 16));
-            on[k] = o;
+            on[k] = o; anyon |= o;
         }
         if (have) dx = nearest(vm);
         if (have && !fits) {
@@ -349,6 +372,7 @@ __device__ __forceinline__ void resolve_window(const ImageShared& S, int wpr, in
             // word, rows in scan order.
             const int icx = __float2int_rn(ccx);
             unsigned long long cand = 0ull;
+            if (anyon)
 #pragma unroll
             for (int k = 0; k < NROW; k++) cand |= (unsigned long long)((uint32_t)(((unsigned long long)on[k] << 4) >> (icx + 16)) & 0x1FFu) << (9 * k);
             if (cand) {
