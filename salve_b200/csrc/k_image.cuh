@@ -54,7 +54,10 @@ constexpr int IMAGE_NT = IMAGE_NT_DEF;
 #ifndef IMAGE_COOP_BAND_DIV
 #define IMAGE_COOP_BAND_DIV 2
 #endif
-constexpr int SITES_BATCH = 8;
+#ifndef SITES_BATCH_DEF
+#define SITES_BATCH_DEF 8
+#endif
+constexpr int SITES_BATCH = SITES_BATCH_DEF;
 constexpr int IMAGE_MAX_FLIPS = 100000;  // safety cap on one descent (never reached: the lift is strictly monotone)
 
 struct ImageArgs {
@@ -568,35 +571,46 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
     // ---- A. winners -> occupancy / non-empty bit rows, sparse image (site colours, rest zero) --------
     // Loads are issued in batches of SITES_BATCH words per lane (keys, then the colour gathers) so that a warp keeps that many
     // independent requests in flight instead of one dependent pair (16 = a whole row of the 501-px grid).
+    // Per row the lane's pointers advance by constants (the unrolled body addresses with immediates); lane k keeps the bit words
+    // of word k of the current 32-word chunk, so that the row summary (count, first, last) and the stores of the bit rows cost a
+    // few instructions per row instead of per word.
     for (int r = warp; r < h; r += NW) {
         int running = 0, first = -1, last = -1, ne_cnt = 0;
-        uint8_t* orow = out + (size_t)(raw ? r : (h - 1 - r)) * w * 3;
-        const uint32_t* krow = keygrid + (size_t)r * w;
-        for (int wi0 = 0; wi0 < wpr; wi0 += SITES_BATCH) {
-            uint32_t key[SITES_BATCH], col[SITES_BATCH];
+        uint8_t* op = out + ((size_t)(raw ? r : (h - 1 - r)) * w + lane) * 3;  // this lane's pixel of the current word
+        const uint32_t* kp = keygrid + (size_t)r * w + lane;
+        for (int wc = 0; wc < wpr; wc += 32) {  // chunks of 32 words (one chunk for grids up to 1 024 pixels wide)
+            uint32_t my_ob = 0u, my_nb = 0u;
+            const int wend = min(wpr, wc + 32);
+            for (int wi0 = wc; wi0 < wend; wi0 += SITES_BATCH, op += SITES_BATCH * 96, kp += SITES_BATCH * 32) {
+                uint32_t key[SITES_BATCH], col[SITES_BATCH];
+                const int c0 = wi0 * 32 + lane;
 #pragma unroll
-            for (int j = 0; j < SITES_BATCH; j++) {
-                const int c = (wi0 + j) * 32 + lane;
-                key[j] = (wi0 + j < wpr && c < w) ? __ldg(krow + c) : 0u;
+                for (int j = 0; j < SITES_BATCH; j++) key[j] = (c0 + j * 32 < w) ? __ldg(kp + j * 32) : 0u;
+#pragma unroll
+                for (int j = 0; j < SITES_BATCH; j++) {
+                    col[j] = 0u;
+                    if (key[j]) col[j] = gather_rgb(csrc, (key[j] - 1u) & KEY_IDX_MASK, A.pano_w);
+                }
+#pragma unroll
+                for (int j = 0; j < SITES_BATCH; j++) {
+                    const uint32_t cr = col[j] & 0xFF, cg = (col[j] >> 8) & 0xFF, cb = col[j] >> 16;
+                    const bool ne = ((cr * cg * cb) & 0xFFu) != 0u;  // uint8 product wraps (interpolation_utils.py:95)
+                    if (c0 + j * 32 < w) { op[j * 96 + 0] = (uint8_t)cr; op[j * 96 + 1] = (uint8_t)cg; op[j * 96 + 2] = (uint8_t)cb; }
+                    const uint32_t ob = __ballot_sync(0xffffffffu, key[j] != 0u);
+                    const uint32_t nb = __ballot_sync(0xffffffffu, ne);
+                    if (lane == ((wi0 + j) & 31)) { my_ob = ob; my_nb = nb; }
+                }
             }
-#pragma unroll
-            for (int j = 0; j < SITES_BATCH; j++) {
-                col[j] = 0u;
-                if (key[j]) col[j] = gather_rgb(csrc, (key[j] - 1u) & KEY_IDX_MASK, A.pano_w);
-            }
-#pragma unroll
-            for (int j = 0; j < SITES_BATCH; j++) {
-                const int wi = wi0 + j;
-                if (wi >= wpr) break;
-                const int c = wi * 32 + lane;
-                const uint32_t cr = col[j] & 0xFF, cg = (col[j] >> 8) & 0xFF, cb = col[j] >> 16;
-                const bool ne = ((cr * cg * cb) & 0xFFu) != 0u;  // uint8 product wraps (interpolation_utils.py:95)
-                if (c < w) { orow[c * 3 + 0] = (uint8_t)cr; orow[c * 3 + 1] = (uint8_t)cg; orow[c * 3 + 2] = (uint8_t)cb; }
-                const uint32_t ob = __ballot_sync(0xffffffffu, key[j] != 0u);
-                const uint32_t nb = __ballot_sync(0xffffffffu, ne);
-                if (lane == 0) { S.occ[r * wpr + wi] = ob; S.keep[r * wpr + wi] = nb; }  // keep plane holds `nonempty` until stage D
-                if (ob) { if (first < 0) first = wi * 32 + __ffs(ob) - 1; last = wi * 32 + 31 - __clz(ob); }
-                running += __popc(ob); ne_cnt += __popc(nb);
+            // bit rows of the chunk (the keep plane holds `nonempty` until stage D) and the row summary
+            if (wc + lane < wpr) { S.occ[r * wpr + wc + lane] = my_ob; S.keep[r * wpr + wc + lane] = my_nb; }
+            const uint32_t nz = __ballot_sync(0xffffffffu, my_ob != 0u);
+            if (nz) {
+                const int fw = __ffs(nz) - 1, lw = 31 - __clz(nz);
+                const uint32_t fo = __shfl_sync(0xffffffffu, my_ob, fw), lo = __shfl_sync(0xffffffffu, my_ob, lw);
+                if (first < 0) first = (wc + fw) * 32 + __ffs(fo) - 1;
+                last = (wc + lw) * 32 + 31 - __clz(lo);
+                running += __reduce_add_sync(0xffffffffu, __popc(my_ob));
+                ne_cnt += __reduce_add_sync(0xffffffffu, __popc(my_nb));
             }
         }
         if (lane == 0) {
@@ -1028,6 +1042,7 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
     if (tid == 0) {
         counts[5] = s_filled; counts[6] = s_maxflips; counts[7] = s_flips;
         if (pclk) {
+            pclk[6] = s_flips; pclk[7] = s_filled;
             pclk[11] = clock64();
             unsigned long long ns; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
             pclk[20] = (long long)ns;

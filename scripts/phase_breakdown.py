@@ -28,6 +28,7 @@ for i, nme in enumerate(names):
     print("  %-18s mean %9.0f  max %9.0f  share %5.1f%%" % (nme, d[:, i].mean(), d[:, i].max(), 100 * d[:, i].sum() / tot.sum()))
 print("queries: window %.0f  cooperative %.0f" % (c[:, 17].mean(), c[:, 14].mean()))
 d15 = c[:, 15]
+print("flips per image: all %.0f, window pass %.0f = %.2f per window query; filled px %.0f" % (c[:, 6].mean(), (c[:, 6] - (d15 & 0xFFFFF)).mean(), (c[:, 6] - (d15 & 0xFFFFF)).mean() / max(c[:, 17].mean(), 1), c[:, 7].mean()))
 print("cooperative pass per image: descents %.0f  waves %.0f  flips %.0f" % ((d15 >> 40).mean(), ((d15 >> 20) & 0xFFFFF).mean(), (d15 & 0xFFFFF).mean()))
 # timeline of the launch from the global timer: how well the persistent CTAs are packed
 c = c[c[:, 19] > 0]
