@@ -274,16 +274,17 @@ __device__ __forceinline__ void resolve_window(const ImageShared& S, int wpr, in
                     bool ok = ml != 0u && mr != 0u;
                     int xl = 0, xr = 0;
                     if (ok) { xl = (31 - __clz(ml)) - 16; xr = __ffs(mr); ok = xr - xl <= MAXGAP; }
-                    int px = 0, py = 0;
-                    bool found = false;
+                    // apex: the nearer of (nearest site of the closest non-empty row above, ... below), |dx| <= 8
+                    int px = 0, py = 0, pxd = 0, pyd = 0;
+                    bool fu = false, fd = false;
 #pragma unroll
                     for (int k = 1; k <= NR; k++) {
-#pragma unroll
-                        for (int sgn = 1; sgn >= -1; sgn -= 2) {
-                            const uint32_t m = wr[NR + sgn * k] & 0x01FFFF00u;  // |dx| <= 8
-                            if (!found && m) { found = true; px = nearest(m); py = sgn * k; }
-                        }
+                        const uint32_t mu = wr[NR + k] & 0x01FFFF00u, md = wr[NR - k] & 0x01FFFF00u;
+                        if (!fu && mu) { fu = true; px = nearest(mu); py = k; }
+                        if (!fd && md) { fd = true; pxd = nearest(md); pyd = -k; }
                     }
+                    const bool found = fu || fd;
+                    if (fd && (!fu || pxd * pxd + pyd * pyd < px * px + py * py)) { px = pxd; py = pyd; }
                     ok = ok && found;
 #if IMAGE_WIN_VINIT
                     // nearest sites above and below in q's own column: q lies on the segment D-U as it lies on L-R.  The shorter
