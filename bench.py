@@ -390,8 +390,48 @@ def run_ours(args):
     te_t = torch.tensor([te], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
+    e2e_seq_value = world * N_HYP * args.steps / float(te_t.item())
+
+    # Two steps in flight (what a caller with a queue of buildings does): a second context with its own stream and its own pinned
+    # output buffers works on step k + 1 while the device->host copies of step k drain, so that the copy engine -- the bottleneck of
+    # this path, 1.02 GB per step -- stays busy.  Every step still uploads its panos and brings all its images to the host inside
+    # the timed region.  libsalve_bev calls release the GIL (ctypes), one Python thread per context.
+    DEPTH = 2
+    h_posed_b = torch.empty(N_HYP * 2 * IMG_BYTES, dtype=torch.uint8).pin_memory()
+    h_unposed_b = torch.empty(N_PANOS * 2 * IMG_BYTES, dtype=torch.uint8).pin_memory()
+    r3 = BevRenderer(pano_h=PANO_H, pano_w=PANO_W, max_panos=N_PANOS, max_images=e2e_chunk, device=local)
+    lanes = [(r2, torch.cuda.Stream(dev), h_posed_np, h_unposed_np), (r3, torch.cuda.Stream(dev), h_posed_b.numpy(), h_unposed_b.numpy())]
+
+    def lane_steps(li, n_steps):
+        torch.cuda.set_device(local)
+        rr, s_, hp, hu = lanes[li]
+        for _ in range(n_steps):
+            for k in range(N_PANOS):
+                rr.upload_pano_ptr(k, h_rgb[k].data_ptr(), h_depth[k].data_ptr(), stream=s_.cuda_stream)
+            ret = rr.render_hypotheses_compact(p1, p2, R, t, posed_out=hp, unposed_out=hu, stream=s_.cuda_stream)
+            if li == 0:
+                e2e_ret["r"] = ret
+
+    def run_pipelined(n_steps):
+        per = [n_steps // DEPTH + (1 if i < n_steps % DEPTH else 0) for i in range(DEPTH)]
+        th = [threading.Thread(target=lane_steps, args=(i, per[i])) for i in range(DEPTH)]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        torch.cuda.synchronize(dev)
+
+    run_pipelined(DEPTH)
+    barrier()
+    t0 = time.perf_counter()
+    run_pipelined(args.steps)
+    te = time.perf_counter() - t0
+    te_t = torch.tensor([te], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
     te = float(te_t.item())
     e2e_value = world * N_HYP * args.steps / te
+    same_b = bool(np.array_equal(h_posed_b.numpy()[: 4 * IMG_BYTES], h_posed_np[: 4 * IMG_BYTES]))
     posed_h, unposed_h, idx_h = e2e_ret["r"][:3]
     full0 = d_ref.reshape(2, 2, 2, IMG, IMG, 3)  # hypotheses 0, 1 of the device path: (surface, posed/un-posed)
     same = all(
@@ -489,7 +529,9 @@ def run_ours(args):
         "config": workload_config(world),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "hypotheses/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "matches_device_path": same},
+                "matches_device_path": bool(same and same_b), "steps_in_flight": DEPTH, "value_one_step_at_a_time": e2e_seq_value,
+                "note": "two contexts / streams / host threads alternate steps; every step uploads its panos and copies all its images to "
+                        "pinned host memory inside the timed region (wall clock over all steps); bound by the device->host copy engine"},
         "gpu_launches": int(launches),
         "value_no_dedup": value_nd, "no_dedup_matches": same_nd, "images_rendered_per_step": int(n_rendered),
         "roofline": roofline,
