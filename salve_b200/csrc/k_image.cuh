@@ -48,6 +48,9 @@ constexpr int IMAGE_NT = IMAGE_NT_DEF;
 #ifndef IMAGE_WIN_VINIT
 #define IMAGE_WIN_VINIT 1
 #endif
+#ifndef IMAGE_COOP_CACHE
+#define IMAGE_COOP_CACHE 1
+#endif
 #ifndef IMAGE_COOP_MIN_BAND
 #define IMAGE_COOP_MIN_BAND 4
 #endif
@@ -428,7 +431,7 @@ __device__ __forceinline__ void resolve_window(const ImageShared& S, int wpr, in
 // determinant itself is widened (32 x 32 -> 64 bit multiplies); larger grids keep everything in int64.
 template <bool SG>
 __device__ __forceinline__ int coop_find_violator(const uint32_t* __restrict__ occ, const float* __restrict__ hlf, const float* __restrict__ hrf, int wpr,
-                                                  int W, int H, const Tri2& t, int qx, int qy, int grid_w, int lane, int& waves) {
+                                                  int W, int H, const Tri2& t, int qx, int qy, int grid_w, int lane, int& waves, unsigned long long& cache) {
     typedef typename std::conditional<SG, int, long long>::type I;
     const I bx = t.bx - t.ax, by = t.by - t.ay, cx = t.cx - t.ax, cy = t.cy - t.ay;
     const I b2 = bx * bx + by * by, c2 = cx * cx + cy * cy;
@@ -487,7 +490,9 @@ __device__ __forceinline__ int coop_find_violator(const uint32_t* __restrict__ o
         const uint32_t dmin = __reduce_min_sync(0xffffffffu, d2);
         if (dmin != 0xFFFFFFFFu) {
             const int src = __ffs(__ballot_sync(0xffffffffu, d2 == dmin)) - 1;
-            return __shfl_sync(0xffffffffu, (int)(uint32_t)best, src);
+            const int v = __shfl_sync(0xffffffffu, (int)(uint32_t)best, src);
+            cache = lane == src ? ~0ull : best;  // the other rows' violators are tried first against the next circle
+            return v;
         }
         // convexity of circle /\ hull: a dead row kills every row beyond it in its direction
         if (__ballot_sync(0xffffffffu, row_dead && !down)) up_dead = true;
@@ -976,8 +981,34 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
             }
 #endif
             int flips = 0, waves = 0;
+            // Each lane keeps the violator its row produced in the last scan.  After a flip these candidates are tested (exactly)
+            // against the new circle before any row is scanned again: consecutive circles overlap, so about half of the flips
+            // are found this way at a tenth of the cost of a scan.  The descent still ends with a full scan that finds nothing.
+            unsigned long long cache = ~0ull;
             while (flips < IMAGE_MAX_FLIPS) {
-                const int v = coop_find_violator<SG>(S.occ, S.hlf, S.hrf, wpr, w, h, t, x, r, w, lane, waves);
+                int v = -1;
+#if IMAGE_COOP_CACHE
+                if (__any_sync(0xffffffffu, cache != ~0ull)) {
+                    bool viol = false;
+                    if (cache != ~0ull) {
+                        const uint32_t va = vlabel(t.ay, t.ax), vb = vlabel(t.by, t.bx), vc = vlabel(t.cy, t.cx);
+                        const uint32_t vd = vlabel((int)((uint32_t)cache >> 16), (int)((uint32_t)cache & 0xFFFFu));
+                        if (vd != va && vd != vb && vd != vc) {
+                            const long long inc = incircle_v(va, vb, vc, vd);
+                            viol = inc > 0 || (inc == 0 && incircle_pert(va, vb, vc, vd, w) > 0);
+                        }
+                        if (!viol) cache = ~0ull;
+                    }
+                    const uint32_t d2 = viol ? (uint32_t)(cache >> 32) : 0xFFFFFFFFu;
+                    const uint32_t dmin = __reduce_min_sync(0xffffffffu, d2);
+                    if (dmin != 0xFFFFFFFFu) {
+                        const int src = __ffs(__ballot_sync(0xffffffffu, d2 == dmin)) - 1;
+                        v = __shfl_sync(0xffffffffu, (int)(uint32_t)cache, src);
+                        if (lane == src) cache = ~0ull;
+                    }
+                }
+#endif
+                if (v < 0) v = coop_find_violator<SG>(S.occ, S.hlf, S.hrf, wpr, w, h, t, x, r, w, lane, waves, cache);
                 if (v < 0 || !flip_to(t, v, x, r)) break;
                 flips++;
             }
