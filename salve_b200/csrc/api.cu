@@ -176,13 +176,13 @@ extern "C" int salve_bev_ctx_create(const salve_bev_config* cfg, salve_bev_ctx**
     {
         int n_sm = 0;
         CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
-        c->image_slots = (int)std::min<size_t>(N, (size_t)2 * n_sm);  // persistent CTAs of image_kernel: 2 per SM
+        c->image_slots = (int)std::min<size_t>(N, (size_t)IMAGE_CTAS * n_sm);  // persistent CTAs of image_kernel
     }
     ALLOC(c->qlist, (size_t)c->image_slots * c->g_stride);
     ALLOC(c->clist, (size_t)c->image_slots * c->g_stride);
     ALLOC(c->qres, (size_t)c->image_slots * c->g_stride);
     ALLOC(c->phase_clk, N * 24);
-    ALLOC(c->keepbits, (size_t)c->image_slots * c->bits_stride);
+    ALLOC(c->keepbits, (size_t)c->image_slots * c->bits_stride * 2);  // keep plane + (IMAGE_TMP_GLOBAL) the second plane
     ALLOC(c->work_counter, 1);
     ALLOC(c->d_order, N);
     ALLOC(c->cache_out, 2 * P * c->img_bytes + 64);  // +64: replicate_images_kernel reads whole words
@@ -401,7 +401,7 @@ static int run_image_stage(salve_bev_ctx* c, int n_img, const GridParams& G, con
     IA.hull = hull; IA.hull_stride = (size_t)G.g;
     IA.qtri = qtri; IA.qtri_stride = (size_t)G.g * 3;
     IA.bits = bits; IA.bits_stride = 3 * (size_t)G.grid_h * G.wpr;
-    IA.qlist = c->qlist; IA.qlist_stride = c->g_stride; IA.qres = c->qres; IA.clist = c->clist; IA.keepbits = c->keepbits; IA.keepbits_stride = c->bits_stride; IA.phase_clk = (n_img <= c->cfg.max_images && keygrid == c->keygrid) ? c->phase_clk : nullptr;
+    IA.qlist = c->qlist; IA.qlist_stride = c->g_stride; IA.qres = c->qres; IA.clist = c->clist; IA.keepbits = c->keepbits; IA.keepbits_stride = c->bits_stride * 2; IA.phase_clk = (n_img <= c->cfg.max_images && keygrid == c->keygrid) ? c->phase_clk : nullptr;
     IA.raw_mode = raw_mode; IA.skip_empty_check = skip_empty;
     // grids of up to 512 x 512 pixels (the reference's 501 x 501 included) take the instantiation with int32 circle parameters
     if (G.grid_h <= 512 && G.grid_w <= 512) image_kernel<true><<<std::min(n_img, c->image_slots), IMAGE_NT, smem, st>>>(IA);

@@ -35,13 +35,10 @@
 
 namespace bev {
 
-#ifndef IMAGE_NT
-#define IMAGE_NT_DEF 512
-#else
-#define IMAGE_NT_DEF IMAGE_NT
-#undef IMAGE_NT
+#ifndef IMAGE_THREADS
+#define IMAGE_THREADS 512     // threads per CTA (a multiple of 32)
 #endif
-constexpr int IMAGE_NT = IMAGE_NT_DEF;
+constexpr int IMAGE_NT = IMAGE_THREADS;
 #ifndef IMAGE_COOP_CHAIN
 #define IMAGE_COOP_CHAIN 1
 #endif
@@ -50,6 +47,15 @@ constexpr int IMAGE_NT = IMAGE_NT_DEF;
 #endif
 #ifndef IMAGE_COOP_CACHE
 #define IMAGE_COOP_CACHE 1
+#endif
+#ifndef IMAGE_WIN_NR
+#define IMAGE_WIN_NR 3
+#endif
+#ifndef IMAGE_CTAS
+#define IMAGE_CTAS 2          // persistent CTAs per SM
+#endif
+#ifndef IMAGE_TMP_GLOBAL
+#define IMAGE_TMP_GLOBAL 0    // 1: the second bit plane (row-dilated mask, then the deferred-query bits) lives in global memory
 #endif
 #ifndef IMAGE_COOP_MIN_BAND
 #define IMAGE_COOP_MIN_BAND 4
@@ -95,8 +101,14 @@ struct ImageArgs {
 __host__ __device__ inline size_t image_smem_bytes(int h, int wpr) {
     const size_t plane = (size_t)h * wpr * 4;
     const size_t rows = ((size_t)h * 2 + 15) & ~(size_t)15;
-    return 2 * plane + 13 * rows + 2 * (((size_t)h * 4 + 15) & ~(size_t)15) + 64;
+    return (IMAGE_TMP_GLOBAL ? 1 : 2) * plane + 13 * rows + 2 * (((size_t)h * 4 + 15) & ~(size_t)15) + 64;
 }
+
+#if IMAGE_TMP_GLOBAL
+#define DEFER_LD(p) __ldcg(p)   // other warps clear bits with atomics (performed in L2): never read them through L1
+#else
+#define DEFER_LD(p) (*(p))
+#endif
 
 struct Tri2 { int ax, ay, bx, by, cx, cy; };
 
@@ -518,7 +530,7 @@ __global__ void __launch_bounds__(256) image_order_kernel(const int32_t* __restr
 }
 
 template <bool SG>
-__global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
+__global__ void __launch_bounds__(IMAGE_NT, IMAGE_CTAS) image_kernel(ImageArgs A) {
     const int slot = blockIdx.x;  // scratch slot of this (persistent) CTA
     const int h = A.G.grid_h, w = A.G.grid_w, wpr = A.G.wpr;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -533,12 +545,17 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
         unsigned char* p = smem_raw;
         S.occ = (uint32_t*)p; p += plane;
         S.keep = A.keepbits + (size_t)slot * A.keepbits_stride;  // global (L2): only list building and the final masking read it
+#if IMAGE_TMP_GLOBAL
+        S.tmp = A.keepbits + (size_t)slot * A.keepbits_stride + A.keepbits_stride / 2;
+#else
         S.tmp = (uint32_t*)p; p += plane;
+#endif
         int16_t** arr[13] = {&S.cnt, &S.first, &S.last, &S.up, &S.dn, &S.hlo, &S.hhi, &S.hl0, &S.hl1, &S.hr0, &S.hr1, &S.stk_l, &S.stk_r};
         for (int i = 0; i < 13; i++) { *arr[i] = (int16_t*)p; p += rows; }
         const size_t frows = ((size_t)h * 4 + 15) & ~(size_t)15;
         S.hlf = (float*)p; p += frows; S.hrf = (float*)p; p += frows;
     }
+    __shared__ uint32_t s_rownz[32];  // rows with at least one site, one bit per row (grid_h <= 1023)
     __shared__ int s_S, s_M, s_mincol, s_maxcol, s_ne_cnt, s_keep_cnt, s_nitems, s_next, s_filled, s_flips, s_maxflips, s_hull_ok, s_img, s_nedge, s_masked;
 
   // Images are handed out dynamically (their cost varies by 3x).  Thread 0 claims the next index while the CTA finishes the
@@ -564,6 +581,7 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
     mark(0);
     if (pclk && tid == 0) {
         pclk[15] = 0;  // cooperative pass: descents << 40 | waves << 20 | flips
+        pclk[4] = 0; pclk[5] = 0; pclk[13] = 0;
         unsigned long long ns; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
         pclk[19] = (long long)ns; pclk[21] = slot; pclk[23] = dst; pclk[4] = counts[0]; pclk[5] = counts[1];
     }
@@ -638,11 +656,15 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
     if (!A.skip_empty_check && counts[1] == 0) status = 1;                         // EMPTY -> None
     else if (nS < 4 || M < 2 || s_mincol == s_maxcol) status = 2;                  // DEGENERATE -> zeros
 
-    // nearest non-empty row above / below every row
+    // nearest non-empty row above / below every row: one bit per row (a warp ballot per 32 rows), then two bit scans per row
+    for (int r0 = warp * 32; r0 < h; r0 += IMAGE_NT) {
+        const uint32_t nz = __ballot_sync(0xffffffffu, r0 + lane < h && S.cnt[r0 + lane] > 0);
+        if (lane == 0) s_rownz[r0 >> 5] = nz;
+    }
+    __syncthreads();
     for (int r = tid; r < h; r += IMAGE_NT) {
-        int u = r + 1; while (u < h && S.cnt[u] == 0) u++;
-        int d = r - 1; while (d >= 0 && S.cnt[d] == 0) d--;
-        S.up[r] = (int16_t)(u < h ? u : -1); S.dn[r] = (int16_t)d;
+        const int u = next_bit(s_rownz, r + 1, h - 1), d = prev_bit(s_rownz, r - 1, 0);
+        S.up[r] = (int16_t)u; S.dn[r] = (int16_t)d;
         S.hlo[r] = 1; S.hhi[r] = 0;  // rows outside the hull: empty range
         S.hlf[r] = __int_as_float(0x7f800000); S.hrf[r] = __int_as_float(0xff800000);
     }
@@ -900,7 +922,7 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
     __syncthreads();
     mark(18);
     if (pclk && tid == 0) pclk[17] = s_nitems;
-    if (status == 0) resolve_window<3>(S, wpr, w, h, qlist, qres, s_nitems, &s_next, defer, lane, my_flips, my_maxflips);
+    if (status == 0) resolve_window<IMAGE_WIN_NR>(S, wpr, w, h, qlist, qres, s_nitems, &s_next, defer, lane, my_flips, my_maxflips);
     __syncthreads();
     mark(16);
     if (status == 0) shade(s_nitems);
@@ -935,6 +957,8 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
         const int n = s_nitems;
         // guided self-scheduling: bands shrink with what is left (long row-major bands first, so that the pixels of one
         // triangle mostly meet the same warp; short ones at the end, so that no warp is left alone with a long band)
+        const long long coop_t0 = clock64();
+        long long longest = 0;
         Tri2 tp = {0, 0, 0, 0, 0, 0};  // final triangle of this warp's previous descent
         bool have_prev = false;
         while (true) {
@@ -951,7 +975,7 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
             const uint32_t idx = clist[i];
             const uint32_t code = qlist[idx];
             const int x = (int)(code & COL_MASK), r = (int)(code >> COL_BITS);
-            if (!((defer[r * wpr + (x >> 5)] >> (x & 31)) & 1u)) continue;  // already filled by another descent's triangle
+            if (!((DEFER_LD(&defer[r * wpr + (x >> 5)]) >> (x & 31)) & 1u)) continue;  // already filled by another descent's triangle
             Tri2 t;
             const unsigned long long part = qres[idx];
             if (part != 0ull) {  // continue the window pass's descent (the entry is not QRES_DONE: it is on this list)
@@ -980,6 +1004,7 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
                 }
             }
 #endif
+            const long long d_t0 = clock64();
             int flips = 0, waves = 0;
             // Each lane keeps the violator its row produced in the last scan.  After a flip these candidates are tested (exactly)
             // against the new circle before any row is scanned again: consecutive circles overlap, so about half of the flips
@@ -1015,13 +1040,14 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
             if (lane == 0) { my_flips += flips; my_maxflips = max(my_maxflips, flips); }
             if (pclk && lane == 0) atomicAdd((unsigned long long*)&pclk[15], (1ull << 40) | ((unsigned long long)waves << 20) | (unsigned long long)flips);
             tp = t; have_prev = true;
+            longest = max(longest, clock64() - d_t0);
             // rasterise t over the deferred pixels it contains: one lane per row of its bounding box
             const uint32_t ca = site_rgb(t.ax, t.ay), cb = site_rgb(t.bx, t.by), cc = site_rgb(t.cx, t.cy);
             const int y0 = min(t.ay, min(t.by, t.cy)), y1 = max(t.ay, max(t.by, t.cy));
             const int bx0 = min(t.ax, min(t.bx, t.cx)), bx1 = max(t.ax, max(t.bx, t.cx));
             for (int y = y0 + lane; y <= y1; y += 32) {
                 for (int wi = bx0 >> 5; wi <= (bx1 >> 5); wi++) {
-                    uint32_t m = defer[y * wpr + wi] & range_mask(wi, bx0, bx1);
+                    uint32_t m = DEFER_LD(&defer[y * wpr + wi]) & range_mask(wi, bx0, bx1);
                     uint32_t done = 0;
                     while (m) {
                         const int b = __ffs(m) - 1; m &= m - 1;
@@ -1034,6 +1060,12 @@ __global__ void __launch_bounds__(IMAGE_NT, 2) image_kernel(ImageArgs A) {
             }
             __syncwarp();
           }
+        }
+        if (pclk && lane == 0) {
+            const long long busy = clock64() - coop_t0;
+            atomicAdd((unsigned long long*)&pclk[5], (unsigned long long)busy);
+            atomicMax((unsigned long long*)&pclk[4], (unsigned long long)busy);
+            atomicMax((unsigned long long*)&pclk[13], (unsigned long long)longest);
         }
     }
     __syncthreads();

@@ -30,6 +30,8 @@ print("queries: window %.0f  cooperative %.0f" % (c[:, 17].mean(), c[:, 14].mean
 d15 = c[:, 15]
 print("flips per image: all %.0f, window pass %.0f = %.2f per window query; filled px %.0f" % (c[:, 6].mean(), (c[:, 6] - (d15 & 0xFFFFF)).mean(), (c[:, 6] - (d15 & 0xFFFFF)).mean() / max(c[:, 17].mean(), 1), c[:, 7].mean()))
 print("cooperative pass per image: descents %.0f  waves %.0f  flips %.0f" % ((d15 >> 40).mean(), ((d15 >> 20) & 0xFFFFF).mean(), (d15 & 0xFFFFF).mean()))
+print("cooperative pass, cycles: phase %.0f, busiest warp %.0f, mean warp %.0f, longest single descent %.0f" % (
+    (c[:, 10] - c[:, 9]).mean(), c[:, 4].mean(), c[:, 5].mean() / 16, c[:, 13].mean()))
 # timeline of the launch from the global timer: how well the persistent CTAs are packed
 c = c[c[:, 19] > 0]
 t0, t1, slot = c[:, 19].astype(np.float64), c[:, 20].astype(np.float64), c[:, 21]
