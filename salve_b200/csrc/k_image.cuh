@@ -271,18 +271,18 @@ __device__ __forceinline__ void resolve_window(const ImageShared& S, int wpr, in
                     x = (int)(code & COL_MASK); r = (int)(code >> COL_BITS); idx = i;
                     active = true; flips = 0;
                     // window
+                    // branch-free: clamped row / word indices, masks for what lies outside the grid
                     const int c0 = x - 16;
                     const int w0 = c0 >> 5, sh = c0 & 31;  // c0 may be negative: arithmetic shift = floor
+                    const int wlo = max(w0, 0), whi = min(w0 + 1, wpr - 1);
+                    const uint32_t mlo = w0 >= 0 ? 0xFFFFFFFFu : 0u, mhi = w0 + 1 < wpr ? 0xFFFFFFFFu : 0u;
 #pragma unroll
                     for (int k = 0; k < NROW; k++) {
                         const int y = r + k - NR;
-                        uint32_t lo = 0u, hi = 0u;
-                        if (y >= 0 && y < H) {
-                            const uint32_t* row = S.occ + y * wpr;
-                            if (w0 >= 0) lo = row[w0];
-                            if (w0 + 1 < wpr) hi = row[w0 + 1];
-                        }
-                        wr[k] = __funnelshift_r(lo, hi, sh);
+                        const int yc = min(max(y, 0), H - 1);
+                        const uint32_t* row = S.occ + yc * wpr;
+                        const uint32_t vm = y == yc ? 0xFFFFFFFFu : 0u;
+                        wr[k] = __funnelshift_r(row[wlo] & mlo & vm, row[whi] & mhi & vm, sh);
                     }
                     // initial triangle: nearest sites left and right on the row, nearest site of the closest non-empty window row
                     const uint32_t ml = wr[NR] & 0xFFFFu, mr = wr[NR] >> 17;
