@@ -370,12 +370,9 @@ __device__ __forceinline__ void resolve_window(const ImageShared& S, int wpr, in
             const uint32_t sites = wr[yy + NR];
             const uint32_t m = sites & im;
             if (m && !have) { have = true; vm = m; dy = yy; }
-            // sites on the circle other than a, b, c
-            uint32_t o = sites & om & ~im;
-            if (yy == ay) o &= ~(1u << (ax + 16));
-            if (yy == by) o &= ~(1u << (bx + 16));
-            if (yy == cy) o &= ~(1u << (cx + 16));
-            on[k] = o; anyon |= o;
+            // sites on the circle (a, b, c among them: they are taken out when the candidates are packed)
+            const uint32_t o = sites & om & ~im;
+            on[k] = o; anyon += __popc(o);
         }
         if (have) dx = nearest(vm);
         if (have && !fits) {
@@ -391,9 +388,14 @@ __device__ __forceinline__ void resolve_window(const ImageShared& S, int wpr, in
             // word, rows in scan order.
             const int icx = __float2int_rn(ccx);
             unsigned long long cand = 0ull;
-            if (anyon)
+            if (anyon > 3u) {
 #pragma unroll
-            for (int k = 0; k < NROW; k++) cand |= (unsigned long long)((uint32_t)(((unsigned long long)on[k] << 4) >> (icx + 16)) & 0x1FFu) << (9 * k);
+                for (int k = 0; k < NROW; k++) cand |= (unsigned long long)((uint32_t)(((unsigned long long)on[k] << 4) >> (icx + 16)) & 0x1FFu) << (9 * k);
+                // row index in scan order of a vertex row vy: 0, +1, -1, +2, ... -> 0, 1, 2, 3, ...
+                cand &= ~(1ull << (9 * (ay > 0 ? 2 * ay - 1 : -2 * ay) + ax - icx + 4));
+                cand &= ~(1ull << (9 * (by > 0 ? 2 * by - 1 : -2 * by) + bx - icx + 4));
+                cand &= ~(1ull << (9 * (cy > 0 ? 2 * cy - 1 : -2 * cy) + cx - icx + 4));
+            }
             if (cand) {
                 const int wa = (int)pert_weight(vlabel(r + ay, x + ax), W), wb = (int)pert_weight(vlabel(r + by, x + bx), W),
                           wc = (int)pert_weight(vlabel(r + cy, x + cx), W);
@@ -895,10 +897,17 @@ __global__ void __launch_bounds__(IMAGE_NT, IMAGE_CTAS) image_kernel(ImageArgs A
     };
     auto flip_to = [&](Tri2& t, int v, int x, int r) {
         const int dx = v & 0xFFFF, dy = v >> 16;
-        // flip inside {a,b,c,d}: keep the new triangle that contains q
-        if (ccw_contains(dx, dy, t.bx, t.by, t.cx, t.cy, x, r)) { t.ax = dx; t.ay = dy; return true; }
-        if (ccw_contains(t.ax, t.ay, dx, dy, t.cx, t.cy, x, r)) { t.bx = dx; t.by = dy; return true; }
-        if (ccw_contains(t.ax, t.ay, t.bx, t.by, dx, dy, x, r)) { t.cx = dx; t.cy = dy; return true; }
+        // flip inside {a,b,c,d}: keep the new triangle that contains q.  In coordinates relative to q the candidates (d,b,c),
+        // (a,d,c), (a,b,d) share six cross products (orient(p,q,s) = p x q + q x s + s x p); |products| <= 2 * 2047^2 < 2^31.
+        const int ax = t.ax - x, ay = t.ay - r, bx = t.bx - x, by = t.by - r, cx = t.cx - x, cy = t.cy - r, ex = dx - x, ey = dy - r;
+        const int Xab = ax * by - ay * bx, Xbc = bx * cy - by * cx, Xca = cx * ay - cy * ax;
+        const int Xad = ax * ey - ay * ex, Xbd = bx * ey - by * ex, Xcd = cx * ey - cy * ex;
+        const bool fa = (Xbd <= 0) & (Xbc >= 0) & (Xcd >= 0) & ((long long)Xbc + Xcd - Xbd > 0);
+        const bool fb = (Xad >= 0) & (Xcd <= 0) & (Xca >= 0) & ((long long)Xad - Xcd + Xca > 0);
+        const bool fc = (Xab >= 0) & (Xbd >= 0) & (Xad <= 0) & ((long long)Xab + Xbd - Xad > 0);
+        if (fa) { t.ax = dx; t.ay = dy; return true; }
+        if (fb) { t.bx = dx; t.by = dy; return true; }
+        if (fc) { t.cx = dx; t.cy = dy; return true; }
         return false;  // cannot happen (d is inside the triangle or across exactly one edge)
     };
     uint32_t* defer = S.tmp;  // bit plane: queries handed to the next pass (the row-dilated plane is dead now)
