@@ -57,6 +57,22 @@ constexpr int IMAGE_NT = IMAGE_THREADS;
 #ifndef IMAGE_TMP_GLOBAL
 #define IMAGE_TMP_GLOBAL 0    // 1: the second bit plane (row-dilated mask, then the deferred-query bits) lives in global memory
 #endif
+#ifndef IMAGE_WIN_REFILL
+#define IMAGE_WIN_REFILL 1   // idle lanes that trigger a refill of the window pass
+#endif
+#ifndef IMAGE_STREAM_HINTS
+#define IMAGE_STREAM_HINTS 1  // key grid loads and first-pass output stores are streaming (evict first): the panos stay in L2
+#endif
+#if IMAGE_STREAM_HINTS & 1
+#define IMAGE_KEY_LD(p) __ldcs(p)
+#else
+#define IMAGE_KEY_LD(p) __ldg(p)
+#endif
+#if IMAGE_STREAM_HINTS & 2
+#define IMAGE_OUT_ST(p, v) __stcs(p, v)
+#else
+#define IMAGE_OUT_ST(p, v) (*(p) = (v))
+#endif
 #ifndef IMAGE_COOP_MIN_BAND
 #define IMAGE_COOP_MIN_BAND 4
 #endif
@@ -64,7 +80,7 @@ constexpr int IMAGE_NT = IMAGE_THREADS;
 #define IMAGE_COOP_BAND_DIV 2
 #endif
 #ifndef SITES_BATCH_DEF
-#define SITES_BATCH_DEF 8
+#define SITES_BATCH_DEF 4   // words per lane and round trip in phase A (4 measured faster than 8 and 16: smaller code, same latency hiding)
 #endif
 constexpr int SITES_BATCH = SITES_BATCH_DEF;
 constexpr int IMAGE_MAX_FLIPS = 100000;  // safety cap on one descent (never reached: the lift is strictly monotone)
@@ -258,7 +274,7 @@ __device__ __forceinline__ void resolve_window(const ImageShared& S, int wpr, in
     while (true) {
         // ---- refill idle lanes
         const unsigned idle = __ballot_sync(FULL, !active);
-        if (idle && !exhausted && (__popc(idle) >= 4 || idle == FULL)) {
+        if (idle && !exhausted && (__popc(idle) >= IMAGE_WIN_REFILL || idle == FULL)) {
             const int leader = __ffs(idle) - 1;
             int base = 0;
             if (lane == leader) base = atomicAdd(s_next, __popc(idle));
@@ -611,17 +627,23 @@ __global__ void __launch_bounds__(IMAGE_NT, IMAGE_CTAS) image_kernel(ImageArgs A
                 uint32_t key[SITES_BATCH], col[SITES_BATCH];
                 const int c0 = wi0 * 32 + lane;
 #pragma unroll
-                for (int j = 0; j < SITES_BATCH; j++) key[j] = (c0 + j * 32 < w) ? __ldg(kp + j * 32) : 0u;
+                for (int j = 0; j < SITES_BATCH; j++) key[j] = (c0 + j * 32 < w) ? IMAGE_KEY_LD(kp + j * 32) : 0u;
 #pragma unroll
                 for (int j = 0; j < SITES_BATCH; j++) {
                     col[j] = 0u;
+#ifndef IMAGE_DIAG_NO_GATHER
                     if (key[j]) col[j] = gather_rgb(csrc, (key[j] - 1u) & KEY_IDX_MASK, A.pano_w);
+#else
+                    col[j] = key[j] * 2654435761u >> 8;
+#endif
                 }
 #pragma unroll
                 for (int j = 0; j < SITES_BATCH; j++) {
                     const uint32_t cr = col[j] & 0xFF, cg = (col[j] >> 8) & 0xFF, cb = col[j] >> 16;
                     const bool ne = ((cr * cg * cb) & 0xFFu) != 0u;  // uint8 product wraps (interpolation_utils.py:95)
-                    if (c0 + j * 32 < w) { op[j * 96 + 0] = (uint8_t)cr; op[j * 96 + 1] = (uint8_t)cg; op[j * 96 + 2] = (uint8_t)cb; }
+#ifndef IMAGE_DIAG_NO_A_STORE
+                    if (c0 + j * 32 < w) { IMAGE_OUT_ST(op + j * 96 + 0, (uint8_t)cr); IMAGE_OUT_ST(op + j * 96 + 1, (uint8_t)cg); IMAGE_OUT_ST(op + j * 96 + 2, (uint8_t)cb); }
+#endif
                     const uint32_t ob = __ballot_sync(0xffffffffu, key[j] != 0u);
                     const uint32_t nb = __ballot_sync(0xffffffffu, ne);
                     if (lane == ((wi0 + j) & 31)) { my_ob = ob; my_nb = nb; }

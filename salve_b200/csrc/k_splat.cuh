@@ -75,7 +75,10 @@ __device__ __forceinline__ bool bbox_pixel(const SplatParams& P, double x, doubl
 constexpr int SPLAT_ROWS = 8;
 constexpr int SPLAT_BATCH = 4;
 
-__global__ void __launch_bounds__(256, 3) splat_pano_kernel(SplatParams P, const SplatJob* __restrict__ jobs,
+#ifndef SPLAT_CTAS
+#define SPLAT_CTAS 3
+#endif
+__global__ void __launch_bounds__(256, SPLAT_CTAS) splat_pano_kernel(SplatParams P, const SplatJob* __restrict__ jobs,
                                                          uint32_t* __restrict__ keygrid_base, size_t keygrid_stride,
                                                          int32_t* __restrict__ counts /* [n_img][8] */) {
     const SplatJob job = jobs[blockIdx.y];
