@@ -300,43 +300,44 @@ __device__ __forceinline__ void resolve_window(const ImageShared& S, int wpr, in
                         const uint32_t vm = y == yc ? 0xFFFFFFFFu : 0u;
                         wr[k] = __funnelshift_r(row[wlo] & mlo & vm, row[whi] & mhi & vm, sh);
                     }
-                    // initial triangle: nearest sites left and right on the row, nearest site of the closest non-empty window row
+                    // initial triangle.  Row pair: nearest sites left and right of q (64: none in the window).
                     const uint32_t ml = wr[NR] & 0xFFFFu, mr = wr[NR] >> 17;
-                    bool ok = ml != 0u && mr != 0u;
-                    int xl = 0, xr = 0;
-                    if (ok) { xl = (31 - __clz(ml)) - 16; xr = __ffs(mr); ok = xr - xl <= MAXGAP; }
-                    // apex: the nearer of (nearest site of the closest non-empty row above, ... below), |dx| <= 8
-                    int px = 0, py = 0, pxd = 0, pyd = 0;
-                    bool fu = false, fd = false;
-#pragma unroll
-                    for (int k = 1; k <= NR; k++) {
-                        const uint32_t mu = wr[NR + k] & 0x01FFFF00u, md = wr[NR - k] & 0x01FFFF00u;
-                        if (!fu && mu) { fu = true; px = nearest(mu); py = k; }
-                        if (!fd && md) { fd = true; pxd = nearest(md); pyd = -k; }
-                    }
-                    const bool found = fu || fd;
-                    if (fd && (!fu || pxd * pxd + pyd * pyd < px * px + py * py)) { px = pxd; py = pyd; }
-                    ok = ok && found;
-#if IMAGE_WIN_VINIT
-                    // nearest sites above and below in q's own column: q lies on the segment D-U as it lies on L-R.  The shorter
-                    // of the two is the likelier Delaunay edge (fewer flips to come), and D-U serves when L or R is missing.
-                    int yu = 0, yd = 0;
+                    const int xl = ml ? (31 - __clz(ml)) - 16 : -64, xr = mr ? __ffs(mr) : 64;
+                    bool ok = xr - xl <= MAXGAP;
+                    // apex candidates: nearest site (|dx| <= 8) of the closest non-empty row above and of the closest below
+                    uint32_t mu = 0u, md = 0u;
+                    int ku = 0, kd = 0, yu = 0, yd = 0;  // yu, yd: nearest sites in q's own column
 #pragma unroll
                     for (int k = NR; k >= 1; k--) {
-                        if (wr[NR + k] & 0x10000u) yu = k;
-                        if (wr[NR - k] & 0x10000u) yd = k;
+                        const uint32_t u = wr[NR + k], d = wr[NR - k];
+                        if (u & 0x01FFFF00u) { mu = u & 0x01FFFF00u; ku = k; }
+                        if (d & 0x01FFFF00u) { md = d & 0x01FFFF00u; kd = k; }
+                        if (u & 0x10000u) yu = k;
+                        if (d & 0x10000u) yd = k;
                     }
-                    if (yu != 0 && yd != 0 && (!ok || yu + yd < xr - xl)) {
+                    int px = 0, py = 0;
+                    if (ku) { px = nearest(mu); py = ku; }
+                    if (kd) {
+                        const int pxd = nearest(md);
+                        if (!ku || pxd * pxd + kd * kd < px * px + py * py) { px = pxd; py = -kd; }  // the nearer of the two
+                    }
+                    const bool found = (ku | kd) != 0;
+                    ok = ok && found;
+                    // Column pair: q lies on the segment D-U as it lies on L-R.  The shorter of the two is the likelier Delaunay
+                    // edge (fewer flips to come), and D-U serves when L or R is missing.
+                    bool vert = false;
+                    if (IMAGE_WIN_VINIT && yu != 0 && yd != 0 && (!ok || yu + yd < xr - xl)) {
                         int qx = 0, qy = 0;  // apex: the nearer of L and R, else the site found in a neighbouring row
-                        if (ml != 0u && (mr == 0u || (16 - (31 - __clz(ml))) <= __ffs(mr))) qx = (31 - __clz(ml)) - 16;
-                        else if (mr != 0u) qx = __ffs(mr);
-                        else if (found && px != 0) { qx = px; qy = py; }
-                        if (qx < 0) { ax = 0; ay = -yd; bx = 0; by = yu; cx = qx; cy = qy; ok = true; }       // (D, U, P): P on the left
-                        else if (qx > 0) { ax = 0; ay = yu; bx = 0; by = -yd; cx = qx; cy = qy; ok = true; }  // (U, D, P): P on the right
-                        else if (ok) { if (py > 0) { ax = xl; bx = xr; } else { ax = xr; bx = xl; } ay = 0; by = 0; cx = px; cy = py; }
-                    } else
-#endif
-                    if (ok) {
+                        if (ml != 0u && -xl <= xr) qx = xl;
+                        else if (mr != 0u) qx = xr;
+                        else if (px != 0) { qx = px; qy = py; }
+                        if (qx != 0) {
+                            vert = true; ok = true;
+                            ax = 0; bx = 0; cx = qx; cy = qy;
+                            if (qx < 0) { ay = -yd; by = yu; } else { ay = yu; by = -yd; }  // (D, U, P) with P on the left, (U, D, P) on the right
+                        }
+                    }
+                    if (ok && !vert) {
                         if (py > 0) { ax = xl; bx = xr; } else { ax = xr; bx = xl; }
                         ay = 0; by = 0; cx = px; cy = py;
                     }
