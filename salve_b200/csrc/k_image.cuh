@@ -35,21 +35,10 @@
 
 namespace bev {
 
+// ---- tuning knobs.  The defaults are the measured best on B200 for the 501 x 501 grid; `salve_b200.build.build(defines=[...],
+// out=...)` compiles variants and scripts/variant_bench.py times them against each other with an identity check of the output.
 #ifndef IMAGE_THREADS
-#define IMAGE_THREADS 512     // threads per CTA (a multiple of 32)
-#endif
-constexpr int IMAGE_NT = IMAGE_THREADS;
-#ifndef IMAGE_COOP_CHAIN
-#define IMAGE_COOP_CHAIN 1
-#endif
-#ifndef IMAGE_WIN_VINIT
-#define IMAGE_WIN_VINIT 1
-#endif
-#ifndef IMAGE_COOP_CACHE
-#define IMAGE_COOP_CACHE 1
-#endif
-#ifndef IMAGE_WIN_NR
-#define IMAGE_WIN_NR 3
+#define IMAGE_THREADS 512     // threads per CTA (a multiple of 32).  2 x 512 beats 4 x 256, 3 x 320, 2 x 384, 1 x 768 and 1 x 1024
 #endif
 #ifndef IMAGE_CTAS
 #define IMAGE_CTAS 2          // persistent CTAs per SM
@@ -57,11 +46,32 @@ constexpr int IMAGE_NT = IMAGE_THREADS;
 #ifndef IMAGE_TMP_GLOBAL
 #define IMAGE_TMP_GLOBAL 0    // 1: the second bit plane (row-dilated mask, then the deferred-query bits) lives in global memory
 #endif
-#ifndef IMAGE_WIN_REFILL
-#define IMAGE_WIN_REFILL 1   // idle lanes that trigger a refill of the window pass
+#ifndef SITES_BATCH_DEF
+#define SITES_BATCH_DEF 4     // phase A: words per lane and round trip (4 beats 8 and 16: smaller code, same latency hiding)
 #endif
 #ifndef IMAGE_STREAM_HINTS
-#define IMAGE_STREAM_HINTS 1  // key grid loads and first-pass output stores are streaming (evict first): the panos stay in L2
+#define IMAGE_STREAM_HINTS 3  // bit 0: key grid loads, bit 1: first-pass output stores are streaming (evict first)
+#endif
+#ifndef IMAGE_WIN_NR
+#define IMAGE_WIN_NR 3        // window pass: rows above and below the query held in registers (2 is slower, 4 does not pack)
+#endif
+#ifndef IMAGE_WIN_REFILL
+#define IMAGE_WIN_REFILL 1    // window pass: idle lanes that trigger a refill
+#endif
+#ifndef IMAGE_WIN_VINIT
+#define IMAGE_WIN_VINIT 1     // window pass: initial triangle on the column pair D-U when it is shorter than the row pair L-R
+#endif
+#ifndef IMAGE_COOP_CHAIN
+#define IMAGE_COOP_CHAIN 1    // cooperative pass: start from the previous final triangle's edge
+#endif
+#ifndef IMAGE_COOP_CACHE
+#define IMAGE_COOP_CACHE 1    // cooperative pass: retry the last scan's violators before scanning again
+#endif
+#ifndef IMAGE_COOP_MIN_BAND
+#define IMAGE_COOP_MIN_BAND 4 // cooperative pass: smallest band of the guided self-scheduling
+#endif
+#ifndef IMAGE_COOP_BAND_DIV
+#define IMAGE_COOP_BAND_DIV 2 // cooperative pass: band = what is left / (IMAGE_COOP_BAND_DIV * warps)
 #endif
 #if IMAGE_STREAM_HINTS & 1
 #define IMAGE_KEY_LD(p) __ldcs(p)
@@ -73,15 +83,7 @@ constexpr int IMAGE_NT = IMAGE_THREADS;
 #else
 #define IMAGE_OUT_ST(p, v) (*(p) = (v))
 #endif
-#ifndef IMAGE_COOP_MIN_BAND
-#define IMAGE_COOP_MIN_BAND 4
-#endif
-#ifndef IMAGE_COOP_BAND_DIV
-#define IMAGE_COOP_BAND_DIV 2
-#endif
-#ifndef SITES_BATCH_DEF
-#define SITES_BATCH_DEF 4   // words per lane and round trip in phase A (4 measured faster than 8 and 16: smaller code, same latency hiding)
-#endif
+constexpr int IMAGE_NT = IMAGE_THREADS;
 constexpr int SITES_BATCH = SITES_BATCH_DEF;
 constexpr int IMAGE_MAX_FLIPS = 100000;  // safety cap on one descent (never reached: the lift is strictly monotone)
 
@@ -632,19 +634,13 @@ __global__ void __launch_bounds__(IMAGE_NT, IMAGE_CTAS) image_kernel(ImageArgs A
 #pragma unroll
                 for (int j = 0; j < SITES_BATCH; j++) {
                     col[j] = 0u;
-#ifndef IMAGE_DIAG_NO_GATHER
                     if (key[j]) col[j] = gather_rgb(csrc, (key[j] - 1u) & KEY_IDX_MASK, A.pano_w);
-#else
-                    col[j] = key[j] * 2654435761u >> 8;
-#endif
                 }
 #pragma unroll
                 for (int j = 0; j < SITES_BATCH; j++) {
                     const uint32_t cr = col[j] & 0xFF, cg = (col[j] >> 8) & 0xFF, cb = col[j] >> 16;
                     const bool ne = ((cr * cg * cb) & 0xFFu) != 0u;  // uint8 product wraps (interpolation_utils.py:95)
-#ifndef IMAGE_DIAG_NO_A_STORE
                     if (c0 + j * 32 < w) { IMAGE_OUT_ST(op + j * 96 + 0, (uint8_t)cr); IMAGE_OUT_ST(op + j * 96 + 1, (uint8_t)cg); IMAGE_OUT_ST(op + j * 96 + 2, (uint8_t)cb); }
-#endif
                     const uint32_t ob = __ballot_sync(0xffffffffu, key[j] != 0u);
                     const uint32_t nb = __ballot_sync(0xffffffffu, ne);
                     if (lane == ((wi0 + j) & 31)) { my_ob = ob; my_nb = nb; }
