@@ -20,12 +20,14 @@
 // (perturbed) Delaunay triangulation over q -- bit-identical to rasterising the full mesh, but the
 // only state is the 32 KB occupancy bitmap in shared memory: no mesh, no atomics, no rounds.
 //
-// Order of work per image (persistent CTAs take images from an atomic counter):
-//   A  winners -> colours, bit rows          B  guards          C  exact convex hull (two monotone chains)
+// Order of work per image (persistent CTAs take images from an atomic counter, longest expected image first):
+//   A  winners -> colours, bit rows          B  guards          C  exact convex hull (pre-filtered monotone chains)
 //   D  keep mask (separable dilation)         F  EDGE RULE (queries between two opposite 4-neighbour sites: mean of two
-//      colours, bit-parallel) + query list    G0 WINDOW PASS (small triangles, 7 x 32 window in registers, exact float
-//      interval classification)               G1 per-lane int64/float64 row scan, circumradius <= 12 px
-//   G2 warp-cooperative pass (32 rows per trip), final triangle shared by all deferred pixels inside it
+//      colours; found bit-parallel, averaged one per thread) + query list
+//   G0 WINDOW PASS (small triangles, 7 x 32 window in registers, exact float interval classification; the initial triangle stands
+//      on the shorter of the row pair and the column pair around the query); what it cannot certify is handed on with its triangle
+//   G2 COOPERATIVE PASS (one warp per query, 32 rows per wave, cached violators, previous final triangle as a start), final
+//      triangle shared by all deferred pixels inside it
 //   H  masked-out sites, counters.
 // The closed convex hull decides which pixels are queries at all (outside it griddata gives NaN -> 0).
 #pragma once
@@ -945,7 +947,7 @@ __global__ void __launch_bounds__(IMAGE_NT, IMAGE_CTAS) image_kernel(ImageArgs A
         }
     };
 
-    // ---- G0 / G1. window pass (small triangles), then the per-lane row scan (bounded work): one query per lane -------------
+    // ---- G0. window pass (small triangles): one query per lane -----------------------------------------------------------
     for (int i = tid; i < nwords; i += IMAGE_NT) defer[i] = 0u;
     __syncthreads();
     mark(18);
