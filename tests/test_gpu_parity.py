@@ -167,6 +167,26 @@ def test_batch_chunking_determinism_and_independence():
     r.close()
 
 
+def test_chunk_larger_than_the_cta_slots_is_order_independent():
+    """A chunk with more images than persistent CTAs goes through image_order_kernel (longest expected image first) and the
+    dynamic hand-out; the bytes must not depend on it: same batch in one chunk of 400 images and in chunks of 12."""
+    from salve_b200.renderer import BevRenderer
+
+    n_p, n_h = 6, 160  # 320 posed + 12 un-posed renders in one chunk > 296 CTA slots
+    rgbs, depths, p1, p2, Rm, t = synth.synth_building(n_p, n_h, 512, 1024, seed=11)
+    big = BevRenderer(max_panos=n_p, max_images=400)
+    small = BevRenderer(max_panos=n_p, max_images=12)
+    for k in range(n_p):
+        big.upload_pano(k, rgbs[k], depths[k])
+        small.upload_pano(k, rgbs[k], depths[k])
+    a, ca, sa = big.render_hypotheses(p1, p2, Rm, t)
+    b, cb, sb = small.render_hypotheses(p1, p2, Rm, t)
+    assert (sa == 0).all() and np.array_equal(sa, sb)
+    assert np.array_equal(ca[..., :6], cb[..., :6])
+    assert np.array_equal(a, b)
+    big.close(); small.close()
+
+
 def test_device_output_path_equals_host_path():
     import torch
 
@@ -522,6 +542,28 @@ def test_interp_dense_fuzz_against_oracle_and_scipy():
         pu.hull_check(want_hull, ~np.isnan(sv[:, 0]).reshape(h, w))
         n_cases += 1
     assert n_cases > 250
+    r.close()
+
+
+def test_interp_dense_on_a_grid_wider_than_512_uses_the_int64_instantiation():
+    """Grids above 512 x 512 run image_kernel<false> (int64 circle parameters in the cooperative pass); the reference's 501 x 501
+    grid never does.  Sparse sites give circles hundreds of pixels wide, dense ones exercise the window pass near the borders."""
+    from salve_b200.renderer import BevRenderer
+
+    h, w = 600, 640
+    r = BevRenderer(max_panos=1, max_images=1, grid_h=h, grid_w=w)
+    rng = np.random.default_rng(7)
+    for density in (0.0008, 0.02, 0.4):
+        occ = rng.random((h, w)) < density
+        rows, cols = np.nonzero(occ)
+        vals = rng.integers(0, 256, (len(rows), 3)).astype(np.float64)
+        perm = rng.permutation(len(rows))
+        img, hull, status = r.interp_dense(np.stack([cols, rows], 1)[perm], vals[perm], h, w, want_hull=True)
+        assert status == 0
+        tri_v, _ = cdt.triangulate(rows, cols, w)
+        want, want_hull, _ = cdt.rasterize(rows, cols, vals.astype(np.uint8), tri_v, h, w)
+        assert np.array_equal(hull, want_hull), f"hull, density {density}"
+        assert np.array_equal(img, want), f"image, density {density}"
     r.close()
 
 
