@@ -226,6 +226,10 @@ constexpr unsigned long long QRES_DONE = 1ull << 63;     // the entry holds the 
 // an entry without QRES_DONE is either 0 (no triangle) or a valid triangle around the query that is not final yet: three distinct
 // 21-bit labels fill bits 0..62, so a triangle never encodes to 0
 
+// bits lo..hi of a 32-bit window (any lo, hi; empty when lo > hi): clamped funnel shifts make every out-of-range case come out right
+__device__ __forceinline__ uint32_t bit_span(int lo, int hi) {
+    return __funnelshift_lc(0u, 0xFFFFFFFFu, (uint32_t)max(lo, 0)) & __funnelshift_rc(0xFFFFFFFFu, 0u, (uint32_t)(31 - min(hi, 31)));
+}
 __device__ __forceinline__ float sqrt_approx(float v) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
 
 // ---- pass 0: small triangles in a register window ---------------------------------------------------------------------------
@@ -362,6 +366,7 @@ __device__ __forceinline__ void resolve_window(const ImageShared& S, int wpr, in
         const float ccx = (float)ax + fU * inv, ccy = (float)ay + fV * inv;
         const float R2 = (fU * fU + fV * fV) * inv * inv;
         const float thr = inv;  // half the smallest possible |distance^2 - R^2| of a lattice point off the circle
+        const float ccx16 = ccx + 16.0f;  // window column of the centre (bit 16 is q's column)
         // does the closed disc stay inside rows +-NR and columns +-15 (conservative, float)?  Only then can the window certify
         // an empty circle; a larger circle can still be searched for violators inside the window (any violator is a valid flip)
         const float Rr = sqrt_approx(R2) + 0.01f;
@@ -380,12 +385,10 @@ __device__ __forceinline__ void resolve_window(const ImageShared& S, int wpr, in
             uint32_t im = 0u, om = 0u;
             if (to >= 0.0f) {
                 const float hwo = sqrt_approx(to);
-                const int o0 = max(__float2int_ru(ccx - hwo) + 16, 0), o1 = min(__float2int_rd(ccx + hwo) + 16, 31);
-                om = (o0 <= o1) ? (((2u << o1) - 1u) & ~((1u << o0) - 1u)) : 0u;
+                om = bit_span(__float2int_ru(ccx16 - hwo), __float2int_rd(ccx16 + hwo));
                 if (ti > 0.0f) {
                     const float hwi = sqrt_approx(ti);
-                    const int i0 = max(__float2int_ru(ccx - hwi) + 16, 0), i1 = min(__float2int_rd(ccx + hwi) + 16, 31);
-                    im = (i0 <= i1) ? (((2u << i1) - 1u) & ~((1u << i0) - 1u)) : 0u;
+                    im = bit_span(__float2int_ru(ccx16 - hwi), __float2int_rd(ccx16 + hwi));
                 }
             }
             const uint32_t sites = wr[yy + NR];
