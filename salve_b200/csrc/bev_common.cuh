@@ -60,6 +60,11 @@ __host__ __device__ __forceinline__ long long pert_weight(uint32_t v, int grid_w
     h ^= h >> 16; h *= 0x7feb352dU; h ^= h >> 15; h *= 0x846ca68bU; h ^= h >> 16;
     return (long long)(h & 0xFFFFF);
 }
+// the same weight from the row-major pixel index row * grid_w + col (no label to pack and unpack)
+__host__ __device__ __forceinline__ int pert_weight_idx(uint32_t h) {
+    h ^= h >> 16; h *= 0x7feb352dU; h ^= h >> 15; h *= 0x846ca68bU; h ^= h >> 16;
+    return (int)(h & 0xFFFFF);
+}
 __host__ __device__ __forceinline__ long long incircle_pert(uint32_t a, uint32_t b, uint32_t c, uint32_t d, int grid_w) {
     return pert_weight(a, grid_w) * orient_v(b, c, d) - pert_weight(b, grid_w) * orient_v(a, c, d) +
            pert_weight(c, grid_w) * orient_v(a, b, d) - pert_weight(d, grid_w) * orient_v(a, b, c);

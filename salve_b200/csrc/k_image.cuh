@@ -300,13 +300,19 @@ __device__ __forceinline__ void resolve_window(const ImageShared& S, int wpr, in
                     const int w0 = c0 >> 5, sh = c0 & 31;  // c0 may be negative: arithmetic shift = floor
                     const int wlo = max(w0, 0), whi = min(w0 + 1, wpr - 1);
                     const uint32_t mlo = w0 >= 0 ? 0xFFFFFFFFu : 0u, mhi = w0 + 1 < wpr ? 0xFFFFFFFFu : 0u;
+                    if (r >= NR && r + NR < H && w0 >= 0 && w0 + 1 < wpr) {  // the window lies inside the grid (almost always)
+                        const uint32_t* row = S.occ + (r - NR) * wpr + w0;
 #pragma unroll
-                    for (int k = 0; k < NROW; k++) {
-                        const int y = r + k - NR;
-                        const int yc = min(max(y, 0), H - 1);
-                        const uint32_t* row = S.occ + yc * wpr;
-                        const uint32_t vm = y == yc ? 0xFFFFFFFFu : 0u;
-                        wr[k] = __funnelshift_r(row[wlo] & mlo & vm, row[whi] & mhi & vm, sh);
+                        for (int k = 0; k < NROW; k++) wr[k] = __funnelshift_r(row[k * wpr], row[k * wpr + 1], sh);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < NROW; k++) {
+                            const int y = r + k - NR;
+                            const int yc = min(max(y, 0), H - 1);
+                            const uint32_t* row = S.occ + yc * wpr;
+                            const uint32_t vm = y == yc ? 0xFFFFFFFFu : 0u;
+                            wr[k] = __funnelshift_r(row[wlo] & mlo & vm, row[whi] & mhi & vm, sh);
+                        }
                     }
                     // initial triangle.  Row pair: nearest sites left and right of q (64: none in the window).
                     const uint32_t ml = wr[NR] & 0xFFFFu, mr = wr[NR] >> 17;
@@ -421,15 +427,16 @@ __device__ __forceinline__ void resolve_window(const ImageShared& S, int wpr, in
                 cand &= ~(1ull << (9 * (cy > 0 ? 2 * cy - 1 : -2 * cy) + cx - icx + 4));
             }
             if (cand) {
-                const int wa = (int)pert_weight(vlabel(r + ay, x + ax), W), wb = (int)pert_weight(vlabel(r + by, x + bx), W),
-                          wc = (int)pert_weight(vlabel(r + cy, x + cx), W);
+                const int qi = r * W + x;  // row-major index of q: a window point (dx, dy) is pixel qi + dy * W + dx
+                const int wa = pert_weight_idx((uint32_t)(qi + ay * W + ax)), wb = pert_weight_idx((uint32_t)(qi + by * W + bx)),
+                          wc = pert_weight_idx((uint32_t)(qi + cy * W + cx));
                 while (cand && !have) {
                     const int b = __ffsll((long long)cand) - 1;
                     cand &= cand - 1ull;
                     const int k = (b * 57) >> 9;  // b / 9 for b < 63
                     const int ddx = b - 9 * k - 4 + icx;
                     const int yy = (k & 1) ? (k + 1) >> 1 : -(k >> 1);
-                    const int wd = (int)pert_weight(vlabel(r + yy, x + ddx), W);
+                    const int wd = pert_weight_idx((uint32_t)(qi + yy * W + ddx));
                     const int obcd = (cx - bx) * (yy - by) - (cy - by) * (ddx - bx);
                     const int oacd = (cx - ax) * (yy - ay) - (cy - ay) * (ddx - ax);
                     const int oabd = (bx - ax) * (yy - ay) - (by - ay) * (ddx - ax);
@@ -878,8 +885,9 @@ __global__ void __launch_bounds__(IMAGE_NT, IMAGE_CTAS) image_kernel(ImageArgs A
             const int x = (int)(code & COL_MASK), r = (int)((code >> COL_BITS) & 0x3FFu);
             bool horiz = (code >> 31) != 0u;
             if (horiz && ((code >> 30) & 1u)) {
-                const long long wh = pert_weight(vlabel(r, x - 1), w) + pert_weight(vlabel(r, x + 1), w);
-                const long long wv = pert_weight(vlabel(r - 1, x), w) + pert_weight(vlabel(r + 1, x), w);
+                const uint32_t qi = (uint32_t)(r * w + x);
+                const int wh = pert_weight_idx(qi - 1u) + pert_weight_idx(qi + 1u);
+                const int wv = pert_weight_idx(qi - (uint32_t)w) + pert_weight_idx(qi + (uint32_t)w);
                 if (wh == wv) {  // residual tie of the perturbation: the general path decides
                     qlist[atomicAdd(&s_nitems, 1)] = code & ((1u << 21) - 1u);
                     continue;
