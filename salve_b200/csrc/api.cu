@@ -352,6 +352,7 @@ static SplatParams make_splat_params(salve_bev_ctx* c) {
     SplatParams P;
     const int H = c->cfg.pano_h, W = c->cfg.pano_w;
     P.H = H; P.W = W; P.crop_rows = c->cfg.crop_rows; P.depth_scale = c->cfg.depth_scale;
+    P.rows_per_thread = 8;  // splat_pano_kernel launches override it (splat_rows_for)
     P.xmin = c->cfg.xmin; P.ymin = c->cfg.ymin; P.xmax = c->cfg.xmax; P.ymax = c->cfg.ymax; P.px_per_m = c->cfg.px_per_m;
     P.a_lo = c->band[0]; P.a_hi = c->band[1]; P.b_lo = c->band[2]; P.b_hi = c->band[3];
     P.grid_w = c->G.grid_w; P.g = c->G.g;
@@ -487,7 +488,8 @@ static int render_chunk(salve_bev_ctx* c, int n_img, const std::vector<SplatJob>
     CU(cudaMemsetAsync(dev_counts, 0, sizeof(int32_t) * 8 * n_img, st));
     SplatParams P = make_splat_params(c);
     const int rows = P.H - 2 * P.crop_rows;
-    dim3 grid((unsigned)(((rows + SPLAT_ROWS - 1) / SPLAT_ROWS) * ((P.W + 1023) >> 10)), (unsigned)jobs.size());
+    P.rows_per_thread = splat_rows_for(jobs.size());
+    dim3 grid((unsigned)(((rows + P.rows_per_thread - 1) / P.rows_per_thread) * ((P.W + 1023) >> 10)), (unsigned)jobs.size());
     splat_pano_kernel<<<grid, 256, 0, st>>>(P, c->d_jobs, c->keygrid, c->g_stride, dev_counts);
     c->launches++;
     CU(cudaGetLastError());
