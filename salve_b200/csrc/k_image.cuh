@@ -112,7 +112,12 @@ struct ImageArgs {
     unsigned long long* qres;                 // per CTA, per list entry: triangle (3 x 21-bit vertex labels), final if | QRES_DONE
     uint32_t* clist;                          // per CTA: list entries the window pass handed on (capacity g)
     uint32_t* keepbits; size_t keepbits_stride;  // per CTA scratch: non-empty, then keep bit rows (grid_h * wpr words)
-    long long* phase_clk;                     // optional diagnostics: per image 16 slots, SM clock at the phase boundaries + list sizes
+    // optional diagnostics, 24 slots per image (scripts/phase_breakdown.py): SM clock at the stage boundaries [0] start, [1] sites,
+    // [2] hull + masks, [18] edge rule + lists, [16] window pass, [3] shading, [9] cooperative list, [10] cooperative pass, [11] end;
+    // [17] / [14] window / cooperative queries; [15] cooperative descents << 40 | waves << 20 | flips; [4] / [5] busiest warp / sum over
+    // warps of the cooperative pass (cycles), [13] longest descent; [6] flips, [7] filled pixels, [22] sites; [19] / [20] global timer
+    // at start / end (ns), [21] CTA slot, [23] destination
+    long long* phase_clk;
     int32_t raw_mode;                 // 1: no keep mask, no flip (interp_dense_grid_from_sparse semantics)
     int32_t skip_empty_check;         // 1: generic interp path (no EMPTY status)
 };
@@ -616,7 +621,7 @@ __global__ void __launch_bounds__(IMAGE_NT, IMAGE_CTAS) image_kernel(ImageArgs A
         pclk[15] = 0;  // cooperative pass: descents << 40 | waves << 20 | flips
         pclk[4] = 0; pclk[5] = 0; pclk[13] = 0;
         unsigned long long ns; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
-        pclk[19] = (long long)ns; pclk[21] = slot; pclk[23] = dst; pclk[4] = counts[0]; pclk[5] = counts[1];
+        pclk[19] = (long long)ns; pclk[21] = slot; pclk[23] = dst;
     }
 
     if (tid == 0) {
