@@ -502,6 +502,9 @@ static int render_chunk(salve_bev_ctx* c, int n_img, const std::vector<SplatJob>
 
 // Copy images between two device buffers at any alignment (an image is 753 003 bytes: consecutive images share no
 // alignment).  Copy k: cache image src_idx[k] -> out image dst_idx[k], plus its counters and status.
+#ifndef REPLICATE_SPLIT
+#define REPLICATE_SPLIT 16  // CTAs per copied image
+#endif
 __global__ void __launch_bounds__(256) replicate_images_kernel(const uint8_t* __restrict__ cache, uint8_t* __restrict__ out,
                                                               const int32_t* __restrict__ src_idx, const int32_t* __restrict__ dst_idx,
                                                               size_t bytes, const int32_t* __restrict__ cache_counts,
@@ -671,7 +674,7 @@ static int render_hyp_dedup(salve_bev_ctx* c, int32_t n_hyp, const int32_t* p1, 
         CU(cudaMemcpyAsync(dsrc, hs.data(), sizeof(int32_t) * n_posed, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(ddst, hd.data(), sizeof(int32_t) * n_posed, cudaMemcpyHostToDevice, st));
         CU(cudaStreamSynchronize(st));  // hs / hd are pageable locals
-        replicate_images_kernel<<<dim3(16, (unsigned)n_posed), 256, 0, st>>>(c->cache_out, out, (const int32_t*)dsrc, (const int32_t*)ddst, ib,
+        replicate_images_kernel<<<dim3(REPLICATE_SPLIT, (unsigned)n_posed), 256, 0, st>>>(c->cache_out, out, (const int32_t*)dsrc, (const int32_t*)ddst, ib,
                                                                             c->cache_counts, counts, c->cache_status, status);
         c->launches++;
         CU(cudaGetLastError());
