@@ -123,3 +123,22 @@ def test_driver_enumeration_follows_the_reference_order(tmp_path):
     got = [(lt, k, os.path.basename(p)) for lt, k, p in driver.enumerate_floor_hypotheses(str(tmp_path), "0007", "floor_02")]
     assert got == [("gt_alignment_approx", 0, "2_5__y.json"), ("gt_alignment_approx", 1, "2_9__z.json"),
                    ("incorrect_alignment", 0, "2_5__a.json"), ("incorrect_alignment", 1, "5_9__b.json")]
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU oracle port on all host cores) needs no GPU and prints one JSON line with the
+    keys the driver reads."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "hypotheses/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["steps"] == 1 and line["n_gpus"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert "workload" in line["config"] and line["gpu_launches"] == 0
