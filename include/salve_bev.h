@@ -257,13 +257,6 @@ int salve_bev_last_timings(salve_bev_ctx* ctx, float* host_ms);
 /* Enable/disable per-stage event timing (off by default: events add sync points at read time only). */
 int salve_bev_enable_timing(salve_bev_ctx* ctx, int32_t on);
 
-/* Diagnostics of image_kernel for the images of the most recent chunk: 24 int64 per image.  [0..11] SM clock at the phase
- * boundaries (start, sites, hull+masks, [3] start of pass 1, pass 1, shade, list, pass 1b, shade, list, pass 2, end); [12..14]
- * number of pixels entering pass 1, pass 1b, pass 2; [15] pass 2: descents << 40 | row waves << 20 | flips; [18] edge rule +
- * list done, [16] window pass done, [17] pixels entering the window pass; rest reserved.  host_clk: n_img * 24 int64.
- * Synchronises the device. */
-int salve_bev_last_phase_clocks(salve_bev_ctx* ctx, int64_t* host_clk, int32_t n_img);
-
 /* Number of kernel launches issued by this context since creation (bench.py's gpu_launches). */
 int64_t salve_bev_launch_count(salve_bev_ctx* ctx);
 

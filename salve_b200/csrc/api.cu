@@ -57,14 +57,19 @@ struct salve_bev_ctx {
     Tri* tris = nullptr;
     unsigned long long* owner = nullptr;
     uint32_t *list0 = nullptr, *list1 = nullptr, *cand = nullptr;
-    uint32_t* qlist = nullptr;  // per image work list of image_kernel (g entries)
-    uint32_t* clist = nullptr;  // per CTA slot: entries handed from the window pass to the cooperative pass
-    unsigned long long* qres = nullptr;  // per image, per list entry: the resolved triangle
-    long long* phase_clk = nullptr;      // diagnostics: 24 slots per image of the last chunk
-    uint32_t* keepbits = nullptr;        // per CTA slot keep-mask bit rows of image_kernel
-    int32_t* work_counter = nullptr;     // image_kernel's dynamic image counter
-    int32_t* d_order = nullptr;          // image_kernel's hand-out order (image_order_kernel)
-    int image_slots = 0;                 // persistent CTAs of image_kernel (scratch slots)
+    // state between the stages of the image pipeline (k_image.cuh), per image of a chunk
+    uint32_t* planes = nullptr;          // 3 bit planes (occupancy, non-empty, keep)
+    unsigned char* rowarr = nullptr;     // row arrays (RA_*), rows_stride bytes per image
+    int32_t* hdr = nullptr;              // HD_STRIDE int32 per image
+    uint32_t* qlist = nullptr;           // query pixels for the window pass (g entries per image)
+    uint32_t* clist = nullptr;           // edge-rule pixels, then the entries handed from the window pass to the cooperative pass
+    unsigned long long* qres = nullptr;  // per list entry: the triangle the window pass reached
+    int32_t* work_counter = nullptr;     // window stage: next block of the chunk-wide query list
+    int32_t* d_order = nullptr;          // finish stage: hand-out order (image_order_kernel)
+    size_t rows_stride = 0;
+    int n_sm = 0;
+    bool clear_keys = false;             // the sites stage zeroes the keys it consumes: no key-grid memset per chunk
+    bool keys_clean = false;             // the key grid is known to be all zero
     // hypothesis-independent (un-posed pano 2) renders of the current call: max_panos x 2 surfaces
     uint8_t* cache_out = nullptr; int32_t* cache_counts = nullptr; int32_t* cache_status = nullptr;
     int32_t* d_dest = nullptr;           // per image of the chunk: destination (see ImageArgs::dest)
@@ -100,7 +105,6 @@ struct salve_bev_ctx {
     int last_chunk_images = 0;
     int32_t* last_counts = nullptr;  // device counters of the last chunk (taps re-run the image kernel on a copy)
     size_t flip_smem = 0;
-    size_t image_smem = 0;           // dynamic shared memory of image_kernel for the context's grid
     int max_smem_optin = 0;
     double band[4] = {-INFINITY, -1.0, 0.5, INFINITY};  // bev_rendering_utils.py:560-566
 };
@@ -173,16 +177,15 @@ extern "C" int salve_bev_ctx_create(const salve_bev_config* cfg, salve_bev_ctx**
     ALLOC(c->d_depth_ptr, P);
     ALLOC(c->d_tables, 2 * H + 2 * W);
     ALLOC(c->keygrid, N * c->g_stride);
-    {
-        int n_sm = 0;
-        CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
-        c->image_slots = (int)std::min<size_t>(N, (size_t)IMAGE_CTAS * n_sm);  // persistent CTAs of image_kernel
-    }
-    ALLOC(c->qlist, (size_t)c->image_slots * c->g_stride);
-    ALLOC(c->clist, (size_t)c->image_slots * c->g_stride);
-    ALLOC(c->qres, (size_t)c->image_slots * c->g_stride);
-    ALLOC(c->phase_clk, N * 24);
-    ALLOC(c->keepbits, (size_t)c->image_slots * c->bits_stride * 2);  // keep plane + (IMAGE_TMP_GLOBAL) the second plane
+    CU(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
+    // lists are sized for the worst case (every pixel of every image a query); only what a chunk really uses is ever touched
+    ALLOC(c->qlist, N * c->g_stride);
+    ALLOC(c->clist, N * c->g_stride);
+    ALLOC(c->qres, N * c->g_stride);
+    ALLOC(c->planes, N * 3 * c->bits_stride);
+    c->rows_stride = image_rows_stride(MAX_GRID_H + 1);  // any grid height the generic interp entry point accepts
+    ALLOC(c->rowarr, N * c->rows_stride);
+    ALLOC(c->hdr, N * HD_STRIDE);
     ALLOC(c->work_counter, 1);
     ALLOC(c->d_order, N);
     ALLOC(c->cache_out, 2 * P * c->img_bytes + 64);  // +64: replicate_images_kernel reads whole words
@@ -230,14 +233,16 @@ extern "C" int salve_bev_ctx_create(const salve_bev_config* cfg, salve_bev_ctx**
     c->flip_smem = ((2 * g + 31) / 32) * 4 + 16;
     CU(cudaFuncSetAttribute(flip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->flip_smem));
     CU(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
-    c->image_smem = image_smem_bytes(c->G.grid_h, c->G.wpr);
     {
-        cudaFuncAttributes fa, fb;
-        CU(cudaFuncGetAttributes(&fa, image_kernel<true>));
-        CU(cudaFuncGetAttributes(&fb, image_kernel<false>));
-        c->max_smem_optin -= (int)std::max(fa.sharedSizeBytes, fb.sharedSizeBytes);  // what is left for dynamic shared memory
-        CU(cudaFuncSetAttribute(image_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
-        CU(cudaFuncSetAttribute(image_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
+        cudaFuncAttributes fa, fb, fc;
+        CU(cudaFuncGetAttributes(&fa, finish_stage_kernel<true>));
+        CU(cudaFuncGetAttributes(&fb, finish_stage_kernel<false>));
+        CU(cudaFuncGetAttributes(&fc, prep_stage_kernel));
+        c->max_smem_optin -= (int)std::max(std::max(fa.sharedSizeBytes, fb.sharedSizeBytes), fc.sharedSizeBytes);  // what is left for dynamic shared memory
+        CU(cudaFuncSetAttribute(finish_stage_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
+        CU(cudaFuncSetAttribute(finish_stage_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
+        CU(cudaFuncSetAttribute(prep_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
+        CU(cudaFuncSetAttribute(sites_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
     }
     *out = c;
     return SALVE_BEV_OK;
@@ -248,7 +253,7 @@ extern "C" void salve_bev_ctx_destroy(salve_bev_ctx* c) {
     cudaSetDevice(c->cfg.device);
     cudaDeviceSynchronize();
     void* ptrs[] = {c->pano_rgb_store, c->pano_rgb2x_store, c->pano_depth_store, c->d_depth_ptr, c->d_tables, c->keygrid, c->color, c->occ, c->nonempty,
-                    c->keep, c->tmpbits, c->wprefix, c->tris, c->owner, c->list0, c->list1, c->cand, c->qlist, c->clist, c->qres, c->phase_clk, c->keepbits, c->work_counter, c->d_order, c->cache_out, c->cache_counts, c->cache_status, c->d_dest, c->headers, c->counts,
+                    c->keep, c->tmpbits, c->wprefix, c->tris, c->owner, c->list0, c->list1, c->cand, c->qlist, c->clist, c->qres, c->planes, c->rowarr, c->hdr, c->work_counter, c->d_order, c->cache_out, c->cache_counts, c->cache_status, c->d_dest, c->headers, c->counts,
                     c->status, c->d_jobs, c->d_color_src, c->out_store};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < N_TMP; i++) if (c->tmp[i]) cudaFree(c->tmp[i]);
@@ -376,39 +381,56 @@ static int stage_event(salve_bev_ctx* c, cudaStream_t st) {
     return SALVE_BEV_OK;
 }
 
-// Everything after the splat for images [0, n_img): image_kernel (sites, masks, hull, query-driven flips).
-static int run_image_stage(salve_bev_ctx* c, int n_img, const GridParams& G, const uint32_t* keygrid, const uint8_t* const* color_src,
+// Everything after the splat for images [0, n_img): the four stages of k_image.cuh (sites, prep, window, finish).
+static int run_image_stage(salve_bev_ctx* c, int n_img, const GridParams& G, uint32_t* keygrid, const uint8_t* const* color_src,
                            uint8_t* dev_out, int32_t* dev_counts, int32_t* dev_status, int raw_mode, int skip_empty, uint8_t* hull,
-                           int32_t* qtri, uint32_t* bits, cudaStream_t st, const int32_t* dest = nullptr, int32_t* counts_out = nullptr) {
+                           int32_t* qtri, cudaStream_t st, const int32_t* dest = nullptr, int32_t* counts_out = nullptr, bool clear_keys = false) {
     const size_t smem = image_smem_bytes(G.grid_h, G.wpr);
-    if (smem > (size_t)c->max_smem_optin) FAIL(SALVE_BEV_E_CAPACITY, "grid too large for image_kernel's shared memory");
-    ImageArgs IA;
-    IA.G = G;
-    IA.n_img = n_img; IA.work_counter = c->work_counter;
-    CU(cudaMemsetAsync(c->work_counter, 0, sizeof(int32_t), st));
-    IA.order = nullptr;
-    if (n_img > c->image_slots && n_img <= c->cfg.max_images && n_img <= 16384) {  // more images than CTAs: longest expected first
-        image_order_kernel<<<(n_img + 255) / 256, 256, 0, st>>>(dev_counts, n_img, c->d_order);
+    if (smem > (size_t)c->max_smem_optin) FAIL(SALVE_BEV_E_CAPACITY, "grid too large for the image stages' shared memory");
+    if (n_img > c->cfg.max_images) FAIL(SALVE_BEV_E_CAPACITY, "more images than the context's scratch holds");
+    // a launch of the window stage indexes at most WIN_MAX_IMAGES images: larger chunks go through in groups
+    for (int g0 = 0; g0 < n_img; g0 += WIN_MAX_IMAGES) {
+        const int n = std::min(WIN_MAX_IMAGES, n_img - g0);
+        ImageArgs IA;
+        IA.G = G;
+        IA.n_img = n;
+        IA.order = nullptr;
+        IA.keygrid = keygrid + (size_t)g0 * c->g_stride; IA.keygrid_stride = c->g_stride;
+        IA.color_src = color_src + g0; IA.pano_w = c->cfg.pano_w;
+        IA.counts = dev_counts + (size_t)g0 * 8; IA.status = dev_status;
+        IA.out = dev_out; IA.out_stride = (size_t)G.g * 3;
+        IA.dest = dest ? dest + g0 : nullptr; IA.counts_out = counts_out;
+        if (!dest) {  // destination = image index: shift the destination arrays with the group
+            IA.out = dev_out + (size_t)g0 * IA.out_stride;
+            IA.status = dev_status ? dev_status + g0 : nullptr;
+            IA.counts_out = counts_out ? counts_out + (size_t)g0 * 8 : nullptr;
+        }
+        IA.cache_out = c->cache_out; IA.cache_counts = c->cache_counts; IA.cache_status = c->cache_status;
+        IA.hull = hull ? hull + (size_t)g0 * G.g : nullptr; IA.hull_stride = (size_t)G.g;
+        IA.qtri = qtri ? qtri + (size_t)g0 * G.g * 3 : nullptr; IA.qtri_stride = (size_t)G.g * 3;
+        IA.planes = c->planes; IA.plane_stride = c->bits_stride;
+        IA.rows = c->rowarr; IA.rows_stride = c->rows_stride; IA.hp = (G.grid_h + 15) & ~15;
+        IA.hdr = c->hdr;
+        IA.qlist = c->qlist; IA.qlist_stride = c->g_stride; IA.qres = c->qres; IA.clist = c->clist;
+        IA.work_counter = c->work_counter;
+        IA.raw_mode = raw_mode; IA.skip_empty_check = skip_empty; IA.clear_keys = clear_keys ? 1 : 0;
+        CU(cudaMemsetAsync(c->work_counter, 0, sizeof(int32_t), st));
+        sites_stage_kernel<<<dim3((unsigned)((G.grid_h + SITES_WARPS - 1) / SITES_WARPS), (unsigned)n), SITES_WARPS * 32, sites_smem_bytes(G.wpr), st>>>(IA);
+        prep_stage_kernel<<<n, PREP_NT, prep_smem_bytes(G.grid_h, G.wpr), st>>>(IA);
+        const int win_ctas = std::max(1, std::min(c->n_sm * IMAGE_WIN_CTAS, (n * 64 + WIN_NT - 1) / WIN_NT));
+        window_stage_kernel<IMAGE_WIN_NR><<<win_ctas, WIN_NT, 0, st>>>(IA);
+        c->launches += 3;
+        if (n > 2 * c->n_sm) {  // more images than CTA slots: longest expected first
+            image_order_kernel<<<(n + 255) / 256, 256, 0, st>>>(c->hdr, n, c->d_order);
+            c->launches++;
+            IA.order = c->d_order;
+        }
+        // grids of up to 512 x 512 pixels (the reference's 501 x 501 included) take the instantiation with int32 circle parameters
+        if (G.grid_h <= 512 && G.grid_w <= 512) finish_stage_kernel<true><<<n, FINISH_NT, finish_smem_bytes(G.grid_h, G.wpr), st>>>(IA);
+        else finish_stage_kernel<false><<<n, FINISH_NT, finish_smem_bytes(G.grid_h, G.wpr), st>>>(IA);
         c->launches++;
         CU(cudaGetLastError());
-        IA.order = c->d_order;
     }
-    IA.keygrid = keygrid; IA.keygrid_stride = c->g_stride;
-    IA.color_src = color_src; IA.pano_w = c->cfg.pano_w;
-    IA.counts = dev_counts; IA.status = dev_status;
-    IA.out = dev_out; IA.out_stride = (size_t)G.g * 3;
-    IA.dest = dest; IA.counts_out = counts_out;
-    IA.cache_out = c->cache_out; IA.cache_counts = c->cache_counts; IA.cache_status = c->cache_status;
-    IA.hull = hull; IA.hull_stride = (size_t)G.g;
-    IA.qtri = qtri; IA.qtri_stride = (size_t)G.g * 3;
-    IA.bits = bits; IA.bits_stride = 3 * (size_t)G.grid_h * G.wpr;
-    IA.qlist = c->qlist; IA.qlist_stride = c->g_stride; IA.qres = c->qres; IA.clist = c->clist; IA.keepbits = c->keepbits; IA.keepbits_stride = c->bits_stride * 2; IA.phase_clk = (n_img <= c->cfg.max_images && keygrid == c->keygrid) ? c->phase_clk : nullptr;
-    IA.raw_mode = raw_mode; IA.skip_empty_check = skip_empty;
-    // grids of up to 512 x 512 pixels (the reference's 501 x 501 included) take the instantiation with int32 circle parameters
-    if (G.grid_h <= 512 && G.grid_w <= 512) image_kernel<true><<<std::min(n_img, c->image_slots), IMAGE_NT, smem, st>>>(IA);
-    else image_kernel<false><<<std::min(n_img, c->image_slots), IMAGE_NT, smem, st>>>(IA);
-    c->launches++;
-    CU(cudaGetLastError());
     return stage_event(c, st);
 }
 
@@ -496,7 +518,7 @@ static int render_chunk(salve_bev_ctx* c, int n_img, const std::vector<SplatJob>
     rc = stage_event(c, st); if (rc) return rc;
     c->last_chunk_images = n_img;
     c->last_counts = dev_counts;
-    return run_image_stage(c, n_img, c->G, c->keygrid, c->d_color_src, dev_out, dev_counts, dev_status, 0, 0, nullptr, nullptr, nullptr, st,
+    return run_image_stage(c, n_img, c->G, c->keygrid, c->d_color_src, dev_out, dev_counts, dev_status, 0, 0, nullptr, nullptr, st,
                            dest ? c->d_dest : nullptr, counts_out);
 }
 
@@ -997,7 +1019,7 @@ extern "C" int salve_bev_render_cloud_host(salve_bev_ctx* c, const double* host_
     }
     c->last_chunk_images = 1;
     c->last_counts = c->counts;
-    rc = run_image_stage(c, 1, c->G, c->keygrid, c->d_color_src, c->out_store, c->counts, c->status, 0, 0, nullptr, nullptr, nullptr, st);
+    rc = run_image_stage(c, 1, c->G, c->keygrid, c->d_color_src, c->out_store, c->counts, c->status, 0, 0, nullptr, nullptr, st);
     if (rc) return rc;
     CU(cudaMemcpyAsync(host_out, c->out_store, c->img_bytes, cudaMemcpyDeviceToHost, st));
     if (host_counts) CU(cudaMemcpyAsync(host_counts, c->counts, sizeof(int32_t) * 8, cudaMemcpyDeviceToHost, st));
@@ -1095,7 +1117,7 @@ extern "C" int salve_bev_interp_dense(salve_bev_ctx* c, const int64_t* host_xy, 
     c->last_chunk_images = 1;
     c->last_counts = c->counts;
     if (image_smem_bytes(G.grid_h, G.wpr) <= (size_t)c->max_smem_optin)
-        rc = run_image_stage(c, 1, G, c->keygrid, c->d_color_src, c->out_store, c->counts, c->status, 1, 1, (uint8_t*)dhull, nullptr, nullptr, st);
+        rc = run_image_stage(c, 1, G, c->keygrid, c->d_color_src, c->out_store, c->counts, c->status, 1, 1, (uint8_t*)dhull, nullptr, st);
     else
         rc = run_mesh_stages(c, G, c->keygrid, c->d_color_src, c->out_store, c->counts, c->status, 1, 1, (uint8_t*)dhull, true, st);
     if (rc) return rc;
@@ -1151,7 +1173,7 @@ extern "C" int salve_bev_tap(salve_bev_ctx* c, int32_t image, int32_t what, void
     CU(cudaSetDevice(c->cfg.device));
     const GridParams& G = c->G;
     const size_t g = G.g, bits = (size_t)G.grid_h * G.wpr;
-    const uint32_t* kg = c->keygrid + (size_t)image * c->g_stride;
+    uint32_t* kg = c->keygrid + (size_t)image * c->g_stride;
     const uint8_t* const* csrc = c->d_color_src + image;
     const bool img_ok = image_smem_bytes(G.grid_h, G.wpr) <= (size_t)c->max_smem_optin;
     // taps recompute from the image's key grid (which the render leaves intact) on a private copy of its counters
@@ -1186,18 +1208,18 @@ extern "C" int salve_bev_tap(salve_bev_ctx* c, int32_t image, int32_t what, void
             if (!img_ok) FAIL(SALVE_BEV_E_CAPACITY, "tap not available for this grid size");
             bytes = (what == SALVE_BEV_TAP_QTRI) ? g * 3 * 4 : bits * 4;
             if ((int64_t)bytes > host_buf_bytes) FAIL(SALVE_BEV_E_CAPACITY, "tap buffer too small");
-            void *dimg, *dbits, *dq = nullptr;
+            void *dimg, *dq = nullptr;
             if ((rc = tmp_get(c, 0, g * 3, &dimg))) return rc;
-            if ((rc = tmp_get(c, 1, bits * 4 * 3, &dbits))) return rc;
             if (what == SALVE_BEV_TAP_QTRI) {
                 if ((rc = tmp_get(c, 2, g * 3 * 4, &dq))) return rc;
                 fill_i32_kernel<<<(unsigned)((g * 3 + 255) / 256), 256, 0, st>>>((int32_t*)dq, g * 3, -1);
                 c->launches++;
             }
-            rc = run_image_stage(c, 1, G, kg, csrc, (uint8_t*)dimg, (int32_t*)dcnt, nullptr, 0, 0, nullptr, (int32_t*)dq, (uint32_t*)dbits, st);
+            rc = run_image_stage(c, 1, G, kg, csrc, (uint8_t*)dimg, (int32_t*)dcnt, nullptr, 0, 0, nullptr, (int32_t*)dq, st);
             if (rc) return rc;
+            // the bit planes are the state the stages keep per image: image 0 of the re-run
             const void* src = what == SALVE_BEV_TAP_QTRI ? dq
-                              : (const void*)((uint32_t*)dbits + (what == SALVE_BEV_TAP_OCC ? 0 : what == SALVE_BEV_TAP_NONEMPTY ? 1 : 2) * bits);
+                              : (const void*)(c->planes + (what == SALVE_BEV_TAP_OCC ? 0 : what == SALVE_BEV_TAP_NONEMPTY ? 1 : 2) * c->bits_stride);
             CU(cudaMemcpyAsync(host_buf, src, bytes, cudaMemcpyDeviceToHost, st));
             break;
         }
@@ -1226,7 +1248,7 @@ extern "C" int salve_bev_tap(salve_bev_ctx* c, int32_t image, int32_t what, void
             if ((rc = tmp_get(c, 0, g * 3, &dimg))) return rc;
             if ((rc = tmp_get(c, 7, g, &dhull))) return rc;
             CU(cudaMemsetAsync(dhull, 0, g, st));
-            if (img_ok) rc = run_image_stage(c, 1, G, kg, csrc, (uint8_t*)dimg, (int32_t*)dcnt, nullptr, 1, 0, (uint8_t*)dhull, nullptr, nullptr, st);
+            if (img_ok) rc = run_image_stage(c, 1, G, kg, csrc, (uint8_t*)dimg, (int32_t*)dcnt, nullptr, 1, 0, (uint8_t*)dhull, nullptr, st);
             else rc = run_mesh_stages(c, G, kg, csrc, (uint8_t*)dimg, (int32_t*)dcnt, nullptr, 1, 0, (uint8_t*)dhull, true, st);
             if (rc) return rc;
             CU(cudaMemcpyAsync(host_buf, what == SALVE_BEV_TAP_INTERP ? dimg : dhull, bytes, cudaMemcpyDeviceToHost, st));
@@ -1259,15 +1281,6 @@ extern "C" int salve_bev_last_timings(salve_bev_ctx* c, float* host_ms) {
         CU(cudaEventElapsedTime(&ms, c->events[k], c->events[k + 2]));
         host_ms[4] += ms;
     }
-    return SALVE_BEV_OK;
-}
-
-extern "C" int salve_bev_last_phase_clocks(salve_bev_ctx* c, int64_t* host_clk, int32_t n_img) {
-    if (!c || !host_clk) FAIL(SALVE_BEV_E_INVALID, "null argument");
-    if (n_img < 0 || n_img > c->cfg.max_images) FAIL(SALVE_BEV_E_CAPACITY, "more images than a chunk holds");
-    CU(cudaSetDevice(c->cfg.device));
-    CU(cudaDeviceSynchronize());
-    CU(cudaMemcpy(host_clk, c->phase_clk, sizeof(long long) * 24 * (size_t)n_img, cudaMemcpyDeviceToHost));
     return SALVE_BEV_OK;
 }
 

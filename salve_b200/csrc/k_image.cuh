@@ -1,5 +1,5 @@
-// k_image.cuh -- one CTA per BEV image, everything after the splat:
-//   winners -> site bit rows (shared memory), sparse colours, emptiness / keep masks, convex hull,
+// k_image.cuh -- everything after the splat, as a pipeline of four kernels over a chunk of BEV images:
+//   winners -> site bit rows, sparse colours, emptiness / keep masks, convex hull,
 //   and the densification itself, with NO triangle mesh in memory.
 //
 // Reference stages covered:
@@ -18,17 +18,23 @@
 // configuration {a,b,c,d} and keep the one new triangle that still contains q.  The lifted plane over
 // q rises strictly with every flip, so the descent ends at the unique triangle of the canonical
 // (perturbed) Delaunay triangulation over q -- bit-identical to rasterising the full mesh, but the
-// only state is the 32 KB occupancy bitmap in shared memory: no mesh, no atomics, no rounds.
+// only state is the 32 KB occupancy bitmap of the image: no mesh, no atomics, no rounds.
 //
-// Order of work per image (persistent CTAs take images from an atomic counter, longest expected image first):
-//   A  winners -> colours, bit rows          B  guards          C  exact convex hull (pre-filtered monotone chains)
-//   D  keep mask (separable dilation)         F  EDGE RULE (queries between two opposite 4-neighbour sites: mean of two
-//      colours; found bit-parallel, averaged one per thread) + query list
-//   G0 WINDOW PASS (small triangles, 7 x 32 window in registers, exact float interval classification; the initial triangle stands
-//      on the shorter of the row pair and the column pair around the query); what it cannot certify is handed on with its triangle
-//   G2 COOPERATIVE PASS (one warp per query, 32 rows per wave, cached violators, previous final triangle as a start), final
-//      triangle shared by all deferred pixels inside it
-//   H  masked-out sites, counters.
+// The four stages (one launch each per chunk; state between them lives in per-image global scratch that the next stage
+// reads through L2):
+//   1 sites_stage_kernel   grid (rows / 8, images), a warp per BEV row: key grid -> winner colours (gather from the pano),
+//                          occupancy / non-empty bit rows, row summaries, the sparse image written with aligned 16-byte stores
+//                          from a row staged in shared memory.  Streaming, HBM bound, 48+ warps per SM.
+//   2 prep_stage_kernel    a CTA per image: guards, exact convex hull (pre-filtered monotone chains), keep mask (separable
+//                          dilation), EDGE RULE (queries between two opposite 4-neighbour sites: mean of two colours) and the
+//                          list of the remaining query pixels.
+//   3 window_stage_kernel  persistent warps over ONE query list for the whole chunk (lanes are filled across image
+//                          boundaries): small triangles, 7 x 32 window in registers, exact float interval classification;
+//                          what it cannot certify is handed on with the triangle it has reached.
+//   4 finish_stage_kernel  a CTA per image (most handed-on queries first): shades what the window pass resolved, then the
+//                          COOPERATIVE PASS (one warp per query, 32 rows per wave, cached violators, previous final
+//                          triangle as a start; a final triangle is shared by all deferred pixels inside it), masked-out
+//                          sites, counters, status.
 // The closed convex hull decides which pixels are queries at all (outside it griddata gives NaN -> 0).
 #pragma once
 #include <type_traits>
@@ -37,19 +43,10 @@
 
 namespace bev {
 
-// ---- tuning knobs.  The defaults are the measured best on B200 for the 501 x 501 grid; `salve_b200.build.build(defines=[...],
-// out=...)` compiles variants and scripts/variant_bench.py times them against each other with an identity check of the output.
-#ifndef IMAGE_THREADS
-#define IMAGE_THREADS 512     // threads per CTA (a multiple of 32).  2 x 512 beats 4 x 256, 3 x 320, 2 x 384, 1 x 768 and 1 x 1024
-#endif
-#ifndef IMAGE_CTAS
-#define IMAGE_CTAS 2          // persistent CTAs per SM
-#endif
-#ifndef IMAGE_TMP_GLOBAL
-#define IMAGE_TMP_GLOBAL 0    // 1: the second bit plane (row-dilated mask, then the deferred-query bits) lives in global memory
-#endif
+// ---- tuning knobs.  `salve_b200.build.build(defines=[...], out=...)` compiles variants and scripts/variant_bench.py times
+// them against each other with an identity check of the output.
 #ifndef SITES_BATCH_DEF
-#define SITES_BATCH_DEF 4     // phase A: words per lane and round trip (4 beats 8 and 16: smaller code, same latency hiding)
+#define SITES_BATCH_DEF 4     // sites stage: words per lane and round trip (4 beats 8 and 16: smaller code, same latency hiding)
 #endif
 #ifndef IMAGE_STREAM_HINTS
 #define IMAGE_STREAM_HINTS 3  // bit 0: key grid loads, bit 1: first-pass output stores are streaming (evict first)
@@ -63,6 +60,15 @@ namespace bev {
 #ifndef IMAGE_WIN_VINIT
 #define IMAGE_WIN_VINIT 1     // window pass: initial triangle on the column pair D-U when it is shorter than the row pair L-R
 #endif
+#ifndef IMAGE_WIN_BLOCK
+#define IMAGE_WIN_BLOCK 256   // window pass: queries a warp takes from the chunk-wide list per atomic
+#endif
+#ifndef IMAGE_WIN_THREADS
+#define IMAGE_WIN_THREADS 256 // window pass: threads per CTA
+#endif
+#ifndef IMAGE_WIN_CTAS
+#define IMAGE_WIN_CTAS 4      // window pass: persistent CTAs per SM
+#endif
 #ifndef IMAGE_COOP_CHAIN
 #define IMAGE_COOP_CHAIN 1    // cooperative pass: start from the previous final triangle's edge
 #endif
@@ -75,6 +81,12 @@ namespace bev {
 #ifndef IMAGE_COOP_BAND_DIV
 #define IMAGE_COOP_BAND_DIV 2 // cooperative pass: band = what is left / (IMAGE_COOP_BAND_DIV * warps)
 #endif
+#ifndef IMAGE_FINISH_THREADS
+#define IMAGE_FINISH_THREADS 512  // finish stage: threads per CTA (two CTAs per SM with both bit planes in shared memory)
+#endif
+#ifndef IMAGE_PREP_THREADS
+#define IMAGE_PREP_THREADS 256    // prep stage: threads per CTA
+#endif
 #if IMAGE_STREAM_HINTS & 1
 #define IMAGE_KEY_LD(p) __ldcs(p)
 #else
@@ -85,16 +97,26 @@ namespace bev {
 #else
 #define IMAGE_OUT_ST(p, v) (*(p) = (v))
 #endif
-constexpr int IMAGE_NT = IMAGE_THREADS;
 constexpr int SITES_BATCH = SITES_BATCH_DEF;
-constexpr int IMAGE_MAX_FLIPS = 100000;  // safety cap on one descent (never reached: the lift is strictly monotone)
+constexpr int SITES_WARPS = 8;            // sites stage: rows (= warps) per CTA
+constexpr int PREP_NT = IMAGE_PREP_THREADS;
+constexpr int WIN_NT = IMAGE_WIN_THREADS;
+constexpr int FINISH_NT = IMAGE_FINISH_THREADS;
+constexpr int WIN_MAX_IMAGES = 2048;      // images one window-stage launch can index (prefix table in shared memory)
+constexpr int IMAGE_MAX_FLIPS = 100000;   // safety cap on one descent (never reached: the lift is strictly monotone)
+
+// per-image row arrays kept in global memory between the stages: RA_N16 int16 arrays of `hp` entries, then RA_NF float arrays
+enum { RA_CNT = 0, RA_FIRST, RA_LAST, RA_NE, RA_UP, RA_DN, RA_HL0, RA_HL1, RA_HR0, RA_HR1, RA_N16 };
+enum { RA_HLF = 0, RA_HRF, RA_NF };
+// per-image header (16 int32)
+enum { HD_STATUS = 0, HD_NQ, HD_EDGE, HD_MASKED, HD_PEND, HD_N };
+constexpr int HD_STRIDE = 16;
 
 struct ImageArgs {
     GridParams G;
-    int32_t n_img;                    // images of this launch; CTAs are persistent and take images from *work_counter
-    int32_t* work_counter;            // zeroed by the host before the launch
-    const int32_t* order;             // k-th image to hand out (longest expected first), or null: k
-    const uint32_t* keygrid; size_t keygrid_stride;
+    int32_t n_img;                    // images of this launch
+    const int32_t* order;             // finish stage: CTA k works on image order[k] (longest expected first), or null: k
+    uint32_t* keygrid; size_t keygrid_stride;
     const uint8_t* const* color_src;  // per image: u8 rgb triples indexed by the key's source index (tagged, see gather_rgb)
     int32_t pano_w;                   // width of the key's index space (for tagged full-resolution sources)
     int32_t* counts;                  // [n_img][8] working counters, indexed like the key grids ([0], [1] come from the splat)
@@ -107,33 +129,49 @@ struct ImageArgs {
     uint8_t* cache_out; int32_t* cache_counts; int32_t* cache_status;
     uint8_t* hull; size_t hull_stride;        // optional tap: 1 inside the closed convex hull
     int32_t* qtri; size_t qtri_stride;        // optional tap: per pixel the 3 vertex pixel ids of its triangle (pre-filled with -1)
-    uint32_t* bits; size_t bits_stride;       // optional tap: occ, nonempty, keep bit planes (3 * grid_h * wpr words per image)
-    uint32_t* qlist; size_t qlist_stride;     // per CTA work list of query pixels (row << 11 | col), capacity g
-    unsigned long long* qres;                 // per CTA, per list entry: triangle (3 x 21-bit vertex labels), final if | QRES_DONE
-    uint32_t* clist;                          // per CTA: list entries the window pass handed on (capacity g)
-    uint32_t* keepbits; size_t keepbits_stride;  // per CTA scratch: non-empty, then keep bit rows (grid_h * wpr words)
-    // optional diagnostics, 24 slots per image (scripts/phase_breakdown.py): SM clock at the stage boundaries [0] start, [1] sites,
-    // [2] hull + masks, [18] edge rule + lists, [16] window pass, [3] shading, [9] cooperative list, [10] cooperative pass, [11] end;
-    // [17] / [14] window / cooperative queries; [15] cooperative descents << 40 | waves << 20 | flips; [4] / [5] busiest warp / sum over
-    // warps of the cooperative pass (cycles), [13] longest descent; [6] flips, [7] filled pixels, [22] sites; [19] / [20] global timer
-    // at start / end (ns), [21] CTA slot, [23] destination
-    long long* phase_clk;
+    // state between the stages, per image of the chunk
+    uint32_t* planes; size_t plane_stride;    // [n_img][3][plane_stride] bit rows: occupancy, non-empty, keep
+    unsigned char* rows; size_t rows_stride;  // [n_img] row arrays (RA_*), rows_stride bytes per image
+    int32_t hp;                               // entries per row array (grid_h rounded up to 16)
+    int32_t* hdr;                             // [n_img][HD_STRIDE]
+    uint32_t* qlist; size_t qlist_stride;     // per image: query pixels (row << 11 | col) for the window pass, capacity g
+    unsigned long long* qres;                 // per image, per list entry: triangle (3 x 21-bit vertex labels), final if | QRES_DONE
+    uint32_t* clist;                          // per image: edge-rule pixels (prep), then the entries handed to the cooperative pass
+    int32_t* work_counter;                    // window stage: next block of the chunk-wide list (zeroed by the host)
     int32_t raw_mode;                 // 1: no keep mask, no flip (interp_dense_grid_from_sparse semantics)
     int32_t skip_empty_check;         // 1: generic interp path (no EMPTY status)
+    int32_t clear_keys;               // 1: the sites stage zeroes the keys it consumes (the next chunk needs no memset)
 };
 
-// shared memory carve-up (bytes) for a grid of (h, wpr)
+__device__ __forceinline__ uint8_t* image_out(const ImageArgs& A, int img, int& dst) {
+    dst = A.dest ? A.dest[img] : img;
+    return dst >= 0 ? A.out + (size_t)dst * A.out_stride : A.cache_out + (size_t)(-1 - dst) * A.out_stride;
+}
+__device__ __forceinline__ int16_t* row_arr(const ImageArgs& A, int img, int k) {
+    return reinterpret_cast<int16_t*>(A.rows + (size_t)img * A.rows_stride) + (size_t)k * A.hp;
+}
+__device__ __forceinline__ float* row_arr_f(const ImageArgs& A, int img, int k) {
+    return reinterpret_cast<float*>(A.rows + (size_t)img * A.rows_stride + (size_t)RA_N16 * A.hp * 2) + (size_t)k * A.hp;
+}
+__host__ __device__ inline size_t image_rows_stride(int hp) { return (size_t)RA_N16 * hp * 2 + (size_t)RA_NF * hp * 4; }
+
+// shared memory (bytes) of the stages for a grid of (h, wpr)
+__host__ __device__ inline size_t image_row_bytes(int h) { return ((size_t)h * 2 + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t sites_row_words(int wpr) { return (size_t)((wpr + SITES_BATCH - 1) / SITES_BATCH) * SITES_BATCH * 24 + 8; }
+__host__ __device__ inline size_t sites_smem_bytes(int wpr) { return SITES_WARPS * sites_row_words(wpr) * 4; }
+__host__ __device__ inline size_t prep_smem_bytes(int h, int wpr) {
+    return (size_t)h * wpr * 4 + 13 * image_row_bytes(h) + 2 * (((size_t)h * 4 + 15) & ~(size_t)15) + 64;
+}
+__host__ __device__ inline size_t finish_smem_bytes(int h, int wpr) {
+    return 2 * (size_t)h * wpr * 4 + 9 * image_row_bytes(h) + 2 * (((size_t)h * 4 + 15) & ~(size_t)15) + 64;
+}
+// the largest of them decides whether a grid can take this path at all (else: explicit-mesh kernels)
 __host__ __device__ inline size_t image_smem_bytes(int h, int wpr) {
-    const size_t plane = (size_t)h * wpr * 4;
-    const size_t rows = ((size_t)h * 2 + 15) & ~(size_t)15;
-    return (IMAGE_TMP_GLOBAL ? 1 : 2) * plane + 13 * rows + 2 * (((size_t)h * 4 + 15) & ~(size_t)15) + 64;
+    const size_t a = prep_smem_bytes(h, wpr), b = finish_smem_bytes(h, wpr), c = sites_smem_bytes(wpr);
+    return a > b ? (a > c ? a : c) : (b > c ? b : c);
 }
 
-#if IMAGE_TMP_GLOBAL
-#define DEFER_LD(p) __ldcg(p)   // other warps clear bits with atomics (performed in L2): never read them through L1
-#else
 #define DEFER_LD(p) (*(p))
-#endif
 
 struct Tri2 { int ax, ay, bx, by, cx, cy; };
 
@@ -237,7 +275,7 @@ __device__ __forceinline__ uint32_t bit_span(int lo, int hi) {
 }
 __device__ __forceinline__ float sqrt_approx(float v) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
 
-// ---- pass 0: small triangles in a register window ---------------------------------------------------------------------------
+// ---- stage 3: small triangles in a register window --------------------------------------------------------------------------
 // 92 % of the queries that are left after the edge rule end in a triangle within 2 px of the pixel with a circumradius of
 // at most 2 px.  For them the whole Lawson descent runs on a (2*NR+1)-row x 32-column window of the occupancy bitmap held in
 // registers, in coordinates relative to the query q = (0, 0):
@@ -247,30 +285,77 @@ __device__ __forceinline__ float sqrt_approx(float v) { float r; asm("sqrt.appro
 //     "on the circle" (|.| <= 1/(2 A2)) are decided EXACTLY by float interval arithmetic per row: no per-point test at all.
 //   * one trip = the strict-interior masks of all rows (unrolled; every lane executes the same code), then either a flip towards
 //     the violator nearest to q or, if the circle is empty, the on-circle sites and their symbolic-perturbation tests.
-// A query whose triangle or circle leaves the window is handed to the general passes.
+// A query whose triangle or circle leaves the window is handed to the cooperative pass.
+//
+// Work distribution: the query lists of all images of the chunk form one index space (prefix sums of the per-image counts,
+// rebuilt in shared memory by every CTA).  A warp takes IMAGE_WIN_BLOCK consecutive indices per atomic and refills its idle
+// lanes from that block, across image boundaries: there is no per-image barrier and no per-image tail.
 template <int NR>
-__device__ __forceinline__ void resolve_window(const ImageShared& S, int wpr, int W, int H, const uint32_t* __restrict__ qlist,
-                                               unsigned long long* __restrict__ qres, int n, int* s_next, uint32_t* defer, int lane,
-                                               int& my_flips, int& my_maxflips) {
+__global__ void __launch_bounds__(WIN_NT, IMAGE_WIN_CTAS) window_stage_kernel(ImageArgs A) {
     constexpr int NROW = 2 * NR + 1;
     static_assert(NROW * 9 <= 64, "on-circle candidates are packed 9 bits per row into one 64-bit word");
+    static_assert(WIN_MAX_IMAGES % WIN_NT == 0, "prefix table: whole entries per thread");
     constexpr int MAXGAP = 14, MAXFLIPS = 16;
+    constexpr int PER = WIN_MAX_IMAGES / WIN_NT;
     const unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int W = A.G.grid_w, H = A.G.grid_h, wpr = A.G.wpr;
+    const int n_img = A.n_img;
+
+    // ---- exclusive prefix of the per-image list lengths: s_off[i] = first global index of image i, s_off[n_img] = total
+    __shared__ int s_off[WIN_MAX_IMAGES + 1];
+    __shared__ int s_warp[WIN_NT / 32];
+    {
+        int v[PER], sum = 0;
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            const int i = tid * PER + k;
+            v[k] = i < n_img ? __ldg(A.hdr + (size_t)i * HD_STRIDE + HD_NQ) : 0;
+            sum += v[k];
+        }
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) s_warp[tid >> 5] = incl;
+        __syncthreads();
+        int base = 0;
+        for (int k = 0; k < (tid >> 5); k++) base += s_warp[k];
+        int run = base + incl - sum;
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            const int i = tid * PER + k;
+            if (i <= n_img) s_off[i] = run;  // entry n_img: every later v is 0, so run is already the total there
+            run += v[k];
+        }
+        __syncthreads();
+    }
+    const int total = s_off[n_img];
+
     bool active = false, exhausted = false;
-    int x = 0, r = 0, idx = 0, flips = 0;
+    int x = 0, r = 0, flips = 0, img = 0;
+    uint32_t gidx = 0;  // img * qlist_stride + index within the image's list
+    int acc_img = -1, acc_flips = 0, acc_max = 0;  // flip statistics of the image this lane last worked on (diagnostic counters)
+    int cur = 0, end = 0, blk_img = 0;  // warp-uniform: this warp's block of the chunk-wide list
     uint32_t wr[NROW];  // wr[dy + NR]: bit 16 + dx <-> pixel (x + dx, r + dy)
 #pragma unroll
     for (int k = 0; k < NROW; k++) wr[k] = 0u;
     int ax = 0, ay = 0, bx = 0, by = 0, cx = 0, cy = 0;
 
+    auto flush_stats = [&]() {
+        if (acc_img >= 0 && acc_flips) {
+            atomicAdd(A.counts + (size_t)acc_img * 8 + 7, acc_flips);
+            atomicMax(A.counts + (size_t)acc_img * 8 + 6, acc_max);
+        }
+        acc_flips = 0; acc_max = 0;
+    };
     // hand the query to the cooperative pass, with the triangle the descent has reached so far (if there is one)
     auto give_up = [&](bool with_tri) {
-        atomicOr(&defer[r * wpr + (x >> 5)], 1u << (x & 31));
         unsigned long long v = 0ull;
         if (with_tri)
             v = (unsigned long long)vlabel(r + ay, x + ax) | ((unsigned long long)vlabel(r + by, x + bx) << 21) |
                 ((unsigned long long)vlabel(r + cy, x + cx) << 42);
-        qres[idx] = v;
+        A.qres[gidx] = v;
+        atomicAdd(A.hdr + (size_t)img * HD_STRIDE + HD_PEND, 1);
         active = false;
     };
     // nearest set bit to dx = 0 in a window row (m != 0): returns dx
@@ -280,43 +365,54 @@ __device__ __forceinline__ void resolve_window(const ImageShared& S, int wpr, in
         return dl <= dr ? -dl : dr;
     };
     auto cross = [](int px, int py, int qx, int qy) { return px * qy - py * qx; };
-    auto contains0 = [&](int px, int py, int qx, int qy, int sx, int sy) {  // CCW (p, q, s) contains the origin (closed)
-        return (qx - px) * (sy - py) - (qy - py) * (sx - px) > 0 && cross(px, py, qx, qy) >= 0 && cross(qx, qy, sx, sy) >= 0 && cross(sx, sy, px, py) >= 0;
-    };
 
     while (true) {
         // ---- refill idle lanes
         const unsigned idle = __ballot_sync(FULL, !active);
         if (idle && !exhausted && (__popc(idle) >= IMAGE_WIN_REFILL || idle == FULL)) {
-            const int leader = __ffs(idle) - 1;
-            int base = 0;
-            if (lane == leader) base = atomicAdd(s_next, __popc(idle));
-            base = __shfl_sync(FULL, base, leader);
-            if (base + __popc(idle) >= n) exhausted = true;
-            if (!active) {
-                const int i = base + __popc(idle & ((1u << lane) - 1u));
-                if (i < n) {
-                    const uint32_t code = qlist[i];
-                    x = (int)(code & COL_MASK); r = (int)(code >> COL_BITS); idx = i;
+            if (cur == end) {  // this warp's block is used up: take the next one
+                int b = 0;
+                if (lane == 0) b = atomicAdd(A.work_counter, IMAGE_WIN_BLOCK);
+                b = __shfl_sync(FULL, b, 0);
+                if (b >= total) exhausted = true;
+                else {
+                    cur = b; end = min(b + IMAGE_WIN_BLOCK, total);
+                    int lo = 0, hi = n_img - 1;  // image that holds index b: the last i with s_off[i] <= b
+                    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_off[mid] <= b) lo = mid; else hi = mid - 1; }
+                    blk_img = lo;
+                }
+            }
+            if (!exhausted) {
+                const int take = min(__popc(idle), end - cur);
+                const int rank = __popc(idle & ((1u << lane) - 1u));
+                if (!active && rank < take) {
+                    const int gi = cur + rank;
+                    int im = blk_img;
+                    while (gi >= s_off[im + 1]) im++;  // gi < total = s_off[n_img]: stops at the image that holds gi
+                    if (im != acc_img) { flush_stats(); acc_img = im; }
+                    img = im;
+                    gidx = (uint32_t)((size_t)im * A.qlist_stride) + (uint32_t)(gi - s_off[im]);
+                    const uint32_t code = A.qlist[gidx];
+                    x = (int)(code & COL_MASK); r = (int)(code >> COL_BITS);
                     active = true; flips = 0;
-                    // window
-                    // branch-free: clamped row / word indices, masks for what lies outside the grid
+                    const uint32_t* occ = A.planes + (size_t)im * 3 * A.plane_stride;
+                    // window: branch-free with clamped row / word indices and masks for what lies outside the grid
                     const int c0 = x - 16;
                     const int w0 = c0 >> 5, sh = c0 & 31;  // c0 may be negative: arithmetic shift = floor
                     const int wlo = max(w0, 0), whi = min(w0 + 1, wpr - 1);
                     const uint32_t mlo = w0 >= 0 ? 0xFFFFFFFFu : 0u, mhi = w0 + 1 < wpr ? 0xFFFFFFFFu : 0u;
                     if (r >= NR && r + NR < H && w0 >= 0 && w0 + 1 < wpr) {  // the window lies inside the grid (almost always)
-                        const uint32_t* row = S.occ + (r - NR) * wpr + w0;
+                        const uint32_t* row = occ + (r - NR) * wpr + w0;
 #pragma unroll
-                        for (int k = 0; k < NROW; k++) wr[k] = __funnelshift_r(row[k * wpr], row[k * wpr + 1], sh);
+                        for (int k = 0; k < NROW; k++) wr[k] = __funnelshift_r(__ldg(row + k * wpr), __ldg(row + k * wpr + 1), sh);
                     } else {
 #pragma unroll
                         for (int k = 0; k < NROW; k++) {
                             const int y = r + k - NR;
                             const int yc = min(max(y, 0), H - 1);
-                            const uint32_t* row = S.occ + yc * wpr;
+                            const uint32_t* row = occ + yc * wpr;
                             const uint32_t vm = y == yc ? 0xFFFFFFFFu : 0u;
-                            wr[k] = __funnelshift_r(row[wlo] & mlo & vm, row[whi] & mhi & vm, sh);
+                            wr[k] = __funnelshift_r(__ldg(row + wlo) & mlo & vm, __ldg(row + whi) & mhi & vm, sh);
                         }
                     }
                     // initial triangle.  Row pair: nearest sites left and right of q (64: none in the window).
@@ -362,6 +458,8 @@ __device__ __forceinline__ void resolve_window(const ImageShared& S, int wpr, in
                     }
                     if (!ok) give_up(false);
                 }
+                cur += take;
+                while (blk_img + 1 < n_img && cur >= s_off[blk_img + 1]) blk_img++;
             }
         }
         if (!__any_sync(FULL, active)) { if (exhausted) break; continue; }
@@ -449,10 +547,10 @@ __device__ __forceinline__ void resolve_window(const ImageShared& S, int wpr, in
                     if (pert > 0) { have = true; dx = ddx; dy = yy; }
                 }
             }
-            const uint32_t va = vlabel(r + ay, x + ax), vb = vlabel(r + by, x + bx), vc = vlabel(r + cy, x + cx);
             if (!have) {  // t is the triangle of the canonical triangulation over q
-                qres[idx] = QRES_DONE | (unsigned long long)va | ((unsigned long long)vb << 21) | ((unsigned long long)vc << 42);
-                my_flips += flips; my_maxflips = max(my_maxflips, flips);
+                const uint32_t va = vlabel(r + ay, x + ax), vb = vlabel(r + by, x + bx), vc = vlabel(r + cy, x + cx);
+                A.qres[gidx] = QRES_DONE | (unsigned long long)va | ((unsigned long long)vb << 21) | ((unsigned long long)vc << 42);
+                acc_flips += flips; acc_max = max(acc_max, flips);
                 active = false;
                 continue;
             }
@@ -472,8 +570,8 @@ __device__ __forceinline__ void resolve_window(const ImageShared& S, int wpr, in
         }
         if (++flips > MAXFLIPS) give_up(true);
     }
+    flush_stats();
 }
-
 // ---- warp-cooperative versions for queries whose triangles are large (wide gaps, hull pockets) -------------------------
 // One lane per row of each 32-row wave (row offsets 0, -1, +1, -2, ... from qy).  Returns, in every lane, the violator
 // nearest to q found in the first wave that has one (x | y << 16), or -1.
@@ -551,163 +649,173 @@ __device__ __forceinline__ int coop_find_violator(const uint32_t* __restrict__ o
     }
 }
 
-// Hand-out order of a chunk's images: longest expected first, so that the launch does not end with a few CTAs working on long
-// images while the rest of the GPU idles (durations vary 6x; measured makespan 10.2 -> 8.4 ms on 1 358 images / 296 CTAs).
-// The predictor is the crop count the splat has already produced (points inside the height band): panos that see more floor or
-// ceiling give larger, sparser footprints, hence more queries.  rank = number of images that come first (ties by index).
-__global__ void __launch_bounds__(256) image_order_kernel(const int32_t* __restrict__ counts, int n, int32_t* __restrict__ order) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int key = counts[i * 8];
-    int rank = 0;
-    for (int j = 0; j < n; j++) {
-        const int kj = __ldg(counts + j * 8);
-        rank += (kj > key || (kj == key && j < i)) ? 1 : 0;
+// ---- stage 1: winners -> occupancy / non-empty bit rows, sparse image (site colours, rest zero) ---------------------------
+// A warp per BEV row.  Loads are issued in batches of SITES_BATCH words per lane (keys, then the colour gathers) so that a warp
+// keeps that many independent requests in flight instead of one dependent pair.  Lane k keeps the bit words of word k of the
+// current 32-word chunk, so that the row summary (count, first, last) and the stores of the bit rows cost a few instructions
+// per row instead of per word.  The 3-byte pixels of the row are packed into words with two shuffles per 32 pixels, staged in
+// shared memory and written out as aligned 16-byte vectors (an image row is 1 503 bytes at an arbitrary alignment).
+__global__ void __launch_bounds__(SITES_WARPS * 32) sites_stage_kernel(ImageArgs A) {
+    extern __shared__ __align__(16) uint32_t sites_smem[];
+    const int img = blockIdx.y;
+    const int h = A.G.grid_h, w = A.G.grid_w, wpr = A.G.wpr;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r = blockIdx.x * SITES_WARPS + warp;
+    if (r >= h) return;  // warps are independent: no block-wide barrier below
+    const unsigned FULL = 0xffffffffu;
+    uint32_t* keygrid = A.keygrid + (size_t)img * A.keygrid_stride;
+    const uint8_t* csrc = A.color_src[img];
+    int dst;
+    uint8_t* out = image_out(A, img, dst);
+    const bool raw = A.raw_mode != 0;
+    uint32_t* sb = sites_smem + (size_t)warp * sites_row_words(wpr);
+    uint32_t* occ = A.planes + (size_t)img * 3 * A.plane_stride;
+    uint32_t* nonempty = occ + A.plane_stride;
+    // word of the packed row this lane builds from 32 pixels: bytes 4*lane .. 4*lane+3 of the 96 = pixels p0 and p0 + 1
+    const int p0 = (lane * 4) / 3, o8 = ((lane * 4) % 3) * 8;
+
+    int running = 0, first = -1, last = -1, ne_cnt = 0;
+    uint32_t* kp = keygrid + (size_t)r * w + lane;
+    for (int wc = 0; wc < wpr; wc += 32) {  // chunks of 32 words (one chunk for grids up to 1 024 pixels wide)
+        uint32_t my_ob = 0u, my_nb = 0u;
+        const int wend = min(wpr, wc + 32);
+        for (int wi0 = wc; wi0 < wend; wi0 += SITES_BATCH, kp += SITES_BATCH * 32) {
+            uint32_t key[SITES_BATCH], col[SITES_BATCH];
+            const int c0 = wi0 * 32 + lane;
+#pragma unroll
+            for (int j = 0; j < SITES_BATCH; j++) key[j] = (c0 + j * 32 < w) ? IMAGE_KEY_LD(kp + j * 32) : 0u;
+            if (A.clear_keys) {
+#pragma unroll
+                for (int j = 0; j < SITES_BATCH; j++) if (key[j]) kp[j * 32] = 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < SITES_BATCH; j++) {
+                col[j] = 0u;
+                if (key[j]) col[j] = gather_rgb(csrc, (key[j] - 1u) & KEY_IDX_MASK, A.pano_w);
+            }
+#pragma unroll
+            for (int j = 0; j < SITES_BATCH; j++) {
+                const uint32_t cr = col[j] & 0xFF, cg = (col[j] >> 8) & 0xFF, cb = col[j] >> 16;
+                const bool ne = ((cr * cg * cb) & 0xFFu) != 0u;  // uint8 product wraps (interpolation_utils.py:95)
+                const uint32_t ob = __ballot_sync(FULL, key[j] != 0u);
+                const uint32_t nb = __ballot_sync(FULL, ne);
+                if (lane == ((wi0 + j) & 31)) { my_ob = ob; my_nb = nb; }
+                const uint32_t a = __shfl_sync(FULL, col[j], p0 & 31), b = __shfl_sync(FULL, col[j], (p0 + 1) & 31);
+                if (lane < 24) sb[(wi0 + j) * 24 + lane] = (a >> o8) | (b << (24 - o8));
+            }
+        }
+        // bit rows of the chunk and the row summary
+        if (wc + lane < wpr) { occ[r * wpr + wc + lane] = my_ob; nonempty[r * wpr + wc + lane] = my_nb; }
+        const uint32_t nz = __ballot_sync(FULL, my_ob != 0u);
+        if (nz) {
+            const int fw = __ffs(nz) - 1, lw = 31 - __clz(nz);
+            const uint32_t fo = __shfl_sync(FULL, my_ob, fw), lo = __shfl_sync(FULL, my_ob, lw);
+            if (first < 0) first = (wc + fw) * 32 + __ffs(fo) - 1;
+            last = (wc + lw) * 32 + 31 - __clz(lo);
+            running += __reduce_add_sync(FULL, __popc(my_ob));
+            ne_cnt += __reduce_add_sync(FULL, __popc(my_nb));
+        }
     }
-    order[rank] = i;
+    if (lane == 0) {
+        row_arr(A, img, RA_CNT)[r] = (int16_t)running; row_arr(A, img, RA_FIRST)[r] = (int16_t)first;
+        row_arr(A, img, RA_LAST)[r] = (int16_t)last; row_arr(A, img, RA_NE)[r] = (int16_t)ne_cnt;
+    }
+    __syncwarp();
+    // ---- the staged row -> global memory: head bytes, aligned 16-byte vectors, tail bytes
+    uint8_t* orow = out + (size_t)(raw ? r : (h - 1 - r)) * w * 3;
+    const uint8_t* sb8 = reinterpret_cast<const uint8_t*>(sb);
+    const int nb = 3 * w;
+    int head = (int)((16u - (uint32_t)((uintptr_t)orow & 15u)) & 15u);
+    if (head > nb) head = nb;
+    const int nv = (nb - head) >> 4, tail0 = head + (nv << 4);
+    const int sw0 = head >> 2, sh = (head & 3) * 8;
+    for (int k = lane; k < nv; k += 32) {
+        const uint32_t* s = sb + sw0 + 4 * k;
+        const uint32_t a0 = s[0], a1 = s[1], a2 = s[2], a3 = s[3], a4 = s[4];  // s[4]: padding words follow the row
+        uint4 v;
+        v.x = __funnelshift_r(a0, a1, sh); v.y = __funnelshift_r(a1, a2, sh); v.z = __funnelshift_r(a2, a3, sh); v.w = __funnelshift_r(a3, a4, sh);
+        IMAGE_OUT_ST(reinterpret_cast<uint4*>(orow + head + 16 * k), v);
+    }
+    if (lane < head) orow[lane] = sb8[lane];
+    if (tail0 + lane < nb) orow[tail0 + lane] = sb8[tail0 + lane];
 }
 
-template <bool SG>
-__global__ void __launch_bounds__(IMAGE_NT, IMAGE_CTAS) image_kernel(ImageArgs A) {
-    const int slot = blockIdx.x;  // scratch slot of this (persistent) CTA
+// ---- stage 2: guards, hull, keep mask, edge rule, query list: a CTA per image -------------------------------------------
+__global__ void __launch_bounds__(PREP_NT) prep_stage_kernel(ImageArgs A) {
+    const int img = blockIdx.x;
     const int h = A.G.grid_h, w = A.G.grid_w, wpr = A.G.wpr;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = IMAGE_NT / 32;
     const int nwords = h * wpr;
+    const unsigned FULL = 0xffffffffu;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ImageShared S;
     {
-        const size_t plane = (size_t)nwords * 4;
-        const size_t rows = ((size_t)h * 2 + 15) & ~(size_t)15;
         unsigned char* p = smem_raw;
-        S.occ = (uint32_t*)p; p += plane;
-        S.keep = A.keepbits + (size_t)slot * A.keepbits_stride;  // global (L2): only list building and the final masking read it
-#if IMAGE_TMP_GLOBAL
-        S.tmp = A.keepbits + (size_t)slot * A.keepbits_stride + A.keepbits_stride / 2;
-#else
-        S.tmp = (uint32_t*)p; p += plane;
-#endif
+        S.tmp = (uint32_t*)p; p += (size_t)nwords * 4;
+        const size_t rows = image_row_bytes(h);
         int16_t** arr[13] = {&S.cnt, &S.first, &S.last, &S.up, &S.dn, &S.hlo, &S.hhi, &S.hl0, &S.hl1, &S.hr0, &S.hr1, &S.stk_l, &S.stk_r};
         for (int i = 0; i < 13; i++) { *arr[i] = (int16_t*)p; p += rows; }
         const size_t frows = ((size_t)h * 4 + 15) & ~(size_t)15;
         S.hlf = (float*)p; p += frows; S.hrf = (float*)p; p += frows;
     }
+    uint32_t* planes = A.planes + (size_t)img * 3 * A.plane_stride;
+    S.occ = planes;                            // global, read-only here (L1)
+    const uint32_t* nonempty = planes + A.plane_stride;
+    S.keep = planes + 2 * A.plane_stride;      // written here
     __shared__ uint32_t s_rownz[32];  // rows with at least one site, one bit per row (grid_h <= 1023)
-    __shared__ int s_S, s_M, s_mincol, s_maxcol, s_ne_cnt, s_keep_cnt, s_nitems, s_next, s_filled, s_flips, s_maxflips, s_hull_ok, s_img, s_nedge, s_masked;
+    __shared__ int s_S, s_M, s_mincol, s_maxcol, s_ne_cnt, s_keep_cnt, s_nitems, s_filled, s_hull_ok, s_nedge, s_masked;
 
-  // Images are handed out dynamically (their cost varies by 3x).  Thread 0 claims the next index while the CTA finishes the
-  // current image (stage H), so that the round trip of the atomic is not paid at the hand-over barrier.
-  int next_img = 0;
-  if (tid == 0) next_img = atomicAdd(A.work_counter, 1);
-  for (;;) {
-    __syncthreads();  // the previous image is finished by every thread (shared state is reused)
-    if (tid == 0) s_img = next_img;
-    __syncthreads();
-    if (s_img >= A.n_img) break;
-    const int img = A.order ? A.order[s_img] : s_img;
-    const uint32_t* keygrid = A.keygrid + (size_t)img * A.keygrid_stride;
-    const uint8_t* csrc = A.color_src[img];
-    const int dst = A.dest ? A.dest[img] : img;
-    uint8_t* out = dst >= 0 ? A.out + (size_t)dst * A.out_stride : A.cache_out + (size_t)(-1 - dst) * A.out_stride;
-    int32_t* counts = A.counts + img * 8;
-    int32_t* counts_final = dst >= 0 ? (A.counts_out ? A.counts_out + (size_t)dst * 8 : nullptr) : A.cache_counts + (size_t)(-1 - dst) * 8;
-    int32_t* status_final = dst >= 0 ? (A.status ? A.status + dst : nullptr) : A.cache_status + (-1 - dst);
+    int dst;
+    uint8_t* out = image_out(A, img, dst);
+    int32_t* counts = A.counts + (size_t)img * 8;
     const bool raw = A.raw_mode != 0;
-    long long* pclk = A.phase_clk ? A.phase_clk + (size_t)img * 24 : nullptr;
-    auto mark = [&](int k) { if (pclk && tid == 0) pclk[k] = clock64(); };
-    mark(0);
-    if (pclk && tid == 0) {
-        pclk[15] = 0;  // cooperative pass: descents << 40 | waves << 20 | flips
-        pclk[4] = 0; pclk[5] = 0; pclk[13] = 0;
-        unsigned long long ns; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
-        pclk[19] = (long long)ns; pclk[21] = slot; pclk[23] = dst;
-    }
-
     if (tid == 0) {
-        s_S = 0; s_M = 0; s_mincol = 1 << 30; s_maxcol = -1; s_ne_cnt = 0; s_keep_cnt = 0; s_nitems = 0; s_next = 0;
-        s_filled = 0; s_flips = 0; s_maxflips = 0; s_hull_ok = 0; s_nedge = 0; s_masked = 0;
+        s_S = 0; s_M = 0; s_mincol = 1 << 30; s_maxcol = -1; s_ne_cnt = 0; s_keep_cnt = 0; s_nitems = 0;
+        s_filled = 0; s_hull_ok = 0; s_nedge = 0; s_masked = 0;
     }
     __syncthreads();
-
-    // ---- A. winners -> occupancy / non-empty bit rows, sparse image (site colours, rest zero) --------
-    // Loads are issued in batches of SITES_BATCH words per lane (keys, then the colour gathers) so that a warp keeps that many
-    // independent requests in flight instead of one dependent pair (16 = a whole row of the 501-px grid).
-    // Per row the lane's pointers advance by constants (the unrolled body addresses with immediates); lane k keeps the bit words
-    // of word k of the current 32-word chunk, so that the row summary (count, first, last) and the stores of the bit rows cost a
-    // few instructions per row instead of per word.
-    for (int r = warp; r < h; r += NW) {
-        int running = 0, first = -1, last = -1, ne_cnt = 0;
-        uint8_t* op = out + ((size_t)(raw ? r : (h - 1 - r)) * w + lane) * 3;  // this lane's pixel of the current word
-        const uint32_t* kp = keygrid + (size_t)r * w + lane;
-        for (int wc = 0; wc < wpr; wc += 32) {  // chunks of 32 words (one chunk for grids up to 1 024 pixels wide)
-            uint32_t my_ob = 0u, my_nb = 0u;
-            const int wend = min(wpr, wc + 32);
-            for (int wi0 = wc; wi0 < wend; wi0 += SITES_BATCH, op += SITES_BATCH * 96, kp += SITES_BATCH * 32) {
-                uint32_t key[SITES_BATCH], col[SITES_BATCH];
-                const int c0 = wi0 * 32 + lane;
-#pragma unroll
-                for (int j = 0; j < SITES_BATCH; j++) key[j] = (c0 + j * 32 < w) ? IMAGE_KEY_LD(kp + j * 32) : 0u;
-#pragma unroll
-                for (int j = 0; j < SITES_BATCH; j++) {
-                    col[j] = 0u;
-                    if (key[j]) col[j] = gather_rgb(csrc, (key[j] - 1u) & KEY_IDX_MASK, A.pano_w);
-                }
-#pragma unroll
-                for (int j = 0; j < SITES_BATCH; j++) {
-                    const uint32_t cr = col[j] & 0xFF, cg = (col[j] >> 8) & 0xFF, cb = col[j] >> 16;
-                    const bool ne = ((cr * cg * cb) & 0xFFu) != 0u;  // uint8 product wraps (interpolation_utils.py:95)
-                    if (c0 + j * 32 < w) { IMAGE_OUT_ST(op + j * 96 + 0, (uint8_t)cr); IMAGE_OUT_ST(op + j * 96 + 1, (uint8_t)cg); IMAGE_OUT_ST(op + j * 96 + 2, (uint8_t)cb); }
-                    const uint32_t ob = __ballot_sync(0xffffffffu, key[j] != 0u);
-                    const uint32_t nb = __ballot_sync(0xffffffffu, ne);
-                    if (lane == ((wi0 + j) & 31)) { my_ob = ob; my_nb = nb; }
-                }
-            }
-            // bit rows of the chunk (the keep plane holds `nonempty` until stage D) and the row summary
-            if (wc + lane < wpr) { S.occ[r * wpr + wc + lane] = my_ob; S.keep[r * wpr + wc + lane] = my_nb; }
-            const uint32_t nz = __ballot_sync(0xffffffffu, my_ob != 0u);
-            if (nz) {
-                const int fw = __ffs(nz) - 1, lw = 31 - __clz(nz);
-                const uint32_t fo = __shfl_sync(0xffffffffu, my_ob, fw), lo = __shfl_sync(0xffffffffu, my_ob, lw);
-                if (first < 0) first = (wc + fw) * 32 + __ffs(fo) - 1;
-                last = (wc + lw) * 32 + 31 - __clz(lo);
-                running += __reduce_add_sync(0xffffffffu, __popc(my_ob));
-                ne_cnt += __reduce_add_sync(0xffffffffu, __popc(my_nb));
-            }
+    // row summaries of the sites stage
+    {
+        const int16_t *g_cnt = row_arr(A, img, RA_CNT), *g_first = row_arr(A, img, RA_FIRST), *g_last = row_arr(A, img, RA_LAST),
+                      *g_ne = row_arr(A, img, RA_NE);
+        int nS = 0, nM = 0, mn = 1 << 30, mx = -1, ne = 0;
+        for (int r = tid; r < h; r += PREP_NT) {
+            const int c = g_cnt[r], f = g_first[r], l = g_last[r];
+            S.cnt[r] = (int16_t)c; S.first[r] = (int16_t)f; S.last[r] = (int16_t)l;
+            if (c > 0) { nS += c; nM++; mn = min(mn, f); mx = max(mx, l); }
+            ne += g_ne[r];
         }
+        nS = __reduce_add_sync(FULL, nS); nM = __reduce_add_sync(FULL, nM); ne = __reduce_add_sync(FULL, ne);
+        mn = __reduce_min_sync(FULL, mn); mx = __reduce_max_sync(FULL, mx);
         if (lane == 0) {
-            S.cnt[r] = (int16_t)running; S.first[r] = (int16_t)first; S.last[r] = (int16_t)last;
-            if (running) { atomicMin(&s_mincol, first); atomicMax(&s_maxcol, last); atomicAdd(&s_S, running); atomicAdd(&s_M, 1); }
-            if (ne_cnt) atomicAdd(&s_ne_cnt, ne_cnt);
+            if (nS) { atomicAdd(&s_S, nS); atomicAdd(&s_M, nM); atomicMin(&s_mincol, mn); atomicMax(&s_maxcol, mx); }
+            if (ne) atomicAdd(&s_ne_cnt, ne);
         }
     }
     __syncthreads();
-    if (A.bits) {
-        uint32_t* b = A.bits + (size_t)img * A.bits_stride;
-        for (int i = tid; i < nwords; i += IMAGE_NT) { b[i] = S.occ[i]; b[nwords + i] = S.keep[i]; }
-    }
 
-    mark(1);
-    // ---- B. guards (interpolation_utils.py:37-42, 57-71) ---------------------------------------------
+    // ---- guards (interpolation_utils.py:37-42, 57-71) ---------------------------------------------
     const int nS = s_S, M = s_M;
     int status = 0;  // SALVE_BEV_IMG_OK
     if (!A.skip_empty_check && counts[1] == 0) status = 1;                         // EMPTY -> None
     else if (nS < 4 || M < 2 || s_mincol == s_maxcol) status = 2;                  // DEGENERATE -> zeros
 
     // nearest non-empty row above / below every row: one bit per row (a warp ballot per 32 rows), then two bit scans per row
-    for (int r0 = warp * 32; r0 < h; r0 += IMAGE_NT) {
-        const uint32_t nz = __ballot_sync(0xffffffffu, r0 + lane < h && S.cnt[r0 + lane] > 0);
+    for (int r0 = warp * 32; r0 < h; r0 += PREP_NT) {
+        const uint32_t nz = __ballot_sync(FULL, r0 + lane < h && S.cnt[r0 + lane] > 0);
         if (lane == 0) s_rownz[r0 >> 5] = nz;
     }
     __syncthreads();
-    for (int r = tid; r < h; r += IMAGE_NT) {
+    for (int r = tid; r < h; r += PREP_NT) {
         const int u = next_bit(s_rownz, r + 1, h - 1), d = prev_bit(s_rownz, r - 1, 0);
         S.up[r] = (int16_t)u; S.dn[r] = (int16_t)d;
         S.hlo[r] = 1; S.hhi[r] = 0;  // rows outside the hull: empty range
+        S.hl0[r] = 0; S.hl1[r] = 0; S.hr0[r] = 0; S.hr1[r] = 0;
         S.hlf[r] = __int_as_float(0x7f800000); S.hrf[r] = __int_as_float(0xff800000);
     }
 
-    // ---- C. exact convex hull from the per-row first / last sites: two monotone chains (warps 0 and 1) ---------------
+    // ---- exact convex hull from the per-row first / last sites: two monotone chains (warps 0 and 1) ---------------
     // The warp pre-filters the rows, lane 0 builds the chain from the survivors; the whole warp then fills the per-row bounds edge by edge.
     __syncthreads();
     if (status == 0 && warp < 2) {
@@ -737,7 +845,7 @@ __global__ void __launch_bounds__(IMAGE_NT, IMAGE_CTAS) image_kernel(ImageArgs A
                     }
                 }
             }
-            const uint32_t m = __ballot_sync(0xffffffffu, alive);
+            const uint32_t m = __ballot_sync(FULL, alive);
             if (alive) cand[ncand + __popc(m & ((1u << lane) - 1u))] = (int16_t)r;
             ncand += __popc(m);
         }
@@ -757,7 +865,9 @@ __global__ void __launch_bounds__(IMAGE_NT, IMAGE_CTAS) image_kernel(ImageArgs A
             }
             if (top <= 2) atomicAdd(&s_hull_ok, left ? 1 : 2);  // this chain has no interior vertex
         }
-        top = __shfl_sync(0xffffffffu, top, 0);
+        top = __shfl_sync(FULL, top, 0);
+        __syncwarp();
+        for (int r = lane; r < h; r += 32) { e0[r] = 0; e1[r] = 0; }  // the pre-filter's scratch: rows outside the hull read 0
         __syncwarp();
         for (int k = 1; k < top; k++) {
             const int r0 = stk[k - 1], r1 = stk[k];
@@ -772,14 +882,14 @@ __global__ void __launch_bounds__(IMAGE_NT, IMAGE_CTAS) image_kernel(ImageArgs A
         }
     }
 
-    // ---- D. keep mask = Chebyshev dilation of `nonempty` by K/2, zero padded ---------------------------
+    // ---- keep mask = Chebyshev dilation of `nonempty` by K/2, zero padded: rows first (into shared memory) -------------
+    const int rad = A.G.K / 2;
     if (!raw) {
-        const int rad = A.G.K / 2;
-        for (int item = tid; item < nwords; item += IMAGE_NT) {
+        for (int item = tid; item < nwords; item += PREP_NT) {
             const int r = item / wpr, wi = item - r * wpr;
-            const uint32_t cur = S.keep[item];
-            const uint32_t prv = (wi > 0) ? S.keep[item - 1] : 0u;
-            const uint32_t nxt = (wi + 1 < wpr) ? S.keep[item + 1] : 0u;
+            const uint32_t cur = __ldg(nonempty + item);
+            const uint32_t prv = (wi > 0) ? __ldg(nonempty + item - 1) : 0u;
+            const uint32_t nxt = (wi + 1 < wpr) ? __ldg(nonempty + item + 1) : 0u;
             const unsigned long long L = ((unsigned long long)cur << 32) | prv, R = ((unsigned long long)nxt << 32) | cur;
             uint32_t o = cur;
             for (int d = 1; d <= rad; d++) o |= (uint32_t)(L >> (32 - d)) | (uint32_t)(R >> d);
@@ -787,71 +897,55 @@ __global__ void __launch_bounds__(IMAGE_NT, IMAGE_CTAS) image_kernel(ImageArgs A
             if (valid < 32) o &= (1u << valid) - 1u;
             S.tmp[item] = o;
         }
-        __syncthreads();
-        int kc = 0;
-        for (int item = tid; item < nwords; item += IMAGE_NT) {
-            const int r = item / wpr, wi = item - r * wpr;
-            uint32_t o = 0;
-            const int r0 = max(r - rad, 0), r1 = min(r + rad, h - 1);
-            for (int rr = r0; rr <= r1; rr++) o |= S.tmp[rr * wpr + wi];
-            S.keep[item] = o;
-            kc += __popc(o);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) kc += __shfl_xor_sync(0xffffffffu, kc, o);
-        if (lane == 0 && kc) atomicAdd(&s_keep_cnt, kc);
-    } else {
-        for (int item = tid; item < nwords; item += IMAGE_NT) {
-            const int wi = item % wpr;
-            S.keep[item] = range_mask(wi, 0, w - 1);  // raw mode: every pixel is kept
-        }
     }
     __syncthreads();
-    if (A.bits) {
-        uint32_t* b = A.bits + (size_t)img * A.bits_stride;
-        for (int i = tid; i < nwords; i += IMAGE_NT) b[2 * nwords + i] = S.keep[i];
-    }
-    if (tid == 0) {
-        counts[2] = nS; counts[3] = s_ne_cnt; counts[4] = raw ? 0 : s_keep_cnt;
-        if (pclk) pclk[22] = nS;
-    }
-
-    mark(2);
     // all sites on one oblique line: every row has one site and neither chain has an interior vertex
     if (status == 0 && s_hull_ok == 3 && nS == M) status = 3;  // COLLINEAR: the reference's Qhull call raises
 
-    // ---- F. edge rule + work list of query pixels (row << 11 | col) in global memory -------------------------------------
+    // ---- columns of the dilation, fused with the EDGE RULE and the work list of query pixels (row << 11 | col) ----------
     // query = kept, not a site, inside the closed hull.
     // Edge rule: a query whose W and E (or N and S) neighbours are both sites lies at the midpoint of a Delaunay edge --
     // the circle of radius 1 around it has no lattice point strictly inside but the query itself -- so its interpolated value is
     // the exact mean of the two site colours whichever triangle it is attributed to (third barycentric weight 0).  With all
     // four neighbours present they are co-circular and the canonical diagonal is decided by the symbolic perturbation
     // (incircle_pert on (E, N, W, S) = 2 * (wE + wW - wN - wS): positive keeps N-S).  About half of all queries end here.
-    int my_filled = 0, my_flips = 0, my_maxflips = 0;
-    uint32_t* qlist = A.qlist + (size_t)slot * A.qlist_stride;
+    uint32_t* qlist = A.qlist + (size_t)img * A.qlist_stride;
+    uint32_t* elist = A.clist + (size_t)img * A.qlist_stride;  // edge-rule pixels (the cooperative pass's list is built later)
     const bool edge_rule = A.qtri == nullptr;  // the triangle tap wants every query resolved to a triangle
-    uint32_t* elist = A.clist + (size_t)slot * A.qlist_stride;  // edge-rule pixels (the cooperative pass's list is built later)
-    if (status == 0) {
+    {
+        int kc = 0;
         const int nw_pad = (nwords + 31) & ~31;
-        for (int item = tid; item < nw_pad; item += IMAGE_NT) {  // a warp takes 32 consecutive words
+        for (int item = tid; item < nw_pad; item += PREP_NT) {  // a warp takes 32 consecutive words
             uint32_t q = 0, he = 0, ve = 0;
+            int r = 0, wi = 0;
             if (item < nwords) {
-                const int r = item / wpr, wi = item - r * wpr;
-                const uint32_t hm = range_mask(wi, S.hlo[r], S.hhi[r]);
-                const uint32_t oc = S.occ[item];
-                const uint32_t kp = S.keep[item];
-                q = kp & ~oc & hm;
-                if (oc & ~kp) s_masked = 1;  // a site the hallucination mask removes: stage H has work (rare)
-                if (A.hull && hm) {
-                    uint8_t* hp = A.hull + (size_t)img * A.hull_stride + (size_t)r * w + wi * 32;
-                    uint32_t m = hm;
-                    while (m) { const int b = __ffs(m) - 1; m &= m - 1; hp[b] = 1; }
+                r = item / wpr; wi = item - r * wpr;
+                uint32_t kp;
+                if (!raw) {
+                    kp = 0u;
+                    const int r0 = max(r - rad, 0), r1 = min(r + rad, h - 1);
+                    for (int rr = r0; rr <= r1; rr++) kp |= S.tmp[rr * wpr + wi];
+                    kc += __popc(kp);
+                } else {
+                    kp = range_mask(wi, 0, w - 1);  // raw mode: every pixel is kept
                 }
-                if (q && edge_rule) {
-                    const uint32_t ol = wi > 0 ? S.occ[item - 1] : 0u, orr = wi + 1 < wpr ? S.occ[item + 1] : 0u;
-                    he = q & ((oc << 1) | (ol >> 31)) & ((oc >> 1) | (orr << 31));
-                    ve = q & (r + 1 < h ? S.occ[item + wpr] : 0u) & (r > 0 ? S.occ[item - wpr] : 0u);
-                    q &= ~(he | ve);
+                S.keep[item] = kp;
+                if (status == 0) {
+                    const uint32_t hm = range_mask(wi, S.hlo[r], S.hhi[r]);
+                    const uint32_t oc = __ldg(S.occ + item);
+                    q = kp & ~oc & hm;
+                    if (oc & ~kp) s_masked = 1;  // a site the hallucination mask removes: the finish stage has work (rare)
+                    if (A.hull && hm) {
+                        uint8_t* hp = A.hull + (size_t)img * A.hull_stride + (size_t)r * w + wi * 32;
+                        uint32_t m = hm;
+                        while (m) { const int b = __ffs(m) - 1; m &= m - 1; hp[b] = 1; }
+                    }
+                    if (q && edge_rule) {
+                        const uint32_t ol = wi > 0 ? __ldg(S.occ + item - 1) : 0u, orr = wi + 1 < wpr ? __ldg(S.occ + item + 1) : 0u;
+                        he = q & ((oc << 1) | (ol >> 31)) & ((oc >> 1) | (orr << 31));
+                        ve = q & (r + 1 < h ? __ldg(S.occ + item + wpr) : 0u) & (r > 0 ? __ldg(S.occ + item - wpr) : 0u);
+                        q &= ~(he | ve);
+                    }
                 }
             }
             // one warp scan for both lists: queries in the low half, edge-rule pixels in the high half (<= 1024 each per warp)
@@ -859,8 +953,8 @@ __global__ void __launch_bounds__(IMAGE_NT, IMAGE_CTAS) image_kernel(ImageArgs A
             const int n = __popc(q) | (__popc(e) << 16);
             int incl = n;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
+            const int total = __shfl_sync(FULL, incl, 31);
             if (total == 0) continue;
             int base_q = 0, base_e = 0;
             if (lane == 0) {
@@ -868,9 +962,8 @@ __global__ void __launch_bounds__(IMAGE_NT, IMAGE_CTAS) image_kernel(ImageArgs A
                 if (total >> 16) base_e = atomicAdd(&s_nedge, total >> 16);
             }
             const int excl = incl - n;
-            base_q = __shfl_sync(0xffffffffu, base_q, 0) + (excl & 0xFFFF);
-            base_e = __shfl_sync(0xffffffffu, base_e, 0) + (excl >> 16);
-            const int r = item / wpr, wi = item - r * wpr;
+            base_q = __shfl_sync(FULL, base_q, 0) + (excl & 0xFFFF);
+            base_e = __shfl_sync(FULL, base_e, 0) + (excl >> 16);
             const uint32_t code0 = ((uint32_t)r << COL_BITS) | (uint32_t)(wi * 32);
             while (q) { const int b = __ffs(q) - 1; q &= q - 1; qlist[base_q++] = code0 + b; }
             uint32_t m = e;
@@ -879,13 +972,18 @@ __global__ void __launch_bounds__(IMAGE_NT, IMAGE_CTAS) image_kernel(ImageArgs A
                 elist[base_e++] = (code0 + b) | (((he >> b) & 1u) << 31) | (((ve >> b) & 1u) << 30);
             }
         }
+        if (!raw) {
+            kc = __reduce_add_sync(FULL, kc);
+            if (lane == 0 && kc) atomicAdd(&s_keep_cnt, kc);
+        }
     }
-    __syncthreads();
+    __syncthreads();  // both lists are complete (and visible to the whole CTA: same-CTA global writes after a barrier)
     // edge-rule pixels, one per thread: the exact mean of the two site colours
+    int my_filled = 0;
     if (status == 0) {
         const ptrdiff_t dn = raw ? (ptrdiff_t)w * 3 : -(ptrdiff_t)w * 3;  // address step to row r + 1 in the (flipped) output
         const int ne = s_nedge;
-        for (int i = tid; i < ne; i += IMAGE_NT) {
+        for (int i = tid; i < ne; i += PREP_NT) {
             const uint32_t code = elist[i];
             const int x = (int)(code & COL_MASK), r = (int)((code >> COL_BITS) & 0x3FFu);
             bool horiz = (code >> 31) != 0u;
@@ -909,11 +1007,103 @@ __global__ void __launch_bounds__(IMAGE_NT, IMAGE_CTAS) image_kernel(ImageArgs A
             my_filled++;
         }
     }
+    my_filled = __reduce_add_sync(FULL, my_filled);
+    if (lane == 0 && my_filled) atomicAdd(&s_filled, my_filled);
+    // row arrays the finish stage needs
+    {
+        int16_t* dsts[6] = {row_arr(A, img, RA_UP), row_arr(A, img, RA_DN), row_arr(A, img, RA_HL0), row_arr(A, img, RA_HL1),
+                            row_arr(A, img, RA_HR0), row_arr(A, img, RA_HR1)};
+        const int16_t* srcs[6] = {S.up, S.dn, S.hl0, S.hl1, S.hr0, S.hr1};
+        float *g_hlf = row_arr_f(A, img, RA_HLF), *g_hrf = row_arr_f(A, img, RA_HRF);
+        for (int r = tid; r < h; r += PREP_NT) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) dsts[k][r] = srcs[k][r];
+            g_hlf[r] = S.hlf[r]; g_hrf[r] = S.hrf[r];
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        counts[2] = nS; counts[3] = s_ne_cnt; counts[4] = raw ? 0 : s_keep_cnt; counts[5] = 0; counts[6] = 0; counts[7] = 0;
+        int32_t* hd = A.hdr + (size_t)img * HD_STRIDE;
+        hd[HD_STATUS] = status; hd[HD_NQ] = status == 0 ? s_nitems : 0; hd[HD_EDGE] = s_filled; hd[HD_MASKED] = s_masked; hd[HD_PEND] = 0;
+    }
+}
+
+// Hand-out order of the finish stage: longest expected image first, so that the launch does not end with a few CTAs working on
+// long images while the rest of the GPU idles.  The predictor is what the stage's cooperative pass has to do: the queries the
+// window pass handed on (ties by the number of window queries, which the stage shades).  rank = number of images that come first.
+__global__ void __launch_bounds__(256) image_order_kernel(const int32_t* __restrict__ hdr, int n, int32_t* __restrict__ order) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long key = ((long long)hdr[(size_t)i * HD_STRIDE + HD_PEND] << 24) + hdr[(size_t)i * HD_STRIDE + HD_NQ];
+    int rank = 0;
+    for (int j = 0; j < n; j++) {
+        const long long kj = ((long long)__ldg(hdr + (size_t)j * HD_STRIDE + HD_PEND) << 24) + __ldg(hdr + (size_t)j * HD_STRIDE + HD_NQ);
+        rank += (kj > key || (kj == key && j < i)) ? 1 : 0;
+    }
+    order[rank] = i;
+}
+
+// ---- stage 4: shade the window pass's results, cooperative pass for what it handed on, masked-out sites, counters ---------
+template <bool SG>
+__global__ void __launch_bounds__(FINISH_NT, 2) finish_stage_kernel(ImageArgs A) {
+    const int img = A.order ? A.order[blockIdx.x] : blockIdx.x;
+    const int h = A.G.grid_h, w = A.G.grid_w, wpr = A.G.wpr;
+    const int tid = threadIdx.x, lane = tid & 31;
+    constexpr int NW = FINISH_NT / 32;
+    const int nwords = h * wpr;
+    const unsigned FULL = 0xffffffffu;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ImageShared S;
+    {
+        unsigned char* p = smem_raw;
+        S.occ = (uint32_t*)p; p += (size_t)nwords * 4;
+        S.tmp = (uint32_t*)p; p += (size_t)nwords * 4;
+        const size_t rows = image_row_bytes(h);
+        int16_t** arr[9] = {&S.cnt, &S.first, &S.last, &S.up, &S.dn, &S.hl0, &S.hl1, &S.hr0, &S.hr1};
+        for (int i = 0; i < 9; i++) { *arr[i] = (int16_t*)p; p += rows; }
+        const size_t frows = ((size_t)h * 4 + 15) & ~(size_t)15;
+        S.hlf = (float*)p; p += frows; S.hrf = (float*)p; p += frows;
+        S.hlo = nullptr; S.hhi = nullptr; S.stk_l = nullptr; S.stk_r = nullptr;
+    }
+    const uint32_t* planes = A.planes + (size_t)img * 3 * A.plane_stride;
+    S.keep = const_cast<uint32_t*>(planes) + 2 * A.plane_stride;  // global (L2): only the masking of sites reads it
+    __shared__ int s_nitems, s_next, s_filled, s_flips, s_maxflips;
+
+    int dst;
+    uint8_t* out = image_out(A, img, dst);
+    int32_t* counts = A.counts + (size_t)img * 8;
+    int32_t* counts_final = dst >= 0 ? (A.counts_out ? A.counts_out + (size_t)dst * 8 : nullptr) : A.cache_counts + (size_t)(-1 - dst) * 8;
+    int32_t* status_final = dst >= 0 ? (A.status ? A.status + dst : nullptr) : A.cache_status + (-1 - dst);
+    const bool raw = A.raw_mode != 0;
+    const int32_t* hd = A.hdr + (size_t)img * HD_STRIDE;
+    const int status = hd[HD_STATUS], n_win = hd[HD_NQ], masked = hd[HD_MASKED];
+    const bool coop = status == 0 && hd[HD_PEND] > 0;  // something was handed on: the bit planes and row arrays are needed
+
+    if (tid == 0) { s_nitems = 0; s_next = 0; s_filled = 0; s_flips = 0; s_maxflips = 0; }
+    uint32_t* defer = S.tmp;  // bit plane: queries handed to the cooperative pass
+    if (coop) {
+        for (int i = tid; i < nwords; i += FINISH_NT) { S.occ[i] = __ldg(planes + i); defer[i] = 0u; }
+        int16_t* d16[9] = {S.cnt, S.first, S.last, S.up, S.dn, S.hl0, S.hl1, S.hr0, S.hr1};
+        const int ks[9] = {RA_CNT, RA_FIRST, RA_LAST, RA_UP, RA_DN, RA_HL0, RA_HL1, RA_HR0, RA_HR1};
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+            const int16_t* g = row_arr(A, img, ks[k]);
+            for (int r = tid; r < h; r += FINISH_NT) d16[k][r] = g[r];
+        }
+        const float *g_hlf = row_arr_f(A, img, RA_HLF), *g_hrf = row_arr_f(A, img, RA_HRF);
+        for (int r = tid; r < h; r += FINISH_NT) { S.hlf[r] = g_hlf[r]; S.hrf[r] = g_hrf[r]; }
+    }
     __syncthreads();
 
+    int my_filled = 0, my_flips = 0, my_maxflips = 0;
     int32_t* qtri = A.qtri ? A.qtri + (size_t)img * A.qtri_stride : nullptr;
+    const uint32_t* qlist = A.qlist + (size_t)img * A.qlist_stride;
+    unsigned long long* qres = A.qres + (size_t)img * A.qlist_stride;
+    uint32_t* clist = A.clist + (size_t)img * A.qlist_stride;
 
-    // one query pixel: initial triangle, flip descent, exact barycentric value
+    // one query pixel: exact barycentric value from its final triangle
     auto site_rgb = [&](int sx, int sy) { return load_rgb(out + ((size_t)(raw ? sy : h - 1 - sy) * w + sx) * 3); };
     auto write_px = [&](const Tri2& t, uint32_t ca, uint32_t cb, uint32_t cc, int x, int r) {
         const uint32_t ua = (uint32_t)orient_i(t.bx, t.by, t.cx, t.cy, x, r), ub = (uint32_t)orient_i(t.cx, t.cy, t.ax, t.ay, x, r),
@@ -947,64 +1137,46 @@ __global__ void __launch_bounds__(IMAGE_NT, IMAGE_CTAS) image_kernel(ImageArgs A
         if (fc) { t.cx = dx; t.cy = dy; return true; }
         return false;  // cannot happen (d is inside the triangle or across exactly one edge)
     };
-    uint32_t* defer = S.tmp;  // bit plane: queries handed to the next pass (the row-dilated plane is dead now)
-    unsigned long long* qres = A.qres + (size_t)slot * A.qlist_stride;
 
-    // interpolate the pixels a pass resolved: gathers, exact barycentrics and stores with every lane busy
-    auto shade = [&](int n) {
-        for (int i = tid; i < n; i += IMAGE_NT) {
-            const unsigned long long rs = qres[i];
-            if (!(rs & QRES_DONE)) continue;
-            const uint32_t code = qlist[i];
-            const uint32_t a = (uint32_t)rs & M21, b = (uint32_t)(rs >> 21) & M21, c = (uint32_t)(rs >> 42) & M21;
-            const Tri2 t = {vcol(a), vrow(a), vcol(b), vrow(b), vcol(c), vrow(c)};
-            write_px(t, site_rgb(t.ax, t.ay), site_rgb(t.bx, t.by), site_rgb(t.cx, t.cy), (int)(code & COL_MASK), (int)(code >> COL_BITS));
-            my_filled++;
-        }
-    };
-
-    // ---- G0. window pass (small triangles): one query per lane -----------------------------------------------------------
-    for (int i = tid; i < nwords; i += IMAGE_NT) defer[i] = 0u;
-    __syncthreads();
-    mark(18);
-    if (pclk && tid == 0) pclk[17] = s_nitems;
-    if (status == 0) resolve_window<IMAGE_WIN_NR>(S, wpr, w, h, qlist, qres, s_nitems, &s_next, defer, lane, my_flips, my_maxflips);
-    __syncthreads();
-    mark(16);
-    if (status == 0) shade(s_nitems);
-    __syncthreads();
-    mark(3);
-    // ---- G2. cooperative pass: what the window pass handed on (hull pockets, wide gaps, the hole under the camera), one warp
-    // per query ----------------------------------------------------------------------------------------------------------
-    // The final triangle of a descent is rasterised over ALL deferred pixels it contains (they share it), which are then
-    // taken off the list: a big triangle across a hole is found about once instead of once per pixel.  Warps take
-    // row-major bands of the list, so that the pixels of one triangle mostly meet the same warp.
-    const int n_win = s_nitems;
-    __syncthreads();
-    if (tid == 0) { s_nitems = 0; s_next = 0; }
-    __syncthreads();
-    uint32_t* clist = A.clist + (size_t)slot * A.qlist_stride;
-    if (status == 0) {  // compact the entries the window pass did not finish (list order is kept within 32 entries)
+    // ---- the window pass's results: interpolate what it resolved (gathers, exact barycentrics and stores with every lane busy),
+    // list what it handed on (list order is kept within 32 entries) and mark those pixels in the deferred plane
+    if (status == 0) {
         const int n_pad = (n_win + 31) & ~31;
-        for (int i = tid; i < n_pad; i += IMAGE_NT) {
-            const bool pend = i < n_win && !(qres[i] & QRES_DONE);
-            const uint32_t m = __ballot_sync(0xffffffffu, pend);
+        for (int i = tid; i < n_pad; i += FINISH_NT) {
+            bool pend = false;
+            if (i < n_win) {
+                const unsigned long long rs = qres[i];
+                const uint32_t code = qlist[i];
+                const int x = (int)(code & COL_MASK), r = (int)(code >> COL_BITS);
+                if (rs & QRES_DONE) {
+                    const uint32_t a = (uint32_t)rs & M21, b = (uint32_t)(rs >> 21) & M21, c = (uint32_t)(rs >> 42) & M21;
+                    const Tri2 t = {vcol(a), vrow(a), vcol(b), vrow(b), vcol(c), vrow(c)};
+                    write_px(t, site_rgb(t.ax, t.ay), site_rgb(t.bx, t.by), site_rgb(t.cx, t.cy), x, r);
+                    my_filled++;
+                } else {
+                    pend = true;
+                    if (coop) atomicOr(&defer[r * wpr + (x >> 5)], 1u << (x & 31));
+                }
+            }
+            const uint32_t m = __ballot_sync(FULL, pend);
             if (!m) continue;
             int base = 0;
             if (lane == 0) base = atomicAdd(&s_nitems, __popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
+            base = __shfl_sync(FULL, base, 0);
             if (pend) clist[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)i;
         }
     }
     __syncthreads();
-    mark(9);
-    if (pclk && tid == 0) pclk[14] = s_nitems;
-    if (status == 0) {
+
+    // ---- cooperative pass: what the window pass handed on (hull pockets, wide gaps, the hole under the camera), one warp
+    // per query ----------------------------------------------------------------------------------------------------------
+    // The final triangle of a descent is rasterised over ALL deferred pixels it contains (they share it), which are then
+    // taken off the list: a big triangle across a hole is found about once instead of once per pixel.  Warps take
+    // row-major bands of the list, so that the pixels of one triangle mostly meet the same warp.
+    if (coop) {
         const int n = s_nitems;
         // guided self-scheduling: bands shrink with what is left (long row-major bands first, so that the pixels of one
         // triangle mostly meet the same warp; short ones at the end, so that no warp is left alone with a long band)
-        const long long coop_t0 = clock64();
-        long long longest = 0;
         Tri2 tp = {0, 0, 0, 0, 0, 0};  // final triangle of this warp's previous descent
         bool have_prev = false;
         while (true) {
@@ -1014,7 +1186,7 @@ __global__ void __launch_bounds__(IMAGE_NT, IMAGE_CTAS) image_kernel(ImageArgs A
                 band = min(max(IMAGE_COOP_MIN_BAND, (n - seen) / (IMAGE_COOP_BAND_DIV * NW)), max(n - seen, 1));
                 i0 = atomicAdd(&s_next, band);
             }
-            i0 = __shfl_sync(0xffffffffu, i0, 0); band = __shfl_sync(0xffffffffu, band, 0);
+            i0 = __shfl_sync(FULL, i0, 0); band = __shfl_sync(FULL, band, 0);
             if (i0 >= n) break;
             const int i_end = min(n, i0 + band);
           for (int i = i0; i < i_end; i++) {
@@ -1050,7 +1222,6 @@ __global__ void __launch_bounds__(IMAGE_NT, IMAGE_CTAS) image_kernel(ImageArgs A
                 }
             }
 #endif
-            const long long d_t0 = clock64();
             int flips = 0, waves = 0;
             // Each lane keeps the violator its row produced in the last scan.  After a flip these candidates are tested (exactly)
             // against the new circle before any row is scanned again: consecutive circles overlap, so about half of the flips
@@ -1059,7 +1230,7 @@ __global__ void __launch_bounds__(IMAGE_NT, IMAGE_CTAS) image_kernel(ImageArgs A
             while (flips < IMAGE_MAX_FLIPS) {
                 int v = -1;
 #if IMAGE_COOP_CACHE
-                if (__any_sync(0xffffffffu, cache != ~0ull)) {
+                if (__any_sync(FULL, cache != ~0ull)) {
                     bool viol = false;
                     if (cache != ~0ull) {
                         const uint32_t va = vlabel(t.ay, t.ax), vb = vlabel(t.by, t.bx), vc = vlabel(t.cy, t.cx);
@@ -1071,10 +1242,10 @@ __global__ void __launch_bounds__(IMAGE_NT, IMAGE_CTAS) image_kernel(ImageArgs A
                         if (!viol) cache = ~0ull;
                     }
                     const uint32_t d2 = viol ? (uint32_t)(cache >> 32) : 0xFFFFFFFFu;
-                    const uint32_t dmin = __reduce_min_sync(0xffffffffu, d2);
+                    const uint32_t dmin = __reduce_min_sync(FULL, d2);
                     if (dmin != 0xFFFFFFFFu) {
-                        const int src = __ffs(__ballot_sync(0xffffffffu, d2 == dmin)) - 1;
-                        v = __shfl_sync(0xffffffffu, (int)(uint32_t)cache, src);
+                        const int src = __ffs(__ballot_sync(FULL, d2 == dmin)) - 1;
+                        v = __shfl_sync(FULL, (int)(uint32_t)cache, src);
                         if (lane == src) cache = ~0ull;
                     }
                 }
@@ -1084,9 +1255,7 @@ __global__ void __launch_bounds__(IMAGE_NT, IMAGE_CTAS) image_kernel(ImageArgs A
                 flips++;
             }
             if (lane == 0) { my_flips += flips; my_maxflips = max(my_maxflips, flips); }
-            if (pclk && lane == 0) atomicAdd((unsigned long long*)&pclk[15], (1ull << 40) | ((unsigned long long)waves << 20) | (unsigned long long)flips);
             tp = t; have_prev = true;
-            longest = max(longest, clock64() - d_t0);
             // rasterise t over the deferred pixels it contains: one lane per row of its bounding box
             const uint32_t ca = site_rgb(t.ax, t.ay), cb = site_rgb(t.bx, t.by), cc = site_rgb(t.cx, t.cy);
             const int y0 = min(t.ay, min(t.by, t.cy)), y1 = max(t.ay, max(t.by, t.cy));
@@ -1107,22 +1276,15 @@ __global__ void __launch_bounds__(IMAGE_NT, IMAGE_CTAS) image_kernel(ImageArgs A
             __syncwarp();
           }
         }
-        if (pclk && lane == 0) {
-            const long long busy = clock64() - coop_t0;
-            atomicAdd((unsigned long long*)&pclk[5], (unsigned long long)busy);
-            atomicMax((unsigned long long*)&pclk[4], (unsigned long long)busy);
-            atomicMax((unsigned long long*)&pclk[13], (unsigned long long)longest);
-        }
     }
     __syncthreads();
 
-    mark(10);
-    if (tid == 0) next_img = atomicAdd(A.work_counter, 1);  // consumed at the hand-over
-    // ---- H. masked-out sites, degenerate images, counters ------------------------------------------------------------
+    // ---- masked-out sites, degenerate images, counters ------------------------------------------------------------------
+    const uint32_t* g_occ = planes;
     if (status == 1 || status == 2) {
         // the reference returns None (empty) or an all-zero interpolation (degenerate): clear the site colours
-        for (int item = tid; item < nwords; item += IMAGE_NT) {
-            uint32_t m = S.occ[item];
+        for (int item = tid; item < nwords; item += FINISH_NT) {
+            uint32_t m = __ldg(g_occ + item);
             const int r = item / wpr, wi = item - r * wpr;
             while (m) {
                 const int b = __ffs(m) - 1; m &= m - 1;
@@ -1130,9 +1292,9 @@ __global__ void __launch_bounds__(IMAGE_NT, IMAGE_CTAS) image_kernel(ImageArgs A
                 o[0] = 0; o[1] = 0; o[2] = 0;
             }
         }
-    } else if (!raw && (s_masked || status != 0)) {
-        for (int item = tid; item < nwords; item += IMAGE_NT) {
-            uint32_t m = S.occ[item] & ~S.keep[item];  // sites the hallucination mask removes
+    } else if (!raw && (masked || status != 0)) {
+        for (int item = tid; item < nwords; item += FINISH_NT) {
+            uint32_t m = __ldg(g_occ + item) & ~__ldg(S.keep + item);  // sites the hallucination mask removes
             const int r = item / wpr, wi = item - r * wpr;
             while (m) {
                 const int b = __ffs(m) - 1; m &= m - 1;
@@ -1143,27 +1305,20 @@ __global__ void __launch_bounds__(IMAGE_NT, IMAGE_CTAS) image_kernel(ImageArgs A
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        my_filled += __shfl_xor_sync(0xffffffffu, my_filled, o);
-        my_flips += __shfl_xor_sync(0xffffffffu, my_flips, o);
-        my_maxflips = max(my_maxflips, __shfl_xor_sync(0xffffffffu, my_maxflips, o));
+        my_filled += __shfl_xor_sync(FULL, my_filled, o);
+        my_flips += __shfl_xor_sync(FULL, my_flips, o);
+        my_maxflips = max(my_maxflips, __shfl_xor_sync(FULL, my_maxflips, o));
     }
     if (lane == 0) { atomicAdd(&s_filled, my_filled); atomicAdd(&s_flips, my_flips); atomicMax(&s_maxflips, my_maxflips); }
     __syncthreads();
     if (tid == 0) {
-        counts[5] = s_filled; counts[6] = s_maxflips; counts[7] = s_flips;
-        if (pclk) {
-            pclk[6] = s_flips; pclk[7] = s_filled;
-            pclk[11] = clock64();
-            unsigned long long ns; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
-            pclk[20] = (long long)ns;
-        }
+        counts[5] = hd[HD_EDGE] + s_filled; counts[6] = max(counts[6], s_maxflips); counts[7] += s_flips;
         if (status_final) *status_final = status;
         if (counts_final) {
 #pragma unroll
             for (int k = 0; k < 8; k++) counts_final[k] = counts[k];
         }
     }
-  }  // next image
 }
 
 // colour word tap: r | g<<8 | b<<16 | 0xFF<<24 at sites, 0 elsewhere

@@ -395,11 +395,5 @@ class BevRenderer:
         nat.check(self._lib.salve_bev_last_timings(self._h, _ptr(ms, ctypes.c_float)))
         return dict(splat=float(ms[0]), image=float(ms[1]), total=float(ms[4]))
 
-    def last_phase_clocks(self, n_img: int) -> np.ndarray:
-        """(n_img, 24) int64 diagnostics of image_kernel for the last chunk (see salve_bev_last_phase_clocks)."""
-        clk = np.zeros((n_img, 24), np.int64)
-        nat.check(self._lib.salve_bev_last_phase_clocks(self._h, _ptr(clk, ctypes.c_int64), n_img))
-        return clk
-
     def launch_count(self) -> int:
         return int(self._lib.salve_bev_launch_count(self._h))
