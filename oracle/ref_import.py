@@ -1,8 +1,10 @@
-"""Import the *unmodified* reference (zillow/salve) with stubbed I/O, to pin the oracle.
+"""Import the *unmodified* reference (zillow/salve) with stubbed I/O, to pin the oracle and to time it.
 
-TEST INFRASTRUCTURE ONLY.  Works only where /root/reference exists (the build container);
-nothing on the GPU box may use it.  It is used by scripts/make_golden.py to freeze golden
-vectors under tests/golden/ and by tests marked `needs_reference`.
+TEST / MEASUREMENT INFRASTRUCTURE ONLY.  The reference is looked up at $SALVE_REFERENCE_ROOT, else /root/reference
+(the build container), else oracle/_ref (unmodified copies of the few modules the path loads, made by
+scripts/make_oracle_ref.py; git-ignored, they travel to the GPU box like the built .so files).  It is used by
+scripts/make_golden.py to freeze golden vectors under tests/golden/, by tests marked `needs_reference`, and by
+bench.py's CPU legs (`--impl reference`, `cpu_baseline`).  Nothing under salve_b200/ imports it.
 
 The reference's hot path imports packages that are absent here (imageio, matplotlib, gtsam,
 gtsfm, colour, ...) but none of them carries hot-path arithmetic; they are replaced by stub
@@ -20,7 +22,20 @@ import types
 from types import SimpleNamespace
 from unittest.mock import MagicMock
 
-REFERENCE_ROOT = os.environ.get("SALVE_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root() -> str:
+    env = os.environ.get("SALVE_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", os.path.join(_HERE, "_ref")):
+        if os.path.isdir(os.path.join(cand, "salve")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 _MISSING = {
     "imageio", "matplotlib", "gtsam", "gtsfm", "colour", "shapely", "rdp", "hydra",
