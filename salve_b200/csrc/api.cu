@@ -417,9 +417,10 @@ static int run_image_stage(salve_bev_ctx* c, int n_img, const GridParams& G, uin
         CU(cudaMemsetAsync(c->work_counter, 0, sizeof(int32_t), st));
         sites_stage_kernel<<<dim3((unsigned)((G.grid_h + SITES_WARPS - 1) / SITES_WARPS), (unsigned)n), SITES_WARPS * 32, sites_smem_bytes(G.wpr), st>>>(IA);
         prep_stage_kernel<<<n, PREP_NT, prep_smem_bytes(G.grid_h, G.wpr), st>>>(IA);
-        const int win_ctas = std::max(1, std::min(c->n_sm * IMAGE_WIN_CTAS, (n * 64 + WIN_NT - 1) / WIN_NT));
+        const int win_ctas = std::max(1, std::min(c->n_sm * IMAGE_WIN_CTAS, n * 16));
         window_stage_kernel<IMAGE_WIN_NR><<<win_ctas, WIN_NT, 0, st>>>(IA);
-        c->launches += 3;
+        shade_stage_kernel<<<dim3(SHADE_SPLIT, (unsigned)n), SHADE_NT, 0, st>>>(IA);
+        c->launches += 4;
         if (n > 2 * c->n_sm) {  // more images than CTA slots: longest expected first
             image_order_kernel<<<(n + 255) / 256, 256, 0, st>>>(c->hdr, n, c->d_order);
             c->launches++;

@@ -109,7 +109,7 @@ constexpr int IMAGE_MAX_FLIPS = 100000;   // safety cap on one descent (never re
 enum { RA_CNT = 0, RA_FIRST, RA_LAST, RA_NE, RA_UP, RA_DN, RA_HL0, RA_HL1, RA_HR0, RA_HR1, RA_N16 };
 enum { RA_HLF = 0, RA_HRF, RA_NF };
 // per-image header (16 int32)
-enum { HD_STATUS = 0, HD_NQ, HD_EDGE, HD_MASKED, HD_PEND, HD_N };
+enum { HD_STATUS = 0, HD_NQ, HD_EDGE, HD_MASKED, HD_PEND, HD_XTRA, HD_N };
 constexpr int HD_STRIDE = 16;
 
 struct ImageArgs {
@@ -680,7 +680,7 @@ __global__ void __launch_bounds__(SITES_WARPS * 32) sites_stage_kernel(ImageArgs
         uint32_t my_ob = 0u, my_nb = 0u;
         const int wend = min(wpr, wc + 32);
         for (int wi0 = wc; wi0 < wend; wi0 += SITES_BATCH, kp += SITES_BATCH * 32) {
-            uint32_t key[SITES_BATCH], col[SITES_BATCH];
+            uint32_t key[SITES_BATCH], col[SITES_BATCH];  // col: rgb in bits 0..23, bit 31 = the pixel is a site
             const int c0 = wi0 * 32 + lane;
 #pragma unroll
             for (int j = 0; j < SITES_BATCH; j++) key[j] = (c0 + j * 32 < w) ? IMAGE_KEY_LD(kp + j * 32) : 0u;
@@ -691,16 +691,17 @@ __global__ void __launch_bounds__(SITES_WARPS * 32) sites_stage_kernel(ImageArgs
 #pragma unroll
             for (int j = 0; j < SITES_BATCH; j++) {
                 col[j] = 0u;
-                if (key[j]) col[j] = gather_rgb(csrc, (key[j] - 1u) & KEY_IDX_MASK, A.pano_w);
+                if (key[j]) col[j] = gather_rgb(csrc, (key[j] - 1u) & KEY_IDX_MASK, A.pano_w) | 0x80000000u;
             }
 #pragma unroll
             for (int j = 0; j < SITES_BATCH; j++) {
-                const uint32_t cr = col[j] & 0xFF, cg = (col[j] >> 8) & 0xFF, cb = col[j] >> 16;
+                const uint32_t cr = col[j] & 0xFF, cg = (col[j] >> 8) & 0xFF, cb = (col[j] >> 16) & 0xFF;
                 const bool ne = ((cr * cg * cb) & 0xFFu) != 0u;  // uint8 product wraps (interpolation_utils.py:95)
-                const uint32_t ob = __ballot_sync(FULL, key[j] != 0u);
+                const uint32_t ob = __ballot_sync(FULL, (col[j] >> 31) != 0u);
                 const uint32_t nb = __ballot_sync(FULL, ne);
                 if (lane == ((wi0 + j) & 31)) { my_ob = ob; my_nb = nb; }
-                const uint32_t a = __shfl_sync(FULL, col[j], p0 & 31), b = __shfl_sync(FULL, col[j], (p0 + 1) & 31);
+                const uint32_t c24 = col[j] & 0xFFFFFFu;
+                const uint32_t a = __shfl_sync(FULL, c24, p0 & 31), b = __shfl_sync(FULL, c24, (p0 + 1) & 31);
                 if (lane < 24) sb[(wi0 + j) * 24 + lane] = (a >> o8) | (b << (24 - o8));
             }
         }
@@ -764,15 +765,13 @@ __global__ void __launch_bounds__(PREP_NT) prep_stage_kernel(ImageArgs A) {
     const uint32_t* nonempty = planes + A.plane_stride;
     S.keep = planes + 2 * A.plane_stride;      // written here
     __shared__ uint32_t s_rownz[32];  // rows with at least one site, one bit per row (grid_h <= 1023)
-    __shared__ int s_S, s_M, s_mincol, s_maxcol, s_ne_cnt, s_keep_cnt, s_nitems, s_filled, s_hull_ok, s_nedge, s_masked;
+    __shared__ int s_S, s_M, s_mincol, s_maxcol, s_ne_cnt, s_keep_cnt, s_nitems, s_hull_ok, s_nedge, s_masked;
 
-    int dst;
-    uint8_t* out = image_out(A, img, dst);
     int32_t* counts = A.counts + (size_t)img * 8;
     const bool raw = A.raw_mode != 0;
     if (tid == 0) {
         s_S = 0; s_M = 0; s_mincol = 1 << 30; s_maxcol = -1; s_ne_cnt = 0; s_keep_cnt = 0; s_nitems = 0;
-        s_filled = 0; s_hull_ok = 0; s_nedge = 0; s_masked = 0;
+        s_hull_ok = 0; s_nedge = 0; s_masked = 0;
     }
     __syncthreads();
     // row summaries of the sites stage
@@ -910,7 +909,7 @@ __global__ void __launch_bounds__(PREP_NT) prep_stage_kernel(ImageArgs A) {
     // four neighbours present they are co-circular and the canonical diagonal is decided by the symbolic perturbation
     // (incircle_pert on (E, N, W, S) = 2 * (wE + wW - wN - wS): positive keeps N-S).  About half of all queries end here.
     uint32_t* qlist = A.qlist + (size_t)img * A.qlist_stride;
-    uint32_t* elist = A.clist + (size_t)img * A.qlist_stride;  // edge-rule pixels (the cooperative pass's list is built later)
+    uint32_t* elist = A.clist + (size_t)img * A.qlist_stride;  // edge-rule pixels for the shade stage (the cooperative pass's list is built later)
     const bool edge_rule = A.qtri == nullptr;  // the triangle tap wants every query resolved to a triangle
     {
         int kc = 0;
@@ -977,38 +976,6 @@ __global__ void __launch_bounds__(PREP_NT) prep_stage_kernel(ImageArgs A) {
             if (lane == 0 && kc) atomicAdd(&s_keep_cnt, kc);
         }
     }
-    __syncthreads();  // both lists are complete (and visible to the whole CTA: same-CTA global writes after a barrier)
-    // edge-rule pixels, one per thread: the exact mean of the two site colours
-    int my_filled = 0;
-    if (status == 0) {
-        const ptrdiff_t dn = raw ? (ptrdiff_t)w * 3 : -(ptrdiff_t)w * 3;  // address step to row r + 1 in the (flipped) output
-        const int ne = s_nedge;
-        for (int i = tid; i < ne; i += PREP_NT) {
-            const uint32_t code = elist[i];
-            const int x = (int)(code & COL_MASK), r = (int)((code >> COL_BITS) & 0x3FFu);
-            bool horiz = (code >> 31) != 0u;
-            if (horiz && ((code >> 30) & 1u)) {
-                const uint32_t qi = (uint32_t)(r * w + x);
-                const int wh = pert_weight_idx(qi - 1u) + pert_weight_idx(qi + 1u);
-                const int wv = pert_weight_idx(qi - (uint32_t)w) + pert_weight_idx(qi + (uint32_t)w);
-                if (wh == wv) {  // residual tie of the perturbation: the general path decides
-                    qlist[atomicAdd(&s_nitems, 1)] = code & ((1u << 21) - 1u);
-                    continue;
-                }
-                horiz = wh < wv;
-            }
-            uint8_t* p = out + ((size_t)(raw ? r : h - 1 - r) * w + x) * 3;
-            const uint8_t* pa = horiz ? p - 3 : p + dn;
-            const uint8_t* pb = horiz ? p + 3 : p - dn;
-            const uint32_t a0 = pa[0], a1 = pa[1], a2 = pa[2], b0 = pb[0], b1 = pb[1], b2 = pb[2];
-            p[0] = (uint8_t)((a0 + b0) >> 1);
-            p[1] = (uint8_t)((a1 + b1) >> 1);
-            p[2] = (uint8_t)((a2 + b2) >> 1);
-            my_filled++;
-        }
-    }
-    my_filled = __reduce_add_sync(FULL, my_filled);
-    if (lane == 0 && my_filled) atomicAdd(&s_filled, my_filled);
     // row arrays the finish stage needs
     {
         int16_t* dsts[6] = {row_arr(A, img, RA_UP), row_arr(A, img, RA_DN), row_arr(A, img, RA_HL0), row_arr(A, img, RA_HL1),
@@ -1025,7 +992,88 @@ __global__ void __launch_bounds__(PREP_NT) prep_stage_kernel(ImageArgs A) {
     if (tid == 0) {
         counts[2] = nS; counts[3] = s_ne_cnt; counts[4] = raw ? 0 : s_keep_cnt; counts[5] = 0; counts[6] = 0; counts[7] = 0;
         int32_t* hd = A.hdr + (size_t)img * HD_STRIDE;
-        hd[HD_STATUS] = status; hd[HD_NQ] = status == 0 ? s_nitems : 0; hd[HD_EDGE] = s_filled; hd[HD_MASKED] = s_masked; hd[HD_PEND] = 0;
+        hd[HD_STATUS] = status; hd[HD_NQ] = status == 0 ? s_nitems : 0; hd[HD_EDGE] = status == 0 ? s_nedge : 0; hd[HD_MASKED] = s_masked;
+        hd[HD_PEND] = 0; hd[HD_XTRA] = 0;
+    }
+}
+
+// ---- exact barycentric value of a query pixel from its final triangle (shade stage, cooperative pass) ----------------------
+__device__ __forceinline__ uint32_t site_rgb_at(const uint8_t* out, bool raw, int h, int w, int sx, int sy) {
+    return load_rgb(out + ((size_t)(raw ? sy : h - 1 - sy) * w + sx) * 3);
+}
+__device__ __forceinline__ void write_px_at(uint8_t* out, int32_t* qtri, bool raw, int h, int w, const Tri2& t, uint32_t ca, uint32_t cb,
+                                            uint32_t cc, int x, int r) {
+    const uint32_t ua = (uint32_t)orient_i(t.bx, t.by, t.cx, t.cy, x, r), ub = (uint32_t)orient_i(t.cx, t.cy, t.ax, t.ay, x, r),
+                   uc = (uint32_t)orient_i(t.ax, t.ay, t.bx, t.by, x, r);
+    const uint32_t A2 = ua + ub + uc;
+    uint8_t* o = out + ((size_t)(raw ? r : h - 1 - r) * w + x) * 3;
+    o[0] = (uint8_t)((ua * (ca & 0xFF) + ub * (cb & 0xFF) + uc * (cc & 0xFF)) / A2);
+    o[1] = (uint8_t)((ua * ((ca >> 8) & 0xFF) + ub * ((cb >> 8) & 0xFF) + uc * ((cc >> 8) & 0xFF)) / A2);
+    o[2] = (uint8_t)((ua * ((ca >> 16) & 0xFF) + ub * ((cb >> 16) & 0xFF) + uc * ((cc >> 16) & 0xFF)) / A2);
+    if (qtri) {
+        // ascending vertex ids: two warps of the cooperative pass may reach the same triangle with different rotations and
+        // write the same pixel concurrently; in canonical order their stores are identical word for word
+        int32_t* q = qtri + ((size_t)r * w + x) * 3;
+        const int i0 = t.ay * w + t.ax, i1 = t.by * w + t.bx, i2 = t.cy * w + t.cx;
+        const int lo = min(i0, min(i1, i2)), hi = max(i0, max(i1, i2));
+        q[0] = lo; q[1] = i0 + i1 + i2 - lo - hi; q[2] = hi;
+    }
+}
+
+// ---- shade stage: one thread per list entry of the chunk, every lane busy -------------------------------------------------
+// Entries of an image: its edge-rule pixels (the exact mean of the two site colours), then what the window pass resolved
+// (three gathers, exact integer barycentrics).  grid = (SHADE_SPLIT, images).
+constexpr int SHADE_SPLIT = 8;
+constexpr int SHADE_NT = 256;
+__global__ void __launch_bounds__(SHADE_NT) shade_stage_kernel(ImageArgs A) {
+    const int img = blockIdx.y;
+    int32_t* hd = A.hdr + (size_t)img * HD_STRIDE;
+    if (hd[HD_STATUS] != 0) return;
+    const int n_edge = hd[HD_EDGE], n_win = hd[HD_NQ];
+    const int n = n_edge + n_win;
+    const int h = A.G.grid_h, w = A.G.grid_w;
+    const bool raw = A.raw_mode != 0;
+    int dst;
+    uint8_t* out = image_out(A, img, dst);
+    int32_t* qtri = A.qtri ? A.qtri + (size_t)img * A.qtri_stride : nullptr;
+    const uint32_t* elist = A.clist + (size_t)img * A.qlist_stride;
+    uint32_t* qlist = A.qlist + (size_t)img * A.qlist_stride;
+    unsigned long long* qres = A.qres + (size_t)img * A.qlist_stride;
+    const ptrdiff_t dn = raw ? (ptrdiff_t)w * 3 : -(ptrdiff_t)w * 3;  // address step to row r + 1 in the (flipped) output
+    for (int i = blockIdx.x * SHADE_NT + threadIdx.x; i < n; i += SHADE_SPLIT * SHADE_NT) {
+        if (i < n_edge) {
+            const uint32_t code = __ldg(elist + i);
+            const int x = (int)(code & COL_MASK), r = (int)((code >> COL_BITS) & 0x3FFu);
+            bool horiz = (code >> 31) != 0u;
+            if (horiz && ((code >> 30) & 1u)) {
+                const uint32_t qi = (uint32_t)(r * w + x);
+                const int wh = pert_weight_idx(qi - 1u) + pert_weight_idx(qi + 1u);
+                const int wv = pert_weight_idx(qi - (uint32_t)w) + pert_weight_idx(qi + (uint32_t)w);
+                if (wh == wv) {  // residual tie of the perturbation: the cooperative pass decides (an entry without a triangle)
+                    const int slot = n_win + atomicAdd(hd + HD_XTRA, 1);
+                    qlist[slot] = code & ((1u << 21) - 1u);
+                    qres[slot] = 0ull;
+                    continue;
+                }
+                horiz = wh < wv;
+            }
+            uint8_t* p = out + ((size_t)(raw ? r : h - 1 - r) * w + x) * 3;
+            const uint8_t* pa = horiz ? p - 3 : p + dn;
+            const uint8_t* pb = horiz ? p + 3 : p - dn;
+            const uint32_t a0 = pa[0], a1 = pa[1], a2 = pa[2], b0 = pb[0], b1 = pb[1], b2 = pb[2];
+            p[0] = (uint8_t)((a0 + b0) >> 1);
+            p[1] = (uint8_t)((a1 + b1) >> 1);
+            p[2] = (uint8_t)((a2 + b2) >> 1);
+        } else {
+            const int j = i - n_edge;
+            const unsigned long long rs = qres[j];
+            if (!(rs & QRES_DONE)) continue;  // handed on to the cooperative pass
+            const uint32_t code = __ldg(qlist + j);
+            const uint32_t a = (uint32_t)rs & M21, b = (uint32_t)(rs >> 21) & M21, c = (uint32_t)(rs >> 42) & M21;
+            const Tri2 t = {vcol(a), vrow(a), vcol(b), vrow(b), vcol(c), vrow(c)};
+            write_px_at(out, qtri, raw, h, w, t, site_rgb_at(out, raw, h, w, t.ax, t.ay), site_rgb_at(out, raw, h, w, t.bx, t.by),
+                        site_rgb_at(out, raw, h, w, t.cx, t.cy), (int)(code & COL_MASK), (int)(code >> COL_BITS));
+        }
     }
 }
 
@@ -1033,12 +1081,18 @@ __global__ void __launch_bounds__(PREP_NT) prep_stage_kernel(ImageArgs A) {
 // long images while the rest of the GPU idles.  The predictor is what the stage's cooperative pass has to do: the queries the
 // window pass handed on (ties by the number of window queries, which the stage shades).  rank = number of images that come first.
 __global__ void __launch_bounds__(256) image_order_kernel(const int32_t* __restrict__ hdr, int n, int32_t* __restrict__ order) {
+    __shared__ uint32_t s_key[WIN_MAX_IMAGES];  // n <= WIN_MAX_IMAGES (run_image_stage cuts larger chunks into groups)
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        const uint32_t pend = (uint32_t)min(hdr[(size_t)j * HD_STRIDE + HD_PEND] + hdr[(size_t)j * HD_STRIDE + HD_XTRA], (1 << 20) - 1);
+        s_key[j] = (pend << 12) | (uint32_t)min(hdr[(size_t)j * HD_STRIDE + HD_NQ] >> 6, 4095);
+    }
+    __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const long long key = ((long long)hdr[(size_t)i * HD_STRIDE + HD_PEND] << 24) + hdr[(size_t)i * HD_STRIDE + HD_NQ];
+    const uint32_t key = s_key[i];
     int rank = 0;
     for (int j = 0; j < n; j++) {
-        const long long kj = ((long long)__ldg(hdr + (size_t)j * HD_STRIDE + HD_PEND) << 24) + __ldg(hdr + (size_t)j * HD_STRIDE + HD_NQ);
+        const uint32_t kj = s_key[j];
         rank += (kj > key || (kj == key && j < i)) ? 1 : 0;
     }
     order[rank] = i;
@@ -1078,8 +1132,9 @@ __global__ void __launch_bounds__(FINISH_NT, 2) finish_stage_kernel(ImageArgs A)
     int32_t* status_final = dst >= 0 ? (A.status ? A.status + dst : nullptr) : A.cache_status + (-1 - dst);
     const bool raw = A.raw_mode != 0;
     const int32_t* hd = A.hdr + (size_t)img * HD_STRIDE;
-    const int status = hd[HD_STATUS], n_win = hd[HD_NQ], masked = hd[HD_MASKED];
-    const bool coop = status == 0 && hd[HD_PEND] > 0;  // something was handed on: the bit planes and row arrays are needed
+    const int status = hd[HD_STATUS], masked = hd[HD_MASKED];
+    const int n_win = hd[HD_NQ] + hd[HD_XTRA];  // window-pass entries + residual ties of the edge rule (shade stage)
+    const bool coop = status == 0 && hd[HD_PEND] + hd[HD_XTRA] > 0;  // something was handed on: the bit planes and row arrays are needed
 
     if (tid == 0) { s_nitems = 0; s_next = 0; s_filled = 0; s_flips = 0; s_maxflips = 0; }
     uint32_t* defer = S.tmp;  // bit plane: queries handed to the cooperative pass
@@ -1103,25 +1158,8 @@ __global__ void __launch_bounds__(FINISH_NT, 2) finish_stage_kernel(ImageArgs A)
     unsigned long long* qres = A.qres + (size_t)img * A.qlist_stride;
     uint32_t* clist = A.clist + (size_t)img * A.qlist_stride;
 
-    // one query pixel: exact barycentric value from its final triangle
-    auto site_rgb = [&](int sx, int sy) { return load_rgb(out + ((size_t)(raw ? sy : h - 1 - sy) * w + sx) * 3); };
-    auto write_px = [&](const Tri2& t, uint32_t ca, uint32_t cb, uint32_t cc, int x, int r) {
-        const uint32_t ua = (uint32_t)orient_i(t.bx, t.by, t.cx, t.cy, x, r), ub = (uint32_t)orient_i(t.cx, t.cy, t.ax, t.ay, x, r),
-                       uc = (uint32_t)orient_i(t.ax, t.ay, t.bx, t.by, x, r);
-        const uint32_t A2 = ua + ub + uc;
-        uint8_t* o = out + ((size_t)(raw ? r : h - 1 - r) * w + x) * 3;
-        o[0] = (uint8_t)((ua * (ca & 0xFF) + ub * (cb & 0xFF) + uc * (cc & 0xFF)) / A2);
-        o[1] = (uint8_t)((ua * ((ca >> 8) & 0xFF) + ub * ((cb >> 8) & 0xFF) + uc * ((cc >> 8) & 0xFF)) / A2);
-        o[2] = (uint8_t)((ua * ((ca >> 16) & 0xFF) + ub * ((cb >> 16) & 0xFF) + uc * ((cc >> 16) & 0xFF)) / A2);
-        if (qtri) {
-            // ascending vertex ids: two warps of the cooperative pass may reach the same triangle with different rotations and
-            // write the same pixel concurrently; in canonical order their stores are identical word for word
-            int32_t* q = qtri + ((size_t)r * w + x) * 3;
-            const int i0 = t.ay * w + t.ax, i1 = t.by * w + t.bx, i2 = t.cy * w + t.cx;
-            const int lo = min(i0, min(i1, i2)), hi = max(i0, max(i1, i2));
-            q[0] = lo; q[1] = i0 + i1 + i2 - lo - hi; q[2] = hi;
-        }
-    };
+    auto site_rgb = [&](int sx, int sy) { return site_rgb_at(out, raw, h, w, sx, sy); };
+    auto write_px = [&](const Tri2& t, uint32_t ca, uint32_t cb, uint32_t cc, int x, int r) { write_px_at(out, qtri, raw, h, w, t, ca, cb, cc, x, r); };
     auto flip_to = [&](Tri2& t, int v, int x, int r) {
         const int dx = v & 0xFFFF, dy = v >> 16;
         // flip inside {a,b,c,d}: keep the new triangle that contains q.  In coordinates relative to q the candidates (d,b,c),
@@ -1138,25 +1176,15 @@ __global__ void __launch_bounds__(FINISH_NT, 2) finish_stage_kernel(ImageArgs A)
         return false;  // cannot happen (d is inside the triangle or across exactly one edge)
     };
 
-    // ---- the window pass's results: interpolate what it resolved (gathers, exact barycentrics and stores with every lane busy),
-    // list what it handed on (list order is kept within 32 entries) and mark those pixels in the deferred plane
-    if (status == 0) {
+    // ---- list what the window pass handed on (list order is kept within 32 entries) and mark those pixels in the deferred plane
+    if (coop) {
         const int n_pad = (n_win + 31) & ~31;
         for (int i = tid; i < n_pad; i += FINISH_NT) {
-            bool pend = false;
-            if (i < n_win) {
-                const unsigned long long rs = qres[i];
+            const bool pend = i < n_win && !(qres[i] & QRES_DONE);
+            if (pend) {
                 const uint32_t code = qlist[i];
                 const int x = (int)(code & COL_MASK), r = (int)(code >> COL_BITS);
-                if (rs & QRES_DONE) {
-                    const uint32_t a = (uint32_t)rs & M21, b = (uint32_t)(rs >> 21) & M21, c = (uint32_t)(rs >> 42) & M21;
-                    const Tri2 t = {vcol(a), vrow(a), vcol(b), vrow(b), vcol(c), vrow(c)};
-                    write_px(t, site_rgb(t.ax, t.ay), site_rgb(t.bx, t.by), site_rgb(t.cx, t.cy), x, r);
-                    my_filled++;
-                } else {
-                    pend = true;
-                    if (coop) atomicOr(&defer[r * wpr + (x >> 5)], 1u << (x & 31));
-                }
+                atomicOr(&defer[r * wpr + (x >> 5)], 1u << (x & 31));
             }
             const uint32_t m = __ballot_sync(FULL, pend);
             if (!m) continue;
@@ -1312,7 +1340,8 @@ __global__ void __launch_bounds__(FINISH_NT, 2) finish_stage_kernel(ImageArgs A)
     if (lane == 0) { atomicAdd(&s_filled, my_filled); atomicAdd(&s_flips, my_flips); atomicMax(&s_maxflips, my_maxflips); }
     __syncthreads();
     if (tid == 0) {
-        counts[5] = hd[HD_EDGE] + s_filled; counts[6] = max(counts[6], s_maxflips); counts[7] += s_flips;
+        // filled = edge-rule pixels + window-pass pixels (what was handed on, residual ties included, is counted by the cooperative pass)
+        counts[5] = status == 0 ? hd[HD_EDGE] + hd[HD_NQ] - s_nitems + s_filled : 0; counts[6] = max(counts[6], s_maxflips); counts[7] += s_flips;
         if (status_final) *status_final = status;
         if (counts_final) {
 #pragma unroll
