@@ -68,8 +68,9 @@ struct salve_bev_ctx {
     int32_t* d_order = nullptr;          // finish stage: hand-out order (image_order_kernel)
     size_t rows_stride = 0;
     int n_sm = 0;
-    bool clear_keys = false;             // the sites stage zeroes the keys it consumes: no key-grid memset per chunk
-    bool keys_clean = false;             // the key grid is known to be all zero
+    // The key grid is all zero between calls: the sites stage zeroes the keys it consumes, so no chunk pays for a memset of
+    // 1 MB per image.  Stage taps re-splat the image they look at from the job table of the last chunk.
+    std::vector<SplatJob> last_jobs;
     // hypothesis-independent (un-posed pano 2) renders of the current call: max_panos x 2 surfaces
     uint8_t* cache_out = nullptr; int32_t* cache_counts = nullptr; int32_t* cache_status = nullptr;
     int32_t* d_dest = nullptr;           // per image of the chunk: destination (see ImageArgs::dest)
@@ -177,6 +178,7 @@ extern "C" int salve_bev_ctx_create(const salve_bev_config* cfg, salve_bev_ctx**
     ALLOC(c->d_depth_ptr, P);
     ALLOC(c->d_tables, 2 * H + 2 * W);
     ALLOC(c->keygrid, N * c->g_stride);
+    CU(cudaMemset(c->keygrid, 0, sizeof(uint32_t) * N * c->g_stride));
     CU(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
     // lists are sized for the worst case (every pixel of every image a query); only what a chunk really uses is ever touched
     ALLOC(c->qlist, N * c->g_stride);
@@ -507,7 +509,6 @@ static int render_chunk(salve_bev_ctx* c, int n_img, const std::vector<SplatJob>
     CU(cudaEventRecord(c->ev_staged[sp], st));
     if (!dev_counts) dev_counts = c->counts;
     rc = stage_event(c, st); if (rc) return rc;
-    CU(cudaMemsetAsync(c->keygrid, 0, sizeof(uint32_t) * c->g_stride * n_img, st));
     CU(cudaMemsetAsync(dev_counts, 0, sizeof(int32_t) * 8 * n_img, st));
     SplatParams P = make_splat_params(c);
     const int rows = P.H - 2 * P.crop_rows;
@@ -519,8 +520,9 @@ static int render_chunk(salve_bev_ctx* c, int n_img, const std::vector<SplatJob>
     rc = stage_event(c, st); if (rc) return rc;
     c->last_chunk_images = n_img;
     c->last_counts = dev_counts;
+    c->last_jobs = jobs;
     return run_image_stage(c, n_img, c->G, c->keygrid, c->d_color_src, dev_out, dev_counts, dev_status, 0, 0, nullptr, nullptr, st,
-                           dest ? c->d_dest : nullptr, counts_out);
+                           dest ? c->d_dest : nullptr, counts_out, true);
 }
 
 // Copy images between two device buffers at any alignment (an image is 753 003 bytes: consecutive images share no
@@ -1010,7 +1012,6 @@ extern "C" int salve_bev_render_cloud_host(salve_bev_ctx* c, const double* host_
     const uint8_t* src = (const uint8_t*)drgb;
     CU(cudaMemcpyAsync(c->d_color_src, &src, sizeof(void*), cudaMemcpyHostToDevice, st));
     CU(cudaStreamSynchronize(st));
-    CU(cudaMemsetAsync(c->keygrid, 0, sizeof(uint32_t) * c->g_stride, st));
     CU(cudaMemsetAsync(c->counts, 0, sizeof(int32_t) * 8, st));
     SplatParams P = make_splat_params(c);
     if (n) {
@@ -1018,9 +1019,10 @@ extern "C" int salve_bev_render_cloud_host(salve_bev_ctx* c, const double* host_
         c->launches++;
         CU(cudaGetLastError());
     }
-    c->last_chunk_images = 1;
+    c->last_chunk_images = 0;  // no stage taps after this entry point
     c->last_counts = c->counts;
-    rc = run_image_stage(c, 1, c->G, c->keygrid, c->d_color_src, c->out_store, c->counts, c->status, 0, 0, nullptr, nullptr, st);
+    c->last_jobs.clear();
+    rc = run_image_stage(c, 1, c->G, c->keygrid, c->d_color_src, c->out_store, c->counts, c->status, 0, 0, nullptr, nullptr, st, nullptr, nullptr, true);
     if (rc) return rc;
     CU(cudaMemcpyAsync(host_out, c->out_store, c->img_bytes, cudaMemcpyDeviceToHost, st));
     if (host_counts) CU(cudaMemcpyAsync(host_counts, c->counts, sizeof(int32_t) * 8, cudaMemcpyDeviceToHost, st));
@@ -1107,7 +1109,6 @@ extern "C" int salve_bev_interp_dense(salve_bev_ctx* c, const int64_t* host_xy, 
     CU(cudaMemcpyAsync(c->d_color_src, &src, sizeof(void*), cudaMemcpyHostToDevice, st));
     CU(cudaStreamSynchronize(st));
     CU(cudaMemsetAsync(derr, 0, sizeof(int), st));
-    CU(cudaMemsetAsync(c->keygrid, 0, sizeof(uint32_t) * c->g_stride, st));
     CU(cudaMemsetAsync(c->counts, 0, sizeof(int32_t) * 8, st));
     if (n) {
         points_to_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const long long*)dxy, (const double*)dval, n, grid_h, grid_w,
@@ -1115,12 +1116,15 @@ extern "C" int salve_bev_interp_dense(salve_bev_ctx* c, const int64_t* host_xy, 
         c->launches++;
         CU(cudaGetLastError());
     }
-    c->last_chunk_images = 1;
+    c->last_chunk_images = 0;  // no stage taps after this entry point
     c->last_counts = c->counts;
-    if (image_smem_bytes(G.grid_h, G.wpr) <= (size_t)c->max_smem_optin)
-        rc = run_image_stage(c, 1, G, c->keygrid, c->d_color_src, c->out_store, c->counts, c->status, 1, 1, (uint8_t*)dhull, nullptr, st);
-    else
+    c->last_jobs.clear();
+    if (image_smem_bytes(G.grid_h, G.wpr) <= (size_t)c->max_smem_optin) {
+        rc = run_image_stage(c, 1, G, c->keygrid, c->d_color_src, c->out_store, c->counts, c->status, 1, 1, (uint8_t*)dhull, nullptr, st, nullptr, nullptr, true);
+    } else {
         rc = run_mesh_stages(c, G, c->keygrid, c->d_color_src, c->out_store, c->counts, c->status, 1, 1, (uint8_t*)dhull, true, st);
+        CU(cudaMemsetAsync(c->keygrid, 0, sizeof(uint32_t) * c->g_stride, st));  // the mesh kernels leave the keys in place
+    }
     if (rc) return rc;
     int herr = 0, hstatus = 0;
     CU(cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -1177,10 +1181,33 @@ extern "C" int salve_bev_tap(salve_bev_ctx* c, int32_t image, int32_t what, void
     uint32_t* kg = c->keygrid + (size_t)image * c->g_stride;
     const uint8_t* const* csrc = c->d_color_src + image;
     const bool img_ok = image_smem_bytes(G.grid_h, G.wpr) <= (size_t)c->max_smem_optin;
-    // taps recompute from the image's key grid (which the render leaves intact) on a private copy of its counters
-    void* dcnt; int rc;
+    // Taps recompute.  The render consumed (zeroed) the image's key grid, so the pano pass that produced it is splatted again
+    // from the job table of the last chunk (both surfaces of that pass), and the slots are cleared again afterwards.
+    int job = -1;
+    for (size_t k = 0; k < c->last_jobs.size(); k++)
+        if (c->last_jobs[k].img_floor == image || c->last_jobs[k].img_ceil == image) { job = (int)k; break; }
+    if (job < 0) FAIL(SALVE_BEV_E_INVALID, "stage taps follow a render of pano images (render_hypotheses / render_images)");
+    const SplatJob& J = c->last_jobs[job];
+    auto clear_slots = [&]() -> int {
+        for (int im : {J.img_floor, J.img_ceil})
+            if (im >= 0) CU(cudaMemsetAsync(c->keygrid + (size_t)im * c->g_stride, 0, sizeof(uint32_t) * c->g_stride, st));
+        return SALVE_BEV_OK;
+    };
+    int rc = clear_slots(); if (rc) return rc;
+    {
+        SplatParams P = make_splat_params(c);
+        const int rows = P.H - 2 * P.crop_rows;
+        P.rows_per_thread = splat_rows_for(1);
+        dim3 grid((unsigned)(((rows + P.rows_per_thread - 1) / P.rows_per_thread) * ((P.W + 1023) >> 10)), 1u);
+        splat_pano_kernel<<<grid, 256, 0, st>>>(P, c->d_jobs + job, c->keygrid, c->g_stride, nullptr);
+        c->launches++;
+        CU(cudaGetLastError());
+    }
+    // ... on a private copy of the image's counters
+    void* dcnt;
     if ((rc = tmp_get(c, 6, 64, &dcnt))) return rc;
     if (c->last_counts) CU(cudaMemcpyAsync(dcnt, c->last_counts + (size_t)image * 8, 32, cudaMemcpyDeviceToDevice, st));
+    auto body = [&]() -> int {
     size_t bytes = 0;
     switch (what) {
         case SALVE_BEV_TAP_KEYGRID: {
@@ -1233,7 +1260,7 @@ extern "C" int salve_bev_tap(salve_bev_ctx* c, int32_t image, int32_t what, void
             CU(cudaStreamSynchronize(st));
             bytes = (size_t)hd.n_tris * 3 * 4;
             if ((int64_t)bytes > host_buf_bytes) FAIL(SALVE_BEV_E_CAPACITY, "tap buffer too small");
-            if (hd.n_tris == 0) return SALVE_BEV_OK;
+            if (hd.n_tris == 0) return SALVE_BEV_OK;  // (leaves the lambda: the slots are cleared below)
             void* d; if ((rc = tmp_get(c, 0, bytes, &d))) return rc;
             tap_tris_kernel<<<(hd.n_tris + 255) / 256, 256, 0, st>>>(c->tris, hd.n_tris, G.grid_w, (int32_t*)d);
             c->launches++;
@@ -1257,6 +1284,12 @@ extern "C" int salve_bev_tap(salve_bev_ctx* c, int32_t image, int32_t what, void
         }
         default: FAIL(SALVE_BEV_E_INVALID, "unknown tap");
     }
+    return SALVE_BEV_OK;
+    };
+    const int rc_body = body();
+    rc = clear_slots();  // also after a failed tap: the key grid stays all zero between calls
+    if (rc_body) return rc_body;
+    if (rc) return rc;
     CU(cudaStreamSynchronize(st));
     return SALVE_BEV_OK;
 }

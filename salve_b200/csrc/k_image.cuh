@@ -684,6 +684,18 @@ __global__ void __launch_bounds__(SITES_WARPS * 32) sites_stage_kernel(ImageArgs
             const int c0 = wi0 * 32 + lane;
 #pragma unroll
             for (int j = 0; j < SITES_BATCH; j++) key[j] = (c0 + j * 32 < w) ? IMAGE_KEY_LD(kp + j * 32) : 0u;
+            {
+                uint32_t any = 0u;
+#pragma unroll
+                for (int j = 0; j < SITES_BATCH; j++) any |= key[j];
+                if (!__any_sync(FULL, any != 0u)) {  // nothing here (70 % of an image lies outside the footprint): zero bytes, zero bits
+                    if (lane < 24) {
+#pragma unroll
+                        for (int j = 0; j < SITES_BATCH; j++) sb[(wi0 + j) * 24 + lane] = 0u;
+                    }
+                    continue;
+                }
+            }
             if (A.clear_keys) {
 #pragma unroll
                 for (int j = 0; j < SITES_BATCH; j++) if (key[j]) kp[j * 32] = 0u;
