@@ -664,9 +664,6 @@ __global__ void __launch_bounds__(SITES_WARPS * 32) sites_stage_kernel(ImageArgs
     if (r >= h) return;  // warps are independent: no block-wide barrier below
     const unsigned FULL = 0xffffffffu;
     uint32_t* keygrid = A.keygrid + (size_t)img * A.keygrid_stride;
-    const uint8_t* csrc = A.color_src[img];
-    int dst;
-    uint8_t* out = image_out(A, img, dst);
     const bool raw = A.raw_mode != 0;
     uint32_t* sb = sites_smem + (size_t)warp * sites_row_words(wpr);
     uint32_t* occ = A.planes + (size_t)img * 3 * A.plane_stride;
@@ -676,14 +673,26 @@ __global__ void __launch_bounds__(SITES_WARPS * 32) sites_stage_kernel(ImageArgs
 
     int running = 0, first = -1, last = -1, ne_cnt = 0;
     uint32_t* kp = keygrid + (size_t)r * w + lane;
+    // the keys of the next batch are in flight while the colours of the current one are gathered: one memory round trip per
+    // batch instead of two dependent ones
+    uint32_t nxt[SITES_BATCH];
+#pragma unroll
+    for (int j = 0; j < SITES_BATCH; j++) nxt[j] = (lane + j * 32 < w) ? IMAGE_KEY_LD(kp + j * 32) : 0u;
+    const uint8_t* csrc = A.color_src[img];
+    int dst;
+    uint8_t* out = image_out(A, img, dst);
     for (int wc = 0; wc < wpr; wc += 32) {  // chunks of 32 words (one chunk for grids up to 1 024 pixels wide)
         uint32_t my_ob = 0u, my_nb = 0u;
         const int wend = min(wpr, wc + 32);
         for (int wi0 = wc; wi0 < wend; wi0 += SITES_BATCH, kp += SITES_BATCH * 32) {
             uint32_t key[SITES_BATCH], col[SITES_BATCH];  // col: rgb in bits 0..23, bit 31 = the pixel is a site
-            const int c0 = wi0 * 32 + lane;
 #pragma unroll
-            for (int j = 0; j < SITES_BATCH; j++) key[j] = (c0 + j * 32 < w) ? IMAGE_KEY_LD(kp + j * 32) : 0u;
+            for (int j = 0; j < SITES_BATCH; j++) key[j] = nxt[j];
+            if (wi0 + SITES_BATCH < wpr) {
+                const int c1 = (wi0 + SITES_BATCH) * 32 + lane;
+#pragma unroll
+                for (int j = 0; j < SITES_BATCH; j++) nxt[j] = (c1 + j * 32 < w) ? IMAGE_KEY_LD(kp + (SITES_BATCH + j) * 32) : 0u;
+            }
             {
                 uint32_t any = 0u;
 #pragma unroll
