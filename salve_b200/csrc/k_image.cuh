@@ -158,7 +158,8 @@ __host__ __device__ inline size_t image_rows_stride(int hp) { return (size_t)RA_
 // shared memory (bytes) of the stages for a grid of (h, wpr)
 __host__ __device__ inline size_t image_row_bytes(int h) { return ((size_t)h * 2 + 15) & ~(size_t)15; }
 __host__ __device__ inline size_t sites_row_words(int wpr) { return (size_t)((wpr + SITES_BATCH - 1) / SITES_BATCH) * SITES_BATCH * 24 + 8; }
-__host__ __device__ inline size_t sites_smem_bytes(int wpr) { return SITES_WARPS * sites_row_words(wpr) * 4; }
+__host__ __device__ inline size_t sites_key_words(int w) { return ((size_t)SITES_WARPS * w + 3 + 3) & ~(size_t)3; }  // rounded-up bulk copy, 16-byte multiple
+__host__ __device__ inline size_t sites_smem_bytes(int w, int wpr) { return (sites_key_words(w) + SITES_WARPS * sites_row_words(wpr)) * 4; }
 __host__ __device__ inline size_t prep_smem_bytes(int h, int wpr) {
     return (size_t)h * wpr * 4 + 13 * image_row_bytes(h) + 2 * (((size_t)h * 4 + 15) & ~(size_t)15) + 64;
 }
@@ -167,7 +168,7 @@ __host__ __device__ inline size_t finish_smem_bytes(int h, int wpr) {
 }
 // the largest of them decides whether a grid can take this path at all (else: explicit-mesh kernels)
 __host__ __device__ inline size_t image_smem_bytes(int h, int wpr) {
-    const size_t a = prep_smem_bytes(h, wpr), b = finish_smem_bytes(h, wpr), c = sites_smem_bytes(wpr);
+    const size_t a = prep_smem_bytes(h, wpr), b = finish_smem_bytes(h, wpr), c = sites_smem_bytes(wpr * 32, wpr);
     return a > b ? (a > c ? a : c) : (b > c ? b : c);
 }
 
@@ -650,60 +651,61 @@ __device__ __forceinline__ int coop_find_violator(const uint32_t* __restrict__ o
 }
 
 // ---- stage 1: winners -> occupancy / non-empty bit rows, sparse image (site colours, rest zero) ---------------------------
-// A warp per BEV row.  Loads are issued in batches of SITES_BATCH words per lane (keys, then the colour gathers) so that a warp
-// keeps that many independent requests in flight instead of one dependent pair.  Lane k keeps the bit words of word k of the
-// current 32-word chunk, so that the row summary (count, first, last) and the stores of the bit rows cost a few instructions
-// per row instead of per word.  The 3-byte pixels of the row are packed into words with two shuffles per 32 pixels, staged in
-// shared memory and written out as aligned 16-byte vectors (an image row is 1 503 bytes at an arbitrary alignment).
+// A CTA per SITES_WARPS consecutive BEV rows, a warp per row.  The rows' keys are one contiguous, 16-byte aligned piece of the
+// key grid: one thread brings it to shared memory with a single bulk copy (TMA engine, mbarrier completion, evict-first in L2),
+// so a row pays one memory round trip for its keys instead of one per batch, and the colour gathers of a batch (SITES_BATCH
+// words per lane) are all in flight together.  Lane k keeps the bit words of word k of the current 32-word chunk, so that the row
+// summary (count, first, last) and the stores of the bit rows cost a few instructions per row instead of per word.  The 3-byte
+// pixels of the row are packed into words with two shuffles per 32 pixels, staged in shared memory and written out as aligned
+// 16-byte vectors (an image row is 1 503 bytes at an arbitrary alignment).
 __global__ void __launch_bounds__(SITES_WARPS * 32) sites_stage_kernel(ImageArgs A) {
     extern __shared__ __align__(16) uint32_t sites_smem[];
+    __shared__ __align__(8) uint64_t s_bar;
     const int img = blockIdx.y;
     const int h = A.G.grid_h, w = A.G.grid_w, wpr = A.G.wpr;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int r = blockIdx.x * SITES_WARPS + warp;
-    if (r >= h) return;  // warps are independent: no block-wide barrier below
+    const int r0 = blockIdx.x * SITES_WARPS, r = r0 + warp;
     const unsigned FULL = 0xffffffffu;
     uint32_t* keygrid = A.keygrid + (size_t)img * A.keygrid_stride;
+    uint32_t* ks = sites_smem;                                         // keys of the CTA's rows
+    uint32_t* sb = sites_smem + sites_key_words(w) + (size_t)warp * sites_row_words(wpr);  // this warp's packed output row
+    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int rows_here = min(SITES_WARPS, h - r0);
+        const uint32_t bytes = ((uint32_t)(rows_here * w) * 4u + 15u) & ~15u;  // may reach into the padding behind the image's grid
+        mbar_expect_tx(&s_bar, bytes);
+        bulk_g2s_stream(ks, keygrid + (size_t)r0 * w, bytes, &s_bar);
+    }
+    if (r >= h) return;  // warps are independent from here on
     const bool raw = A.raw_mode != 0;
-    uint32_t* sb = sites_smem + (size_t)warp * sites_row_words(wpr);
     uint32_t* occ = A.planes + (size_t)img * 3 * A.plane_stride;
     uint32_t* nonempty = occ + A.plane_stride;
     // word of the packed row this lane builds from 32 pixels: bytes 4*lane .. 4*lane+3 of the 96 = pixels p0 and p0 + 1
     const int p0 = (lane * 4) / 3, o8 = ((lane * 4) % 3) * 8;
-
-    int running = 0, first = -1, last = -1, ne_cnt = 0;
-    uint32_t* kp = keygrid + (size_t)r * w + lane;
-    // the keys of the next batch are in flight while the colours of the current one are gathered: one memory round trip per
-    // batch instead of two dependent ones
-    uint32_t nxt[SITES_BATCH];
-#pragma unroll
-    for (int j = 0; j < SITES_BATCH; j++) nxt[j] = (lane + j * 32 < w) ? IMAGE_KEY_LD(kp + j * 32) : 0u;
     const uint8_t* csrc = A.color_src[img];
     int dst;
     uint8_t* out = image_out(A, img, dst);
+    mbar_wait(&s_bar, 0);
+
+    int running = 0, first = -1, last = -1, ne_cnt = 0;
+    const uint32_t* kr = ks + warp * w + lane;                 // this lane's key of word 0 (shared memory)
+    uint32_t* kp = keygrid + (size_t)r * w + lane;             // ... and its home in the key grid
     for (int wc = 0; wc < wpr; wc += 32) {  // chunks of 32 words (one chunk for grids up to 1 024 pixels wide)
         uint32_t my_ob = 0u, my_nb = 0u;
         const int wend = min(wpr, wc + 32);
-        for (int wi0 = wc; wi0 < wend; wi0 += SITES_BATCH, kp += SITES_BATCH * 32) {
+        for (int wi0 = wc; wi0 < wend; wi0 += SITES_BATCH, kr += SITES_BATCH * 32, kp += SITES_BATCH * 32) {
             uint32_t key[SITES_BATCH], col[SITES_BATCH];  // col: rgb in bits 0..23, bit 31 = the pixel is a site
+            const int c0 = wi0 * 32 + lane;
+            uint32_t any = 0u;
 #pragma unroll
-            for (int j = 0; j < SITES_BATCH; j++) key[j] = nxt[j];
-            if (wi0 + SITES_BATCH < wpr) {
-                const int c1 = (wi0 + SITES_BATCH) * 32 + lane;
+            for (int j = 0; j < SITES_BATCH; j++) { key[j] = (c0 + j * 32 < w) ? kr[j * 32] : 0u; any |= key[j]; }
+            if (!__any_sync(FULL, any != 0u)) {  // nothing here (70 % of an image lies outside the footprint): zero bytes, zero bits
+                if (lane < 24) {
 #pragma unroll
-                for (int j = 0; j < SITES_BATCH; j++) nxt[j] = (c1 + j * 32 < w) ? IMAGE_KEY_LD(kp + (SITES_BATCH + j) * 32) : 0u;
-            }
-            {
-                uint32_t any = 0u;
-#pragma unroll
-                for (int j = 0; j < SITES_BATCH; j++) any |= key[j];
-                if (!__any_sync(FULL, any != 0u)) {  // nothing here (70 % of an image lies outside the footprint): zero bytes, zero bits
-                    if (lane < 24) {
-#pragma unroll
-                        for (int j = 0; j < SITES_BATCH; j++) sb[(wi0 + j) * 24 + lane] = 0u;
-                    }
-                    continue;
+                    for (int j = 0; j < SITES_BATCH; j++) sb[(wi0 + j) * 24 + lane] = 0u;
                 }
+                continue;
             }
             if (A.clear_keys) {
 #pragma unroll
