@@ -417,7 +417,7 @@ static int run_image_stage(salve_bev_ctx* c, int n_img, const GridParams& G, uin
         IA.work_counter = c->work_counter;
         IA.raw_mode = raw_mode; IA.skip_empty_check = skip_empty; IA.clear_keys = clear_keys ? 1 : 0;
         CU(cudaMemsetAsync(c->work_counter, 0, sizeof(int32_t), st));
-        sites_stage_kernel<<<dim3((unsigned)((G.grid_h + SITES_WARPS - 1) / SITES_WARPS), (unsigned)n), SITES_WARPS * 32, sites_smem_bytes(G.grid_w, G.wpr), st>>>(IA);
+        sites_stage_kernel<<<dim3((unsigned)((G.grid_h + SITES_WARPS * SITES_GROUPS - 1) / (SITES_WARPS * SITES_GROUPS)), (unsigned)n), SITES_WARPS * 32, sites_smem_bytes(G.grid_w, G.wpr), st>>>(IA);
         prep_stage_kernel<<<n, PREP_NT, prep_smem_bytes(G.grid_h, G.wpr), st>>>(IA);
         const int win_ctas = std::max(1, std::min(c->n_sm * IMAGE_WIN_CTAS, n * 16));
         window_stage_kernel<IMAGE_WIN_NR><<<win_ctas, WIN_NT, 0, st>>>(IA);

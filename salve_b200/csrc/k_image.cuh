@@ -98,7 +98,11 @@ namespace bev {
 #define IMAGE_OUT_ST(p, v) (*(p) = (v))
 #endif
 constexpr int SITES_BATCH = SITES_BATCH_DEF;
-constexpr int SITES_WARPS = 8;            // sites stage: rows (= warps) per CTA
+constexpr int SITES_WARPS = 8;            // sites stage: rows (= warps) per group
+#ifndef SITES_GROUPS_DEF
+#define SITES_GROUPS_DEF 4
+#endif
+constexpr int SITES_GROUPS = SITES_GROUPS_DEF;  // sites stage: groups of rows a CTA works through (double-buffered key fetch)
 constexpr int PREP_NT = IMAGE_PREP_THREADS;
 constexpr int WIN_NT = IMAGE_WIN_THREADS;
 constexpr int FINISH_NT = IMAGE_FINISH_THREADS;
@@ -159,7 +163,7 @@ __host__ __device__ inline size_t image_rows_stride(int hp) { return (size_t)RA_
 __host__ __device__ inline size_t image_row_bytes(int h) { return ((size_t)h * 2 + 15) & ~(size_t)15; }
 __host__ __device__ inline size_t sites_row_words(int wpr) { return (size_t)((wpr + SITES_BATCH - 1) / SITES_BATCH) * SITES_BATCH * 24 + 8; }
 __host__ __device__ inline size_t sites_key_words(int w) { return ((size_t)SITES_WARPS * w + 3 + 3) & ~(size_t)3; }  // rounded-up bulk copy, 16-byte multiple
-__host__ __device__ inline size_t sites_smem_bytes(int w, int wpr) { return (sites_key_words(w) + SITES_WARPS * sites_row_words(wpr)) * 4; }
+__host__ __device__ inline size_t sites_smem_bytes(int w, int wpr) { return (2 * sites_key_words(w) + SITES_WARPS * sites_row_words(wpr)) * 4; }
 __host__ __device__ inline size_t prep_smem_bytes(int h, int wpr) {
     return (size_t)h * wpr * 4 + 13 * image_row_bytes(h) + 2 * (((size_t)h * 4 + 15) & ~(size_t)15) + 64;
 }
@@ -660,24 +664,27 @@ __device__ __forceinline__ int coop_find_violator(const uint32_t* __restrict__ o
 // 16-byte vectors (an image row is 1 503 bytes at an arbitrary alignment).
 __global__ void __launch_bounds__(SITES_WARPS * 32) sites_stage_kernel(ImageArgs A) {
     extern __shared__ __align__(16) uint32_t sites_smem[];
-    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ __align__(8) uint64_t s_bar[2];
     const int img = blockIdx.y;
     const int h = A.G.grid_h, w = A.G.grid_w, wpr = A.G.wpr;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int r0 = blockIdx.x * SITES_WARPS, r = r0 + warp;
     const unsigned FULL = 0xffffffffu;
     uint32_t* keygrid = A.keygrid + (size_t)img * A.keygrid_stride;
-    uint32_t* ks = sites_smem;                                         // keys of the CTA's rows
-    uint32_t* sb = sites_smem + sites_key_words(w) + (size_t)warp * sites_row_words(wpr);  // this warp's packed output row
-    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    const size_t kwords = sites_key_words(w);
+    uint32_t* sb = sites_smem + 2 * kwords + (size_t)warp * sites_row_words(wpr);  // this warp's packed output row
+    // groups of SITES_WARPS rows this CTA works through, the keys of the next group in flight while the current one is processed
+    const int g_first = blockIdx.x * SITES_GROUPS;
+    const int n_groups = min(SITES_GROUPS, (h + SITES_WARPS - 1) / SITES_WARPS - g_first);
+    auto fetch = [&](int g) {  // thread 0: keys of group g -> buffer g & 1
+        const int r0 = (g_first + g) * SITES_WARPS;
         const int rows_here = min(SITES_WARPS, h - r0);
         const uint32_t bytes = ((uint32_t)(rows_here * w) * 4u + 15u) & ~15u;  // may reach into the padding behind the image's grid
-        mbar_expect_tx(&s_bar, bytes);
-        bulk_g2s_stream(ks, keygrid + (size_t)r0 * w, bytes, &s_bar);
-    }
-    if (r >= h) return;  // warps are independent from here on
+        mbar_expect_tx(&s_bar[g & 1], bytes);
+        bulk_g2s_stream(sites_smem + (size_t)(g & 1) * kwords, keygrid + (size_t)r0 * w, bytes, &s_bar[g & 1]);
+    };
+    if (threadIdx.x == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
+    __syncthreads();
+    if (threadIdx.x == 0) { fetch(0); if (n_groups > 1) fetch(1); }
     const bool raw = A.raw_mode != 0;
     uint32_t* occ = A.planes + (size_t)img * 3 * A.plane_stride;
     uint32_t* nonempty = occ + A.plane_stride;
@@ -686,11 +693,14 @@ __global__ void __launch_bounds__(SITES_WARPS * 32) sites_stage_kernel(ImageArgs
     const uint8_t* csrc = A.color_src[img];
     int dst;
     uint8_t* out = image_out(A, img, dst);
-    mbar_wait(&s_bar, 0);
 
+  for (int g = 0; g < n_groups; g++) {
+    const int r = (g_first + g) * SITES_WARPS + warp;
+    mbar_wait(&s_bar[g & 1], (uint32_t)(g >> 1) & 1u);
+    if (r < h) {
     int running = 0, first = -1, last = -1, ne_cnt = 0;
-    const uint32_t* kr = ks + warp * w + lane;                 // this lane's key of word 0 (shared memory)
-    uint32_t* kp = keygrid + (size_t)r * w + lane;             // ... and its home in the key grid
+    const uint32_t* kr = sites_smem + (size_t)(g & 1) * kwords + warp * w + lane;  // this lane's key of word 0 (shared memory)
+    uint32_t* kp = keygrid + (size_t)r * w + lane;                                 // ... and its home in the key grid
     for (int wc = 0; wc < wpr; wc += 32) {  // chunks of 32 words (one chunk for grids up to 1 024 pixels wide)
         uint32_t my_ob = 0u, my_nb = 0u;
         const int wend = min(wpr, wc + 32);
@@ -762,6 +772,13 @@ __global__ void __launch_bounds__(SITES_WARPS * 32) sites_stage_kernel(ImageArgs
     }
     if (lane < head) orow[lane] = sb8[lane];
     if (tail0 + lane < nb) orow[tail0 + lane] = sb8[tail0 + lane];
+    }  // r < h
+    if (g + 2 < n_groups) {  // every warp is done with buffer g & 1: refill it with the keys of group g + 2
+        __syncthreads();
+        if (threadIdx.x == 0) fetch(g + 2);
+    }
+    __syncwarp();  // the packed row is read back by other lanes before the next group overwrites it
+  }
 }
 
 // ---- stage 2: guards, hull, keep mask, edge rule, query list: a CTA per image -------------------------------------------
