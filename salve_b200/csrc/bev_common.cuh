@@ -84,6 +84,9 @@ __host__ __device__ __forceinline__ uint32_t hash32(uint32_t h) {
     return h;
 }
 
+#ifndef GATHER_WORDS
+#define GATHER_WORDS 1
+#endif
 // ---- colour gather ---------------------------------------------------------------------------
 // A colour source is a u8 rgb array indexed by the key's source index.  Bit 0 of the pointer (sources are 2-byte aligned)
 // tags a FULL-RESOLUTION pano of (2H, 2W): the colour of pano pixel (v, u) is then the rounded mean of its 2x2 block,
@@ -93,7 +96,19 @@ __device__ __forceinline__ uint32_t load_rgb(const uint8_t* p) { return (uint32_
 __device__ __forceinline__ uint32_t gather_rgb(const uint8_t* tagged, uint32_t idx, int pano_w) {
     const uintptr_t a = (uintptr_t)tagged;
     const uint8_t* base = reinterpret_cast<const uint8_t*>(a & ~(uintptr_t)1);
-    if (!(a & 1)) return load_rgb(base + (size_t)idx * 3);
+    if (!(a & 1)) {
+#if GATHER_WORDS
+        // the 3 bytes lie in one aligned word or straddle two: aligned 32-bit loads + funnel shift (one or two L1 wavefronts instead
+        // of three).  An aligned word that overlaps the array never leaves its allocation (cudaMalloc granularity).
+        const uintptr_t p = (uintptr_t)base + (size_t)idx * 3;
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(p & ~(uintptr_t)3);
+        const uint32_t sh = (uint32_t)(p & 3) * 8;
+        const uint32_t w0 = __ldg(wp), w1 = sh > 8 ? __ldg(wp + 1) : 0u;
+        return __funnelshift_r(w0, w1, sh) & 0xFFFFFFu;
+#else
+        return load_rgb(base + (size_t)idx * 3);
+#endif
+    }
     const uint32_t v = idx / (uint32_t)pano_w, u = idx - v * (uint32_t)pano_w;
     const size_t pitch = (size_t)pano_w * 6;
     const uint8_t* p = base + (size_t)(2 * v) * pitch + (size_t)u * 6;

@@ -99,6 +99,12 @@ namespace bev {
 #endif
 constexpr int SITES_BATCH = SITES_BATCH_DEF;
 constexpr int SITES_WARPS = 8;            // sites stage: rows (= warps) per group
+#ifndef SITES_DBG
+#define SITES_DBG 0
+#endif
+#ifndef SITES_CLEAR_WARP
+#define SITES_CLEAR_WARP 0
+#endif
 #ifndef SITES_GROUPS_DEF
 #define SITES_GROUPS_DEF 4
 #endif
@@ -717,14 +723,25 @@ __global__ void __launch_bounds__(SITES_WARPS * 32) sites_stage_kernel(ImageArgs
                 }
                 continue;
             }
+#if !(SITES_DBG & 4)
             if (A.clear_keys) {
+#if SITES_CLEAR_WARP
+#pragma unroll
+                for (int j = 0; j < SITES_BATCH; j++) if (__any_sync(FULL, key[j] != 0u) && c0 + j * 32 < w) kp[j * 32] = 0u;  // whole sectors: no read-modify-write in L2
+#else
 #pragma unroll
                 for (int j = 0; j < SITES_BATCH; j++) if (key[j]) kp[j * 32] = 0u;
+#endif
             }
+#endif
 #pragma unroll
             for (int j = 0; j < SITES_BATCH; j++) {
                 col[j] = 0u;
+#if SITES_DBG & 1
+                if (key[j]) col[j] = (key[j] & 0xFFFFFFu) | 0x80000000u;
+#else
                 if (key[j]) col[j] = gather_rgb(csrc, (key[j] - 1u) & KEY_IDX_MASK, A.pano_w) | 0x80000000u;
+#endif
             }
 #pragma unroll
             for (int j = 0; j < SITES_BATCH; j++) {
@@ -763,6 +780,9 @@ __global__ void __launch_bounds__(SITES_WARPS * 32) sites_stage_kernel(ImageArgs
     if (head > nb) head = nb;
     const int nv = (nb - head) >> 4, tail0 = head + (nv << 4);
     const int sw0 = head >> 2, sh = (head & 3) * 8;
+#if SITES_DBG & 2
+    if (nv < 0)
+#endif
     for (int k = lane; k < nv; k += 32) {
         const uint32_t* s = sb + sw0 + 4 * k;
         const uint32_t a0 = s[0], a1 = s[1], a2 = s[2], a3 = s[3], a4 = s[4];  // s[4]: padding words follow the row
@@ -1063,6 +1083,10 @@ __device__ __forceinline__ void write_px_at(uint8_t* out, int32_t* qtri, bool ra
 // ---- shade stage: one thread per list entry of the chunk, every lane busy -------------------------------------------------
 // Entries of an image: its edge-rule pixels (the exact mean of the two site colours), then what the window pass resolved
 // (three gathers, exact integer barycentrics).  grid = (SHADE_SPLIT, images).
+#ifndef SHADE_UNROLL_DEF
+#define SHADE_UNROLL_DEF 4
+#endif
+constexpr int SHADE_UNROLL = SHADE_UNROLL_DEF;
 constexpr int SHADE_SPLIT = 8;
 constexpr int SHADE_NT = 256;
 __global__ void __launch_bounds__(SHADE_NT) shade_stage_kernel(ImageArgs A) {
@@ -1070,7 +1094,6 @@ __global__ void __launch_bounds__(SHADE_NT) shade_stage_kernel(ImageArgs A) {
     int32_t* hd = A.hdr + (size_t)img * HD_STRIDE;
     if (hd[HD_STATUS] != 0) return;
     const int n_edge = hd[HD_EDGE], n_win = hd[HD_NQ];
-    const int n = n_edge + n_win;
     const int h = A.G.grid_h, w = A.G.grid_w;
     const bool raw = A.raw_mode != 0;
     int dst;
@@ -1080,39 +1103,68 @@ __global__ void __launch_bounds__(SHADE_NT) shade_stage_kernel(ImageArgs A) {
     uint32_t* qlist = A.qlist + (size_t)img * A.qlist_stride;
     unsigned long long* qres = A.qres + (size_t)img * A.qlist_stride;
     const ptrdiff_t dn = raw ? (ptrdiff_t)w * 3 : -(ptrdiff_t)w * 3;  // address step to row r + 1 in the (flipped) output
-    for (int i = blockIdx.x * SHADE_NT + threadIdx.x; i < n; i += SHADE_SPLIT * SHADE_NT) {
-        if (i < n_edge) {
-            const uint32_t code = __ldg(elist + i);
-            const int x = (int)(code & COL_MASK), r = (int)((code >> COL_BITS) & 0x3FFu);
-            bool horiz = (code >> 31) != 0u;
-            if (horiz && ((code >> 30) & 1u)) {
+    constexpr int STRIDE = SHADE_SPLIT * SHADE_NT;
+    // Every entry is a chain of dependent memory round trips (list entry -> colours -> store): SHADE_UNROLL entries per thread are in
+    // flight together.
+    for (int i0 = blockIdx.x * SHADE_NT + threadIdx.x; i0 < n_edge; i0 += SHADE_UNROLL * STRIDE) {
+        uint32_t code[SHADE_UNROLL];
+        uint8_t* p[SHADE_UNROLL];
+        uint32_t ca[SHADE_UNROLL], cb[SHADE_UNROLL];
+#pragma unroll
+        for (int u = 0; u < SHADE_UNROLL; u++) code[u] = i0 + u * STRIDE < n_edge ? __ldg(elist + i0 + u * STRIDE) : 0u;  // 0: no pair bits = nothing
+#pragma unroll
+        for (int u = 0; u < SHADE_UNROLL; u++) {
+            p[u] = nullptr;
+            if (!(code[u] >> 30)) continue;
+            const int x = (int)(code[u] & COL_MASK), r = (int)((code[u] >> COL_BITS) & 0x3FFu);
+            bool horiz = (code[u] >> 31) != 0u;
+            if (horiz && ((code[u] >> 30) & 1u)) {
                 const uint32_t qi = (uint32_t)(r * w + x);
                 const int wh = pert_weight_idx(qi - 1u) + pert_weight_idx(qi + 1u);
                 const int wv = pert_weight_idx(qi - (uint32_t)w) + pert_weight_idx(qi + (uint32_t)w);
                 if (wh == wv) {  // residual tie of the perturbation: the cooperative pass decides (an entry without a triangle)
                     const int slot = n_win + atomicAdd(hd + HD_XTRA, 1);
-                    qlist[slot] = code & ((1u << 21) - 1u);
+                    qlist[slot] = code[u] & ((1u << 21) - 1u);
                     qres[slot] = 0ull;
                     continue;
                 }
                 horiz = wh < wv;
             }
-            uint8_t* p = out + ((size_t)(raw ? r : h - 1 - r) * w + x) * 3;
-            const uint8_t* pa = horiz ? p - 3 : p + dn;
-            const uint8_t* pb = horiz ? p + 3 : p - dn;
-            const uint32_t a0 = pa[0], a1 = pa[1], a2 = pa[2], b0 = pb[0], b1 = pb[1], b2 = pb[2];
-            p[0] = (uint8_t)((a0 + b0) >> 1);
-            p[1] = (uint8_t)((a1 + b1) >> 1);
-            p[2] = (uint8_t)((a2 + b2) >> 1);
-        } else {
-            const int j = i - n_edge;
-            const unsigned long long rs = qres[j];
-            if (!(rs & QRES_DONE)) continue;  // handed on to the cooperative pass
-            const uint32_t code = __ldg(qlist + j);
-            const uint32_t a = (uint32_t)rs & M21, b = (uint32_t)(rs >> 21) & M21, c = (uint32_t)(rs >> 42) & M21;
+            p[u] = out + ((size_t)(raw ? r : h - 1 - r) * w + x) * 3;
+            ca[u] = load_rgb(horiz ? p[u] - 3 : p[u] + dn);
+            cb[u] = load_rgb(horiz ? p[u] + 3 : p[u] - dn);
+        }
+#pragma unroll
+        for (int u = 0; u < SHADE_UNROLL; u++) {
+            if (!p[u]) continue;
+            p[u][0] = (uint8_t)(((ca[u] & 0xFF) + (cb[u] & 0xFF)) >> 1);
+            p[u][1] = (uint8_t)((((ca[u] >> 8) & 0xFF) + ((cb[u] >> 8) & 0xFF)) >> 1);
+            p[u][2] = (uint8_t)(((ca[u] >> 16) + (cb[u] >> 16)) >> 1);
+        }
+    }
+    for (int j0 = blockIdx.x * SHADE_NT + threadIdx.x; j0 < n_win; j0 += SHADE_UNROLL * STRIDE) {
+        unsigned long long rs[SHADE_UNROLL];
+        uint32_t code[SHADE_UNROLL], ca[SHADE_UNROLL], cb[SHADE_UNROLL], cc[SHADE_UNROLL];
+#pragma unroll
+        for (int u = 0; u < SHADE_UNROLL; u++) {
+            const int j = j0 + u * STRIDE;
+            rs[u] = j < n_win ? qres[j] : 0ull;  // without QRES_DONE: handed on to the cooperative pass (or beyond the list)
+            code[u] = j < n_win ? __ldg(qlist + j) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < SHADE_UNROLL; u++) {
+            if (!(rs[u] & QRES_DONE)) continue;
+            const uint32_t a = (uint32_t)rs[u] & M21, b = (uint32_t)(rs[u] >> 21) & M21, c = (uint32_t)(rs[u] >> 42) & M21;
+            ca[u] = site_rgb_at(out, raw, h, w, vcol(a), vrow(a));
+            cb[u] = site_rgb_at(out, raw, h, w, vcol(b), vrow(b));
+            cc[u] = site_rgb_at(out, raw, h, w, vcol(c), vrow(c));
+        }
+#pragma unroll
+        for (int u = 0; u < SHADE_UNROLL; u++) {
+            if (!(rs[u] & QRES_DONE)) continue;
+            const uint32_t a = (uint32_t)rs[u] & M21, b = (uint32_t)(rs[u] >> 21) & M21, c = (uint32_t)(rs[u] >> 42) & M21;
             const Tri2 t = {vcol(a), vrow(a), vcol(b), vrow(b), vcol(c), vrow(c)};
-            write_px_at(out, qtri, raw, h, w, t, site_rgb_at(out, raw, h, w, t.ax, t.ay), site_rgb_at(out, raw, h, w, t.bx, t.by),
-                        site_rgb_at(out, raw, h, w, t.cx, t.cy), (int)(code & COL_MASK), (int)(code >> COL_BITS));
+            write_px_at(out, qtri, raw, h, w, t, ca[u], cb[u], cc[u], (int)(code[u] & COL_MASK), (int)(code[u] >> COL_BITS));
         }
     }
 }
