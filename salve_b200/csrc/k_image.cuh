@@ -60,15 +60,6 @@ namespace bev {
 #ifndef IMAGE_WIN_VINIT
 #define IMAGE_WIN_VINIT 1     // window pass: initial triangle on the column pair D-U when it is shorter than the row pair L-R
 #endif
-#ifndef IMAGE_WIN_SLOTS
-#define IMAGE_WIN_SLOTS 2     // window pass: queries per lane parked in shared memory
-#endif
-#ifndef IMAGE_WIN_PMIN
-#define IMAGE_WIN_PMIN 16     // window pass: lanes with an idle slot that trigger a prepare phase
-#endif
-#ifndef IMAGE_WIN_OMIN
-#define IMAGE_WIN_OMIN 24     // window pass: lanes waiting for the on-circle tests that trigger that phase
-#endif
 #ifndef IMAGE_WIN_BLOCK
 #define IMAGE_WIN_BLOCK 256   // window pass: queries a warp takes from the chunk-wide list per atomic
 #endif
@@ -297,25 +288,19 @@ __device__ __forceinline__ float sqrt_approx(float v) { float r; asm("sqrt.appro
 
 // ---- stage 3: small triangles in a register window --------------------------------------------------------------------------
 // 92 % of the queries that are left after the edge rule end in a triangle within 2 px of the pixel with a circumradius of
-// at most 2 px.  For them the whole Lawson descent runs on a (2*NR+1)-row x 32-column window of the occupancy bitmap,
-// in coordinates relative to the query q = (0, 0):
+// at most 2 px.  For them the whole Lawson descent runs on a (2*NR+1)-row x 32-column window of the occupancy bitmap held in
+// registers, in coordinates relative to the query q = (0, 0):
 //   * circle of (a, b, c): A2 = twice the area, (U, V) = 2*A2 * (centre - a); a lattice point p has
 //     |p - centre|^2 - R^2 = -inc(p) / A2 with inc an integer, so points off the circle miss it by at least 1/A2 in squared
 //     distance.  With |coordinates| <= 16 every float below is exact to ~1e-5, hence "strictly inside" (margin > 1/(2 A2)) and
 //     "on the circle" (|.| <= 1/(2 A2)) are decided EXACTLY by float interval arithmetic per row: no per-point test at all.
-//   * one trip = the strict-interior masks of all rows (unrolled; every lane executes the same code), then a flip towards
-//     the violator nearest to q; if the circle is empty, the sites ON it decide by their symbolic-perturbation tests.
+//   * one trip = the strict-interior masks of all rows (unrolled; every lane executes the same code), then either a flip towards
+//     the violator nearest to q or, if the circle is empty, the on-circle sites and their symbolic-perturbation tests.
 // A query whose triangle or circle leaves the window is handed to the cooperative pass.
 //
 // Work distribution: the query lists of all images of the chunk form one index space (prefix sums of the per-image counts,
-// rebuilt in shared memory by every CTA).  A warp takes IMAGE_WIN_BLOCK consecutive indices per atomic, across image boundaries:
-// there is no per-image barrier and no per-image tail.
-//
-// Schedule inside a warp: a descent is a little state machine (prepare -> trip -> ... -> on-circle test -> done), and lanes in
-// different states would serialise.  So the states are run as PHASES over a pool of IMAGE_WIN_SLOTS queries per lane parked in
-// shared memory (window rows, triangle, on-circle masks): a phase is entered only when most lanes have a query waiting for it,
-// and every lane then executes the same code -- prepare (load the window, initial triangle), trip (circle + rows + flip),
-// on-circle (perturbation tests + flip).  The arithmetic per query is unchanged; only the order in which queries advance is.
+// rebuilt in shared memory by every CTA).  A warp takes IMAGE_WIN_BLOCK consecutive indices per atomic and refills its idle
+// lanes from that block, across image boundaries: there is no per-image barrier and no per-image tail.
 template <int NR>
 __global__ void __launch_bounds__(WIN_NT, IMAGE_WIN_CTAS) window_stage_kernel(ImageArgs A) {
     constexpr int NROW = 2 * NR + 1;
@@ -323,18 +308,14 @@ __global__ void __launch_bounds__(WIN_NT, IMAGE_WIN_CTAS) window_stage_kernel(Im
     static_assert(WIN_MAX_IMAGES % WIN_NT == 0, "prefix table: whole entries per thread");
     constexpr int MAXGAP = 14, MAXFLIPS = 16;
     constexpr int PER = WIN_MAX_IMAGES / WIN_NT;
-    constexpr int S = IMAGE_WIN_SLOTS;
-    // item words: list slot, pixel, window rows, triangle (two words), on-circle masks
-    constexpr int W_GIDX = 0, W_CODE = 1, W_WR = 2, W_T0 = 2 + NROW, W_T1 = 3 + NROW, W_ON = 4 + NROW, NWORDS = 4 + 2 * NROW;
     const unsigned FULL = 0xffffffffu;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int W = A.G.grid_w, H = A.G.grid_h, wpr = A.G.wpr;
     const int n_img = A.n_img;
 
     // ---- exclusive prefix of the per-image list lengths: s_off[i] = first global index of image i, s_off[n_img] = total
     __shared__ int s_off[WIN_MAX_IMAGES + 1];
     __shared__ int s_warp[WIN_NT / 32];
-    __shared__ uint32_t s_pool[WIN_NT / 32][NWORDS][S * 32];  // struct of arrays: lane l owns entries l, l + 32, ... (its own bank)
     {
         int v[PER], sum = 0;
 #pragma unroll
@@ -357,310 +338,251 @@ __global__ void __launch_bounds__(WIN_NT, IMAGE_WIN_CTAS) window_stage_kernel(Im
             if (i <= n_img) s_off[i] = run;  // entry n_img: every later v is 0, so run is already the total there
             run += v[k];
         }
-        if (tid == WIN_NT - 1) s_off[WIN_MAX_IMAGES] = run;  // n_img == WIN_MAX_IMAGES
         __syncthreads();
     }
     const int total = s_off[n_img];
-    uint32_t (*pool)[S * 32] = s_pool[warp];
 
-    int st[S];  // state of this lane's slots: 0 free, 1 waits for a trip, 2 waits for the on-circle tests
+    bool active = false, exhausted = false;
+    int x = 0, r = 0, flips = 0, img = 0;
+    uint32_t gidx = 0;  // img * qlist_stride + index within the image's list
+    int acc_img = -1, acc_flips = 0, acc_max = 0;  // flip statistics of the image this lane last worked on (diagnostic counters)
+    int cur = 0, end = 0, blk_img = 0;  // warp-uniform: this warp's block of the chunk-wide list
+    uint32_t wr[NROW];  // wr[dy + NR]: bit 16 + dx <-> pixel (x + dx, r + dy)
 #pragma unroll
-    for (int s = 0; s < S; s++) st[s] = 0;
-    bool exhausted = false;
-    int cur = 0, end = 0, blk_img = 0;    // warp-uniform: this warp's block of the chunk-wide list
-    int acc_flips = 0, acc_max = 0;       // flips of the queries this lane finished in the current block (diagnostic counters)
+    for (int k = 0; k < NROW; k++) wr[k] = 0u;
+    int ax = 0, ay = 0, bx = 0, by = 0, cx = 0, cy = 0;
 
-    auto cross = [](int px, int py, int qx, int qy) { return px * qy - py * qx; };
+    auto flush_stats = [&]() {
+        if (acc_img >= 0 && acc_flips) {
+            atomicAdd(A.counts + (size_t)acc_img * 8 + 7, acc_flips);
+            atomicMax(A.counts + (size_t)acc_img * 8 + 6, acc_max);
+        }
+        acc_flips = 0; acc_max = 0;
+    };
+    // hand the query to the cooperative pass, with the triangle the descent has reached so far (if there is one)
+    auto give_up = [&](bool with_tri) {
+        unsigned long long v = 0ull;
+        if (with_tri)
+            v = (unsigned long long)vlabel(r + ay, x + ax) | ((unsigned long long)vlabel(r + by, x + bx) << 21) |
+                ((unsigned long long)vlabel(r + cy, x + cx) << 42);
+        A.qres[gidx] = v;
+        atomicAdd(A.hdr + (size_t)img * HD_STRIDE + HD_PEND, 1);
+        active = false;
+    };
     // nearest set bit to dx = 0 in a window row (m != 0): returns dx
     auto nearest = [](uint32_t m) -> int {
         const uint32_t lo = m & 0x1FFFFu, hi = m >> 17;  // dx <= 0, dx >= 1
         const int dl = lo ? 16 - (31 - __clz(lo)) : 64, dr = hi ? __ffs(hi) : 64;  // distances
         return dl <= dr ? -dl : dr;
     };
-    auto pack0 = [](int ax, int ay, int bx, int by) { return (uint32_t)(ax & 0xFF) | ((uint32_t)(ay & 0xFF) << 8) | ((uint32_t)(bx & 0xFF) << 16) | ((uint32_t)(by & 0xFF) << 24); };
-    auto pack1 = [](int cx, int cy, int flips) { return (uint32_t)(cx & 0xFF) | ((uint32_t)(cy & 0xFF) << 8) | ((uint32_t)flips << 16); };
-    auto sb8 = [](uint32_t v, int k) { return (int)(int8_t)(v >> (8 * k)); };
-    // the flip statistics of a finished block go to the image it started in (counters 6 and 7 are diagnostics)
-    auto flush_stats = [&]() {
-        const int f = __reduce_add_sync(FULL, acc_flips), m = __reduce_max_sync(FULL, acc_max);
-        if (lane == 0 && f) { atomicAdd(A.counts + (size_t)blk_img * 8 + 7, f); atomicMax(A.counts + (size_t)blk_img * 8 + 6, m); }
-        acc_flips = 0; acc_max = 0;
-    };
-    // results.  e = pool entry of the item; its pixel and list slot are read back only here
-    auto result = [&](int e, unsigned long long flag, bool with_tri, int ax, int ay, int bx, int by, int cx, int cy) {
-        const uint32_t gidx = pool[W_GIDX][e], code = pool[W_CODE][e];
-        const int x = (int)(code & COL_MASK), r = (int)(code >> COL_BITS);
-        unsigned long long v = 0ull;
-        if (with_tri)
-            v = flag | (unsigned long long)vlabel(r + ay, x + ax) | ((unsigned long long)vlabel(r + by, x + bx) << 21) |
-                ((unsigned long long)vlabel(r + cy, x + cx) << 42);
-        A.qres[gidx] = v;
-        if (!flag) atomicAdd(A.hdr + (size_t)(gidx / (uint32_t)A.qlist_stride) * HD_STRIDE + HD_PEND, 1);  // handed on
-    };
-    // Lawson flip inside {a, b, c, d}: keep the new triangle that contains q (the origin).  The three candidates (d,b,c), (a,d,c),
-    // (a,b,d) share six cross products; orient(p,q,s) = p x q + q x s + s x p.  No branches.
-    auto flip = [&](int& ax, int& ay, int& bx, int& by, int& cx, int& cy, int dx, int dy) -> bool {
-        const int Xab = cross(ax, ay, bx, by), Xbc = cross(bx, by, cx, cy), Xca = cross(cx, cy, ax, ay);
-        const int Xad = cross(ax, ay, dx, dy), Xbd = cross(bx, by, dx, dy), Xcd = cross(cx, cy, dx, dy);
-        const bool fa = (-Xbd >= 0) & (Xbc >= 0) & (Xcd >= 0) & (Xbc + Xcd - Xbd > 0);
-        const bool fb = (Xad >= 0) & (-Xcd >= 0) & (Xca >= 0) & (Xad - Xcd + Xca > 0);
-        const bool fc = (Xab >= 0) & (Xbd >= 0) & (-Xad >= 0) & (Xab + Xbd - Xad > 0);
-        if (fa) { ax = dx; ay = dy; }
-        else if (fb) { bx = dx; by = dy; }
-        else if (fc) { cx = dx; cy = dy; }
-        return fa | fb | fc;  // false cannot happen
-    };
+    auto cross = [](int px, int py, int qx, int qy) { return px * qy - py * qx; };
 
     while (true) {
-        int s_free = -1, s_trip = -1, s_onc = -1;  // one slot of this lane in each state (or -1)
-#pragma unroll
-        for (int s = S - 1; s >= 0; s--) {
-            if (st[s] == 0) s_free = s;
-            if (st[s] == 1) s_trip = s;
-            if (st[s] == 2) s_onc = s;
-        }
-        const unsigned m_free = __ballot_sync(FULL, s_free >= 0);
-        const int n_trip = __popc(__ballot_sync(FULL, s_trip >= 0)), n_onc = __popc(__ballot_sync(FULL, s_onc >= 0));
-
-        // ---- PREPARE: idle slots take the next queries of the block (window rows, initial triangle) --------------------------
-        if (!exhausted && __popc(m_free) >= IMAGE_WIN_PMIN) {
+        // ---- refill idle lanes
+        const unsigned idle = __ballot_sync(FULL, !active);
+        if (idle && !exhausted && (__popc(idle) >= IMAGE_WIN_REFILL || idle == FULL)) {
             if (cur == end) {  // this warp's block is used up: take the next one
-                flush_stats();
                 int b = 0;
                 if (lane == 0) b = atomicAdd(A.work_counter, IMAGE_WIN_BLOCK);
                 b = __shfl_sync(FULL, b, 0);
-                if (b >= total) { exhausted = true; continue; }
-                cur = b; end = min(b + IMAGE_WIN_BLOCK, total);
-                int lo = 0, hi = n_img - 1;  // image that holds index b: the last i with s_off[i] <= b
-                while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_off[mid] <= b) lo = mid; else hi = mid - 1; }
-                blk_img = lo;
-            }
-            const int take = min(__popc(m_free), end - cur);
-            const int rank = __popc(m_free & ((1u << lane) - 1u));
-            if (s_free >= 0 && rank < take) {
-                const int e = s_free * 32 + lane;
-                const int gi = cur + rank;
-                int im = blk_img;
-                while (gi >= s_off[im + 1]) im++;  // gi < total = s_off[n_img]: stops at the image that holds gi
-                const uint32_t gidx = (uint32_t)((size_t)im * A.qlist_stride) + (uint32_t)(gi - s_off[im]);
-                const uint32_t code = A.qlist[gidx];
-                const int x = (int)(code & COL_MASK), r = (int)(code >> COL_BITS);
-                const uint32_t* occ = A.planes + (size_t)im * 3 * A.plane_stride;
-                uint32_t wr[NROW];  // wr[dy + NR]: bit 16 + dx <-> pixel (x + dx, r + dy)
-                // window: branch-free with clamped row / word indices and masks for what lies outside the grid
-                const int c0 = x - 16;
-                const int w0 = c0 >> 5, sh = c0 & 31;  // c0 may be negative: arithmetic shift = floor
-                const int wlo = max(w0, 0), whi = min(w0 + 1, wpr - 1);
-                const uint32_t mlo = w0 >= 0 ? 0xFFFFFFFFu : 0u, mhi = w0 + 1 < wpr ? 0xFFFFFFFFu : 0u;
-                if (r >= NR && r + NR < H && w0 >= 0 && w0 + 1 < wpr) {  // the window lies inside the grid (almost always)
-                    const uint32_t* row = occ + (r - NR) * wpr + w0;
-#pragma unroll
-                    for (int k = 0; k < NROW; k++) wr[k] = __funnelshift_r(__ldg(row + k * wpr), __ldg(row + k * wpr + 1), sh);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < NROW; k++) {
-                        const int y = r + k - NR;
-                        const int yc = min(max(y, 0), H - 1);
-                        const uint32_t* row = occ + yc * wpr;
-                        const uint32_t vm = y == yc ? 0xFFFFFFFFu : 0u;
-                        wr[k] = __funnelshift_r(__ldg(row + wlo) & mlo & vm, __ldg(row + whi) & mhi & vm, sh);
-                    }
-                }
-                // initial triangle.  Row pair: nearest sites left and right of q (64: none in the window).
-                int ax = 0, ay = 0, bx = 0, by = 0, cx = 0, cy = 0;
-                const uint32_t ml = wr[NR] & 0xFFFFu, mr = wr[NR] >> 17;
-                const int xl = ml ? (31 - __clz(ml)) - 16 : -64, xr = mr ? __ffs(mr) : 64;
-                bool ok = xr - xl <= MAXGAP;
-                // apex candidates: nearest site (|dx| <= 8) of the closest non-empty row above and of the closest below
-                uint32_t mu = 0u, md = 0u;
-                int ku = 0, kd = 0, yu = 0, yd = 0;  // yu, yd: nearest sites in q's own column
-#pragma unroll
-                for (int k = NR; k >= 1; k--) {
-                    const uint32_t u = wr[NR + k], d = wr[NR - k];
-                    if (u & 0x01FFFF00u) { mu = u & 0x01FFFF00u; ku = k; }
-                    if (d & 0x01FFFF00u) { md = d & 0x01FFFF00u; kd = k; }
-                    if (u & 0x10000u) yu = k;
-                    if (d & 0x10000u) yd = k;
-                }
-                int px = 0, py = 0;
-                if (ku) { px = nearest(mu); py = ku; }
-                if (kd) {
-                    const int pxd = nearest(md);
-                    if (!ku || pxd * pxd + kd * kd < px * px + py * py) { px = pxd; py = -kd; }  // the nearer of the two
-                }
-                const bool found = (ku | kd) != 0;
-                ok = ok && found;
-                // Column pair: q lies on the segment D-U as it lies on L-R.  The shorter of the two is the likelier Delaunay
-                // edge (fewer flips to come), and D-U serves when L or R is missing.
-                bool vert = false;
-                if (IMAGE_WIN_VINIT && yu != 0 && yd != 0 && (!ok || yu + yd < xr - xl)) {
-                    int qx = 0, qy = 0;  // apex: the nearer of L and R, else the site found in a neighbouring row
-                    if (ml != 0u && -xl <= xr) qx = xl;
-                    else if (mr != 0u) qx = xr;
-                    else if (px != 0) { qx = px; qy = py; }
-                    if (qx != 0) {
-                        vert = true; ok = true;
-                        ax = 0; bx = 0; cx = qx; cy = qy;
-                        if (qx < 0) { ay = -yd; by = yu; } else { ay = yu; by = -yd; }  // (D, U, P) with P on the left, (U, D, P) on the right
-                    }
-                }
-                if (ok && !vert) {
-                    if (py > 0) { ax = xl; bx = xr; } else { ax = xr; bx = xl; }
-                    ay = 0; by = 0; cx = px; cy = py;
-                }
-                if (!ok) {  // no triangle inside the window: the cooperative pass starts from scratch
-                    A.qres[gidx] = 0ull;
-                    atomicAdd(A.hdr + (size_t)im * HD_STRIDE + HD_PEND, 1);
-                } else {
-                    pool[W_GIDX][e] = gidx; pool[W_CODE][e] = code;
-#pragma unroll
-                    for (int k = 0; k < NROW; k++) pool[W_WR + k][e] = wr[k];
-                    pool[W_T0][e] = pack0(ax, ay, bx, by); pool[W_T1][e] = pack1(cx, cy, 0);
-#pragma unroll
-                    for (int s = 0; s < S; s++) if (s == s_free) st[s] = 1;
+                if (b >= total) exhausted = true;
+                else {
+                    cur = b; end = min(b + IMAGE_WIN_BLOCK, total);
+                    int lo = 0, hi = n_img - 1;  // image that holds index b: the last i with s_off[i] <= b
+                    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_off[mid] <= b) lo = mid; else hi = mid - 1; }
+                    blk_img = lo;
                 }
             }
-            cur += take;
-            while (blk_img + 1 < n_img && cur >= s_off[blk_img + 1]) blk_img++;
-            continue;
-        }
-        if (n_trip == 0 && n_onc == 0) { if (exhausted) break; continue; }
-
-        if (n_onc < IMAGE_WIN_OMIN && n_trip > 0 && n_trip >= n_onc) {
-            // ---- TRIP: circle of (a, b, c), one pass over the window rows, flip --------------------------------------------------
-            if (s_trip >= 0) {
-                const int e = s_trip * 32 + lane;
-                const uint32_t t0 = pool[W_T0][e], t1 = pool[W_T1][e];
-                int ax = sb8(t0, 0), ay = sb8(t0, 1), bx = sb8(t0, 2), by = sb8(t0, 3), cx = sb8(t1, 0), cy = sb8(t1, 1);
-                int flips = (int)(t1 >> 16);
-                const int ux = bx - ax, uy = by - ay, vx = cx - ax, vy = cy - ay;
-                const int b2 = ux * ux + uy * uy, c2 = vx * vx + vy * vy;
-                const int A2 = ux * vy - uy * vx;  // > 0
-                const int U = b2 * vy - uy * c2, V = ux * c2 - b2 * vx;
-                const float inv = 0.5f / (float)A2;
-                const float fU = (float)U, fV = (float)V;
-                const float ccx = (float)ax + fU * inv, ccy = (float)ay + fV * inv;
-                const float R2 = (fU * fU + fV * fV) * inv * inv;
-                const float thr = inv;  // half the smallest possible |distance^2 - R^2| of a lattice point off the circle
-                const float ccx16 = ccx + 16.0f;  // window column of the centre (bit 16 is q's column)
-                // does the closed disc stay inside rows +-NR and columns +-15 (conservative, float)?  Only then can the window certify
-                // an empty circle; a larger circle can still be searched for violators inside the window (any violator is a valid flip)
-                const float Rr = sqrt_approx(R2) + 0.01f;
-                const bool fits = fabsf(ccy) + Rr < (float)NR + 0.99f && fabsf(ccx) + Rr < 15.0f;
-                // one pass over the window rows (q's row first, then +-1, +-2, ...): strict interior (the violator nearest to q wins)
-                // and the sites ON the circle
-                bool have = false;
-                int dx = 0, dy = 0;
-                uint32_t on[NROW], vm = 0u, anyon = 0u;
+            if (!exhausted) {
+                const int take = min(__popc(idle), end - cur);
+                const int rank = __popc(idle & ((1u << lane) - 1u));
+                if (!active && rank < take) {
+                    const int gi = cur + rank;
+                    int im = blk_img;
+                    while (gi >= s_off[im + 1]) im++;  // gi < total = s_off[n_img]: stops at the image that holds gi
+                    if (im != acc_img) { flush_stats(); acc_img = im; }
+                    img = im;
+                    gidx = (uint32_t)((size_t)im * A.qlist_stride) + (uint32_t)(gi - s_off[im]);
+                    const uint32_t code = A.qlist[gidx];
+                    x = (int)(code & COL_MASK); r = (int)(code >> COL_BITS);
+                    active = true; flips = 0;
+                    const uint32_t* occ = A.planes + (size_t)im * 3 * A.plane_stride;
+                    // window: branch-free with clamped row / word indices and masks for what lies outside the grid
+                    const int c0 = x - 16;
+                    const int w0 = c0 >> 5, sh = c0 & 31;  // c0 may be negative: arithmetic shift = floor
+                    const int wlo = max(w0, 0), whi = min(w0 + 1, wpr - 1);
+                    const uint32_t mlo = w0 >= 0 ? 0xFFFFFFFFu : 0u, mhi = w0 + 1 < wpr ? 0xFFFFFFFFu : 0u;
+                    if (r >= NR && r + NR < H && w0 >= 0 && w0 + 1 < wpr) {  // the window lies inside the grid (almost always)
+                        const uint32_t* row = occ + (r - NR) * wpr + w0;
 #pragma unroll
-                for (int k = 0; k < NROW; k++) {
-                    const int yy = (k == 0) ? 0 : ((k & 1) ? (k + 1) / 2 : -(k / 2));
-                    const float ee = (float)yy - ccy;
-                    const float base = R2 - ee * ee;
-                    const float ti = base - thr, to = base + thr;
-                    uint32_t im = 0u, om = 0u;
-                    if (to >= 0.0f) {
-                        const float hwo = sqrt_approx(to);
-                        om = bit_span(__float2int_ru(ccx16 - hwo), __float2int_rd(ccx16 + hwo));
-                        if (ti > 0.0f) {
-                            const float hwi = sqrt_approx(ti);
-                            im = bit_span(__float2int_ru(ccx16 - hwi), __float2int_rd(ccx16 + hwi));
+                        for (int k = 0; k < NROW; k++) wr[k] = __funnelshift_r(__ldg(row + k * wpr), __ldg(row + k * wpr + 1), sh);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < NROW; k++) {
+                            const int y = r + k - NR;
+                            const int yc = min(max(y, 0), H - 1);
+                            const uint32_t* row = occ + yc * wpr;
+                            const uint32_t vm = y == yc ? 0xFFFFFFFFu : 0u;
+                            wr[k] = __funnelshift_r(__ldg(row + wlo) & mlo & vm, __ldg(row + whi) & mhi & vm, sh);
                         }
                     }
-                    const uint32_t sites = pool[W_WR + yy + NR][e];
-                    const uint32_t m = sites & im;
-                    if (m && !have) { have = true; vm = m; dy = yy; }
-                    // sites on the circle (a, b, c among them: they are taken out when the candidates are packed)
-                    const uint32_t o = sites & om & ~im;
-                    on[k] = o; anyon += __popc(o);
-                }
-                int next = 1;  // state of the slot after this trip
-                if (have) {
-                    dx = nearest(vm);
-                    if (!fits) {
-                        // large circle: float may misjudge points near it -- confirm the violator exactly (int32: |coordinates| <= 16)
-                        const int ex = dx - ax, ey = dy - ay;
-                        if (U * ex + V * ey - A2 * (ex * ex + ey * ey) <= 0) { result(e, 0ull, true, ax, ay, bx, by, cx, cy); next = 0; }
-                    }
-                    if (next) {
-                        if (!flip(ax, ay, bx, by, cx, cy, dx, dy)) { result(e, 0ull, false, 0, 0, 0, 0, 0, 0); next = 0; }  // cannot happen
-                        else if (++flips > MAXFLIPS) { result(e, 0ull, true, ax, ay, bx, by, cx, cy); next = 0; }
-                        else { pool[W_T0][e] = pack0(ax, ay, bx, by); pool[W_T1][e] = pack1(cx, cy, flips); }
-                    }
-                } else if (!fits) {
-                    result(e, 0ull, true, ax, ay, bx, by, cx, cy); next = 0;
-                } else if (anyon <= 3u) {  // empty circle, nothing on it but a, b, c: the triangle of the canonical triangulation over q
-                    result(e, QRES_DONE, true, ax, ay, bx, by, cx, cy);
-                    acc_flips += flips; acc_max = max(acc_max, flips);
-                    next = 0;
-                } else {  // empty circle with sites on it: the symbolic perturbation decides (next phase)
+                    // initial triangle.  Row pair: nearest sites left and right of q (64: none in the window).
+                    const uint32_t ml = wr[NR] & 0xFFFFu, mr = wr[NR] >> 17;
+                    const int xl = ml ? (31 - __clz(ml)) - 16 : -64, xr = mr ? __ffs(mr) : 64;
+                    bool ok = xr - xl <= MAXGAP;
+                    // apex candidates: nearest site (|dx| <= 8) of the closest non-empty row above and of the closest below
+                    uint32_t mu = 0u, md = 0u;
+                    int ku = 0, kd = 0, yu = 0, yd = 0;  // yu, yd: nearest sites in q's own column
 #pragma unroll
-                    for (int k = 0; k < NROW; k++) pool[W_ON + k][e] = on[k];
-                    next = 2;
+                    for (int k = NR; k >= 1; k--) {
+                        const uint32_t u = wr[NR + k], d = wr[NR - k];
+                        if (u & 0x01FFFF00u) { mu = u & 0x01FFFF00u; ku = k; }
+                        if (d & 0x01FFFF00u) { md = d & 0x01FFFF00u; kd = k; }
+                        if (u & 0x10000u) yu = k;
+                        if (d & 0x10000u) yd = k;
+                    }
+                    int px = 0, py = 0;
+                    if (ku) { px = nearest(mu); py = ku; }
+                    if (kd) {
+                        const int pxd = nearest(md);
+                        if (!ku || pxd * pxd + kd * kd < px * px + py * py) { px = pxd; py = -kd; }  // the nearer of the two
+                    }
+                    const bool found = (ku | kd) != 0;
+                    ok = ok && found;
+                    // Column pair: q lies on the segment D-U as it lies on L-R.  The shorter of the two is the likelier Delaunay
+                    // edge (fewer flips to come), and D-U serves when L or R is missing.
+                    bool vert = false;
+                    if (IMAGE_WIN_VINIT && yu != 0 && yd != 0 && (!ok || yu + yd < xr - xl)) {
+                        int qx = 0, qy = 0;  // apex: the nearer of L and R, else the site found in a neighbouring row
+                        if (ml != 0u && -xl <= xr) qx = xl;
+                        else if (mr != 0u) qx = xr;
+                        else if (px != 0) { qx = px; qy = py; }
+                        if (qx != 0) {
+                            vert = true; ok = true;
+                            ax = 0; bx = 0; cx = qx; cy = qy;
+                            if (qx < 0) { ay = -yd; by = yu; } else { ay = yu; by = -yd; }  // (D, U, P) with P on the left, (U, D, P) on the right
+                        }
+                    }
+                    if (ok && !vert) {
+                        if (py > 0) { ax = xl; bx = xr; } else { ax = xr; bx = xl; }
+                        ay = 0; by = 0; cx = px; cy = py;
+                    }
+                    if (!ok) give_up(false);
                 }
-#pragma unroll
-                for (int s = 0; s < S; s++) if (s == s_trip) st[s] = next;
+                cur += take;
+                while (blk_img + 1 < n_img && cur >= s_off[blk_img + 1]) blk_img++;
             }
-        } else {
-            // ---- ON-CIRCLE: the circle is empty; sites ON it decide by the symbolic perturbation (same rule as incircle_pert(), in
-            // window coordinates: weights < 2^20, |orient| <= 2 * 31 * 6, so int32 holds every term and the sum).  The circle fits
-            // (R < 4), so an on-circle site has |dx - rint(ccx)| <= 4: 9 bits per row, NROW rows in one 64-bit word, in scan order.
-            if (s_onc >= 0) {
-                const int e = s_onc * 32 + lane;
-                const uint32_t t0 = pool[W_T0][e], t1 = pool[W_T1][e], code = pool[W_CODE][e];
-                int ax = sb8(t0, 0), ay = sb8(t0, 1), bx = sb8(t0, 2), by = sb8(t0, 3), cx = sb8(t1, 0), cy = sb8(t1, 1);
-                int flips = (int)(t1 >> 16);
-                const int x = (int)(code & COL_MASK), r = (int)(code >> COL_BITS);
-                const int ux = bx - ax, uy = by - ay, vx = cx - ax, vy = cy - ay;
-                const int b2 = ux * ux + uy * uy, c2 = vx * vx + vy * vy;
-                const int A2 = ux * vy - uy * vx;
-                const int U = b2 * vy - uy * c2;
-                const float inv = 0.5f / (float)A2;
-                const float ccx = (float)ax + (float)U * inv;  // the same operations as in the trip: the same value
-                const int icx = __float2int_rn(ccx);
-                unsigned long long cand = 0ull;
+        }
+        if (!__any_sync(FULL, active)) { if (exhausted) break; continue; }
+        if (!active) continue;
+
+        // ---- circle of (a, b, c)
+        const int ux = bx - ax, uy = by - ay, vx = cx - ax, vy = cy - ay;
+        const int b2 = ux * ux + uy * uy, c2 = vx * vx + vy * vy;
+        const int A2 = ux * vy - uy * vx;  // > 0
+        const int U = b2 * vy - uy * c2, V = ux * c2 - b2 * vx;
+        const float inv = 0.5f / (float)A2;
+        const float fU = (float)U, fV = (float)V;
+        const float ccx = (float)ax + fU * inv, ccy = (float)ay + fV * inv;
+        const float R2 = (fU * fU + fV * fV) * inv * inv;
+        const float thr = inv;  // half the smallest possible |distance^2 - R^2| of a lattice point off the circle
+        const float ccx16 = ccx + 16.0f;  // window column of the centre (bit 16 is q's column)
+        // does the closed disc stay inside rows +-NR and columns +-15 (conservative, float)?  Only then can the window certify
+        // an empty circle; a larger circle can still be searched for violators inside the window (any violator is a valid flip)
+        const float Rr = sqrt_approx(R2) + 0.01f;
+        const bool fits = fabsf(ccy) + Rr < (float)NR + 0.99f && fabsf(ccx) + Rr < 15.0f;
+        // ---- one pass over the window rows (q's row first, then +-1, +-2, ...): strict interior (the violator nearest to q wins)
+        // and the sites ON the circle.  Every lane runs the same code whether its circle turns out empty or not.
+        bool have = false;
+        int dx = 0, dy = 0;
+        uint32_t on[NROW], vm = 0u, anyon = 0u;
 #pragma unroll
-                for (int k = 0; k < NROW; k++) cand |= (unsigned long long)((uint32_t)(((unsigned long long)pool[W_ON + k][e] << 4) >> (icx + 16)) & 0x1FFu) << (9 * k);
+        for (int k = 0; k < NROW; k++) {
+            const int yy = (k == 0) ? 0 : ((k & 1) ? (k + 1) / 2 : -(k / 2));
+            const float e = (float)yy - ccy;
+            const float base = R2 - e * e;
+            const float ti = base - thr, to = base + thr;
+            uint32_t im = 0u, om = 0u;
+            if (to >= 0.0f) {
+                const float hwo = sqrt_approx(to);
+                om = bit_span(__float2int_ru(ccx16 - hwo), __float2int_rd(ccx16 + hwo));
+                if (ti > 0.0f) {
+                    const float hwi = sqrt_approx(ti);
+                    im = bit_span(__float2int_ru(ccx16 - hwi), __float2int_rd(ccx16 + hwi));
+                }
+            }
+            const uint32_t sites = wr[yy + NR];
+            const uint32_t m = sites & im;
+            if (m && !have) { have = true; vm = m; dy = yy; }
+            // sites on the circle (a, b, c among them: they are taken out when the candidates are packed)
+            const uint32_t o = sites & om & ~im;
+            on[k] = o; anyon += __popc(o);
+        }
+        if (have) dx = nearest(vm);
+        if (have && !fits) {
+            // large circle: float may misjudge points near it -- confirm the violator exactly (int32: |coordinates| <= 16)
+            const int ex = dx - ax, ey = dy - ay;
+            if (U * ex + V * ey - A2 * (ex * ex + ey * ey) <= 0) { give_up(true); continue; }
+        }
+        if (!have && !fits) { give_up(true); continue; }
+        if (!have) {
+            // ---- empty circle: sites ON it decide by the symbolic perturbation (same rule as incircle_pert(), in window
+            // coordinates: weights < 2^20, |orient| <= 2 * 31 * 6, so int32 holds every term and the sum)
+            // The circle fits (R < 4), so an on-circle site has |dx - rint(ccx)| <= 4: 9 bits per row, NROW rows in one 64-bit
+            // word, rows in scan order.
+            const int icx = __float2int_rn(ccx);
+            unsigned long long cand = 0ull;
+            if (anyon > 3u) {
+#pragma unroll
+                for (int k = 0; k < NROW; k++) cand |= (unsigned long long)((uint32_t)(((unsigned long long)on[k] << 4) >> (icx + 16)) & 0x1FFu) << (9 * k);
                 // row index in scan order of a vertex row vy: 0, +1, -1, +2, ... -> 0, 1, 2, 3, ...
                 cand &= ~(1ull << (9 * (ay > 0 ? 2 * ay - 1 : -2 * ay) + ax - icx + 4));
                 cand &= ~(1ull << (9 * (by > 0 ? 2 * by - 1 : -2 * by) + bx - icx + 4));
                 cand &= ~(1ull << (9 * (cy > 0 ? 2 * cy - 1 : -2 * cy) + cx - icx + 4));
-                bool have = false;
-                int dx = 0, dy = 0;
-                if (cand) {
-                    const int qi = r * W + x;  // row-major index of q: a window point (dx, dy) is pixel qi + dy * W + dx
-                    const int wa = pert_weight_idx((uint32_t)(qi + ay * W + ax)), wb = pert_weight_idx((uint32_t)(qi + by * W + bx)),
-                              wc = pert_weight_idx((uint32_t)(qi + cy * W + cx));
-                    while (cand && !have) {
-                        const int b = __ffsll((long long)cand) - 1;
-                        cand &= cand - 1ull;
-                        const int k = (b * 57) >> 9;  // b / 9 for b < 63
-                        const int ddx = b - 9 * k - 4 + icx;
-                        const int yy = (k & 1) ? (k + 1) >> 1 : -(k >> 1);
-                        const int wd = pert_weight_idx((uint32_t)(qi + yy * W + ddx));
-                        const int obcd = (cx - bx) * (yy - by) - (cy - by) * (ddx - bx);
-                        const int oacd = (cx - ax) * (yy - ay) - (cy - ay) * (ddx - ax);
-                        const int oabd = (bx - ax) * (yy - ay) - (by - ay) * (ddx - ax);
-                        const int pert = wa * obcd - wb * oacd + wc * oabd - wd * A2;
-                        if (pert > 0) { have = true; dx = ddx; dy = yy; }
-                    }
+            }
+            if (cand) {
+                const int qi = r * W + x;  // row-major index of q: a window point (dx, dy) is pixel qi + dy * W + dx
+                const int wa = pert_weight_idx((uint32_t)(qi + ay * W + ax)), wb = pert_weight_idx((uint32_t)(qi + by * W + bx)),
+                          wc = pert_weight_idx((uint32_t)(qi + cy * W + cx));
+                while (cand && !have) {
+                    const int b = __ffsll((long long)cand) - 1;
+                    cand &= cand - 1ull;
+                    const int k = (b * 57) >> 9;  // b / 9 for b < 63
+                    const int ddx = b - 9 * k - 4 + icx;
+                    const int yy = (k & 1) ? (k + 1) >> 1 : -(k >> 1);
+                    const int wd = pert_weight_idx((uint32_t)(qi + yy * W + ddx));
+                    const int obcd = (cx - bx) * (yy - by) - (cy - by) * (ddx - bx);
+                    const int oacd = (cx - ax) * (yy - ay) - (cy - ay) * (ddx - ax);
+                    const int oabd = (bx - ax) * (yy - ay) - (by - ay) * (ddx - ax);
+                    const int pert = wa * obcd - wb * oacd + wc * oabd - wd * A2;
+                    if (pert > 0) { have = true; dx = ddx; dy = yy; }
                 }
-                int next = 1;
-                if (!have) {  // the triangle of the canonical triangulation over q
-                    result(e, QRES_DONE, true, ax, ay, bx, by, cx, cy);
-                    acc_flips += flips; acc_max = max(acc_max, flips);
-                    next = 0;
-                } else if (!flip(ax, ay, bx, by, cx, cy, dx, dy)) { result(e, 0ull, false, 0, 0, 0, 0, 0, 0); next = 0; }  // cannot happen
-                else if (++flips > MAXFLIPS) { result(e, 0ull, true, ax, ay, bx, by, cx, cy); next = 0; }
-                else { pool[W_T0][e] = pack0(ax, ay, bx, by); pool[W_T1][e] = pack1(cx, cy, flips); }
-#pragma unroll
-                for (int s = 0; s < S; s++) if (s == s_onc) st[s] = next;
+            }
+            if (!have) {  // t is the triangle of the canonical triangulation over q
+                const uint32_t va = vlabel(r + ay, x + ax), vb = vlabel(r + by, x + bx), vc = vlabel(r + cy, x + cx);
+                A.qres[gidx] = QRES_DONE | (unsigned long long)va | ((unsigned long long)vb << 21) | ((unsigned long long)vc << 42);
+                acc_flips += flips; acc_max = max(acc_max, flips);
+                active = false;
+                continue;
             }
         }
+        // ---- Lawson flip inside {a, b, c, d}: keep the new triangle that contains q (the origin).  The three candidates
+        // (d,b,c), (a,d,c), (a,b,d) share six cross products; orient(p,q,s) = p x q + q x s + s x p.  No branches.
+        {
+            const int Xab = cross(ax, ay, bx, by), Xbc = cross(bx, by, cx, cy), Xca = cross(cx, cy, ax, ay);
+            const int Xad = cross(ax, ay, dx, dy), Xbd = cross(bx, by, dx, dy), Xcd = cross(cx, cy, dx, dy);
+            const bool fa = (-Xbd >= 0) & (Xbc >= 0) & (Xcd >= 0) & (Xbc + Xcd - Xbd > 0);
+            const bool fb = (Xad >= 0) & (-Xcd >= 0) & (Xca >= 0) & (Xad - Xcd + Xca > 0);
+            const bool fc = (Xab >= 0) & (Xbd >= 0) & (-Xad >= 0) & (Xab + Xbd - Xad > 0);
+            if (fa) { ax = dx; ay = dy; }
+            else if (fb) { bx = dx; by = dy; }
+            else if (fc) { cx = dx; cy = dy; }
+            else { give_up(false); continue; }  // cannot happen
+        }
+        if (++flips > MAXFLIPS) give_up(true);
     }
     flush_stats();
 }
-
 // ---- warp-cooperative versions for queries whose triangles are large (wide gaps, hull pockets) -------------------------
 // One lane per row of each 32-row wave (row offsets 0, -1, +1, -2, ... from qy).  Returns, in every lane, the violator
 // nearest to q found in the first wave that has one (x | y << 16), or -1.
