@@ -1,22 +1,28 @@
 #!/usr/bin/env python
-"""bench.py -- BEV hypothesis pairs rendered / s on N B200s, with roofline and CPU baseline.
+"""bench.py -- BEV hypothesis pairs rendered / s on N B200s, with roofline, parity and CPU baseline.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c3|c4|c5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" renders one synthetic building (BASELINE.json configs[1]): 40 panos of 512x1024, 640
-alignment hypotheses, floor + ceiling  =>  2560 BEV images of 501x501x3 per GPU per step.
-One hypothesis = 4 images.  Multi-GPU shards by building (one building per rank, weak scaling,
-no collective on the data path; NCCL only for the barrier and the max-over-ranks time).
+Configurations (BASELINE.json `configs`; the default, c2, is the one the headline metric is quoted on):
+  c2  one synthetic building per GPU: 40 panos of 512x1024, 640 alignment hypotheses, floor + ceiling => 2560 BEV images of
+      501x501x3 per GPU per step.  One hypothesis = 4 images.
+  c3  full-resolution panos: 16 panos of 1024x2048, batch of 256 hypotheses, floor + ceiling, one GPU.
+  c4  test-split-scale sweep: 158 buildings of unequal size (~100 k hypotheses) sharded by building over the ranks (greedy by
+      hypothesis count), panos uploaded per building, renders stay on the device.  One step = the whole sweep.
+  c5  c2's renders kept on the device -> fused verifier pre-processing -> ResNet-152 early-fusion verifier (random-init weights).
+Multi-GPU shards by building (weak scaling for c2/c3/c5: one building per rank; c4: strong scaling of the fixed sweep), no
+collective on the data path; NCCL only carries the barrier and the max-over-ranks time.
 
-`value`  : device-resident inputs and outputs, CUDA events on the launching stream, L2 flushed
-           between timed steps.
-`e2e`    : the same step through the host-buffer C ABI (pinned host panos -> H2D -> render ->
-           D2H of all images), wall clock with synchronize on both sides.
-`roofline`: dominant kernel (image_kernel), algorithmic bytes per launch / CUDA-event time.
-`cpu_baseline` / `--impl reference`: the oracle port (numpy + SciPy restatement of the reference,
-           bit-identical to it) on all host cores with multiprocessing.Pool -- the reference's own
-           parallel mechanism (scripts/render_dataset_bev.py:111-113).
+`value`   : device-resident inputs and outputs, CUDA events on the launching stream, L2 flushed between timed steps.
+`e2e`     : the same step through the host-buffer C ABI (pinned host panos -> H2D -> render -> D2H of all images), wall clock.
+`roofline`: the image pipeline (sites / prep / window / shade / finish kernels, the dominant share of the step) and every kernel
+            on its own: algorithmic bytes per launch / CUDA-event time, against the measured HBM peak.
+`parity`  : after the timed loop, a seeded sample of the step's hypotheses is rendered by the CPU oracle and compared.
+`cpu_baseline` / `--impl reference`: the reference's own render_bev_pair (unmodified copies under oracle/_ref, made by
+            scripts/make_oracle_ref.py; the bit-identical port oracle/bev_oracle.py when they are absent or the pano size is not
+            the reference's 512x1024) on all host cores with multiprocessing.Pool -- the reference's own parallel mechanism
+            (scripts/render_dataset_bev.py:111-113, default 15 processes :201).
 """
 
 from __future__ import annotations
@@ -34,12 +40,34 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-PANO_H, PANO_W = 512, 1024
-N_PANOS, N_HYP = 40, 640
 IMG = 501
 IMG_BYTES = IMG * IMG * 3
-# compulsory bytes per hypothesis (floor+ceiling), 512x1024 panos
-ALG_BYTES_PER_HYP = 2 * 360448 * 5 + 4 * IMG_BYTES
+METRIC = "BEV hypothesis pairs rendered/sec"
+
+
+def cropped_px(H, W):
+    return (H - 2 * int(H * 80 / 512)) * W
+
+
+def alg_bytes_per_hyp(H, W):
+    """compulsory bytes per hypothesis (floor+ceiling): two panos' cropped rows in (5 B/px), four images out."""
+    return 2 * cropped_px(H, W) * 5 + 4 * IMG_BYTES
+
+
+CONFIGS = {
+    "c2": dict(pano_hw=(512, 1024), panos=40, hyp=640, chunk=1480, e2e_chunk=444,
+               workload="one synthetic building per GPU: 40 panos 512x1024 (u8 RGB + u16 depth), 640 alignment hypotheses, "
+                        "floor+ceiling BEV pairs (4 images of 501x501x3 per hypothesis), default BEVParams"),
+    "c3": dict(pano_hw=(1024, 2048), panos=16, hyp=256, chunk=1088, e2e_chunk=272,
+               workload="full-resolution panos: 16 panos 1024x2048 (u8 RGB + u16 depth), batch of 256 alignment hypotheses, "
+                        "floor+ceiling BEV pairs (4 images of 501x501x3 per hypothesis), default BEVParams"),
+    "c4": dict(pano_hw=(512, 1024), panos=8, buildings=158, hyp=633, chunk=1480,
+               workload="test-split-scale sweep: 158 synthetic buildings of 506..759 hypotheses (~100 k in total) over 8 panos 512x1024 "
+                        "each, sharded by building across the ranks (greedy by hypothesis count), floor+ceiling, renders stay on device"),
+    "c5": dict(pano_hw=(512, 1024), panos=40, hyp=640, chunk=1480,
+               workload="c2's building per GPU, renders kept on device -> fused resize 234 / crop 224 / normalise / concat -> "
+                        "EarlyFusionCEResnet(152, random init, 2 classes) inference in bf16, one replica per GPU"),
+}
 
 
 def load_peaks():
@@ -47,112 +75,168 @@ def load_peaks():
     if os.path.exists(p):
         with open(p) as f:
             d = json.load(f)
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: oracle port on host cores
+# CPU arm: the reference (or its port) on host cores, and the parity checker
 # ------------------------------------------------------------------------------------------------
-def _cpu_init():
-    os.environ["CUDA_VISIBLE_DEVICES"] = ""
+_W = {}  # per-worker state
+
+
+def reference_available(pano_hw) -> bool:
+    return tuple(pano_hw) == (512, 1024) and os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "salve"))
+
+
+def _cpu_init(pano_hw, n_panos, use_ref):
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""  # the reference's box filter would otherwise run on the GPU (interpolation_utils.py:104)
     for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
         os.environ[k] = "1"
-
-
-def _cpu_warm(_):
-    import scipy.interpolate  # noqa: F401
-    import scipy.spatial  # noqa: F401
-    from oracle import bev_oracle, synth  # noqa: F401
-
-    return 0
-
-
-def _cpu_one(args):
-    """One hypothesis = floor + ceiling pairs through the oracle port."""
     import warnings
 
     warnings.simplefilter("ignore")
-    from oracle import bev_oracle as bo
+    import scipy.interpolate  # noqa: F401
+    import scipy.spatial  # noqa: F401
+
     from oracle import synth
 
-    k1, k2, j = args
-    rgb1, d1 = synth.synth_pano(PANO_H, PANO_W, k1, "iid", jitter=0.2)
-    rgb2, d2 = synth.synth_pano(PANO_H, PANO_W, k2, "iid", jitter=0.2)
-    R, t = synth.synth_pose(j)
-    t0 = time.perf_counter()
+    # inputs are synthesised here, outside every timed region
+    _W["panos"] = [synth.synth_pano(pano_hw[0], pano_hw[1], k, "iid", jitter=0.2) for k in range(n_panos)]
+    _W["synth"] = synth
+    if use_ref:
+        os.environ["SALVE_REFERENCE_ROOT"] = os.path.join(ROOT, "oracle", "_ref")
+        from oracle import ref_import
+
+        ref_import.load()
+        _W["render"] = lambda a, b, R, t, surf: ref_import.render_bev_pair(a[0], a[1], b[0], b[1], R, t, surf)
+    else:
+        from oracle import bev_oracle as bo
+
+        _W["render"] = lambda a, b, R, t, surf: bo.render_pair_images(a[0], a[1], b[0], b[1], R, t, surf)
+
+
+def _cpu_warm(_):
+    return 0
+
+
+def _cpu_one(job):
+    """One hypothesis = render_bev_pair for floor and for ceiling (4 images)."""
+    k1, k2, j = job
+    R, t = _W["synth"].synth_pose(j)
     for surf in ("floor", "ceiling"):
-        bo.render_pair_images(rgb1, d1, rgb2, d2, R, t, surf)
-    return time.perf_counter() - t0
+        _W["render"](_W["panos"][k1], _W["panos"][k2], R, t, surf)
+    return 0
 
 
-def cpu_throughput(n_hyp: int, procs: int):
-    """hypotheses/s of the oracle port with a Pool of `procs` workers (input synthesis excluded
-    from nothing: it is ~3% of a hypothesis and keeps workers independent)."""
-    import multiprocessing as mp
+class CpuArm:
+    """A persistent multiprocessing.Pool of `procs` single-threaded workers running the reference's render_bev_pair."""
 
-    ctx = mp.get_context("spawn")
-    jobs = [(2 * i, 2 * i + 1, i) for i in range(n_hyp)]
-    with ctx.Pool(procs, initializer=_cpu_init) as pool:
-        pool.map(_cpu_warm, range(procs * 2), chunksize=1)  # warm imports, untimed
+    N_PANOS = 4
+
+    def __init__(self, pano_hw, procs):
+        import multiprocessing as mp
+
+        self.use_ref = reference_available(pano_hw)
+        self.kind = "reference" if self.use_ref else "port"
+        self.procs = procs
+        self.pool = mp.get_context("spawn").Pool(procs, initializer=_cpu_init, initargs=(tuple(pano_hw), self.N_PANOS, self.use_ref))
+        self.pool.map(_cpu_warm, range(procs * 2), chunksize=1)  # imports + input synthesis, untimed
+
+    def run(self, n_hyp, first=0):
+        jobs = [((first + i) % self.N_PANOS, (first + i + 1) % self.N_PANOS, first + i) for i in range(n_hyp)]
         t0 = time.perf_counter()
-        pool.map(_cpu_one, jobs, chunksize=1)
-        dt = time.perf_counter() - t0
-    return n_hyp / dt, dt
+        self.pool.map(_cpu_one, jobs, chunksize=1)
+        return time.perf_counter() - t0
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+    def what(self):
+        return ("unmodified reference render_bev_pair (oracle/_ref, scripts/make_oracle_ref.py)" if self.use_ref
+                else "oracle port (numpy + SciPy restatement, bit-identical to the reference at 512x1024)")
+
+
+def _parity_one(job):
+    """Oracle renders of one hypothesis (floor + ceiling, posed + un-posed) against the GPU images of the timed step."""
+    import warnings
+
+    warnings.simplefilter("ignore")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import parity_utils as pu
+    from oracle import bev_oracle as bo
+
+    rgb1, d1, rgb2, d2, R, t, gpu = job
+    out = dict(images=0, mismatches=0, kept=0, safe=0, safe_gt1=0, all_gt1=0)
+    for si, surf in enumerate(("floor", "ceiling")):
+        s1, s2 = bo.render_pair(rgb1, d1, rgb2, d2, R, t, surf)
+        for pi, st in enumerate((s1, s2)):
+            img = gpu[si][pi]
+            out["images"] += 1
+            if st.degenerate:
+                out["mismatches"] += int(img.any())
+                continue
+            can = pu.oracle_canonical(st)
+            out["mismatches"] += int(not np.array_equal(img, pu.canonical_final(st, can)))  # bit-exact vs the canonical-tie oracle
+            rep = pu.rgb_report(img, st, can)  # vs the reference's own (SciPy) image
+            safe = int(round(rep["safe_frac"] * rep["kept"]))
+            out["kept"] += rep["kept"]; out["safe"] += safe
+            out["safe_gt1"] += int(round(rep["safe_gt1"] * safe)); out["all_gt1"] += int(round(rep["all_gt1"] * rep["kept"]))
+            out["mismatches"] += int(rep["outside_kept_diff"] != 0)
+    return out
+
+
+def parity_block(pool, jobs):
+    res = pool.map(_parity_one, jobs, chunksize=1)
+    tot = {k: sum(r[k] for r in res) for k in res[0]}
+    return {"images_checked": tot["images"], "mismatches": tot["mismatches"],
+            "safe_gt1": tot["safe_gt1"] / max(tot["safe"], 1), "all_gt1": tot["all_gt1"] / max(tot["kept"], 1),
+            "safe_frac": tot["safe"] / max(tot["kept"], 1),
+            "what": "mismatches: images of the timed step not bit-identical to the canonical-tie CPU oracle (masks, hull, interpolation, final image); "
+                    "safe_gt1 / all_gt1: fraction of tie-independent / all kept pixels that differ by more than 1/255 from the reference's own "
+                    "(SciPy) image -- the latter is the reference's tie-break ambiguity (5-7 % under input reordering, SURVEY.md appendix C)"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    cfg = CONFIGS[args.config]
     cores = os.cpu_count() or 1
-    n_hyp = max(cores, 8)
-    vals = []
     t_all = time.perf_counter()
-    for _ in range(args.warmup):
-        pass  # worker warm-up happens inside cpu_throughput (imports); no separate untimed pass needed
-    for _ in range(args.steps):
-        v, dt = cpu_throughput(n_hyp, cores)
-        vals.append((v, dt))
-    value = sum(n_hyp for _ in vals) / sum(dt for _, dt in vals)
+    arm = CpuArm(cfg["pano_hw"], cores)
+    n_hyp = cores  # one hypothesis (4 images, ~7 s of one core) per worker and step: a bounded sample of the workload
+    for w in range(args.warmup and 1):
+        arm.run(min(n_hyp, 4))
+    dts = [arm.run(n_hyp, first=k * n_hyp) for k in range(args.steps)]
+    arm.close()
+    value = n_hyp * len(dts) / sum(dts)
     line = {
-        "impl": "reference",
-        "metric": "BEV hypothesis pairs rendered/sec",
-        "value": value,
-        "unit": "hypotheses/s",
-        "n_gpus": args.gpus,
-        "steps": args.steps,
-        "warmup": args.warmup,
-        "ms_per_step": 1e3 * sum(dt for _, dt in vals) / len(vals),
-        "higher_is_better": True,
-        "scaling": "weak",
-        "vs_baseline": None,
-        "dtype": "f64",
-        "data": "synthetic",
-        "config": workload_config(args.gpus),
-        "cpu_baseline": {
-            "value": value, "unit": "hypotheses/s", "cores": cores, "kind": "port",
-            "sample": f"{n_hyp} hypotheses (floor+ceiling, 4 images each) per step x {args.steps} steps, multiprocessing.Pool({cores})",
-        },
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "hypotheses/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sum(dts) / len(dts), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_config(args.config, args.gpus),
+        "cpu_baseline": {"value": value, "unit": "hypotheses/s", "cores": cores, "kind": arm.kind,
+                         "sample": f"{n_hyp} hypotheses (floor+ceiling, 4 images each) per step x {args.steps} steps, persistent "
+                                   f"multiprocessing.Pool({cores}), inputs synthesised outside the timed region; {arm.what()}"},
         "e2e": {"value": value, "unit": "hypotheses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-        "wall_s": time.perf_counter() - t_all,
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t_all,
     }
     print(json.dumps(line))
     return 0
 
 
-def workload_config(n_gpus: int):
-    return {
-        "workload": "one synthetic building per GPU: 40 panos 512x1024 (u8 RGB + u16 depth), 640 alignment hypotheses, "
-        "floor+ceiling BEV pairs (4 images of 501x501x3 per hypothesis), default BEVParams",
-        "panos": N_PANOS, "hypotheses_per_gpu": N_HYP, "images_per_hypothesis": 4, "pano_hw": [PANO_H, PANO_W],
-        "bev_grid": [IMG, IMG], "parallelism": f"dp{n_gpus} (sharded by building, no collective)",
-        "l2": "256 MiB scratch write between timed steps (L2 flush); per-step working set is > 2 GB",
-        "unposed_render_dedup": "within a step every distinct (pano 2, surface) image is rendered once and copied into each hypothesis' slot "
-        "(img2 does not depend on the hypothesis, reference bev_rendering_utils.py:451-455); all 4 images of every hypothesis are "
-        "materialised in the output; nothing is carried across steps; value_no_dedup renders all 2560 images from scratch",
-    }
+def workload_config(name, n_gpus):
+    c = CONFIGS[name]
+    d = {"workload": c["workload"], "name": name, "panos": c["panos"], "images_per_hypothesis": 4, "pano_hw": list(c["pano_hw"]),
+         "bev_grid": [IMG, IMG], "parallelism": f"dp{n_gpus} (sharded by building, no collective)",
+         "l2": "256 MiB scratch write between timed steps (L2 flush); per-step working set is > 2 GB"}
+    if name in ("c2", "c3", "c5"):
+        d["hypotheses_per_gpu"] = c["hyp"]
+        d["unposed_render_dedup"] = ("within a step every distinct (pano 2, surface) image is rendered once and copied into each hypothesis' slot "
+                                     "(img2 does not depend on the hypothesis, reference bev_rendering_utils.py:451-455); all 4 images of every hypothesis are "
+                                     "materialised in the output; nothing is carried across steps; value_no_dedup renders every image from scratch")
+    return d
 
 
 # ------------------------------------------------------------------------------------------------
@@ -250,48 +334,121 @@ class ClockSampler:
             for n, v in zip(names, f[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        return {
-            "sm_mhz": float(np.median(sm)) if sm else None,
-            "sm_max_mhz": max(mx) if mx else None,
-            "reasons": sorted(reasons),
-            "samples": len(sm),
-            "source": "nvidia-smi",
-        }
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------
-# GPU arm
+# GPU arm, shared plumbing
 # ------------------------------------------------------------------------------------------------
-def run_ours(args):
+class Dist:
+    def __init__(self):
+        import torch
+
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist_
+
+            self.dist = dist_
+            dist_.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def max(self, x: float) -> float:
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum(self, x: float) -> float:
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def done(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+STAGES = ("splat", "sites", "prep", "window", "shade", "finish")
+KERNEL_NAMES = {"splat": "splat_pano_kernel", "sites": "sites_stage_kernel", "prep": "prep_stage_kernel", "window": "window_stage_kernel",
+                "shade": "shade_stage_kernel", "finish": "image_order_kernel + finish_stage_kernel"}
+
+
+def traffic_table():
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            with open(p) as f:
+                return json.load(f), "profiles/" + name
+    return {}, None
+
+
+def roofline_block(stage_ms, steps, alg, n_rendered, n_jobs, chunks_per_step, value, world, H, W):
+    """Roofline of the image pipeline (the dominant share of the step) and of every kernel."""
+    peak, peak_src = load_peaks()
+    kernels = {}
+    for name in STAGES:
+        ms = stage_ms[name] / steps
+        a = alg.get(name)
+        gbs = a / (ms * 1e-3) / 1e9 if (a and ms > 0) else None
+        kernels[name] = {"kernel": KERNEL_NAMES[name], "ms_per_step": ms, "alg_bytes_per_step": a, "achieved_gbs": gbs,
+                         "frac": gbs / peak if gbs else None, "share_of_step": stage_ms[name] / max(stage_ms["total"], 1e-9)}
+    img_ms = sum(stage_ms[k] for k in STAGES[1:]) / steps
+    img_gbs = alg["image"] / (img_ms * 1e-3) / 1e9 if img_ms > 0 else 0.0
+    tj, tsrc = traffic_table()
+    traffic = None
+    if tj:
+        per_img = sum((tj[k]["dram_bytes_read"] + tj[k]["dram_bytes_write"]) / tj[k]["images_in_launch"] for k in tj if k != "splat_pano_kernel" and "images_in_launch" in tj[k])
+        traffic = per_img * n_rendered / chunks_per_step if per_img else None
+    abh = alg_bytes_per_hyp(H, W)
+    return {
+        "kernel": "image pipeline: sites_stage + prep_stage + window_stage + shade_stage + finish_stage kernels (one launch each per chunk)",
+        "bound": "hbm", "achieved": img_gbs, "peak": peak, "unit": "GB/s", "frac": img_gbs / peak, "traffic": traffic,
+        "traffic_source": (tsrc + " (dram__bytes_read.sum + dram__bytes_write.sum of the five kernels, ncu --set full, scaled to this launch's image count)") if traffic else None,
+        "peak_source": peak_src, "alg_bytes_per_launch": alg["image"] / chunks_per_step, "avg_launch_ms": img_ms / chunks_per_step,
+        "launches_timed": steps * chunks_per_step, "share_of_step": img_ms * steps / max(stage_ms["total"], 1e-9),
+        "alg_bytes": "key grid in (4 B x 501^2) + winner colours in (3 B x sites) + final image out (753 003 B), per image",
+        "path": {"alg_bytes_per_hypothesis": abh, "achieved_gbs": value / world * abh / 1e9, "frac": value / world * abh / 1e9 / peak},
+        "kernels": kernels,
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# c2 / c3: one building per GPU
+# ------------------------------------------------------------------------------------------------
+def run_building(args):
     import torch
 
     from oracle import synth  # input generator only (no rendering arithmetic)
     from salve_b200.renderer import BevRenderer
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_
+    cfg = CONFIGS[args.config]
+    H, W = cfg["pano_hw"]
+    N_PANOS, N_HYP = cfg["panos"], cfg["hyp"]
+    D = Dist()
+    rank, world, local, dev = D.rank, D.world, D.local, D.dev
 
-        dist = dist_
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    dev = torch.device("cuda", local)
-
-    # ---- synthetic building for this rank ----------------------------------------------------------
-    rgbs, depths, p1, p2, R, t = synth.synth_building(N_PANOS, N_HYP, PANO_H, PANO_W, seed=rank)
+    rgbs, depths, p1, p2, R, t = synth.synth_building(N_PANOS, N_HYP, H, W, seed=rank)
     n_img = N_HYP * 4
-    dev_chunk = int(os.environ.get("BENCH_DEV_CHUNK", "1480"))  # images per internal chunk (10 per SM): one launch per step
-    e2e_chunk = int(os.environ.get("BENCH_E2E_CHUNK", "444"))   # host path: smaller chunks so that D2H overlaps rendering
-    r = BevRenderer(pano_h=PANO_H, pano_w=PANO_W, max_panos=N_PANOS, max_images=dev_chunk, device=local)
+    dev_chunk = int(os.environ.get("BENCH_DEV_CHUNK", str(cfg["chunk"])))      # images per internal chunk: one launch of each kernel per step
+    e2e_chunk = int(os.environ.get("BENCH_E2E_CHUNK", str(cfg["e2e_chunk"])))  # host path: smaller chunks so that D2H overlaps rendering
+    r = BevRenderer(pano_h=H, pano_w=W, max_panos=N_PANOS, max_images=dev_chunk, device=local)
     stream = torch.cuda.current_stream(dev)
     sh = stream.cuda_stream
 
-    # device-resident inputs
     d_rgb = torch.from_numpy(rgbs).to(dev)
     d_depth = torch.from_numpy(depths.view(np.int16)).to(dev)
     for k in range(N_PANOS):
@@ -304,14 +461,10 @@ def run_ours(args):
     def step_device():
         r.render_hypotheses_device(p1, p2, R, t, d_out, d_counts, d_status, stream=sh)
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step_device()
-    barrier()
+    D.barrier()
 
     # ---- `value`: K timed steps, CUDA events on the launching stream, L2 flush between ------------
     r.enable_timing(True)
@@ -320,30 +473,38 @@ def run_ours(args):
         sampler.start()
     launches0 = r.launch_count()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    stage_ms = {"splat": 0.0, "image": 0.0, "total": 0.0}
-    barrier()
+    stage_ms = {k: 0.0 for k in STAGES + ("total",)}
+    host_ms = 0.0
+    D.barrier()
     for k in range(args.steps):
         flush.fill_(k & 0xFF)
         evs[k][0].record(stream)
+        t0 = time.perf_counter()
         step_device()
+        host_ms += (time.perf_counter() - t0) * 1e3  # how long the (asynchronous) call keeps the host
         evs[k][1].record(stream)
         torch.cuda.synchronize(dev)
         tm = r.last_timings()
         for key in stage_ms:
             stage_ms[key] += tm[key]
-    barrier()
+    D.barrier()
     launches = r.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     r.enable_timing(False)
-    t_ms = sum(a.elapsed_time(b) for a, b in evs)
-    tt = torch.tensor([t_ms], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    t_ms = float(tt.item())
+    t_ms = D.max(sum(a.elapsed_time(b) for a, b in evs))
     value = world * N_HYP * args.steps / (t_ms / 1e3)
     counts_h = d_counts.cpu().numpy().reshape(n_img, 8)
     status_h = d_status.cpu().numpy()
     d_ref = d_out[: 8 * IMG_BYTES].cpu().numpy().copy()
+
+    # ---- parity sample of the timed step (rank 0 checks its own building) -----------------------------
+    n_par = max(8, (args.parity_images + 3) // 4)
+    par_h = np.random.default_rng(4242).choice(N_HYP, size=min(n_par, N_HYP), replace=False)
+    par_jobs = []
+    if rank == 0 and not args.no_parity:
+        for h in par_h:
+            g = d_out[int(h) * 4 * IMG_BYTES:(int(h) + 1) * 4 * IMG_BYTES].cpu().numpy().reshape(2, 2, IMG, IMG, 3).copy()
+            par_jobs.append((rgbs[p1[h]], depths[p1[h]], rgbs[p2[h]], depths[p2[h]], R[h], t[h], g))
 
     # ---- the same without the de-duplication of un-posed renders (every image from scratch) -------------------
     r.set_dedup_unposed(False)
@@ -351,18 +512,16 @@ def run_ours(args):
     torch.cuda.synchronize(dev)
     same_nd = bool(np.array_equal(d_out[: 8 * IMG_BYTES].cpu().numpy(), d_ref))
     ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
+    D.barrier()
     for k in range(args.steps):
         flush.fill_(k & 0xFF)
         ev2[k][0].record(stream)
         step_device()
         ev2[k][1].record(stream)
-    barrier()
-    t2 = torch.tensor([sum(a.elapsed_time(b) for a, b in ev2)], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    value_nd = world * N_HYP * args.steps / (float(t2.item()) / 1e3)
+    D.barrier()
+    value_nd = world * N_HYP * args.steps / (D.max(sum(a.elapsed_time(b) for a, b in ev2)) / 1e3)
     r.set_dedup_unposed(True)
+    del d_out
 
     # ---- `e2e`: host buffers through the C ABI, H2D + D2H inside the timed region --------------------
     h_rgb = torch.from_numpy(rgbs).pin_memory()
@@ -371,7 +530,7 @@ def run_ours(args):
     # images are in host memory when the call returns (img2 shared through the returned index)
     h_posed = torch.empty(N_HYP * 2 * IMG_BYTES, dtype=torch.uint8).pin_memory()
     h_unposed = torch.empty(N_PANOS * 2 * IMG_BYTES, dtype=torch.uint8).pin_memory()
-    r2 = BevRenderer(pano_h=PANO_H, pano_w=PANO_W, max_panos=N_PANOS, max_images=e2e_chunk, device=local)
+    r2 = BevRenderer(pano_h=H, pano_w=W, max_panos=N_PANOS, max_images=e2e_chunk, device=local)
     h_posed_np, h_unposed_np = h_posed.numpy(), h_unposed.numpy()
     e2e_ret = {}
 
@@ -381,25 +540,21 @@ def run_ours(args):
         e2e_ret["r"] = r2.render_hypotheses_compact(p1, p2, R, t, posed_out=h_posed_np, unposed_out=h_unposed_np, stream=sh)
 
     step_e2e()
-    barrier()
+    D.barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step_e2e()
     torch.cuda.synchronize(dev)
-    te = time.perf_counter() - t0
-    te_t = torch.tensor([te], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
-    e2e_seq_value = world * N_HYP * args.steps / float(te_t.item())
+    e2e_seq_value = world * N_HYP * args.steps / D.max(time.perf_counter() - t0)
 
     # Two steps in flight (what a caller with a queue of buildings does): a second context with its own stream and its own pinned
     # output buffers works on step k + 1 while the device->host copies of step k drain, so that the copy engine -- the bottleneck of
-    # this path, 1.02 GB per step -- stays busy.  Every step still uploads its panos and brings all its images to the host inside
-    # the timed region.  libsalve_bev calls release the GIL (ctypes), one Python thread per context.
+    # this path -- stays busy.  Every step still uploads its panos and brings all its images to the host inside the timed region.
+    # libsalve_bev calls release the GIL (ctypes), one Python thread per context.
     DEPTH = 2
     h_posed_b = torch.empty(N_HYP * 2 * IMG_BYTES, dtype=torch.uint8).pin_memory()
     h_unposed_b = torch.empty(N_PANOS * 2 * IMG_BYTES, dtype=torch.uint8).pin_memory()
-    r3 = BevRenderer(pano_h=PANO_H, pano_w=PANO_W, max_panos=N_PANOS, max_images=e2e_chunk, device=local)
+    r3 = BevRenderer(pano_h=H, pano_w=W, max_panos=N_PANOS, max_images=e2e_chunk, device=local)
     lanes = [(r2, torch.cuda.Stream(dev), h_posed_np, h_unposed_np), (r3, torch.cuda.Stream(dev), h_posed_b.numpy(), h_unposed_b.numpy())]
 
     def lane_steps(li, n_steps):
@@ -422,32 +577,36 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
 
     run_pipelined(DEPTH)
-    barrier()
+    D.barrier()
     t0 = time.perf_counter()
     run_pipelined(args.steps)
-    te = time.perf_counter() - t0
-    te_t = torch.tensor([te], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
-    te = float(te_t.item())
-    e2e_value = world * N_HYP * args.steps / te
+    e2e_value = world * N_HYP * args.steps / D.max(time.perf_counter() - t0)
     same_b = bool(np.array_equal(h_posed_b.numpy()[: 4 * IMG_BYTES], h_posed_np[: 4 * IMG_BYTES]))
     posed_h, unposed_h, idx_h = e2e_ret["r"][:3]
     full0 = d_ref.reshape(2, 2, 2, IMG, IMG, 3)  # hypotheses 0, 1 of the device path: (surface, posed/un-posed)
-    same = all(
-        np.array_equal(posed_h[h, s], full0[h, s, 0]) and np.array_equal(unposed_h[idx_h[h], s], full0[h, s, 1]) for h in range(2) for s in range(2)
-    )
+    same = all(np.array_equal(posed_h[h, s], full0[h, s, 0]) and np.array_equal(unposed_h[idx_h[h], s], full0[h, s, 1]) for h in range(2) for s in range(2))
     n_unique = int(unposed_h.shape[0])
-    h2d = N_PANOS * PANO_H * PANO_W * 5 + N_HYP * (2 * 4 + 6 * 4)
+    h2d = N_PANOS * H * W * 5 + N_HYP * (2 * 4 + 6 * 4)
     d2h = (N_HYP * 2 + n_unique * 2) * (IMG_BYTES + 9 * 4)
 
+    # what the host can absorb: the plain device->host copy of the same bytes into the same pinned buffers, all ranks at once
+    d_probe = torch.empty(N_HYP * 2 * IMG_BYTES, dtype=torch.uint8, device=dev)
+    h_posed.copy_(d_probe, non_blocking=True)
+    D.barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        h_posed.copy_(d_probe, non_blocking=True)
+        h_unposed.copy_(d_probe[: h_unposed.numel()], non_blocking=True)
+    torch.cuda.synchronize(dev)
+    t_probe = D.max(time.perf_counter() - t0) / 3
+    d2h_gbs = (h_posed.numel() + h_unposed.numel()) / t_probe / 1e9
+    host_ceiling = world * N_HYP / t_probe
+
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
+        D.done()
         return 0
 
-    # ---- roofline of the dominant kernel ---------------------------------------------------------------
-    peak, peak_src = load_peaks()
+    # ---- roofline ------------------------------------------------------------------------------------------
     # images the kernels really rendered in a (de-duplicated) step: all posed ones + one per distinct (pano 2, surface)
     c4 = counts_h.reshape(N_HYP, 2, 2, 8)
     first = {int(p): h for h, p in reversed(list(enumerate(p2)))}
@@ -457,105 +616,355 @@ def run_ours(args):
     sites = rendered[:, 2].astype(np.int64)
     filled = rendered[:, 5].astype(np.int64)
     chunks_per_step = (n_rendered + dev_chunk - 1) // dev_chunk
-    n_launch = args.steps * chunks_per_step
-    # algorithmic bytes per stage and step
+    plane = IMG * ((IMG + 31) // 32) * 4
     alg = {
         # depth in (2 B/px per pano pass) + one 4 B key update per point inside the box
-        "splat": n_jobs * 360448 * 2 + int(rendered[:, 1].sum()) * 4,
-        # key grid in, winner colours in (3 B gathered per site), final image out
+        "splat": n_jobs * cropped_px(H, W) * 2 + int(rendered[:, 1].sum()) * 4,
+        # key grid in, winner colours in (3 B gathered per site), sparse image + two bit planes out
+        "sites": n_rendered * (IMG * IMG * 4 + IMG_BYTES + 2 * plane) + int(sites.sum()) * 3,
+        "prep": n_rendered * 3 * plane,                      # occupancy + non-empty planes in, keep plane out (lists are intermediates)
+        "window": n_rendered * plane,                        # occupancy plane in (lists are intermediates)
+        "shade": int(filled.sum()) * (3 * 3 + 3),            # three vertex colours in, one pixel out per interpolated pixel
+        "finish": n_rendered * plane,
+        # the image pipeline as a whole: key grid in, winner colours in, final image out
         "image": n_rendered * IMG * IMG * 4 + int(sites.sum()) * 3 + n_rendered * IMG_BYTES,
     }
-    kernels = {}
-    for name in ("splat", "image"):
-        ms = stage_ms[name] / args.steps
-        gbs = alg[name] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
-        kernels[name] = {"ms_per_step": ms, "alg_bytes_per_step": alg[name], "achieved_gbs": gbs, "frac": gbs / peak,
-                         "share_of_step": stage_ms[name] / max(stage_ms["total"], 1e-9)}
-    dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
-    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this same step
-    traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tpath):
-        with open(tpath) as f:
-            tj = json.load(f)
-        kname = {"splat": "splat_pano_kernel", "image": "image_kernel"}[dom]
-        if kname in tj:
-            e = tj[kname]
-            per_unit = (e["dram_bytes_read"] + e["dram_bytes_write"]) / e.get("images_in_launch", e.get("pano_passes_in_launch", 1))
-            units = (n_rendered if dom == "image" else n_jobs) / chunks_per_step
-            traffic = per_unit * units
-            traffic_src = "profiles/r01_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, scaled to this launch's unit count)"
-    roofline = {
-        "kernel": {"splat": "splat_pano_kernel", "image": "image_kernel"}[dom],
-        "bound": "hbm",
-        "achieved": kernels[dom]["achieved_gbs"],
-        "peak": peak,
-        "unit": "GB/s",
-        "frac": kernels[dom]["frac"],
-        "traffic": traffic,
-        "traffic_source": traffic_src,
-        "peak_source": peak_src,
-        "alg_bytes_per_launch": alg[dom] / chunks_per_step,
-        "avg_launch_ms": kernels[dom]["ms_per_step"] / chunks_per_step,
-        "launches_timed": n_launch,
-        "path": {"alg_bytes_per_hypothesis": ALG_BYTES_PER_HYP, "achieved_gbs": value / world * ALG_BYTES_PER_HYP / 1e9,
-                 "frac": value / world * ALG_BYTES_PER_HYP / 1e9 / peak},
-        "kernels": kernels,
-    }
+    roofline = roofline_block(stage_ms, args.steps, alg, n_rendered, n_jobs, chunks_per_step, value, world, H, W)
 
-    # ---- CPU baseline (bounded sample) -------------------------------------------------------------------
-    cpu = None
-    if not args.no_cpu and world >= 1:
+    # ---- CPU legs: parity of the timed step, then the reference's throughput on a bounded sample ---------------------
+    cpu, parity = None, None
+    if not args.no_cpu or not args.no_parity:
         cores = os.cpu_count() or 1
-        n_s = max(cores, 8)
-        v, dt = cpu_throughput(n_s, cores)
-        cpu = {"value": v, "unit": "hypotheses/s", "cores": cores, "kind": "port",
-               "sample": f"{n_s} hypotheses (floor+ceiling) in {dt:.1f} s, multiprocessing.Pool({cores}), oracle port (numpy+SciPy)"}
+        arm = CpuArm((H, W), cores)
+        if not args.no_parity:
+            parity = parity_block(arm.pool, par_jobs)
+        if not args.no_cpu:
+            n_s = max(64, 2 * cores) if (H, W) == (512, 1024) else max(16, cores)
+            arm.run(min(cores, 8))  # untimed
+            dt = min(arm.run(n_s), arm.run(n_s, first=n_s)) if (H, W) == (512, 1024) and not args.quick_cpu else arm.run(n_s)
+            cpu = {"value": n_s / dt, "unit": "hypotheses/s", "cores": cores, "kind": arm.kind,
+                   "sample": f"{n_s} hypotheses (floor+ceiling) in {dt:.1f} s (best of 2), persistent multiprocessing.Pool({cores}); {arm.what()}"}
+            if cores > 15 and not args.quick_cpu:  # the reference script's default worker count (scripts/render_dataset_bev.py:201)
+                arm15 = CpuArm((H, W), 15)
+                n15 = 60
+                dt15 = arm15.run(n15)
+                arm15.close()
+                cpu["value_15_procs"] = n15 / dt15
+        arm.close()
 
     line = {
-        "metric": "BEV hypothesis pairs rendered/sec",
-        "value": value,
-        "unit": "hypotheses/s",
-        "n_gpus": world,
-        "steps": args.steps,
-        "warmup": max(args.warmup, 3),
-        "ms_per_step": t_ms / args.steps,
-        "higher_is_better": True,
-        "scaling": "weak",
-        "vs_baseline": None,
-        "dtype": "f64",
+        "metric": METRIC, "value": value, "unit": "hypotheses/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
+        "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "dtype_detail": "f64 geometry (f32 pose parameters), exact int32/int64 predicates, u8 colour, exact u32 barycentrics",
-        "data": "synthetic",
-        "config": workload_config(world),
-        "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "hypotheses/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        "data": "synthetic", "config": workload_config(args.config, world), "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "hypotheses/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "layout": "compact",
+                "layout_note": "img1 of every hypothesis and surface + img2 once per distinct (pano 2, surface) with an index per hypothesis: "
+                               "53 % of the bytes of the reference's (img1, img2)-per-hypothesis return shape",
                 "matches_device_path": bool(same and same_b), "steps_in_flight": DEPTH, "value_one_step_at_a_time": e2e_seq_value,
+                "host_ceiling_hyp_s": host_ceiling, "host_d2h_gbs": d2h_gbs, "frac_of_host_ceiling": e2e_value / host_ceiling,
                 "note": "two contexts / streams / host threads alternate steps; every step uploads its panos and copies all its images to "
-                        "pinned host memory inside the timed region (wall clock over all steps); bound by the device->host copy engine"},
-        "gpu_launches": int(launches),
+                        "pinned host memory inside the timed region (wall clock over all steps); host_ceiling = the plain device->host copy of "
+                        "the same bytes into the same pinned buffers on all ranks at once"},
+        "gpu_launches": int(launches), "host_ms_per_call": host_ms / args.steps,
         "value_no_dedup": value_nd, "no_dedup_matches": same_nd, "images_rendered_per_step": int(n_rendered),
-        "roofline": roofline,
-        "cpu_baseline": cpu,
+        "roofline": roofline, "parity": parity, "cpu_baseline": cpu,
         "images_ok": int((status_h == 0).sum()), "images": int(n_img),
         "mean_sites": float(sites.mean()), "mean_filled_px": float(filled.mean()), "mean_flips_per_filled_px": float(counts_h[:, 7].sum() / max(filled.sum(), 1)),
     }
     print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
+    D.done()
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# c4: sweep over 158 unequal buildings sharded by building
+# ------------------------------------------------------------------------------------------------
+def run_c4(args):
+    import torch
+
+    from oracle import synth
+    from salve_b200.renderer import BevRenderer
+    from salve_b200.sharding import assign_buildings
+
+    cfg = CONFIGS["c4"]
+    H, W = cfg["pano_hw"]
+    NP, NB = cfg["panos"], cfg["buildings"]
+    D = Dist()
+    rank, world, local, dev = D.rank, D.world, D.local, D.dev
+    rng = np.random.default_rng(2024)
+    counts = [int(cfg["hyp"] * (0.8 + 0.4 * rng.random())) for _ in range(NB)]
+    parts = assign_buildings(counts, world)
+    mine = parts[rank]
+    # pano pixels of a pool of 8 synthetic buildings (their synthesis on the host is what takes time, not the render); every one of the
+    # 158 buildings has its own hypothesis list (pairs and poses)
+    POOL = 8
+    pool = [synth.synth_building(NP, 1, H, W, seed=1000 + k)[:2] for k in range(POOL)]
+    pinned = [(torch.from_numpy(p[0]).pin_memory(), torch.from_numpy(p[1].view(np.int16)).pin_memory()) for p in pool]
+    hyps = {}
+    for b in mine:
+        R = np.empty((counts[b], 2, 2), np.float32); t = np.empty((counts[b], 2), np.float32)
+        for j in range(counts[b]):
+            R[j], t[j] = synth.synth_pose(b * 100_000 + j)
+        prng = np.random.default_rng(b)
+        i1 = prng.integers(0, NP, counts[b]); i2 = (i1 + 1 + prng.integers(0, NP - 1, counts[b])) % NP
+        hyps[b] = (np.minimum(i1, i2).astype(np.int32), np.maximum(i1, i2).astype(np.int32), R, t)
+    r = BevRenderer(pano_h=H, pano_w=W, max_panos=NP, max_images=cfg["chunk"], device=local)
+    cap = max(counts)
+    d_posed = torch.empty(cap * 2 * IMG_BYTES, dtype=torch.uint8, device=dev)
+    d_unposed = torch.empty(NP * 2 * IMG_BYTES, dtype=torch.uint8, device=dev)
+    d_cp = torch.zeros(cap * 2 * 8, dtype=torch.int32, device=dev); d_cu = torch.zeros(NP * 2 * 8, dtype=torch.int32, device=dev)
+    d_sp = torch.zeros(cap * 2, dtype=torch.int32, device=dev); d_su = torch.zeros(NP * 2, dtype=torch.int32, device=dev)
+    h_sp = torch.zeros(cap * 2, dtype=torch.int32).pin_memory()
+    stream = torch.cuda.current_stream(dev)
+    sh = stream.cuda_stream
+    keep = {}
+
+    def sweep(timed_render):
+        """All buildings of this rank: upload the building's panos (pinned -> device), render, read the per-image status back."""
+        t_r, bad = 0.0, 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for b in mine:
+            hr, hd = pinned[b % POOL]
+            for k in range(NP):
+                r.upload_pano_ptr(k, hr[k].data_ptr(), hd[k].data_ptr(), stream=sh)
+            p1, p2, R, t = hyps[b]
+            e0.record(stream)
+            idx, nu = r.render_hypotheses_compact_device(p1, p2, R, t, d_posed, d_unposed, d_cp, d_cu, d_sp, d_su, stream=sh)
+            e1.record(stream)
+            h_sp[: counts[b] * 2].copy_(d_sp[: counts[b] * 2], non_blocking=True)
+            torch.cuda.synchronize(dev)
+            bad += int((h_sp[: counts[b] * 2] != 0).sum())
+            if timed_render:
+                t_r += e0.elapsed_time(e1) / 1e3
+            if b == mine[0]:
+                keep["first"] = (idx, d_posed[: 8 * IMG_BYTES].cpu().numpy().copy(), d_unposed[: NP * 2 * IMG_BYTES].cpu().numpy().copy())
+        return t_r, bad
+
+    for _ in range(min(args.warmup, 1) or 1):
+        sweep(False)
+    D.barrier()
+    sampler = ClockSampler(local, uuid=str(torch.cuda.get_device_properties(local).uuid))
+    if rank == 0:
+        sampler.start()
+    launches0 = r.launch_count()
+    t_render, t_wall, bad = 0.0, 0.0, 0
+    steps = args.steps
+    D.barrier()
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        tr, bd = sweep(True)
+        t_wall += time.perf_counter() - t0
+        t_render += tr; bad += bd
+    D.barrier()
+    launches = r.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    my_hyp = sum(counts[b] for b in mine)
+    t_render_max, t_wall_max = D.max(t_render), D.max(t_wall)
+    total_hyp = sum(counts)
+    value = total_hyp * steps / t_render_max
+    e2e_value = total_hyp * steps / t_wall_max
+    per_rank_hyp = [sum(counts[b] for b in p) for p in parts]
+    # parity: the first 4 hypotheses of this rank's first building against the oracle (rank 0 reports)
+    par_jobs = []
+    if rank == 0 and not args.no_parity:
+        b = mine[0]
+        p1, p2, R, t = hyps[b]
+        rg, dp = pool[b % POOL]
+        idx, posed, unposed = keep["first"]
+        posed = posed.reshape(4, 2, IMG, IMG, 3); unposed = unposed.reshape(NP, 2, IMG, IMG, 3)
+        for h in range(4):
+            g = np.stack([np.stack([posed[h, s], unposed[idx[h], s]]) for s in range(2)])
+            par_jobs.append((rg[p1[h]], dp[p1[h]], rg[p2[h]], dp[p2[h]], R[h], t[h], g))
+    if rank != 0:
+        D.done()
+        return 0
+    peak, peak_src = load_peaks()
+    abh = alg_bytes_per_hyp(H, W)
+    cpu, parity = None, None
+    if not args.no_cpu or not args.no_parity:
+        cores = os.cpu_count() or 1
+        arm = CpuArm((H, W), cores)
+        if not args.no_parity:
+            parity = parity_block(arm.pool, par_jobs)
+        if not args.no_cpu:
+            n_s = max(32, cores)
+            arm.run(min(cores, 8))
+            dt = arm.run(n_s)
+            cpu = {"value": n_s / dt, "unit": "hypotheses/s", "cores": cores, "kind": arm.kind,
+                   "sample": f"{n_s} hypotheses (floor+ceiling) in {dt:.1f} s, persistent multiprocessing.Pool({cores}); {arm.what()}"}
+        arm.close()
+    line = {
+        "metric": METRIC, "value": value, "unit": "hypotheses/s", "n_gpus": world, "steps": steps, "warmup": 1,
+        "ms_per_step": 1e3 * t_render_max / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": dict(workload_config("c4", world), buildings=NB, hypotheses=total_hyp, hypotheses_per_rank=per_rank_hyp,
+                                             buildings_per_rank=[len(p) for p in parts], load_imbalance=max(per_rank_hyp) / (total_hyp / world)),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "hypotheses/s", "h2d_bytes_per_step": len(mine) * NP * H * W * 5, "d2h_bytes_per_step": my_hyp * 2 * 4,
+                "note": "wall clock of the sweep: per building the panos go pinned host -> device, the render runs, and the per-image status comes back "
+                        "to the host; the rendered images stay on the device (they feed the verifier, BASELINE.json north_star)",
+                "upload_and_sync_share": 1.0 - t_render_max / t_wall_max},
+        "gpu_launches": int(launches), "images_not_ok": int(bad),
+        "roofline": {"kernel": "whole path", "bound": "hbm", "achieved": value / world * abh / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": value / world * abh / 1e9 / peak, "traffic": None, "peak_source": peak_src, "alg_bytes_per_hypothesis": abh},
+        "parity": parity, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    D.done()
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# c5: render -> verifier pre-processing -> ResNet-152 early fusion
+# ------------------------------------------------------------------------------------------------
+def run_c5(args):
+    import torch
+    from torch import nn
+    from torchvision import models
+
+    from oracle import synth
+    from salve_b200.renderer import BevRenderer
+
+    class EarlyFusionCEResnet152(nn.Module):
+        """The reference's architecture unchanged (salve/models/early_fusion.py:14-83): torchvision resnet152 whose conv1 takes 12
+        channels (x1c, x2c, x1f, x2f) and whose fc has 2 classes.  A consumer of this repo's output, not part of it."""
+
+        def __init__(self):
+            super().__init__()
+            self.resnet = models.resnet152(weights=None)
+            self.conv1 = nn.Conv2d(12, 64, kernel_size=7, stride=2, padding=3, bias=False)
+            self.fc = nn.Linear(2048, 2)
+
+        def forward(self, x):
+            r = self.resnet
+            x = r.maxpool(r.relu(r.bn1(self.conv1(x))))
+            x = r.layer4(r.layer3(r.layer2(r.layer1(x))))
+            return self.fc(torch.flatten(r.avgpool(x), 1))
+
+    cfg = CONFIGS["c5"]
+    H, W = cfg["pano_hw"]
+    NP, NH = cfg["panos"], cfg["hyp"]
+    D = Dist()
+    rank, world, local, dev = D.rank, D.world, D.local, D.dev
+    rgbs, depths, p1, p2, R, t = synth.synth_building(NP, NH, H, W, seed=rank)
+    r = BevRenderer(pano_h=H, pano_w=W, max_panos=NP, max_images=cfg["chunk"], device=local)
+    h_rgb = torch.from_numpy(rgbs).pin_memory(); h_dep = torch.from_numpy(depths.view(np.int16)).pin_memory()
+    d_posed = torch.empty(NH * 2 * IMG_BYTES, dtype=torch.uint8, device=dev)
+    d_unposed = torch.empty(NP * 2 * IMG_BYTES, dtype=torch.uint8, device=dev)
+    x = torch.empty((NH, 12, 224, 224), dtype=torch.float32, device=dev)
+    torch.manual_seed(0)
+    model = EarlyFusionCEResnet152().to(dev).eval().to(torch.bfloat16).to(memory_format=torch.channels_last)
+    BATCH = 256
+    stream = torch.cuda.current_stream(dev)
+    sh = stream.cuda_stream
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    h_logits = torch.empty((NH, 2), dtype=torch.float32).pin_memory()
+
+    def step(upload):
+        if upload:
+            for k in range(NP):
+                r.upload_pano_ptr(k, h_rgb[k].data_ptr(), h_dep[k].data_ptr(), stream=sh)
+        ev[0].record(stream)
+        idx, nu = r.render_hypotheses_compact_device(p1, p2, R, t, d_posed, d_unposed, stream=sh)
+        ev[1].record(stream)
+        r.verifier_preprocess(r.quadruplet_pointers_compact(d_posed, d_unposed, idx), x, stream=sh)
+        ev[2].record(stream)
+        outs = []
+        with torch.no_grad():
+            for b0 in range(0, NH, BATCH):
+                xb = x[b0: b0 + BATCH].to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+                outs.append(model(xb).float())
+        logits = torch.cat(outs)
+        ev[3].record(stream)
+        if upload:
+            h_logits.copy_(logits, non_blocking=True)
+        return logits
+
+    for _ in range(max(args.warmup, 3)):
+        step(True)
+    D.barrier()
+    sampler = ClockSampler(local, uuid=str(torch.cuda.get_device_properties(local).uuid))
+    if rank == 0:
+        sampler.start()
+    launches0 = r.launch_count()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    tot = np.zeros(3)
+    D.barrier()
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)
+        step(False)
+        torch.cuda.synchronize(dev)
+        tot += [ev[i].elapsed_time(ev[i + 1]) for i in range(3)]
+    D.barrier()
+    launches = r.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t_ms = D.max(float(tot.sum()))
+    value = world * NH * args.steps / (t_ms / 1e3)
+    # e2e: pinned host panos -> device, render, pre-process, verifier, logits -> host
+    step(True)
+    D.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step(True)
+    torch.cuda.synchronize(dev)
+    e2e_value = world * NH * args.steps / D.max(time.perf_counter() - t0)
+    finite = bool(np.isfinite(h_logits.numpy()).all())
+    if rank != 0:
+        D.done()
+        return 0
+    peak, peak_src = load_peaks()
+    abh = alg_bytes_per_hyp(H, W)
+    cpu = None
+    if not args.no_cpu:
+        cores = os.cpu_count() or 1
+        arm = CpuArm((H, W), cores)
+        n_s = max(32, cores)
+        arm.run(min(cores, 8))
+        dt = arm.run(n_s)
+        arm.close()
+        cpu = {"value": n_s / dt, "unit": "hypotheses/s", "cores": cores, "kind": arm.kind,
+               "sample": f"{n_s} hypotheses rendered (floor+ceiling) in {dt:.1f} s, persistent multiprocessing.Pool({cores}); render only, the "
+                         f"reference's verifier runs on the GPU in both arms; {arm.what()}"}
+    ms = tot / args.steps
+    line = {
+        "metric": METRIC + " through the ResNet-152 verifier", "value": value, "unit": "hypotheses/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64 render / bf16 verifier", "data": "synthetic", "config": dict(workload_config("c5", world), verifier_batch=BATCH),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "hypotheses/s", "h2d_bytes_per_step": NP * H * W * 5, "d2h_bytes_per_step": NH * 2 * 4,
+                "note": "pinned host panos -> device, render, pre-process, verifier, logits -> pinned host memory, wall clock"},
+        "gpu_launches": int(launches),
+        "stages_ms_per_step": {"render": ms[0], "preprocess": ms[1], "resnet152_bf16": ms[2]}, "verifier_share": ms[2] / ms.sum(),
+        "logits_finite": finite,
+        "roofline": {"kernel": "render path (the verifier is a library consumer)", "bound": "hbm", "achieved": NH / (ms[0] * 1e-3) * abh / 1e9, "peak": peak,
+                     "unit": "GB/s", "frac": NH / (ms[0] * 1e-3) * abh / 1e9 / peak, "traffic": None, "peak_source": peak_src, "alg_bytes_per_hypothesis": abh},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    D.done()
     return 0
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed step")
+    ap.add_argument("--quick-cpu", action="store_true", help="cpu_baseline: one sample, no 15-process run")
+    ap.add_argument("--parity-images", type=int, default=32)
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = {"c2": 20, "c3": 10, "c4": 3, "c5": 5}[args.config]
     if args.impl == "reference":
         return run_reference(args)
-    return run_ours(args)
+    if args.config == "c4":
+        return run_c4(args)
+    if args.config == "c5":
+        return run_c5(args)
+    return run_building(args)
 
 
 if __name__ == "__main__":

@@ -251,8 +251,10 @@ int salve_bev_remove_hallucinated(salve_bev_ctx* ctx, const uint8_t* host_sparse
                                     flip descent ended in; -1 elsewhere */
 int salve_bev_tap(salve_bev_ctx* ctx, int32_t image, int32_t what, void* host_buf, int64_t host_buf_bytes, void* stream);
 
-/* Per-stage device time (ms, CUDA events) of the most recent render call, summed over its chunks:
- * [0] splat (memset + splat_pano_kernel)  [1] image_kernel  [2], [3] reserved (0)  [4] total.  host_ms: 5 floats. */
+/* Per-stage device time (ms, CUDA events) of the most recent pano render call, summed over its chunks.  host_ms: SALVE_BEV_NTIMINGS floats:
+ * [0] splat_pano_kernel  [1] sites stage  [2] prep stage  [3] window stage  [4] shade stage  [5] order + finish stage  [6] reserved (0)
+ * [7] total (chunk start to the end of the finish stage). */
+#define SALVE_BEV_NTIMINGS 8
 int salve_bev_last_timings(salve_bev_ctx* ctx, float* host_ms);
 /* Enable/disable per-stage event timing (off by default: events add sync points at read time only). */
 int salve_bev_enable_timing(salve_bev_ctx* ctx, int32_t on);

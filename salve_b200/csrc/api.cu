@@ -35,7 +35,7 @@ static void set_err(const char* fmt, const char* a, const char* b, int line) { s
     } while (0)
 
 constexpr int N_TMP = 8;
-constexpr int N_STAGE_EVENTS = 3;  // chunk start, after splat, after the image kernel
+constexpr int N_STAGE_EVENTS = 7;  // chunk start, after: splat, sites, prep, window, shade, finish
 
 struct salve_bev_ctx {
     salve_bev_config cfg;
@@ -48,7 +48,10 @@ struct salve_bev_ctx {
     std::vector<const uint8_t*> h_rgb_ptr;
     std::vector<const uint16_t*> h_depth_ptr;
     const uint16_t** d_depth_ptr = nullptr;
+    const uint16_t** h_depth_pin = nullptr;  // pinned staging of the pointer table: its upload never blocks the host
+    cudaEvent_t ev_ptr = nullptr;
     bool ptr_dirty = true;
+    int32_t* h_rep = nullptr; size_t h_rep_cap = 0; cudaEvent_t ev_rep = nullptr;  // pinned staging of replicate_images_kernel's index tables
     // sphere tables (cos_phi[H], neg_sin_phi[H], cos_theta[W], sin_theta[W])
     double* d_tables = nullptr;
     // per-image scratch (strides in elements)
@@ -148,6 +151,8 @@ static void compute_tables_libm(int H, int W, std::vector<double>& t) {
     }
 }
 
+static int ctx_init(salve_bev_ctx* c, const salve_bev_config* cfg);
+
 extern "C" int salve_bev_ctx_create(const salve_bev_config* cfg, salve_bev_ctx** out) {
     if (!cfg || !out) FAIL(SALVE_BEV_E_INVALID, "null argument");
     int ndev = 0;
@@ -163,6 +168,13 @@ extern "C" int salve_bev_ctx_create(const salve_bev_config* cfg, salve_bev_ctx**
     if (cfg->crop_rows < 0 || 2 * cfg->crop_rows >= cfg->pano_h) FAIL(SALVE_BEV_E_INVALID, "bad crop_rows");
     CU(cudaSetDevice(cfg->device));
     salve_bev_ctx* c = new salve_bev_ctx();
+    const int rc = ctx_init(c, cfg);
+    if (rc != SALVE_BEV_OK) { salve_bev_ctx_destroy(c); return rc; }  // frees whatever was allocated before the failure
+    *out = c;
+    return SALVE_BEV_OK;
+}
+
+static int ctx_init(salve_bev_ctx* c, const salve_bev_config* cfg) {
     c->cfg = *cfg;
     c->G.grid_h = cfg->grid_h; c->G.grid_w = cfg->grid_w; c->G.wpr = (cfg->grid_w + 31) / 32;
     c->G.g = cfg->grid_h * cfg->grid_w; c->G.K = cfg->kernel_sz;
@@ -215,6 +227,9 @@ extern "C" int salve_bev_ctx_create(const salve_bev_config* cfg, salve_bev_ctx**
 #undef ALLOC
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&c->ev_cache, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_ptr, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_rep, cudaEventDisableTiming));
+    CU(cudaMallocHost((void**)&c->h_depth_pin, sizeof(void*) * P));
     for (int k = 0; k < 2; k++) {
         CU(cudaEventCreateWithFlags(&c->ev_done[k], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&c->ev_copied[k], cudaEventDisableTiming));
@@ -246,7 +261,6 @@ extern "C" int salve_bev_ctx_create(const salve_bev_config* cfg, salve_bev_ctx**
         CU(cudaFuncSetAttribute(prep_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
         CU(cudaFuncSetAttribute(sites_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
     }
-    *out = c;
     return SALVE_BEV_OK;
 }
 
@@ -269,6 +283,10 @@ extern "C" void salve_bev_ctx_destroy(salve_bev_ctx* c) {
         if (c->h_dest[k]) cudaFreeHost(c->h_dest[k]);
     }
     if (c->ev_cache) cudaEventDestroy(c->ev_cache);
+    if (c->ev_ptr) cudaEventDestroy(c->ev_ptr);
+    if (c->ev_rep) cudaEventDestroy(c->ev_rep);
+    if (c->h_depth_pin) cudaFreeHost(c->h_depth_pin);
+    if (c->h_rep) cudaFreeHost(c->h_rep);
     if (c->ev_pp) cudaEventDestroy(c->ev_pp);
     if (c->h_pp_src) cudaFreeHost(c->h_pp_src);
     if (c->d_pp_src) cudaFree(c->d_pp_src);
@@ -370,8 +388,10 @@ static SplatParams make_splat_params(salve_bev_ctx* c) {
 
 static int sync_ptr_tables(salve_bev_ctx* c, cudaStream_t st) {
     if (!c->ptr_dirty) return SALVE_BEV_OK;
-    CU(cudaMemcpyAsync(c->d_depth_ptr, c->h_depth_ptr.data(), sizeof(void*) * c->cfg.max_panos, cudaMemcpyHostToDevice, st));
-    CU(cudaStreamSynchronize(st));  // the host vector may change before the copy is consumed
+    CU(cudaEventSynchronize(c->ev_ptr));  // the previous upload out of the pinned table is done (it was issued a bind ago)
+    memcpy(c->h_depth_pin, c->h_depth_ptr.data(), sizeof(void*) * c->cfg.max_panos);
+    CU(cudaMemcpyAsync(c->d_depth_ptr, c->h_depth_pin, sizeof(void*) * c->cfg.max_panos, cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(c->ev_ptr, st));
     c->ptr_dirty = false;
     return SALVE_BEV_OK;
 }
@@ -386,7 +406,7 @@ static int stage_event(salve_bev_ctx* c, cudaStream_t st) {
 // Everything after the splat for images [0, n_img): the four stages of k_image.cuh (sites, prep, window, finish).
 static int run_image_stage(salve_bev_ctx* c, int n_img, const GridParams& G, uint32_t* keygrid, const uint8_t* const* color_src,
                            uint8_t* dev_out, int32_t* dev_counts, int32_t* dev_status, int raw_mode, int skip_empty, uint8_t* hull,
-                           int32_t* qtri, cudaStream_t st, const int32_t* dest = nullptr, int32_t* counts_out = nullptr, bool clear_keys = false) {
+                           int32_t* qtri, cudaStream_t st, const int32_t* dest = nullptr, int32_t* counts_out = nullptr, bool clear_keys = false, bool timed = false) {
     const size_t smem = image_smem_bytes(G.grid_h, G.wpr);
     if (smem > (size_t)c->max_smem_optin) FAIL(SALVE_BEV_E_CAPACITY, "grid too large for the image stages' shared memory");
     if (n_img > c->cfg.max_images) FAIL(SALVE_BEV_E_CAPACITY, "more images than the context's scratch holds");
@@ -417,11 +437,17 @@ static int run_image_stage(salve_bev_ctx* c, int n_img, const GridParams& G, uin
         IA.work_counter = c->work_counter;
         IA.raw_mode = raw_mode; IA.skip_empty_check = skip_empty; IA.clear_keys = clear_keys ? 1 : 0;
         CU(cudaMemsetAsync(c->work_counter, 0, sizeof(int32_t), st));
+        const bool ev = timed && n_img <= WIN_MAX_IMAGES;  // per-stage events: one group per chunk (else only the chunk total is kept)
+        int rc;
         sites_stage_kernel<<<dim3((unsigned)((G.grid_h + SITES_WARPS * SITES_GROUPS - 1) / (SITES_WARPS * SITES_GROUPS)), (unsigned)n), SITES_WARPS * 32, sites_smem_bytes(G.grid_w, G.wpr), st>>>(IA);
+        if (ev && (rc = stage_event(c, st))) return rc;
         prep_stage_kernel<<<n, PREP_NT, prep_smem_bytes(G.grid_h, G.wpr), st>>>(IA);
+        if (ev && (rc = stage_event(c, st))) return rc;
         const int win_ctas = std::max(1, std::min(c->n_sm * IMAGE_WIN_CTAS, n * 16));
         window_stage_kernel<IMAGE_WIN_NR><<<win_ctas, WIN_NT, 0, st>>>(IA);
+        if (ev && (rc = stage_event(c, st))) return rc;
         shade_stage_kernel<<<dim3(SHADE_SPLIT, (unsigned)n), SHADE_NT, 0, st>>>(IA);
+        if (ev && (rc = stage_event(c, st))) return rc;
         c->launches += 4;
         if (n > 2 * c->n_sm) {  // more images than CTA slots: longest expected first
             image_order_kernel<<<(n + 255) / 256, 256, 0, st>>>(c->hdr, n, c->d_order);
@@ -434,7 +460,9 @@ static int run_image_stage(salve_bev_ctx* c, int n_img, const GridParams& G, uin
         c->launches++;
         CU(cudaGetLastError());
     }
-    return stage_event(c, st);
+    if (timed && n_img > WIN_MAX_IMAGES)
+        for (int k = 0; k < 4; k++) { int rc = stage_event(c, st); if (rc) return rc; }  // keep the event layout: stages not separated
+    return timed ? stage_event(c, st) : SALVE_BEV_OK;
 }
 
 // Explicit-mesh path on ONE image (mesh scratch): sites + zipper, parallel Lawson flips, and (optionally) the rasteriser.
@@ -522,7 +550,7 @@ static int render_chunk(salve_bev_ctx* c, int n_img, const std::vector<SplatJob>
     c->last_counts = dev_counts;
     c->last_jobs = jobs;
     return run_image_stage(c, n_img, c->G, c->keygrid, c->d_color_src, dev_out, dev_counts, dev_status, 0, 0, nullptr, nullptr, st,
-                           dest ? c->d_dest : nullptr, counts_out, true);
+                           dest ? c->d_dest : nullptr, counts_out, true, true);
 }
 
 // Copy images between two device buffers at any alignment (an image is 753 003 bytes: consecutive images share no
@@ -690,15 +718,22 @@ static int render_hyp_dedup(salve_bev_ctx* c, int32_t n_hyp, const int32_t* p1, 
         void *dsrc, *ddst;
         if ((rc = tmp_get(c, 5, sizeof(int32_t) * n_posed, &dsrc))) return rc;
         if ((rc = tmp_get(c, 6, sizeof(int32_t) * n_posed, &ddst))) return rc;
-        std::vector<int32_t> hs(n_posed), hd(n_posed);
+        CU(cudaEventSynchronize(c->ev_rep));  // the previous call's copies out of the pinned tables are done
+        if (c->h_rep_cap < 2 * n_posed) {
+            if (c->h_rep) CU(cudaFreeHost(c->h_rep));
+            c->h_rep = nullptr; c->h_rep_cap = 0;
+            CU(cudaMallocHost((void**)&c->h_rep, sizeof(int32_t) * 2 * n_posed));
+            c->h_rep_cap = 2 * n_posed;
+        }
+        int32_t *hs = c->h_rep, *hd = c->h_rep + n_posed;
         for (int h = 0; h < n_hyp; h++)
             for (int s = 0; s < nsurf; s++) {
                 hs[(size_t)h * nsurf + s] = plan.uniq_of_hyp[h] * nsurf + s;
                 hd[(size_t)h * nsurf + s] = (h * nsurf + s) * 2 + 1;
             }
-        CU(cudaMemcpyAsync(dsrc, hs.data(), sizeof(int32_t) * n_posed, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(ddst, hd.data(), sizeof(int32_t) * n_posed, cudaMemcpyHostToDevice, st));
-        CU(cudaStreamSynchronize(st));  // hs / hd are pageable locals
+        CU(cudaMemcpyAsync(dsrc, hs, sizeof(int32_t) * n_posed, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ddst, hd, sizeof(int32_t) * n_posed, cudaMemcpyHostToDevice, st));
+        CU(cudaEventRecord(c->ev_rep, st));
         replicate_images_kernel<<<dim3(REPLICATE_SPLIT, (unsigned)n_posed), 256, 0, st>>>(c->cache_out, out, (const int32_t*)dsrc, (const int32_t*)ddst, ib,
                                                                             c->cache_counts, counts, c->cache_status, status);
         c->launches++;
@@ -1302,18 +1337,18 @@ extern "C" int salve_bev_enable_timing(salve_bev_ctx* c, int32_t on) {
 
 extern "C" int salve_bev_last_timings(salve_bev_ctx* c, float* host_ms) {
     if (!c || !host_ms) FAIL(SALVE_BEV_E_INVALID, "null argument");
-    for (int i = 0; i < 5; i++) host_ms[i] = 0.f;
+    for (int i = 0; i < SALVE_BEV_NTIMINGS; i++) host_ms[i] = 0.f;
     if (!c->timing || c->events_used == 0) return SALVE_BEV_OK;
     CU(cudaSetDevice(c->cfg.device));
     CU(cudaEventSynchronize(c->events[c->events_used - 1]));
     for (size_t k = 0; k + N_STAGE_EVENTS <= c->events_used; k += N_STAGE_EVENTS) {
         float ms = 0.f;
-        CU(cudaEventElapsedTime(&ms, c->events[k], c->events[k + 1]));
-        host_ms[0] += ms;
-        CU(cudaEventElapsedTime(&ms, c->events[k + 1], c->events[k + 2]));
-        host_ms[1] += ms;
-        CU(cudaEventElapsedTime(&ms, c->events[k], c->events[k + 2]));
-        host_ms[4] += ms;
+        for (int s = 0; s + 1 < N_STAGE_EVENTS; s++) {  // splat, sites, prep, window, shade, finish
+            CU(cudaEventElapsedTime(&ms, c->events[k + s], c->events[k + s + 1]));
+            host_ms[s] += ms;
+        }
+        CU(cudaEventElapsedTime(&ms, c->events[k], c->events[k + N_STAGE_EVENTS - 1]));
+        host_ms[SALVE_BEV_NTIMINGS - 1] += ms;
     }
     return SALVE_BEV_OK;
 }

@@ -7,6 +7,7 @@ raw device pointers across ctypes.
 from __future__ import annotations
 
 import ctypes
+import threading
 from typing import Optional, Sequence, Tuple
 
 import numpy as np
@@ -58,6 +59,18 @@ def _vp(x) -> Optional[int]:
     raise TypeError(type(x))
 
 
+def _locked(fn):
+    """Serialise calls on one renderer (a context is not thread-safe); the lock is re-entrant, so a caller may hold it around a sequence."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *a, **kw):
+        with self.lock:
+            return fn(self, *a, **kw)
+
+    return wrapper
+
+
 class BevRenderer:
     def __init__(
         self,
@@ -77,6 +90,7 @@ class BevRenderer:
         numpy_tables: bool = True,
     ) -> None:
         self._lib = nat.load()
+        self.lock = threading.RLock()  # a context is not thread-safe: callers that share a renderer hold this around a sequence of calls
         cfg = nat.Config()
         self._lib.salve_bev_default_config(ctypes.byref(cfg), pano_h, pano_w)
         cfg.device = device
@@ -114,6 +128,7 @@ class BevRenderer:
             pass
 
     # -- panos -----------------------------------------------------------------------------------
+    @_locked
     def upload_pano(self, slot: int, rgb: np.ndarray, depth: np.ndarray, stream: int = 0) -> None:
         rgb = np.ascontiguousarray(rgb, np.uint8)
         depth = np.ascontiguousarray(depth, np.uint16)
@@ -121,10 +136,12 @@ class BevRenderer:
             raise ValueError(f"pano must be ({self.pano_h},{self.pano_w},3) uint8 + ({self.pano_h},{self.pano_w}) uint16")
         nat.check(self._lib.salve_bev_upload_pano(self._h, slot, rgb.ctypes.data, depth.ctypes.data, stream or None))
 
+    @_locked
     def upload_pano_ptr(self, slot: int, rgb_ptr: int, depth_ptr: int, stream: int = 0) -> None:
         """Host pointers (e.g. pinned torch tensors): asynchronous H2D on `stream`."""
         nat.check(self._lib.salve_bev_upload_pano(self._h, slot, rgb_ptr, depth_ptr, stream or None))
 
+    @_locked
     def upload_pano_fullres(self, slot: int, rgb_2x: np.ndarray, depth: np.ndarray, stream: int = 0) -> None:
         """Full-resolution colour: rgb_2x (2H, 2W, 3) uint8 with the (H, W) depth map.  Equivalent to uploading
         cv2.resize(rgb_2x, (W, H), INTER_LINEAR) (reference bev_rendering_utils.py:373-375); the 2x2 mean is fused into the colour gather."""
@@ -134,9 +151,11 @@ class BevRenderer:
             raise ValueError(f"need rgb ({2 * self.pano_h},{2 * self.pano_w},3) uint8 + depth ({self.pano_h},{self.pano_w}) uint16")
         nat.check(self._lib.salve_bev_upload_pano_fullres(self._h, slot, rgb_2x.ctypes.data, depth.ctypes.data, stream or None))
 
+    @_locked
     def bind_pano_fullres(self, slot: int, dev_rgb_2x, dev_depth) -> None:
         nat.check(self._lib.salve_bev_bind_pano_fullres(self._h, slot, _vp(dev_rgb_2x), _vp(dev_depth)))
 
+    @_locked
     def bind_pano(self, slot: int, dev_rgb, dev_depth) -> None:
         nat.check(self._lib.salve_bev_bind_pano(self._h, slot, _vp(dev_rgb), _vp(dev_depth)))
 
@@ -156,6 +175,7 @@ class BevRenderer:
         t = np.ascontiguousarray(t, np.float32).reshape(n, 2)
         return n, p1, p2, R, t
 
+    @_locked
     def render_hypotheses(self, pano1, pano2, R, t, surfaces=("floor", "ceiling"), out: Optional[np.ndarray] = None, stream: int = 0):
         """Host-output render.  Returns (images (n, nsurf, 2, gh, gw, 3) u8, counts (n,nsurf,2,8), status (n,nsurf,2))."""
         n, p1, p2, R, t = self._hyp_args(pano1, pano2, R, t)
@@ -175,6 +195,7 @@ class BevRenderer:
         )
         return out.reshape(shape), counts, status
 
+    @_locked
     def render_hypotheses_device(self, pano1, pano2, R, t, dev_out, dev_counts=None, dev_status=None, surfaces=("floor", "ceiling"), stream: int = 0) -> int:
         """Device-output render (asynchronous on `stream`).  dev_* are device pointers / torch CUDA tensors.
         Returns the number of images written."""
@@ -188,6 +209,7 @@ class BevRenderer:
         )
         return n * bin(mask).count("1") * 2
 
+    @_locked
     def render_hypotheses_compact(self, pano1, pano2, R, t, surfaces=("floor", "ceiling"), posed_out: Optional[np.ndarray] = None,
                                   unposed_out: Optional[np.ndarray] = None, stream: int = 0):
         """Host-output render without duplicates: img2 of a pair does not depend on the hypothesis
@@ -223,6 +245,7 @@ class BevRenderer:
         unposed = unposed_out.reshape(-1)[: k * nsurf * int(np.prod(self.img_shape))].reshape((k, nsurf) + self.img_shape)
         return posed, unposed, idx, cp, cu[:k], sp, su[:k]
 
+    @_locked
     def render_hypotheses_compact_device(self, pano1, pano2, R, t, dev_posed, dev_unposed, dev_counts_posed=None, dev_counts_unposed=None,
                                          dev_status_posed=None, dev_status_unposed=None, surfaces=("floor", "ceiling"), stream: int = 0):
         """Device-output variant (asynchronous on `stream`).  Returns (unposed_of_hyp (n,) int32, n_unique)."""
@@ -257,6 +280,7 @@ class BevRenderer:
         two = np.uint64(2)
         return np.stack([p + (h * two + 1) * np.uint64(ib), q + (u * two + 1) * np.uint64(ib), p + (h * two) * np.uint64(ib), q + (u * two) * np.uint64(ib)], 1)
 
+    @_locked
     def verifier_preprocess(self, src_ptrs: np.ndarray, dev_out, resize_hw: int = 234, crop_hw: int = 224, stream: int = 0) -> None:
         """Fused val/test transform of the reference (resize 234 -> centre crop 224 -> CHW float32 -> ImageNet normalise -> channel
         concatenation; salve/train_utils.py:126-159).  src_ptrs: (n, 4) uint64 device addresses of 501x501x3 uint8 renders in the
@@ -264,9 +288,11 @@ class BevRenderer:
         src = np.ascontiguousarray(src_ptrs, np.uint64).reshape(-1, 4)
         nat.check(self._lib.salve_bev_verifier_preprocess(self._h, src.shape[0], src.ctypes.data, int(resize_hw), int(crop_hw), _vp(dev_out), stream or None))
 
+    @_locked
     def set_dedup_unposed(self, on: bool) -> None:
         nat.check(self._lib.salve_bev_set_dedup_unposed(self._h, int(on)))
 
+    @_locked
     def render_images(self, slots, surfaces: Sequence[str], posed, R, t, stream: int = 0):
         """Individual images.  Returns (images (n, gh, gw, 3), counts (n,8), status (n,))."""
         slots = np.ascontiguousarray(slots, np.int32).reshape(-1)
@@ -286,9 +312,11 @@ class BevRenderer:
         )
         return out, counts, status
 
+    @_locked
     def set_bands(self, a=(-float("inf"), -1.0), b=(0.5, float("inf"))) -> None:
         nat.check(self._lib.salve_bev_set_bands(self._h, float(a[0]), float(a[1]), float(b[0]), float(b[1])))
 
+    @_locked
     def backproject(self, slot: int, z_lo: float, z_hi: float, frame: int = 0, R=None, t=None, stream: int = 0) -> np.ndarray:
         """frame 0: HoHoNet frame; 1: ZInD frame; 2: posed by (R, t) into pano 2's frame."""
         n = ctypes.c_int64(0)
@@ -301,6 +329,7 @@ class BevRenderer:
             nat.check(self._lib.salve_bev_backproject(*a, _ptr(out, ctypes.c_double), ctypes.byref(n), stream or None))
         return out
 
+    @_locked
     def render_cloud(self, xyzrgb: np.ndarray, stream: int = 0):
         xyzrgb = np.ascontiguousarray(xyzrgb, np.float64)
         if xyzrgb.ndim != 2 or xyzrgb.shape[1] != 6:
@@ -316,6 +345,7 @@ class BevRenderer:
         )
         return out, counts, int(status[0])
 
+    @_locked
     def choose_elevated(self, x, y, z, zmin: float, zmax: float, num_slices: int) -> np.ndarray:
         x = np.ascontiguousarray(x, np.int64).reshape(-1)
         y = np.ascontiguousarray(y, np.int64).reshape(-1)
@@ -329,6 +359,7 @@ class BevRenderer:
         )
         return valid.astype(bool)
 
+    @_locked
     def interp_dense(self, points_xy: np.ndarray, values: np.ndarray, grid_h: int, grid_w: int, want_hull: bool = False):
         """Returns (img or None if degenerate, hull or None, status)."""
         pts = np.ascontiguousarray(points_xy, np.int64).reshape(-1, 2)
@@ -346,6 +377,7 @@ class BevRenderer:
             return None, None, status.value
         return img, (hull.astype(bool) if want_hull else None), status.value
 
+    @_locked
     def remove_hallucinated(self, sparse: np.ndarray, interp: np.ndarray, K: int) -> np.ndarray:
         sparse = np.ascontiguousarray(sparse, np.uint8)
         interp = np.ascontiguousarray(interp, np.uint8)
@@ -354,12 +386,14 @@ class BevRenderer:
         nat.check(self._lib.salve_bev_remove_hallucinated(self._h, _ptr(sparse, ctypes.c_uint8), _ptr(interp, ctypes.c_uint8), h, w, int(K), _ptr(out, ctypes.c_uint8), None))
         return out
 
+    @_locked
     def uni_sphere_xyz(self) -> np.ndarray:
         out = np.empty((self.pano_h, self.pano_w, 3), np.float64)
         nat.check(self._lib.salve_bev_get_uni_sphere_xyz(self._h, _ptr(out, ctypes.c_double)))
         return out
 
     # -- taps / diagnostics ------------------------------------------------------------------------------
+    @_locked
     def tap(self, image: int, what: str) -> np.ndarray:
         g = self.grid_h * self.grid_w
         wpr = (self.grid_w + 31) // 32
@@ -387,13 +421,19 @@ class BevRenderer:
             return buf.astype(bool)
         return buf
 
+    @_locked
     def enable_timing(self, on: bool = True) -> None:
         nat.check(self._lib.salve_bev_enable_timing(self._h, int(on)))
 
+    @_locked
     def last_timings(self) -> dict:
-        ms = np.zeros(5, np.float32)
+        """Per-stage device time (ms) of the last pano render call: splat, the five stages of the image pipeline, `image` (their sum)
+        and `total`."""
+        ms = np.zeros(8, np.float32)
         nat.check(self._lib.salve_bev_last_timings(self._h, _ptr(ms, ctypes.c_float)))
-        return dict(splat=float(ms[0]), image=float(ms[1]), total=float(ms[4]))
+        d = dict(splat=float(ms[0]), sites=float(ms[1]), prep=float(ms[2]), window=float(ms[3]), shade=float(ms[4]), finish=float(ms[5]), total=float(ms[7]))
+        d["image"] = d["sites"] + d["prep"] + d["window"] + d["shade"] + d["finish"]
+        return d
 
     def launch_count(self) -> int:
         return int(self._lib.salve_bev_launch_count(self._h))

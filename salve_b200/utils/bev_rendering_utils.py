@@ -118,8 +118,9 @@ def get_xyzrgb_from_depth(args: Union[SimpleNamespace, Namespace], depth_fpath: 
         raise NotImplementedError("is_semantics=True is dead code in the reference")
     rgb, depth = _load_pano(depth_fpath, rgb_fpath)
     r = _pano_renderer(args)
-    r.upload_pano(0, rgb, depth)
-    return r.backproject(0, args.crop_z_range[0], args.crop_z_range[1], frame=0)
+    with r.lock:
+        r.upload_pano(0, rgb, depth)
+        return r.backproject(0, args.crop_z_range[0], args.crop_z_range[1], frame=0)
 
 
 def get_bev_pair_xyzrgb(args, building_id: str, floor_id: str, i1: int, i2: int, i2Ti1: Sim2, is_semantics: bool):
@@ -130,11 +131,12 @@ def get_bev_pair_xyzrgb(args, building_id: str, floor_id: str, i1: int, i2: int,
     r = _pano_renderer(args)
     rgb1, d1 = _load_pano(args.depth_i1, args.img_i1)
     rgb2, d2 = _load_pano(args.depth_i2, args.img_i2)
-    r.upload_pano(0, rgb1, d1)
-    r.upload_pano(1, rgb2, d2)
     print(i2Ti1)
     lo, hi = args.crop_z_range
-    return r.backproject(0, lo, hi, frame=2, R=i2Ti1.rotation, t=i2Ti1.translation), r.backproject(1, lo, hi, frame=1)
+    with r.lock:
+        r.upload_pano(0, rgb1, d1)
+        r.upload_pano(1, rgb2, d2)
+        return r.backproject(0, lo, hi, frame=2, R=i2Ti1.rotation, t=i2Ti1.translation), r.backproject(1, lo, hi, frame=1)
 
 
 def render_bev_pair(args, building_id: str, floor_id: str, i1: int, i2: int, i2Ti1: Sim2, is_semantics: bool):
@@ -152,13 +154,14 @@ def render_bev_pair_arrays(rgb1, depth1, rgb2, depth2, i2Ti1: Sim2, crop_z_range
     """render_bev_pair on in-memory panos of any (H, W) (W a multiple of 4)."""
     H, W = depth1.shape
     r = _ctx.get(pano_h=H, pano_w=W, crop_ratio=float(crop_ratio), depth_scale=float(scale))
-    r.upload_pano(0, rgb1, depth1)
-    r.upload_pano(1, rgb2, depth2)
-    r.set_bands(a=(crop_z_range[0], crop_z_range[1]))
-    try:
-        imgs, counts, status = r.render_hypotheses([0], [1], i2Ti1.rotation[None], i2Ti1.translation[None], surfaces=("floor",))
-    finally:
-        r.set_bands()
+    with r.lock:  # the band is a property of the (shared, cached) context: set, render and restore under its lock
+        r.upload_pano(0, rgb1, depth1)
+        r.upload_pano(1, rgb2, depth2)
+        r.set_bands(a=(crop_z_range[0], crop_z_range[1]))
+        try:
+            imgs, counts, status = r.render_hypotheses([0], [1], i2Ti1.rotation[None], i2Ti1.translation[None], surfaces=("floor",))
+        finally:
+            r.set_bands()
     for k in range(2):
         print(f"Rendering {counts[0, 0, k, 1]/1e6} million points")
     if (status == IMG_EMPTY).any():

@@ -36,8 +36,17 @@ def interp_dense_grid_from_sparse(bev_img: np.ndarray, points: np.ndarray, rgb_v
         raise NotImplementedError("semantic (nearest) interpolation is dead code in the reference (bev_rendering_utils.py:555)")
     if points.shape[0] < MIN_REQUIRED_POINTS_SIMPLEX or is_collinear(points):
         return bev_img
+    # Limits of the CUDA entry point (include/salve_bev.h, salve_bev_interp_dense): values are interpolated as the uint8 colours
+    # the path produces (the reference interpolates float64 and truncates afterwards: the same for integral values in 0..255,
+    # which is all the render path ever passes), and every point must lie inside the grid.
+    vals = np.asarray(rgb_values, np.float64)
+    if not (np.all(vals == np.floor(vals)) and vals.min() >= 0 and vals.max() <= 255):
+        raise NotImplementedError("interp_dense_grid_from_sparse: only integral colour values in [0, 255] are supported by the CUDA path")
+    pts = np.asarray(points)[:, :2]
+    if (pts < 0).any() or (pts[:, 0] >= grid_w).any() or (pts[:, 1] >= grid_h).any():
+        raise NotImplementedError("interp_dense_grid_from_sparse: points outside the (grid_h, grid_w) grid are not supported by the CUDA path")
     r = _ctx.get(grid_h=max(grid_h, 2), grid_w=max(grid_w, 2))
-    img, _, status = r.interp_dense(np.asarray(points)[:, :2], rgb_values, grid_h, grid_w)
+    img, _, status = r.interp_dense(pts, vals, grid_h, grid_w)
     if status == IMG_DEGENERATE:
         return bev_img
     if status == IMG_COLLINEAR or img is None:

@@ -126,8 +126,8 @@ def test_driver_enumeration_follows_the_reference_order(tmp_path):
 
 
 def test_bench_reference_arm_prints_the_contract_line():
-    """`bench.py --impl reference` (the CPU oracle port on all host cores) needs no GPU and prints one JSON line with the
-    keys the driver reads."""
+    """`bench.py --impl reference` (the reference's render_bev_pair from oracle/_ref, or the oracle port when those copies are absent,
+    on all host cores) needs no GPU and prints one JSON line with the keys the driver reads."""
     import json
     import subprocess
     import sys
@@ -140,5 +140,6 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["unit"] == "hypotheses/s" and line["higher_is_better"] is True
     assert line["value"] > 0 and line["steps"] == 1 and line["n_gpus"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    have_ref = os.path.isdir(os.path.join(root, "oracle", "_ref", "salve"))
+    assert line["cpu_baseline"]["kind"] == ("reference" if have_ref else "port") and line["cpu_baseline"]["cores"] >= 1
     assert "workload" in line["config"] and line["gpu_launches"] == 0
