@@ -19,6 +19,7 @@ from oracle import canonical_dt as cdt
 from oracle import synth
 
 pytestmark = pytest.mark.gpu
+ROOT_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 RGB_TOL = 1  # per channel, /255
 RGB_FRAC = 0.999  # of tie-independent kept pixels within RGB_TOL of the reference
@@ -116,6 +117,16 @@ def test_golden_reference_images(R, golden, golden_inputs):
             keep = np.flipud(np.unpackbits(g[f"{name}_keep"])[: 501 * 501].reshape(501, 501).astype(bool))
             assert d[~keep].max() == 0
             assert (d[keep] > 1).mean() < 0.08  # tie-break ambiguity floor of the reference itself (5-7 %)
+    # the tight contract on the reference-held vectors: the oracle's stages of the same inputs (its final image IS the golden one),
+    # every stage bit-exact, 0 tie-independent pixels off by more than 1/255, all five fractions reported
+    reps = []
+    for si, surf in enumerate(("floor", "ceiling")):
+        s1, s2 = bo.render_pair(rgb1, d1, rgb2, d2, Rm, t, surf)
+        for pi, st in enumerate((s1, s2)):
+            assert np.array_equal(st.final, g[f"{surf}_{pi + 1}_final"]), "oracle != golden image of the unmodified reference"
+            rep = check_image_against_oracle(R, si * 2 + pi, imgs[0, si, pi], counts[0, si, pi], st, reps)
+            assert rep["safe_gt1"] == 0.0 and rep["safe_max"] <= RGB_TOL and rep["all_gt1"] < 0.08, rep
+    print("golden images, RGB vs the reference:", json.dumps(reps))
 
 
 def test_c3_full_resolution_panos():
@@ -673,3 +684,147 @@ def test_batched_floor_driver_writes_the_reference_tree(tmp_path):
             assert np.array_equal(cv2.imread(str(tmp_path / "bev" / lt / b / f)), cv2.imread(str(tmp_path / "bev_ref" / lt / b / f))), f
     st2 = driver.render_building_floor_pairs(str(dep), str(tmp_path / "bev"), str(hyp), str(raw), b, floor)
     assert st2["skipped_existing"] == 4 and st2["files_written"] == 0
+
+
+# ---- bench-scale batch against the oracle -------------------------------------------------------------------------------
+def test_c2_scale_batch_sample_against_oracle():
+    """BASELINE configs[1] at full size: 40 panos, 640 hypotheses, one chunk of 1 480 image slots (the configuration the headline
+    number is quoted on: de-duplicated un-posed renders, hand-out order, replicate kernel), a seeded sample against the oracle."""
+    import torch
+
+    from salve_b200.renderer import BevRenderer
+
+    n_p, n_h = 40, 640
+    rgbs, depths, p1, p2, Rm, t = synth.synth_building(n_p, n_h, 512, 1024, seed=0)
+    r = BevRenderer(max_panos=n_p, max_images=1480)
+    for k in range(n_p):
+        r.upload_pano(k, rgbs[k], depths[k])
+    ib = 501 * 501 * 3
+    out = torch.empty(n_h * 4 * ib, dtype=torch.uint8, device="cuda")
+    counts = torch.zeros(n_h * 4 * 8, dtype=torch.int32, device="cuda")
+    status = torch.zeros(n_h * 4, dtype=torch.int32, device="cuda")
+    for _ in range(2):  # the second pass runs on a key grid the first one left clean
+        r.render_hypotheses_device(p1, p2, Rm, t, out, counts, status)
+    torch.cuda.synchronize()
+    assert (status.cpu().numpy() == 0).all()
+    c = counts.cpu().numpy().reshape(n_h, 2, 2, 8)
+    for h in np.random.default_rng(7).choice(n_h, 3, replace=False):
+        imgs = out[int(h) * 4 * ib:(int(h) + 1) * 4 * ib].cpu().numpy().reshape(2, 2, 501, 501, 3)
+        for si, surf in enumerate(("floor", "ceiling")):
+            s1, s2 = bo.render_pair(rgbs[p1[h]], depths[p1[h]], rgbs[p2[h]], depths[p2[h]], Rm[h], t[h], surf)
+            for pi, st in enumerate((s1, s2)):
+                can = pu.oracle_canonical(st)
+                assert np.array_equal(imgs[si, pi], pu.canonical_final(st, can)), (h, surf, pi)
+                cc = c[h, si, pi]
+                assert (cc[0], cc[1], cc[2], cc[3], cc[4]) == (st.count_crop, st.count_bbox, len(st.site_rc), int(st.nonempty.sum()), int(st.keep.sum()))
+                assert cc[5] == int((st.keep & can["hull"] & (st.key_grid == 0)).sum())
+                rep = pu.rgb_report(imgs[si, pi], st, can)
+                assert rep["safe_gt1"] == 0.0 and rep["outside_kept_diff"] == 0, rep
+    r.close()
+
+
+def test_device_render_is_asynchronous():
+    """salve_bev_render_hypotheses returns before the device has finished (include/salve_bev.h: calls with dev_* outputs are
+    asynchronous on `stream`): two renders are queued back to back without a host synchronisation in between."""
+    import time
+
+    import torch
+
+    from salve_b200.renderer import BevRenderer
+
+    n_p, n_h = 8, 200
+    rgbs, depths, p1, p2, Rm, t = synth.synth_building(n_p, n_h, 512, 1024, seed=5)
+    r = BevRenderer(max_panos=n_p, max_images=1480)
+    d_rgb = torch.from_numpy(rgbs).cuda(); d_dep = torch.from_numpy(depths.view(np.int16)).cuda()
+    for k in range(n_p):
+        r.bind_pano(k, d_rgb[k], d_dep[k])
+    ib = 501 * 501 * 3
+    a = torch.empty(n_h * 4 * ib, dtype=torch.uint8, device="cuda"); b = torch.empty_like(a)
+    st = torch.cuda.Stream()
+    r.render_hypotheses_device(p1, p2, Rm, t, a, stream=st.cuda_stream)  # warm-up (first-use allocations)
+    st.synchronize()
+    t0 = time.perf_counter()
+    r.render_hypotheses_device(p1, p2, Rm, t, a, stream=st.cuda_stream)
+    r.render_hypotheses_device(p1, p2, Rm, t, b, stream=st.cuda_stream)
+    host_s = time.perf_counter() - t0
+    pending = not st.query()  # the device is still working on what the two calls queued
+    st.synchronize()
+    dev_s = time.perf_counter() - t0
+    assert pending, "the calls returned only after the device had finished"
+    assert host_s < 0.5 * dev_s, (host_s, dev_s)
+    assert torch.equal(a, b)
+    r.close()
+
+
+# ---- drop-in entry points that had no test ---------------------------------------------------------------------------------
+def _write_pair_files(tmp_path, seeds=(61, 62)):
+    import cv2
+
+    out = []
+    for k, sd in enumerate(seeds):
+        rgb, d = synth.synth_pano(512, 1024, sd, "smooth" if k else "iid")
+        p = tmp_path / f"pano_{k}.png"
+        cv2.imwrite(str(p), rgb[:, :, ::-1])
+        cv2.imwrite(str(tmp_path / f"pano_{k}.depth.png"), d)
+        out.append((rgb, d, str(p), str(tmp_path / f"pano_{k}.depth.png")))
+    return out
+
+
+def test_get_bev_pair_xyzrgb_dropin(tmp_path):
+    """get_bev_pair_xyzrgb (reference bev_rendering_utils.py:483-522): both clouds in pano 2's frame, float64 bit-exact, order kept."""
+    from types import SimpleNamespace
+
+    from salve_b200.common.sim2 import Sim2
+    from salve_b200.utils import bev_rendering_utils as bru
+
+    (rgb1, d1, f1, z1), (rgb2, d2, f2, z2) = _write_pair_files(tmp_path)
+    Rm, t = synth.synth_pose(12)
+    band = bo.BANDS["ceiling"]
+    args = SimpleNamespace(img_i1=f1, img_i2=f2, depth_i1=z1, depth_i2=z2, scale=0.001, crop_ratio=80 / 512, crop_z_range=list(band))
+    c1, c2 = bru.get_bev_pair_xyzrgb(args, "b", "f", 0, 1, Sim2(Rm, t, 1.0), False)
+    w1, _, _ = bo.backproject(rgb1, d1, band); bo.to_zind_frame(w1); bo.apply_pose(w1, Rm, t)
+    w2, _, _ = bo.backproject(rgb2, d2, band); bo.to_zind_frame(w2)
+    assert c1.dtype == np.float64 and c1.shape == w1.shape and np.array_equal(c1, w1)
+    assert c2.shape == w2.shape and np.array_equal(c2, w2)
+    with pytest.raises(NotImplementedError):
+        bru.get_bev_pair_xyzrgb(args, "b", "f", 0, 1, Sim2(Rm, t, 1.0), True)
+
+
+def test_dropin_install_routes_the_reference_module_names(tmp_path):
+    """salve_b200.dropin.install(): `import salve.utils.bev_rendering_utils` (what scripts/render_dataset_bev.py:20 and
+    scripts/visualize_backprojected_depthmap.py:23 do) resolves to the CUDA path.  Run in a fresh interpreter."""
+    import subprocess
+    import sys
+
+    (rgb1, d1, f1, z1), (rgb2, d2, f2, z2) = _write_pair_files(tmp_path)
+    Rm, t = synth.synth_pose(13)
+    np.savez(tmp_path / "pose.npz", R=Rm, t=t)
+    code = f"""
+import sys, numpy as np
+sys.path.insert(0, {ROOT_DIR!r})
+import salve_b200.dropin
+salve_b200.dropin.install()
+import salve.utils.bev_rendering_utils as bev_rendering_utils        # the reference's own import lines
+from salve.common.sim2 import Sim2
+from salve.common.bevparams import BEVParams
+from salve.utils.interpolation_utils import remove_hallucinated_content
+from types import SimpleNamespace
+assert bev_rendering_utils.__name__ == "salve_b200.utils.bev_rendering_utils"
+p = np.load({str(tmp_path / 'pose.npz')!r})
+args = SimpleNamespace(img_i1={f1!r}, img_i2={f2!r}, depth_i1={z1!r}, depth_i2={z2!r}, scale=0.001, crop_ratio=80 / 512, crop_z_range=[-float("inf"), -1.0])
+i1, i2 = bev_rendering_utils.render_bev_pair(args, "b", "f", 0, 1, Sim2(p["R"], p["t"], 1.0), False)
+xyzrgb = bev_rendering_utils.get_xyzrgb_from_depth(args, {z2!r}, {f2!r}, False)      # scripts/visualize_backprojected_depthmap.py:48
+img = bev_rendering_utils.render_bev_image(BEVParams(), xyzrgb, False)
+np.savez({str(tmp_path / 'out.npz')!r}, i1=i1, i2=i2, img=img, n=xyzrgb.shape[0])
+"""
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-3000:]
+    o = np.load(tmp_path / "out.npz")
+    s1, s2 = bo.render_pair(rgb1, d1, rgb2, d2, Rm, t, "floor")
+    for img, st in ((o["i1"], s1), (o["i2"], s2)):
+        assert np.array_equal(img, pu.canonical_final(st, pu.oracle_canonical(st)))
+    # get_xyzrgb_from_depth is in the HoHoNet frame; render_bev_image of that cloud is the un-rotated pano 2
+    w2, src, _ = bo.backproject(rgb2, d2, bo.BANDS["floor"])
+    assert int(o["n"]) == w2.shape[0]
+    st = bo.render_image(w2, src, 1024)
+    assert np.array_equal(o["img"], pu.canonical_final(st, pu.oracle_canonical(st)))
