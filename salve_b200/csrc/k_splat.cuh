@@ -184,6 +184,139 @@ __global__ void __launch_bounds__(256, SPLAT_CTAS) splat_pano_kernel(SplatParams
     }
 }
 
+// ---- the same splat with the hypothesis-independent half hoisted ------------------------------------------------------------
+// Everything up to the ZInD frame depends on the pano only: depth scale, sphere factors, height bands, z-slice, rotmat2d(-90).
+// A building's 640 hypotheses use 40 panos, so that half was computed 16 times per pano.  prepass_pano_kernel computes it once per
+// pano and call and leaves the survivors of either band as a compact list (x1, y1 float64 in the ZInD frame + a packed word);
+// splat_list_kernel then needs, per point and hypothesis, only the pose (2 FMA + 2 MUL + 2 ADD), the box test, two rint and
+// the atomicMax.  Lists are read through L2 (a pano's list, 20 B x ~280 k points, is reused by all its passes).
+constexpr uint32_t PM_SRC_MASK = (1u << 26) - 1;  // pano pixel index (H * W <= 2^26)
+constexpr int PM_SLICE_SHIFT = 26;                // z-slice 0..3
+constexpr uint32_t PM_HAS_SLICE = 1u << 28;       // z inside [-2, 2): the point takes part in the z-order rule
+constexpr uint32_t PM_IN_A = 1u << 29;            // inside band A ("floor")
+constexpr uint32_t PM_IN_B = 1u << 30;            // inside band B ("ceiling")
+
+struct PanoLists {
+    double* x;        // [max_panos][cap] ZInD-frame x of the survivors
+    double* y;
+    uint32_t* meta;   // [max_panos][cap]
+    int32_t* hdr;     // [max_panos][4]: survivors, of which in band A, in band B
+    size_t cap;       // entries per pano slot ((H - 2 crop) * W)
+};
+struct SlotList { int32_t n; int32_t slot[63]; };
+
+// grid = (ceil(rows * W / 1024), n_slots), block = 256; one thread = 4 consecutive pano pixels (one 8-byte depth load)
+__global__ void __launch_bounds__(256) prepass_pano_kernel(SplatParams P, SlotList S, PanoLists L) {
+    const int slot = S.slot[blockIdx.y];
+    const int rows = P.H - 2 * P.crop_rows;
+    const int i0 = (blockIdx.x * 256 + threadIdx.x) * 4;  // index within the cropped rows; W is a multiple of 4: one row per thread
+    const int lane = threadIdx.x & 31;
+    double x1[4], y1[4]; uint32_t meta[4];
+    uint32_t keep = 0u;  // which of the 4 pixels survive
+    int n_a = 0, n_b = 0;
+    if (i0 < rows * P.W) {
+        const int rr = i0 / P.W, u0 = i0 - rr * P.W, v = P.crop_rows + rr;
+        const uint2 raw = __ldg(reinterpret_cast<const uint2*>(P.depth[slot] + (size_t)v * P.W + u0));
+        const uint32_t d16[4] = {raw.x & 0xFFFFu, raw.x >> 16, raw.y & 0xFFFFu, raw.y >> 16};
+        const double cphi = __ldg(P.cos_phi + v), sz = __ldg(P.neg_sin_phi + v);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const double d = (double)__fmul_rn((float)d16[k], P.depth_scale);
+            const double z = __dmul_rn(d, sz);
+            const bool in_a = (z > P.a_lo && z <= P.a_hi), in_b = (z > P.b_lo && z <= P.b_hi);
+            if (!in_a && !in_b) continue;
+            const double x = __dmul_rn(d, __dmul_rn(cphi, __ldg(P.cos_theta + u0 + k)));
+            const double y = __dmul_rn(d, __dmul_rn(cphi, __ldg(P.sin_theta + u0 + k)));
+            x1[k] = __dadd_rn(y, __dmul_rn(x, C90));   // fma(y, 1.0, round(x*c90))
+            y1[k] = __fma_rn(y, C90, -x);              // fma(y, c90, round(x*-1.0))
+            const int sl = z_slice4(z);
+            meta[k] = (uint32_t)(v * P.W + u0 + k) | (sl >= 0 ? ((uint32_t)sl << PM_SLICE_SHIFT) | PM_HAS_SLICE : 0u) | (in_a ? PM_IN_A : 0u) | (in_b ? PM_IN_B : 0u);
+            n_a += in_a; n_b += in_b;
+            keep |= 1u << k;
+        }
+    }
+    const int cnt = __popc(keep);
+    // warp-aggregated append, pano raster order kept within the warp (neighbouring pixels stay neighbours in the list)
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    n_a = __reduce_add_sync(0xffffffffu, n_a); n_b = __reduce_add_sync(0xffffffffu, n_b);
+    if (total == 0) return;
+    int base = 0;
+    if (lane == 0) {
+        base = atomicAdd(L.hdr + slot * 4 + 0, total);
+        if (n_a) atomicAdd(L.hdr + slot * 4 + 1, n_a);
+        if (n_b) atomicAdd(L.hdr + slot * 4 + 2, n_b);
+    }
+    base = __shfl_sync(0xffffffffu, base, 0) + incl - cnt;
+    const size_t o0 = (size_t)slot * L.cap + base;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if ((keep >> k) & 1u) {
+            const size_t o = o0 + __popc(keep & ((1u << k) - 1u));
+            L.x[o] = x1[k]; L.y[o] = y1[k]; L.meta[o] = meta[k];
+        }
+}
+
+// grid = (ceil(cap / (256 * SPLAT_LIST_PTS)), n_jobs), block = 256
+#ifndef SPLAT_LIST_PTS
+#define SPLAT_LIST_PTS 4
+#endif
+__global__ void __launch_bounds__(256) splat_list_kernel(SplatParams P, const SplatJob* __restrict__ jobs, PanoLists L,
+                                                         uint32_t* __restrict__ keygrid_base, size_t keygrid_stride,
+                                                         int32_t* __restrict__ counts /* [n_img][8] */) {
+    const SplatJob job = jobs[blockIdx.y];
+    const int n = L.hdr[job.pano_slot * 4 + 0];
+    const int i0 = blockIdx.x * (256 * SPLAT_LIST_PTS) + threadIdx.x;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && counts != nullptr) {  // points inside the height band: known from the pre-pass
+        if (job.img_floor >= 0) counts[job.img_floor * 8 + 0] = L.hdr[job.pano_slot * 4 + 1];
+        if (job.img_ceil >= 0) counts[job.img_ceil * 8 + 0] = L.hdr[job.pano_slot * 4 + 2];
+    }
+    if (blockIdx.x * (256 * SPLAT_LIST_PTS) >= n) return;
+    const double tx = (double)__fmul_rn(job.t[0], 1.5f), ty = (double)__fmul_rn(job.t[1], 1.5f);
+    const double R0 = (double)job.R[0], R1 = (double)job.R[1], R2 = (double)job.R[2], R3 = (double)job.R[3];
+    const bool posed = job.posed != 0;
+    uint32_t* kg_f = job.img_floor >= 0 ? keygrid_base + (size_t)job.img_floor * keygrid_stride : nullptr;
+    uint32_t* kg_c = job.img_ceil >= 0 ? keygrid_base + (size_t)job.img_ceil * keygrid_stride : nullptr;
+    const size_t o0 = (size_t)job.pano_slot * L.cap;
+    int n_box_f = 0, n_box_c = 0;
+    double px[SPLAT_LIST_PTS], py[SPLAT_LIST_PTS]; uint32_t pm[SPLAT_LIST_PTS];
+#pragma unroll
+    for (int k = 0; k < SPLAT_LIST_PTS; k++) {
+        const int i = i0 + k * 256;
+        pm[k] = 0u;
+        if (i < n) { px[k] = __ldg(L.x + o0 + i); py[k] = __ldg(L.y + o0 + i); pm[k] = __ldg(L.meta + o0 + i); }
+    }
+#pragma unroll
+    for (int k = 0; k < SPLAT_LIST_PTS; k++) {
+        const uint32_t m = pm[k];
+        const bool do_f = (m & PM_IN_A) && kg_f != nullptr, do_c = (m & PM_IN_B) && kg_c != nullptr;
+        if (!do_f && !do_c) continue;
+        double wx = px[k], wy = py[k];
+        if (posed) {
+            const double x2 = __dadd_rn(__fma_rn(py[k], R1, __dmul_rn(px[k], R0)), tx);
+            const double y2 = __dadd_rn(__fma_rn(py[k], R3, __dmul_rn(px[k], R2)), ty);
+            wx = x2; wy = y2;
+        }
+        int row, col;
+        if (!bbox_pixel(P, wx, wy, row, col)) continue;
+        n_box_f += do_f; n_box_c += do_c;
+        if (!(m & PM_HAS_SLICE)) continue;
+        const uint32_t key = ((((m >> PM_SLICE_SHIFT) & 3u) << KEY_IDX_BITS) | (m & PM_SRC_MASK)) + 1u;
+        const int pix = row * P.grid_w + col;
+        if (do_f) atomicMax(kg_f + pix, key);
+        if (do_c) atomicMax(kg_c + pix, key);
+    }
+    if (counts != nullptr) {
+        n_box_f = __reduce_add_sync(0xffffffffu, n_box_f); n_box_c = __reduce_add_sync(0xffffffffu, n_box_c);
+        if ((threadIdx.x & 31) == 0) {
+            if (job.img_floor >= 0 && n_box_f) atomicAdd(counts + job.img_floor * 8 + 1, n_box_f);
+            if (job.img_ceil >= 0 && n_box_c) atomicAdd(counts + job.img_ceil * 8 + 1, n_box_c);
+        }
+    }
+}
+
 // ---- arbitrary cloud (render_bev_image on an (N,6) float64 array) -----------------------------
 // Also converts the cloud's colours to the u8 triple the reference stores in the sparse image
 // (rgb*255 truncated to uint8, bev_rendering_utils.py:266,307-308).

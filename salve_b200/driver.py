@@ -78,10 +78,11 @@ def render_building_floor_pairs(
     num_processes: int = 1,
     renderer: Optional[BevRenderer] = None,
     write_threads: int = 8,
+    batch_hypotheses: int = 256,
 ) -> Dict[str, int]:
     """Same arguments as the reference's render_building_floor_pairs (scripts/render_dataset_bev.py:34-117);
     `multiprocess_building_panos` / `num_processes` are accepted and ignored (the batch replaces the pool).
-    Returns counters {hypotheses, rendered, skipped_existing, skipped_empty, files_written}."""
+    The floor is rendered in batches of `batch_hypotheses`.  Returns counters {hypotheses, rendered, skipped_existing, skipped_empty, files_written}."""
     if "layout" in render_modalities:
         raise NotImplementedError("the layout modality is outside this build's scope (SURVEY.md section 8f, row 4)")
     stats = dict(hypotheses=0, rendered=0, skipped_existing=0, skipped_empty=0, files_written=0)
@@ -122,31 +123,44 @@ def render_building_floor_pairs(
             f = img_fpaths_dict[pid]
             rgb, depth, full = _load_pano_any(f"{depth_save_root}/{building_id}/{Path(f).stem}.depth.png", f)
             (r.upload_pano_fullres if full else r.upload_pano)(slot[pid], rgb, depth)
-        p1 = [slot[t[3]] for t in todo]
-        p2 = [slot[t[4]] for t in todo]
-        R = np.stack([t[5].rotation for t in todo]).astype(np.float32)
-        tt = np.stack([t[5].translation for t in todo]).astype(np.float32)
-        posed, unposed, idx, cp, cu, sp, su = r.render_hypotheses_compact(p1, p2, R, tt, surfaces=SURFACES)
-        if (sp == IMG_COLLINEAR).any() or (su == IMG_COLLINEAR).any():
+        # Hypotheses go through in batches with re-used output buffers: a ZInD floor can have ~10 k hypotheses (15 GB of renders), and a
+        # batch's files are on disk before the next one is rendered, so that nothing is lost if a later batch fails.
+        img_shape = (len(SURFACES),) + r.img_shape
+        posed_buf = np.empty((min(batch_hypotheses, len(todo)),) + img_shape, np.uint8)
+        unposed_buf = np.empty((min(batch_hypotheses, len(todo), int(r.cfg.max_panos)),) + img_shape, np.uint8)
+        collinear = []
+        with ThreadPoolExecutor(max(write_threads, 1)) as pool:
+            for b0 in range(0, len(todo), batch_hypotheses):
+                batch = todo[b0:b0 + batch_hypotheses]
+                p1 = [slot[t[3]] for t in batch]
+                p2 = [slot[t[4]] for t in batch]
+                R = np.stack([t[5].rotation for t in batch]).astype(np.float32)
+                tt = np.stack([t[5].translation for t in batch]).astype(np.float32)
+                posed, unposed, idx, cp, cu, sp, su = r.render_hypotheses_compact(
+                    p1, p2, R, tt, surfaces=SURFACES, posed_out=posed_buf[: len(batch)], unposed_out=unposed_buf)
+                futs = []
+                for h, t in enumerate(batch):
+                    for si, s in enumerate(SURFACES):
+                        if s not in t[6]:
+                            continue
+                        if sp[h, si] == IMG_EMPTY or su[idx[h], si] == IMG_EMPTY:  # (None, None): nothing is written (:626-627)
+                            stats["skipped_empty"] += 1
+                            continue
+                        if sp[h, si] == IMG_COLLINEAR or su[idx[h], si] == IMG_COLLINEAR:
+                            collinear.append((t[0], t[1], s))  # the reference's Qhull call raises for this pair only
+                            continue
+                        f1, f2 = t[6][s]
+                        futs.append(pool.submit(bru._imwrite, f1, posed[h, si]))
+                        futs.append(pool.submit(bru._imwrite, f2, unposed[idx[h], si]))
+                        stats["rendered"] += 1
+                for f in futs:  # the buffers are re-used by the next batch
+                    f.result()
+                stats["files_written"] += len(futs)
+        if collinear:
             from .utils.interpolation_utils import QhullError
 
-            raise QhullError("initial simplex is flat: all sites are collinear")
-        with ThreadPoolExecutor(max(write_threads, 1)) as pool:
-            futs = []
-            for h, t in enumerate(todo):
-                for si, s in enumerate(SURFACES):
-                    if s not in t[6]:
-                        continue
-                    if sp[h, si] == IMG_EMPTY or su[idx[h], si] == IMG_EMPTY:  # (None, None): nothing is written (:626-627)
-                        stats["skipped_empty"] += 1
-                        continue
-                    f1, f2 = t[6][s]
-                    futs.append(pool.submit(bru._imwrite, f1, posed[h, si]))
-                    futs.append(pool.submit(bru._imwrite, f2, unposed[idx[h], si]))
-                    stats["rendered"] += 1
-            for f in futs:
-                f.result()
-            stats["files_written"] = len(futs)
+            raise QhullError(f"initial simplex is flat (all sites collinear) for {len(collinear)} render(s), first: {collinear[0]}; "
+                             "every other pair of the floor has been written")
     finally:
         if own:
             r.close()

@@ -675,7 +675,7 @@ def test_batched_floor_driver_writes_the_reference_tree(tmp_path):
         for pair_idx, pf in enumerate(sorted((hyp / b / floor / lt).glob("*.json"))):
             for s in ("floor", "ceiling"):
                 bru.generate_texture_maps_for_pair(paths, s, str(pf), pair_idx, lt, str(tmp_path / "bev_ref"), b, floor, str(dep), ["rgb_texture"], None, None)
-    st = driver.render_building_floor_pairs(str(dep), str(tmp_path / "bev"), str(hyp), str(raw), b, floor)
+    st = driver.render_building_floor_pairs(str(dep), str(tmp_path / "bev"), str(hyp), str(raw), b, floor, batch_hypotheses=3)  # several batches
     assert st["hypotheses"] == 4 and st["rendered"] == 8 and st["files_written"] == 16
     for lt in driver.LABEL_TYPES:
         ref_files = sorted(os.listdir(tmp_path / "bev_ref" / lt / b))
