@@ -93,6 +93,8 @@ struct salve_bev_ctx {
     int32_t* counts = nullptr;
     int32_t* status = nullptr;
     SplatJob* d_jobs = nullptr;
+    SplatGroup* d_groups = nullptr; SplatGroup* h_groups[2] = {nullptr, nullptr};  // passes over the same pano, grouped (splat_list_kernel)
+    int n_groups = 0;
     const uint8_t** d_color_src = nullptr;
     uint8_t* out_store = nullptr;  // 2 x max_images images (double buffered), for the *_host variants
     // host-output pipeline: chunk k+1 renders while chunk k is copied device->host on copy_stream
@@ -234,6 +236,7 @@ static int ctx_init(salve_bev_ctx* c, const salve_bev_config* cfg) {
     ALLOC(c->counts, 2 * N * 8);
     ALLOC(c->status, 2 * N);
     ALLOC(c->d_jobs, N);
+    ALLOC(c->d_groups, N);
     ALLOC(c->d_color_src, N);
     ALLOC(c->out_store, 2 * N * c->img_bytes);
 #undef ALLOC
@@ -247,6 +250,7 @@ static int ctx_init(salve_bev_ctx* c, const salve_bev_config* cfg) {
         CU(cudaEventCreateWithFlags(&c->ev_copied[k], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&c->ev_staged[k], cudaEventDisableTiming));
         CU(cudaMallocHost((void**)&c->h_jobs[k], sizeof(SplatJob) * N));
+        CU(cudaMallocHost((void**)&c->h_groups[k], sizeof(SplatGroup) * N));
         CU(cudaMallocHost((void**)&c->h_src[k], sizeof(void*) * N));
         CU(cudaMallocHost((void**)&c->h_dest[k], sizeof(int32_t) * N));
     }
@@ -283,7 +287,7 @@ extern "C" void salve_bev_ctx_destroy(salve_bev_ctx* c) {
     cudaDeviceSynchronize();
     void* ptrs[] = {c->pano_rgb_store, c->pano_rgb2x_store, c->pano_depth_store, c->d_depth_ptr, c->d_tables, c->keygrid, c->color, c->occ, c->nonempty,
                     c->keep, c->tmpbits, c->wprefix, c->tris, c->owner, c->list0, c->list1, c->cand, c->qlist, c->clist, c->qres, c->planes, c->rowarr, c->hdr, c->lists.x, c->lists.y, c->lists.meta, c->lists.hdr, c->work_counter, c->d_order, c->cache_out, c->cache_counts, c->cache_status, c->d_dest, c->headers, c->counts,
-                    c->status, c->d_jobs, c->d_color_src, c->out_store};
+                    c->status, c->d_jobs, c->d_groups, c->d_color_src, c->out_store};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < N_TMP; i++) if (c->tmp[i]) cudaFree(c->tmp[i]);
     for (cudaEvent_t e : c->events) cudaEventDestroy(e);
@@ -292,6 +296,7 @@ extern "C" void salve_bev_ctx_destroy(salve_bev_ctx* c) {
         if (c->ev_copied[k]) cudaEventDestroy(c->ev_copied[k]);
         if (c->ev_staged[k]) cudaEventDestroy(c->ev_staged[k]);
         if (c->h_jobs[k]) cudaFreeHost(c->h_jobs[k]);
+        if (c->h_groups[k]) cudaFreeHost(c->h_groups[k]);
         if (c->h_src[k]) cudaFreeHost(c->h_src[k]);
         if (c->h_dest[k]) cudaFreeHost(c->h_dest[k]);
     }
@@ -546,7 +551,7 @@ static int prepass_slots(salve_bev_ctx* c, const std::vector<int32_t>& slots, cu
     }
     return SALVE_BEV_OK;
 }
-static int launch_splat(salve_bev_ctx* c, const SplatJob* d_jobs, size_t n_jobs, int32_t* dev_counts, cudaStream_t st) {
+static int launch_splat(salve_bev_ctx* c, const SplatJob* d_jobs, size_t n_jobs, const SplatGroup* d_groups, int n_groups, int32_t* dev_counts, cudaStream_t st) {
     SplatParams P = make_splat_params(c);
     const int rows = P.H - 2 * P.crop_rows;
     if (c->splat_fused) {
@@ -554,8 +559,8 @@ static int launch_splat(salve_bev_ctx* c, const SplatJob* d_jobs, size_t n_jobs,
         dim3 grid((unsigned)(((rows + P.rows_per_thread - 1) / P.rows_per_thread) * ((P.W + 1023) >> 10)), (unsigned)n_jobs);
         splat_pano_kernel<<<grid, 256, 0, st>>>(P, d_jobs, c->keygrid, c->g_stride, dev_counts);
     } else {
-        dim3 grid((unsigned)((c->lists.cap + 256 * SPLAT_LIST_PTS - 1) / (256 * SPLAT_LIST_PTS)), (unsigned)n_jobs);
-        splat_list_kernel<<<grid, 256, 0, st>>>(P, d_jobs, c->lists, c->keygrid, c->g_stride, dev_counts);
+        dim3 grid((unsigned)((c->lists.cap + SPLAT_LIST_SEG - 1) / SPLAT_LIST_SEG), (unsigned)n_groups);
+        splat_list_kernel<<<grid, 256, 0, st>>>(P, d_jobs, d_groups, c->lists, c->keygrid, c->g_stride, dev_counts);
     }
     c->launches++;
     CU(cudaGetLastError());
@@ -575,8 +580,18 @@ static int render_chunk(salve_bev_ctx* c, int n_img, const std::vector<SplatJob>
         if (img_slot[i] < 0 || img_slot[i] >= c->cfg.max_panos) FAIL(SALVE_BEV_E_CAPACITY, "pano slot out of range");
         c->h_src[sp][i] = c->h_rgb_ptr[img_slot[i]];
     }
-    memcpy(c->h_jobs[sp], jobs.data(), sizeof(SplatJob) * jobs.size());
+    // jobs of one pano next to each other: its point list stays in L2 from one pass to the next (the image indices travel with the job)
+    std::vector<SplatJob> sorted_jobs(jobs);
+    std::stable_sort(sorted_jobs.begin(), sorted_jobs.end(), [](const SplatJob& a, const SplatJob& b) { return a.pano_slot < b.pano_slot; });
+    memcpy(c->h_jobs[sp], sorted_jobs.data(), sizeof(SplatJob) * sorted_jobs.size());
     CU(cudaMemcpyAsync(c->d_jobs, c->h_jobs[sp], sizeof(SplatJob) * jobs.size(), cudaMemcpyHostToDevice, st));
+    c->n_groups = 0;
+    for (size_t j = 0; j < sorted_jobs.size(); j++) {
+        SplatGroup* g = c->h_groups[sp];
+        if (c->n_groups && g[c->n_groups - 1].n < SPLAT_GROUP && sorted_jobs[g[c->n_groups - 1].first].pano_slot == sorted_jobs[j].pano_slot) g[c->n_groups - 1].n++;
+        else { g[c->n_groups].first = (int32_t)j; g[c->n_groups].n = 1; c->n_groups++; }
+    }
+    CU(cudaMemcpyAsync(c->d_groups, c->h_groups[sp], sizeof(SplatGroup) * c->n_groups, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(c->d_color_src, c->h_src[sp], sizeof(void*) * n_img, cudaMemcpyHostToDevice, st));
     if (dest) {
         memcpy(c->h_dest[sp], dest->data(), sizeof(int32_t) * n_img);
@@ -592,11 +607,11 @@ static int render_chunk(salve_bev_ctx* c, int n_img, const std::vector<SplatJob>
             if (c->slot_call[j.pano_slot] != c->call_id) { c->slot_call[j.pano_slot] = c->call_id; need.push_back(j.pano_slot); }
         rc = prepass_slots(c, need, st); if (rc) return rc;
     }
-    rc = launch_splat(c, c->d_jobs, jobs.size(), dev_counts, st); if (rc) return rc;
+    rc = launch_splat(c, c->d_jobs, jobs.size(), c->d_groups, c->n_groups, dev_counts, st); if (rc) return rc;
     rc = stage_event(c, st); if (rc) return rc;
     c->last_chunk_images = n_img;
     c->last_counts = dev_counts;
-    c->last_jobs = jobs;
+    c->last_jobs = sorted_jobs;
     return run_image_stage(c, n_img, c->G, c->keygrid, c->d_color_src, dev_out, dev_counts, dev_status, 0, 0, nullptr, nullptr, st,
                            dest ? c->d_dest : nullptr, counts_out, true, true);
 }
@@ -1278,7 +1293,14 @@ extern "C" int salve_bev_tap(salve_bev_ctx* c, int32_t image, int32_t what, void
     };
     int rc = clear_slots(); if (rc) return rc;
     if ((rc = prepass_slots(c, std::vector<int32_t>(1, J.pano_slot), st))) return rc;
-    if ((rc = launch_splat(c, c->d_jobs + job, 1, nullptr, st))) return rc;
+    {
+        void* dg;
+        if ((rc = tmp_get(c, 5, sizeof(SplatGroup), &dg))) return rc;
+        const SplatGroup one = {job, 1};
+        CU(cudaMemcpyAsync(dg, &one, sizeof(one), cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));  // `one` is a local
+        if ((rc = launch_splat(c, c->splat_fused ? c->d_jobs + job : c->d_jobs, 1, (const SplatGroup*)dg, 1, nullptr, st))) return rc;
+    }
     // ... on a private copy of the image's counters
     void* dcnt;
     if ((rc = tmp_get(c, 6, 64, &dcnt))) return rc;

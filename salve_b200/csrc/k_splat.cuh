@@ -259,61 +259,101 @@ __global__ void __launch_bounds__(256) prepass_pano_kernel(SplatParams P, SlotLi
         }
 }
 
-// grid = (ceil(cap / (256 * SPLAT_LIST_PTS)), n_jobs), block = 256
+// grid = (ceil(cap / SPLAT_LIST_SEG), n_groups), block = 256.  A group = up to SPLAT_GROUP jobs (passes) over the SAME pano: a CTA
+// walks a segment of SPLAT_LIST_SEG consecutive list entries, SPLAT_LIST_PTS loads per thread in flight at a time, and applies every
+// pose of the group to the points it holds in registers -- the list is read once per group instead of once per hypothesis.
 #ifndef SPLAT_LIST_PTS
 #define SPLAT_LIST_PTS 4
 #endif
-__global__ void __launch_bounds__(256) splat_list_kernel(SplatParams P, const SplatJob* __restrict__ jobs, PanoLists L,
-                                                         uint32_t* __restrict__ keygrid_base, size_t keygrid_stride,
+#ifndef SPLAT_LIST_ROUNDS
+#define SPLAT_LIST_ROUNDS 4
+#endif
+#ifndef SPLAT_GROUP_DEF
+#define SPLAT_GROUP_DEF 8
+#endif
+constexpr int SPLAT_GROUP = SPLAT_GROUP_DEF;
+constexpr int SPLAT_LIST_SEG = 256 * SPLAT_LIST_PTS * SPLAT_LIST_ROUNDS;
+struct SplatGroup { int32_t first, n; };  // jobs [first, first + n) of the (pano-sorted) job table
+struct SplatPose { double R0, R1, R2, R3, tx, ty; uint32_t* kg_f; uint32_t* kg_c; int32_t posed, pad; };
+__global__ void __launch_bounds__(256) splat_list_kernel(SplatParams P, const SplatJob* __restrict__ jobs, const SplatGroup* __restrict__ groups,
+                                                         PanoLists L, uint32_t* __restrict__ keygrid_base, size_t keygrid_stride,
                                                          int32_t* __restrict__ counts /* [n_img][8] */) {
-    const SplatJob job = jobs[blockIdx.y];
-    const int n = L.hdr[job.pano_slot * 4 + 0];
-    const int i0 = blockIdx.x * (256 * SPLAT_LIST_PTS) + threadIdx.x;
-    if (blockIdx.x == 0 && threadIdx.x == 0 && counts != nullptr) {  // points inside the height band: known from the pre-pass
-        if (job.img_floor >= 0) counts[job.img_floor * 8 + 0] = L.hdr[job.pano_slot * 4 + 1];
-        if (job.img_ceil >= 0) counts[job.img_ceil * 8 + 0] = L.hdr[job.pano_slot * 4 + 2];
+    __shared__ SplatPose s_pose[SPLAT_GROUP];
+    __shared__ int s_box[SPLAT_GROUP][2];
+    const SplatGroup grp = groups[blockIdx.y];
+    const int slot = jobs[grp.first].pano_slot;
+    const int n = L.hdr[slot * 4 + 0];
+    if (blockIdx.x == 0 && threadIdx.x < grp.n && counts != nullptr) {  // points inside the height band: known from the pre-pass
+        const SplatJob job = jobs[grp.first + threadIdx.x];
+        if (job.img_floor >= 0) counts[job.img_floor * 8 + 0] = L.hdr[slot * 4 + 1];
+        if (job.img_ceil >= 0) counts[job.img_ceil * 8 + 0] = L.hdr[slot * 4 + 2];
     }
-    if (blockIdx.x * (256 * SPLAT_LIST_PTS) >= n) return;
-    const double tx = (double)__fmul_rn(job.t[0], 1.5f), ty = (double)__fmul_rn(job.t[1], 1.5f);
-    const double R0 = (double)job.R[0], R1 = (double)job.R[1], R2 = (double)job.R[2], R3 = (double)job.R[3];
-    const bool posed = job.posed != 0;
-    uint32_t* kg_f = job.img_floor >= 0 ? keygrid_base + (size_t)job.img_floor * keygrid_stride : nullptr;
-    uint32_t* kg_c = job.img_ceil >= 0 ? keygrid_base + (size_t)job.img_ceil * keygrid_stride : nullptr;
-    const size_t o0 = (size_t)job.pano_slot * L.cap;
-    int n_box_f = 0, n_box_c = 0;
-    double px[SPLAT_LIST_PTS], py[SPLAT_LIST_PTS]; uint32_t pm[SPLAT_LIST_PTS];
+    const int seg0 = blockIdx.x * SPLAT_LIST_SEG;
+    if (seg0 >= n) return;
+    if (threadIdx.x < grp.n) {
+        const SplatJob job = jobs[grp.first + threadIdx.x];
+        SplatPose q;
+        q.R0 = (double)job.R[0]; q.R1 = (double)job.R[1]; q.R2 = (double)job.R[2]; q.R3 = (double)job.R[3];
+        q.tx = (double)__fmul_rn(job.t[0], 1.5f); q.ty = (double)__fmul_rn(job.t[1], 1.5f);
+        q.kg_f = job.img_floor >= 0 ? keygrid_base + (size_t)job.img_floor * keygrid_stride : nullptr;
+        q.kg_c = job.img_ceil >= 0 ? keygrid_base + (size_t)job.img_ceil * keygrid_stride : nullptr;
+        q.posed = job.posed; q.pad = 0;
+        s_pose[threadIdx.x] = q;
+        s_box[threadIdx.x][0] = 0; s_box[threadIdx.x][1] = 0;
+    }
+    __syncthreads();
+    const size_t o0 = (size_t)slot * L.cap;
+#pragma unroll 1
+    for (int rd = 0; rd < SPLAT_LIST_ROUNDS; rd++) {
+        const int i0 = seg0 + rd * (256 * SPLAT_LIST_PTS) + threadIdx.x;
+        if (i0 - (int)threadIdx.x >= n) break;
+        double px[SPLAT_LIST_PTS], py[SPLAT_LIST_PTS]; uint32_t pm[SPLAT_LIST_PTS];
 #pragma unroll
-    for (int k = 0; k < SPLAT_LIST_PTS; k++) {
-        const int i = i0 + k * 256;
-        pm[k] = 0u;
-        if (i < n) { px[k] = __ldg(L.x + o0 + i); py[k] = __ldg(L.y + o0 + i); pm[k] = __ldg(L.meta + o0 + i); }
-    }
+        for (int k = 0; k < SPLAT_LIST_PTS; k++) {
+            const int i = i0 + k * 256;
+            pm[k] = 0u; px[k] = 0.0; py[k] = 0.0;
+            if (i < n) { px[k] = __ldg(L.x + o0 + i); py[k] = __ldg(L.y + o0 + i); pm[k] = __ldg(L.meta + o0 + i); }
+        }
+#pragma unroll 1
+        for (int j = 0; j < grp.n; j++) {
+            const SplatPose& q = s_pose[j];
+            uint32_t* kg_f = q.kg_f; uint32_t* kg_c = q.kg_c;
+            const bool posed = q.posed != 0;
+            int n_box_f = 0, n_box_c = 0;
 #pragma unroll
-    for (int k = 0; k < SPLAT_LIST_PTS; k++) {
-        const uint32_t m = pm[k];
-        const bool do_f = (m & PM_IN_A) && kg_f != nullptr, do_c = (m & PM_IN_B) && kg_c != nullptr;
-        if (!do_f && !do_c) continue;
-        double wx = px[k], wy = py[k];
-        if (posed) {
-            const double x2 = __dadd_rn(__fma_rn(py[k], R1, __dmul_rn(px[k], R0)), tx);
-            const double y2 = __dadd_rn(__fma_rn(py[k], R3, __dmul_rn(px[k], R2)), ty);
-            wx = x2; wy = y2;
+            for (int k = 0; k < SPLAT_LIST_PTS; k++) {
+                const uint32_t m = pm[k];
+                const bool do_f = (m & PM_IN_A) && kg_f != nullptr, do_c = (m & PM_IN_B) && kg_c != nullptr;
+                if (!do_f && !do_c) continue;
+                double wx = px[k], wy = py[k];
+                if (posed) {
+                    const double x2 = __dadd_rn(__fma_rn(py[k], q.R1, __dmul_rn(px[k], q.R0)), q.tx);
+                    const double y2 = __dadd_rn(__fma_rn(py[k], q.R3, __dmul_rn(px[k], q.R2)), q.ty);
+                    wx = x2; wy = y2;
+                }
+                int row, col;
+                if (!bbox_pixel(P, wx, wy, row, col)) continue;
+                n_box_f += do_f; n_box_c += do_c;
+                if (!(m & PM_HAS_SLICE)) continue;
+                const uint32_t key = ((((m >> PM_SLICE_SHIFT) & 3u) << KEY_IDX_BITS) | (m & PM_SRC_MASK)) + 1u;
+                const int pix = row * P.grid_w + col;
+                if (do_f) atomicMax(kg_f + pix, key);
+                if (do_c) atomicMax(kg_c + pix, key);
+            }
+            if (counts != nullptr) {
+                n_box_f = __reduce_add_sync(0xffffffffu, n_box_f); n_box_c = __reduce_add_sync(0xffffffffu, n_box_c);
+                if ((threadIdx.x & 31) == 0) {
+                    if (n_box_f) atomicAdd(&s_box[j][0], n_box_f);
+                    if (n_box_c) atomicAdd(&s_box[j][1], n_box_c);
+                }
+            }
         }
-        int row, col;
-        if (!bbox_pixel(P, wx, wy, row, col)) continue;
-        n_box_f += do_f; n_box_c += do_c;
-        if (!(m & PM_HAS_SLICE)) continue;
-        const uint32_t key = ((((m >> PM_SLICE_SHIFT) & 3u) << KEY_IDX_BITS) | (m & PM_SRC_MASK)) + 1u;
-        const int pix = row * P.grid_w + col;
-        if (do_f) atomicMax(kg_f + pix, key);
-        if (do_c) atomicMax(kg_c + pix, key);
     }
-    if (counts != nullptr) {
-        n_box_f = __reduce_add_sync(0xffffffffu, n_box_f); n_box_c = __reduce_add_sync(0xffffffffu, n_box_c);
-        if ((threadIdx.x & 31) == 0) {
-            if (job.img_floor >= 0 && n_box_f) atomicAdd(counts + job.img_floor * 8 + 1, n_box_f);
-            if (job.img_ceil >= 0 && n_box_c) atomicAdd(counts + job.img_ceil * 8 + 1, n_box_c);
-        }
+    __syncthreads();
+    if (counts != nullptr && threadIdx.x < grp.n) {
+        const SplatJob job = jobs[grp.first + threadIdx.x];
+        if (job.img_floor >= 0 && s_box[threadIdx.x][0]) atomicAdd(counts + job.img_floor * 8 + 1, s_box[threadIdx.x][0]);
+        if (job.img_ceil >= 0 && s_box[threadIdx.x][1]) atomicAdd(counts + job.img_ceil * 8 + 1, s_box[threadIdx.x][1]);
     }
 }
 
