@@ -2,7 +2,6 @@
 // See include/salve_bev.h for the contract of each function and the reference code it replaces.
 #include <math.h>
 #include <stdio.h>
-#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -75,11 +74,6 @@ struct salve_bev_ctx {
     // The key grid is all zero between calls: the sites stage zeroes the keys it consumes, so no chunk pays for a memset of
     // 1 MB per image.  Stage taps re-splat the image they look at from the job table of the last chunk.
     std::vector<SplatJob> last_jobs;
-    // hypothesis-independent half of the splat: per pano slot a compact list of the points inside either height band (k_splat.cuh)
-    PanoLists lists = {nullptr, nullptr, nullptr, nullptr, 0};
-    bool splat_fused = false;  // SALVE_BEV_SPLAT_FUSED=1: the single-kernel splat (developer switch for A/B timing)
-    uint64_t call_id = 0;                 // one per public render call: a pano's list is rebuilt once per call (nothing is kept across calls)
-    std::vector<uint64_t> slot_call;      // per pano slot: the call its list was built for
     // hypothesis-independent (un-posed pano 2) renders of the current call: max_panos x 2 surfaces
     uint8_t* cache_out = nullptr; int32_t* cache_counts = nullptr; int32_t* cache_status = nullptr;
     int32_t* d_dest = nullptr;           // per image of the chunk: destination (see ImageArgs::dest)
@@ -93,8 +87,6 @@ struct salve_bev_ctx {
     int32_t* counts = nullptr;
     int32_t* status = nullptr;
     SplatJob* d_jobs = nullptr;
-    SplatGroup* d_groups = nullptr; SplatGroup* h_groups[2] = {nullptr, nullptr};  // passes over the same pano, grouped (splat_list_kernel)
-    int n_groups = 0;
     const uint8_t** d_color_src = nullptr;
     uint8_t* out_store = nullptr;  // 2 x max_images images (double buffered), for the *_host variants
     // host-output pipeline: chunk k+1 renders while chunk k is copied device->host on copy_stream
@@ -167,7 +159,7 @@ extern "C" int salve_bev_ctx_create(const salve_bev_config* cfg, salve_bev_ctx**
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) FAIL(SALVE_BEV_E_NODEVICE, "no CUDA device: this library has no CPU fallback");
     if (cfg->device < 0 || cfg->device >= ndev) FAIL(SALVE_BEV_E_INVALID, "bad device ordinal");
     if (cfg->pano_h < 1 || cfg->pano_w < 4 || (cfg->pano_w & 3)) FAIL(SALVE_BEV_E_INVALID, "pano_w must be a positive multiple of 4");
-    if ((int64_t)cfg->pano_h * cfg->pano_w > ((int64_t)1 << 26)) FAIL(SALVE_BEV_E_INVALID, "pano too large (pano_h * pano_w <= 2^26)");
+    if ((int64_t)cfg->pano_h * cfg->pano_w > ((int64_t)1 << KEY_IDX_BITS)) FAIL(SALVE_BEV_E_INVALID, "pano too large");
     if (cfg->grid_h < 2 || cfg->grid_h > MAX_GRID_H || cfg->grid_w < 2 || cfg->grid_w > 2047 ||
         (int64_t)cfg->grid_h * cfg->grid_w > 800000)
         FAIL(SALVE_BEV_E_INVALID, "grid must satisfy 2 <= grid_h <= 1023, 2 <= grid_w <= 2047, grid_h*grid_w <= 800000");
@@ -197,12 +189,6 @@ static int ctx_init(salve_bev_ctx* c, const salve_bev_config* cfg) {
     ALLOC(c->pano_depth_store, P * H * W);
     ALLOC(c->d_depth_ptr, P);
     ALLOC(c->d_tables, 2 * H + 2 * W);
-    c->lists.cap = (H - 2 * (size_t)cfg->crop_rows) * W;
-    ALLOC(c->lists.x, P * c->lists.cap);
-    ALLOC(c->lists.y, P * c->lists.cap);
-    ALLOC(c->lists.meta, P * c->lists.cap);
-    ALLOC(c->lists.hdr, P * 4);
-    { const char* e = getenv("SALVE_BEV_SPLAT_FUSED"); c->splat_fused = e && e[0] == '1'; }
     ALLOC(c->keygrid, N * c->g_stride);
     CU(cudaMemset(c->keygrid, 0, sizeof(uint32_t) * N * c->g_stride));
     CU(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
@@ -236,7 +222,6 @@ static int ctx_init(salve_bev_ctx* c, const salve_bev_config* cfg) {
     ALLOC(c->counts, 2 * N * 8);
     ALLOC(c->status, 2 * N);
     ALLOC(c->d_jobs, N);
-    ALLOC(c->d_groups, N);
     ALLOC(c->d_color_src, N);
     ALLOC(c->out_store, 2 * N * c->img_bytes);
 #undef ALLOC
@@ -250,11 +235,9 @@ static int ctx_init(salve_bev_ctx* c, const salve_bev_config* cfg) {
         CU(cudaEventCreateWithFlags(&c->ev_copied[k], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&c->ev_staged[k], cudaEventDisableTiming));
         CU(cudaMallocHost((void**)&c->h_jobs[k], sizeof(SplatJob) * N));
-        CU(cudaMallocHost((void**)&c->h_groups[k], sizeof(SplatGroup) * N));
         CU(cudaMallocHost((void**)&c->h_src[k], sizeof(void*) * N));
         CU(cudaMallocHost((void**)&c->h_dest[k], sizeof(int32_t) * N));
     }
-    c->slot_call.assign(P, 0);
     c->h_rgb_ptr.assign(P, nullptr);
     c->h_depth_ptr.assign(P, nullptr);
     for (size_t s = 0; s < P; s++) {
@@ -286,8 +269,8 @@ extern "C" void salve_bev_ctx_destroy(salve_bev_ctx* c) {
     cudaSetDevice(c->cfg.device);
     cudaDeviceSynchronize();
     void* ptrs[] = {c->pano_rgb_store, c->pano_rgb2x_store, c->pano_depth_store, c->d_depth_ptr, c->d_tables, c->keygrid, c->color, c->occ, c->nonempty,
-                    c->keep, c->tmpbits, c->wprefix, c->tris, c->owner, c->list0, c->list1, c->cand, c->qlist, c->clist, c->qres, c->planes, c->rowarr, c->hdr, c->lists.x, c->lists.y, c->lists.meta, c->lists.hdr, c->work_counter, c->d_order, c->cache_out, c->cache_counts, c->cache_status, c->d_dest, c->headers, c->counts,
-                    c->status, c->d_jobs, c->d_groups, c->d_color_src, c->out_store};
+                    c->keep, c->tmpbits, c->wprefix, c->tris, c->owner, c->list0, c->list1, c->cand, c->qlist, c->clist, c->qres, c->planes, c->rowarr, c->hdr, c->work_counter, c->d_order, c->cache_out, c->cache_counts, c->cache_status, c->d_dest, c->headers, c->counts,
+                    c->status, c->d_jobs, c->d_color_src, c->out_store};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < N_TMP; i++) if (c->tmp[i]) cudaFree(c->tmp[i]);
     for (cudaEvent_t e : c->events) cudaEventDestroy(e);
@@ -296,7 +279,6 @@ extern "C" void salve_bev_ctx_destroy(salve_bev_ctx* c) {
         if (c->ev_copied[k]) cudaEventDestroy(c->ev_copied[k]);
         if (c->ev_staged[k]) cudaEventDestroy(c->ev_staged[k]);
         if (c->h_jobs[k]) cudaFreeHost(c->h_jobs[k]);
-        if (c->h_groups[k]) cudaFreeHost(c->h_groups[k]);
         if (c->h_src[k]) cudaFreeHost(c->h_src[k]);
         if (c->h_dest[k]) cudaFreeHost(c->h_dest[k]);
     }
@@ -532,41 +514,6 @@ static int run_mesh_stages(salve_bev_ctx* c, const GridParams& G, const uint32_t
     return SALVE_BEV_OK;
 }
 
-// Hypothesis-independent half of the splat for the given pano slots (once per call and pano): the lists splat_list_kernel reads.
-static int prepass_slots(salve_bev_ctx* c, const std::vector<int32_t>& slots, cudaStream_t st) {
-    if (c->splat_fused || slots.empty()) return SALVE_BEV_OK;
-    int rc = sync_ptr_tables(c, st); if (rc) return rc;
-    SplatParams P = make_splat_params(c);
-    const int rows = P.H - 2 * P.crop_rows;
-    for (size_t s0 = 0; s0 < slots.size(); s0 += 63) {
-        SlotList S;
-        S.n = (int32_t)std::min<size_t>(63, slots.size() - s0);
-        for (int k = 0; k < S.n; k++) {
-            S.slot[k] = slots[s0 + k];
-            CU(cudaMemsetAsync(c->lists.hdr + 4 * S.slot[k], 0, sizeof(int32_t) * 4, st));
-        }
-        prepass_pano_kernel<<<dim3((unsigned)((rows * P.W + 1023) / 1024), (unsigned)S.n), 256, 0, st>>>(P, S, c->lists);
-        c->launches++;
-        CU(cudaGetLastError());
-    }
-    return SALVE_BEV_OK;
-}
-static int launch_splat(salve_bev_ctx* c, const SplatJob* d_jobs, size_t n_jobs, const SplatGroup* d_groups, int n_groups, int32_t* dev_counts, cudaStream_t st) {
-    SplatParams P = make_splat_params(c);
-    const int rows = P.H - 2 * P.crop_rows;
-    if (c->splat_fused) {
-        P.rows_per_thread = splat_rows_for(n_jobs);
-        dim3 grid((unsigned)(((rows + P.rows_per_thread - 1) / P.rows_per_thread) * ((P.W + 1023) >> 10)), (unsigned)n_jobs);
-        splat_pano_kernel<<<grid, 256, 0, st>>>(P, d_jobs, c->keygrid, c->g_stride, dev_counts);
-    } else {
-        dim3 grid((unsigned)((c->lists.cap + SPLAT_LIST_SEG - 1) / SPLAT_LIST_SEG), (unsigned)n_groups);
-        splat_list_kernel<<<grid, 256, 0, st>>>(P, d_jobs, d_groups, c->lists, c->keygrid, c->g_stride, dev_counts);
-    }
-    c->launches++;
-    CU(cudaGetLastError());
-    return SALVE_BEV_OK;
-}
-
 // One chunk of pano-sourced images.  jobs / color slots are host arrays.
 static int render_chunk(salve_bev_ctx* c, int n_img, const std::vector<SplatJob>& jobs, const std::vector<int>& img_slot, uint8_t* dev_out,
                         int32_t* dev_counts, int32_t* dev_status, cudaStream_t st, const std::vector<int32_t>* dest = nullptr,
@@ -580,18 +527,8 @@ static int render_chunk(salve_bev_ctx* c, int n_img, const std::vector<SplatJob>
         if (img_slot[i] < 0 || img_slot[i] >= c->cfg.max_panos) FAIL(SALVE_BEV_E_CAPACITY, "pano slot out of range");
         c->h_src[sp][i] = c->h_rgb_ptr[img_slot[i]];
     }
-    // jobs of one pano next to each other: its point list stays in L2 from one pass to the next (the image indices travel with the job)
-    std::vector<SplatJob> sorted_jobs(jobs);
-    std::stable_sort(sorted_jobs.begin(), sorted_jobs.end(), [](const SplatJob& a, const SplatJob& b) { return a.pano_slot < b.pano_slot; });
-    memcpy(c->h_jobs[sp], sorted_jobs.data(), sizeof(SplatJob) * sorted_jobs.size());
+    memcpy(c->h_jobs[sp], jobs.data(), sizeof(SplatJob) * jobs.size());
     CU(cudaMemcpyAsync(c->d_jobs, c->h_jobs[sp], sizeof(SplatJob) * jobs.size(), cudaMemcpyHostToDevice, st));
-    c->n_groups = 0;
-    for (size_t j = 0; j < sorted_jobs.size(); j++) {
-        SplatGroup* g = c->h_groups[sp];
-        if (c->n_groups && g[c->n_groups - 1].n < SPLAT_GROUP && sorted_jobs[g[c->n_groups - 1].first].pano_slot == sorted_jobs[j].pano_slot) g[c->n_groups - 1].n++;
-        else { g[c->n_groups].first = (int32_t)j; g[c->n_groups].n = 1; c->n_groups++; }
-    }
-    CU(cudaMemcpyAsync(c->d_groups, c->h_groups[sp], sizeof(SplatGroup) * c->n_groups, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(c->d_color_src, c->h_src[sp], sizeof(void*) * n_img, cudaMemcpyHostToDevice, st));
     if (dest) {
         memcpy(c->h_dest[sp], dest->data(), sizeof(int32_t) * n_img);
@@ -601,17 +538,17 @@ static int render_chunk(salve_bev_ctx* c, int n_img, const std::vector<SplatJob>
     if (!dev_counts) dev_counts = c->counts;
     rc = stage_event(c, st); if (rc) return rc;
     CU(cudaMemsetAsync(dev_counts, 0, sizeof(int32_t) * 8 * n_img, st));
-    {   // pano lists this chunk needs and this call has not built yet
-        std::vector<int32_t> need;
-        for (const SplatJob& j : jobs)
-            if (c->slot_call[j.pano_slot] != c->call_id) { c->slot_call[j.pano_slot] = c->call_id; need.push_back(j.pano_slot); }
-        rc = prepass_slots(c, need, st); if (rc) return rc;
-    }
-    rc = launch_splat(c, c->d_jobs, jobs.size(), c->d_groups, c->n_groups, dev_counts, st); if (rc) return rc;
+    SplatParams P = make_splat_params(c);
+    const int rows = P.H - 2 * P.crop_rows;
+    P.rows_per_thread = splat_rows_for(jobs.size());
+    dim3 grid((unsigned)(((rows + P.rows_per_thread - 1) / P.rows_per_thread) * ((P.W + 1023) >> 10)), (unsigned)jobs.size());
+    splat_pano_kernel<<<grid, 256, 0, st>>>(P, c->d_jobs, c->keygrid, c->g_stride, dev_counts);
+    c->launches++;
+    CU(cudaGetLastError());
     rc = stage_event(c, st); if (rc) return rc;
     c->last_chunk_images = n_img;
     c->last_counts = dev_counts;
-    c->last_jobs = sorted_jobs;
+    c->last_jobs = jobs;
     return run_image_stage(c, n_img, c->G, c->keygrid, c->d_color_src, dev_out, dev_counts, dev_status, 0, 0, nullptr, nullptr, st,
                            dest ? c->d_dest : nullptr, counts_out, true, true);
 }
@@ -836,7 +773,7 @@ static int render_hyp_impl(salve_bev_ctx* c, int32_t n_hyp, const int32_t* p1, c
     const int hyp_per_chunk = c->cfg.max_images / per_hyp;
     if (hyp_per_chunk < 1) FAIL(SALVE_BEV_E_CAPACITY, "max_images too small for one hypothesis");
     CU(cudaSetDevice(c->cfg.device));
-    c->events_used = 0; c->call_id++;
+    c->events_used = 0;
     for (int h = 0; h < n_hyp; h++)
         if (p1[h] < 0 || p1[h] >= c->cfg.max_panos || p2[h] < 0 || p2[h] >= c->cfg.max_panos) FAIL(SALVE_BEV_E_CAPACITY, "pano slot out of range");
     if (c->dedup_unposed && n_hyp > 1) {
@@ -927,7 +864,7 @@ static int render_compact(salve_bev_ctx* c, int32_t n_hyp, const int32_t* p1, co
     for (int h = 0; h < n_hyp; h++)
         if (p1[h] < 0 || p1[h] >= c->cfg.max_panos || p2[h] < 0 || p2[h] >= c->cfg.max_panos) FAIL(SALVE_BEV_E_CAPACITY, "pano slot out of range");
     CU(cudaSetDevice(c->cfg.device));
-    c->events_used = 0; c->call_id++;
+    c->events_used = 0;
     HypPlan plan;
     make_plan(n_hyp, p2, c->cfg.max_panos, plan);
     *n_unique = (int32_t)plan.uniq.size();
@@ -1029,7 +966,7 @@ extern "C" int salve_bev_render_images_host(salve_bev_ctx* c, int32_t n_img, con
     if (!c || !slot || !surface || !posed || !R || !t || !host_out) FAIL(SALVE_BEV_E_INVALID, "null argument");
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaSetDevice(c->cfg.device));
-    c->events_used = 0; c->call_id++;
+    c->events_used = 0;
     std::vector<SplatJob> jobs;
     std::vector<int> slots;
     for (int i0 = 0; i0 < n_img; i0 += c->cfg.max_images) {
@@ -1102,7 +1039,7 @@ extern "C" int salve_bev_render_cloud_host(salve_bev_ctx* c, const double* host_
     if (n < 0 || n >= ((int64_t)1 << KEY_IDX_BITS)) FAIL(SALVE_BEV_E_CAPACITY, "cloud too large (n < 2^29)");
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaSetDevice(c->cfg.device));
-    c->events_used = 0; c->call_id++;
+    c->events_used = 0;
     void *dc, *drgb;
     int rc = tmp_get(c, 0, sizeof(double) * 6 * (size_t)std::max<int64_t>(n, 1), &dc); if (rc) return rc;
     rc = tmp_get(c, 3, 3 * (size_t)std::max<int64_t>(n, 1), &drgb); if (rc) return rc;
@@ -1191,7 +1128,7 @@ extern "C" int salve_bev_interp_dense(salve_bev_ctx* c, const int64_t* host_xy, 
     if (n < 0 || n > ((int64_t)1 << 28)) FAIL(SALVE_BEV_E_CAPACITY, "too many points");
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaSetDevice(c->cfg.device));
-    c->events_used = 0; c->call_id++;
+    c->events_used = 0;
     void *dxy, *dval, *drgb, *derr, *dhull = nullptr;
     int rc;
     if ((rc = tmp_get(c, 0, sizeof(int64_t) * 2 * (size_t)std::max<int64_t>(n, 1), &dxy))) return rc;
@@ -1292,14 +1229,14 @@ extern "C" int salve_bev_tap(salve_bev_ctx* c, int32_t image, int32_t what, void
         return SALVE_BEV_OK;
     };
     int rc = clear_slots(); if (rc) return rc;
-    if ((rc = prepass_slots(c, std::vector<int32_t>(1, J.pano_slot), st))) return rc;
     {
-        void* dg;
-        if ((rc = tmp_get(c, 5, sizeof(SplatGroup), &dg))) return rc;
-        const SplatGroup one = {job, 1};
-        CU(cudaMemcpyAsync(dg, &one, sizeof(one), cudaMemcpyHostToDevice, st));
-        CU(cudaStreamSynchronize(st));  // `one` is a local
-        if ((rc = launch_splat(c, c->splat_fused ? c->d_jobs + job : c->d_jobs, 1, (const SplatGroup*)dg, 1, nullptr, st))) return rc;
+        SplatParams P = make_splat_params(c);
+        const int rows = P.H - 2 * P.crop_rows;
+        P.rows_per_thread = splat_rows_for(1);
+        dim3 grid((unsigned)(((rows + P.rows_per_thread - 1) / P.rows_per_thread) * ((P.W + 1023) >> 10)), 1u);
+        splat_pano_kernel<<<grid, 256, 0, st>>>(P, c->d_jobs + job, c->keygrid, c->g_stride, nullptr);
+        c->launches++;
+        CU(cudaGetLastError());
     }
     // ... on a private copy of the image's counters
     void* dcnt;

@@ -184,179 +184,6 @@ __global__ void __launch_bounds__(256, SPLAT_CTAS) splat_pano_kernel(SplatParams
     }
 }
 
-// ---- the same splat with the hypothesis-independent half hoisted ------------------------------------------------------------
-// Everything up to the ZInD frame depends on the pano only: depth scale, sphere factors, height bands, z-slice, rotmat2d(-90).
-// A building's 640 hypotheses use 40 panos, so that half was computed 16 times per pano.  prepass_pano_kernel computes it once per
-// pano and call and leaves the survivors of either band as a compact list (x1, y1 float64 in the ZInD frame + a packed word);
-// splat_list_kernel then needs, per point and hypothesis, only the pose (2 FMA + 2 MUL + 2 ADD), the box test, two rint and
-// the atomicMax.  Lists are read through L2 (a pano's list, 20 B x ~280 k points, is reused by all its passes).
-constexpr uint32_t PM_SRC_MASK = (1u << 26) - 1;  // pano pixel index (H * W <= 2^26)
-constexpr int PM_SLICE_SHIFT = 26;                // z-slice 0..3
-constexpr uint32_t PM_HAS_SLICE = 1u << 28;       // z inside [-2, 2): the point takes part in the z-order rule
-constexpr uint32_t PM_IN_A = 1u << 29;            // inside band A ("floor")
-constexpr uint32_t PM_IN_B = 1u << 30;            // inside band B ("ceiling")
-
-struct PanoLists {
-    double* x;        // [max_panos][cap] ZInD-frame x of the survivors
-    double* y;
-    uint32_t* meta;   // [max_panos][cap]
-    int32_t* hdr;     // [max_panos][4]: survivors, of which in band A, in band B
-    size_t cap;       // entries per pano slot ((H - 2 crop) * W)
-};
-struct SlotList { int32_t n; int32_t slot[63]; };
-
-// grid = (ceil(rows * W / 1024), n_slots), block = 256; one thread = 4 consecutive pano pixels (one 8-byte depth load)
-__global__ void __launch_bounds__(256) prepass_pano_kernel(SplatParams P, SlotList S, PanoLists L) {
-    const int slot = S.slot[blockIdx.y];
-    const int rows = P.H - 2 * P.crop_rows;
-    const int i0 = (blockIdx.x * 256 + threadIdx.x) * 4;  // index within the cropped rows; W is a multiple of 4: one row per thread
-    const int lane = threadIdx.x & 31;
-    double x1[4], y1[4]; uint32_t meta[4];
-    uint32_t keep = 0u;  // which of the 4 pixels survive
-    int n_a = 0, n_b = 0;
-    if (i0 < rows * P.W) {
-        const int rr = i0 / P.W, u0 = i0 - rr * P.W, v = P.crop_rows + rr;
-        const uint2 raw = __ldg(reinterpret_cast<const uint2*>(P.depth[slot] + (size_t)v * P.W + u0));
-        const uint32_t d16[4] = {raw.x & 0xFFFFu, raw.x >> 16, raw.y & 0xFFFFu, raw.y >> 16};
-        const double cphi = __ldg(P.cos_phi + v), sz = __ldg(P.neg_sin_phi + v);
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const double d = (double)__fmul_rn((float)d16[k], P.depth_scale);
-            const double z = __dmul_rn(d, sz);
-            const bool in_a = (z > P.a_lo && z <= P.a_hi), in_b = (z > P.b_lo && z <= P.b_hi);
-            if (!in_a && !in_b) continue;
-            const double x = __dmul_rn(d, __dmul_rn(cphi, __ldg(P.cos_theta + u0 + k)));
-            const double y = __dmul_rn(d, __dmul_rn(cphi, __ldg(P.sin_theta + u0 + k)));
-            x1[k] = __dadd_rn(y, __dmul_rn(x, C90));   // fma(y, 1.0, round(x*c90))
-            y1[k] = __fma_rn(y, C90, -x);              // fma(y, c90, round(x*-1.0))
-            const int sl = z_slice4(z);
-            meta[k] = (uint32_t)(v * P.W + u0 + k) | (sl >= 0 ? ((uint32_t)sl << PM_SLICE_SHIFT) | PM_HAS_SLICE : 0u) | (in_a ? PM_IN_A : 0u) | (in_b ? PM_IN_B : 0u);
-            n_a += in_a; n_b += in_b;
-            keep |= 1u << k;
-        }
-    }
-    const int cnt = __popc(keep);
-    // warp-aggregated append, pano raster order kept within the warp (neighbouring pixels stay neighbours in the list)
-    int incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    n_a = __reduce_add_sync(0xffffffffu, n_a); n_b = __reduce_add_sync(0xffffffffu, n_b);
-    if (total == 0) return;
-    int base = 0;
-    if (lane == 0) {
-        base = atomicAdd(L.hdr + slot * 4 + 0, total);
-        if (n_a) atomicAdd(L.hdr + slot * 4 + 1, n_a);
-        if (n_b) atomicAdd(L.hdr + slot * 4 + 2, n_b);
-    }
-    base = __shfl_sync(0xffffffffu, base, 0) + incl - cnt;
-    const size_t o0 = (size_t)slot * L.cap + base;
-#pragma unroll
-    for (int k = 0; k < 4; k++)
-        if ((keep >> k) & 1u) {
-            const size_t o = o0 + __popc(keep & ((1u << k) - 1u));
-            L.x[o] = x1[k]; L.y[o] = y1[k]; L.meta[o] = meta[k];
-        }
-}
-
-// grid = (ceil(cap / SPLAT_LIST_SEG), n_groups), block = 256.  A group = up to SPLAT_GROUP jobs (passes) over the SAME pano: a CTA
-// walks a segment of SPLAT_LIST_SEG consecutive list entries, SPLAT_LIST_PTS loads per thread in flight at a time, and applies every
-// pose of the group to the points it holds in registers -- the list is read once per group instead of once per hypothesis.
-#ifndef SPLAT_LIST_PTS
-#define SPLAT_LIST_PTS 4
-#endif
-#ifndef SPLAT_LIST_ROUNDS
-#define SPLAT_LIST_ROUNDS 4
-#endif
-#ifndef SPLAT_GROUP_DEF
-#define SPLAT_GROUP_DEF 8
-#endif
-constexpr int SPLAT_GROUP = SPLAT_GROUP_DEF;
-constexpr int SPLAT_LIST_SEG = 256 * SPLAT_LIST_PTS * SPLAT_LIST_ROUNDS;
-struct SplatGroup { int32_t first, n; };  // jobs [first, first + n) of the (pano-sorted) job table
-struct SplatPose { double R0, R1, R2, R3, tx, ty; uint32_t* kg_f; uint32_t* kg_c; int32_t posed, pad; };
-__global__ void __launch_bounds__(256) splat_list_kernel(SplatParams P, const SplatJob* __restrict__ jobs, const SplatGroup* __restrict__ groups,
-                                                         PanoLists L, uint32_t* __restrict__ keygrid_base, size_t keygrid_stride,
-                                                         int32_t* __restrict__ counts /* [n_img][8] */) {
-    __shared__ SplatPose s_pose[SPLAT_GROUP];
-    __shared__ int s_box[SPLAT_GROUP][2];
-    const SplatGroup grp = groups[blockIdx.y];
-    const int slot = jobs[grp.first].pano_slot;
-    const int n = L.hdr[slot * 4 + 0];
-    if (blockIdx.x == 0 && threadIdx.x < grp.n && counts != nullptr) {  // points inside the height band: known from the pre-pass
-        const SplatJob job = jobs[grp.first + threadIdx.x];
-        if (job.img_floor >= 0) counts[job.img_floor * 8 + 0] = L.hdr[slot * 4 + 1];
-        if (job.img_ceil >= 0) counts[job.img_ceil * 8 + 0] = L.hdr[slot * 4 + 2];
-    }
-    const int seg0 = blockIdx.x * SPLAT_LIST_SEG;
-    if (seg0 >= n) return;
-    if (threadIdx.x < grp.n) {
-        const SplatJob job = jobs[grp.first + threadIdx.x];
-        SplatPose q;
-        q.R0 = (double)job.R[0]; q.R1 = (double)job.R[1]; q.R2 = (double)job.R[2]; q.R3 = (double)job.R[3];
-        q.tx = (double)__fmul_rn(job.t[0], 1.5f); q.ty = (double)__fmul_rn(job.t[1], 1.5f);
-        q.kg_f = job.img_floor >= 0 ? keygrid_base + (size_t)job.img_floor * keygrid_stride : nullptr;
-        q.kg_c = job.img_ceil >= 0 ? keygrid_base + (size_t)job.img_ceil * keygrid_stride : nullptr;
-        q.posed = job.posed; q.pad = 0;
-        s_pose[threadIdx.x] = q;
-        s_box[threadIdx.x][0] = 0; s_box[threadIdx.x][1] = 0;
-    }
-    __syncthreads();
-    const size_t o0 = (size_t)slot * L.cap;
-#pragma unroll 1
-    for (int rd = 0; rd < SPLAT_LIST_ROUNDS; rd++) {
-        const int i0 = seg0 + rd * (256 * SPLAT_LIST_PTS) + threadIdx.x;
-        if (i0 - (int)threadIdx.x >= n) break;
-        double px[SPLAT_LIST_PTS], py[SPLAT_LIST_PTS]; uint32_t pm[SPLAT_LIST_PTS];
-#pragma unroll
-        for (int k = 0; k < SPLAT_LIST_PTS; k++) {
-            const int i = i0 + k * 256;
-            pm[k] = 0u; px[k] = 0.0; py[k] = 0.0;
-            if (i < n) { px[k] = __ldg(L.x + o0 + i); py[k] = __ldg(L.y + o0 + i); pm[k] = __ldg(L.meta + o0 + i); }
-        }
-#pragma unroll 1
-        for (int j = 0; j < grp.n; j++) {
-            const SplatPose& q = s_pose[j];
-            uint32_t* kg_f = q.kg_f; uint32_t* kg_c = q.kg_c;
-            const bool posed = q.posed != 0;
-            int n_box_f = 0, n_box_c = 0;
-#pragma unroll
-            for (int k = 0; k < SPLAT_LIST_PTS; k++) {
-                const uint32_t m = pm[k];
-                const bool do_f = (m & PM_IN_A) && kg_f != nullptr, do_c = (m & PM_IN_B) && kg_c != nullptr;
-                if (!do_f && !do_c) continue;
-                double wx = px[k], wy = py[k];
-                if (posed) {
-                    const double x2 = __dadd_rn(__fma_rn(py[k], q.R1, __dmul_rn(px[k], q.R0)), q.tx);
-                    const double y2 = __dadd_rn(__fma_rn(py[k], q.R3, __dmul_rn(px[k], q.R2)), q.ty);
-                    wx = x2; wy = y2;
-                }
-                int row, col;
-                if (!bbox_pixel(P, wx, wy, row, col)) continue;
-                n_box_f += do_f; n_box_c += do_c;
-                if (!(m & PM_HAS_SLICE)) continue;
-                const uint32_t key = ((((m >> PM_SLICE_SHIFT) & 3u) << KEY_IDX_BITS) | (m & PM_SRC_MASK)) + 1u;
-                const int pix = row * P.grid_w + col;
-                if (do_f) atomicMax(kg_f + pix, key);
-                if (do_c) atomicMax(kg_c + pix, key);
-            }
-            if (counts != nullptr) {
-                n_box_f = __reduce_add_sync(0xffffffffu, n_box_f); n_box_c = __reduce_add_sync(0xffffffffu, n_box_c);
-                if ((threadIdx.x & 31) == 0) {
-                    if (n_box_f) atomicAdd(&s_box[j][0], n_box_f);
-                    if (n_box_c) atomicAdd(&s_box[j][1], n_box_c);
-                }
-            }
-        }
-    }
-    __syncthreads();
-    if (counts != nullptr && threadIdx.x < grp.n) {
-        const SplatJob job = jobs[grp.first + threadIdx.x];
-        if (job.img_floor >= 0 && s_box[threadIdx.x][0]) atomicAdd(counts + job.img_floor * 8 + 1, s_box[threadIdx.x][0]);
-        if (job.img_ceil >= 0 && s_box[threadIdx.x][1]) atomicAdd(counts + job.img_ceil * 8 + 1, s_box[threadIdx.x][1]);
-    }
-}
-
 // ---- arbitrary cloud (render_bev_image on an (N,6) float64 array) -----------------------------
 // Also converts the cloud's colours to the u8 triple the reference stores in the sparse image
 // (rgb*255 truncated to uint8, bev_rendering_utils.py:266,307-308).
