@@ -233,6 +233,20 @@ int salve_bev_remove_hallucinated(salve_bev_ctx* ctx, const uint8_t* host_sparse
                                   int32_t K, uint8_t* host_out, void* stream);
 
 /*
+ * Layout modality: room polygon + window / door / opening strokes rasterised into grid_h x grid_w x 3 images.
+ * Replaces the cv2 calls behind rasterize_single_layout / rasterize_room_layout_pair (bev_rendering_utils.py:48-251): cv2.fillPoly of
+ * the room polygon (bit-identical for polygons inside the image), cv2.line(LINE_AA, thickness) strokes (identical in the stroke's
+ * interior, toleranced on its anti-aliased rim), np.flipud.
+ *   host_desc    : int32 words, one descriptor per image: [n_poly, n_strokes, poly_rgb (r | g<<8 | b<<16), flip,
+ *                  n_poly x (x, y) pixel vertices (n_poly <= 128), n_strokes x (x0, y0, x1, y1, rgb, thickness)]
+ *   host_offsets : n_img + 1 word offsets of the descriptors in host_desc
+ *   host_init    : n_img initial images to draw onto (may be NULL: black)
+ *   host_out     : n_img x grid_h x grid_w x 3 uint8
+ */
+int salve_bev_rasterize_layouts_host(salve_bev_ctx* ctx, int32_t n_img, const int32_t* host_desc, const int64_t* host_offsets,
+                                     const uint8_t* host_init, uint8_t* host_out, void* stream);
+
+/*
  * Stage taps of the most recent render call (parity tests).  image = index within the last internal chunk (for a call that
  * was de-duplicated the chunks hold the unique un-posed images first, then the posed ones).
  * what: see SALVE_BEV_TAP_*.  host_buf must be large enough (sizes in comments, g = grid_h*grid_w,

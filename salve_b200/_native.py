@@ -59,6 +59,7 @@ SYMBOLS = {
     "salve_bev_render_hypotheses_compact": (ctypes.c_int, [c_vp, ctypes.c_int32, c_i32p, c_i32p, c_f32p, c_f32p, ctypes.c_uint32, c_vp, c_vp, c_i32p, c_i32p, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "salve_bev_render_hypotheses_compact_host": (ctypes.c_int, [c_vp, ctypes.c_int32, c_i32p, c_i32p, c_f32p, c_f32p, ctypes.c_uint32, c_vp, c_vp, c_i32p, c_i32p, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "salve_bev_verifier_preprocess": (ctypes.c_int, [c_vp, ctypes.c_int32, c_vp, ctypes.c_int32, ctypes.c_int32, c_vp, c_vp]),
+    "salve_bev_rasterize_layouts_host": (ctypes.c_int, [c_vp, ctypes.c_int32, c_i32p, c_i64p, c_vp, c_vp, c_vp]),
     "salve_bev_set_dedup_unposed": (ctypes.c_int, [c_vp, ctypes.c_int32]),
     "salve_bev_render_images_host": (ctypes.c_int, [c_vp, ctypes.c_int32, c_i32p, c_i32p, c_i32p, c_f32p, c_f32p, c_vp, c_vp, c_vp, c_vp]),
     "salve_bev_set_bands": (ctypes.c_int, [c_vp, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double]),

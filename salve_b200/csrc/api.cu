@@ -11,6 +11,7 @@
 #include "bev_common.cuh"
 #include "k_flip.cuh"
 #include "k_image.cuh"
+#include "k_layout.cuh"
 #include "k_preprocess.cuh"
 #include "k_raster.cuh"
 #include "k_sites.cuh"
@@ -951,6 +952,42 @@ extern "C" int salve_bev_verifier_preprocess(salve_bev_ctx* c, int32_t n, const 
     verifier_preprocess_kernel<<<grid, 256, 0, st>>>(A);
     c->launches++;
     CU(cudaGetLastError());
+    return SALVE_BEV_OK;
+}
+
+extern "C" int salve_bev_rasterize_layouts_host(salve_bev_ctx* c, int32_t n_img, const int32_t* host_desc, const int64_t* host_offsets,
+                                                const uint8_t* host_init, uint8_t* host_out, void* stream) {
+    if (!c || !host_desc || !host_offsets || !host_out) FAIL(SALVE_BEV_E_INVALID, "null argument");
+    if (n_img < 0) FAIL(SALVE_BEV_E_INVALID, "negative n_img");
+    if (n_img == 0) return SALVE_BEV_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(c->cfg.device));
+    const long long n_words = host_offsets[n_img];
+    for (int i = 0; i < n_img; i++) {
+        const long long o = host_offsets[i];
+        if (o < 0 || o + LD_HDR > host_offsets[i + 1] || host_offsets[i + 1] > n_words) FAIL(SALVE_BEV_E_INVALID, "bad descriptor offsets");
+        const int32_t np = host_desc[o + LD_NPOLY], ns = host_desc[o + LD_NSEG];
+        if (np < 0 || np > LAYOUT_MAX_POLY || ns < 0 || o + LD_HDR + 2LL * np + 6LL * ns != host_offsets[i + 1])
+            FAIL(SALVE_BEV_E_CAPACITY, "layout descriptor: at most 128 polygon vertices; sizes must match the offsets");
+    }
+    const size_t ib = c->img_bytes;
+    void *dd, *doff, *dout, *dinit = nullptr;
+    int rc;
+    if ((rc = tmp_get(c, 0, sizeof(int32_t) * (size_t)n_words, &dd))) return rc;
+    if ((rc = tmp_get(c, 1, sizeof(long long) * (size_t)(n_img + 1), &doff))) return rc;
+    if ((rc = tmp_get(c, 2, ib * n_img, &dout))) return rc;
+    if (host_init && (rc = tmp_get(c, 3, ib * n_img, &dinit))) return rc;
+    CU(cudaMemcpyAsync(dd, host_desc, sizeof(int32_t) * (size_t)n_words, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(doff, host_offsets, sizeof(long long) * (size_t)(n_img + 1), cudaMemcpyHostToDevice, st));
+    if (host_init) CU(cudaMemcpyAsync(dinit, host_init, ib * n_img, cudaMemcpyHostToDevice, st));
+    LayoutArgs A;
+    A.desc = (const int32_t*)dd; A.offset = (const long long*)doff; A.out = (uint8_t*)dout; A.out_stride = ib;
+    A.init = (const uint8_t*)dinit; A.h = c->G.grid_h; A.w = c->G.grid_w;
+    layout_raster_kernel<<<n_img, LAYOUT_NT, 0, st>>>(A);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(host_out, dout, ib * n_img, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     return SALVE_BEV_OK;
 }
 

@@ -84,7 +84,8 @@ def render_building_floor_pairs(
     `multiprocess_building_panos` / `num_processes` are accepted and ignored (the batch replaces the pool).
     The floor is rendered in batches of `batch_hypotheses`.  Returns counters {hypotheses, rendered, skipped_existing, skipped_empty, files_written}."""
     if "layout" in render_modalities:
-        raise NotImplementedError("the layout modality is outside this build's scope (SURVEY.md section 8f, row 4)")
+        raise NotImplementedError("the batched driver renders texture maps; for the layout modality call generate_texture_maps_for_pair with a "
+                                  "floor pose graph (rasterize_room_layout_pair), as scripts/render_dataset_bev.py:64-117 does")
     stats = dict(hypotheses=0, rendered=0, skipped_existing=0, skipped_empty=0, files_written=0)
     if "rgb_texture" not in render_modalities:
         return stats

@@ -289,6 +289,33 @@ class BevRenderer:
         nat.check(self._lib.salve_bev_verifier_preprocess(self._h, src.shape[0], src.ctypes.data, int(resize_hw), int(crop_hw), _vp(dev_out), stream or None))
 
     @_locked
+    def rasterize_layouts(self, layouts, init: Optional[np.ndarray] = None, stream: int = 0) -> np.ndarray:
+        """Layout modality.  layouts: one dict per image with `polygon` ((n, 2) integer pixel vertices or None), `polygon_rgb`,
+        `strokes` (list of (x0, y0, x1, y1, (r, g, b), thickness)) and `flip`.  Returns (n, gh, gw, 3) uint8."""
+        words, offs = [], [0]
+        for L in layouts:
+            poly = np.zeros((0, 2), np.int64) if L.get("polygon") is None else np.asarray(L["polygon"], np.int64).reshape(-1, 2)
+            r, g, b = (int(v) & 0xFF for v in L.get("polygon_rgb", (255, 255, 255)))
+            strokes = L.get("strokes", [])
+            w = [poly.shape[0], len(strokes), r | (g << 8) | (b << 16), int(bool(L.get("flip", False)))]
+            w += [int(v) for v in np.clip(poly, -(1 << 20), 1 << 20).reshape(-1)]
+            for x0, y0, x1, y1, col, th in strokes:
+                cr, cg, cb = (int(v) & 0xFF for v in col)
+                w += [int(np.clip(v, -(1 << 20), 1 << 20)) for v in (x0, y0, x1, y1)] + [cr | (cg << 8) | (cb << 16), int(th)]
+            words += w
+            offs.append(len(words))
+        desc = np.ascontiguousarray(words, np.int32)
+        off = np.ascontiguousarray(offs, np.int64)
+        n = len(layouts)
+        out = np.empty((n,) + self.img_shape, np.uint8)
+        if init is not None:
+            init = np.ascontiguousarray(init, np.uint8)
+            assert init.shape == out.shape
+        nat.check(self._lib.salve_bev_rasterize_layouts_host(self._h, n, _ptr(desc, ctypes.c_int32), _ptr(off, ctypes.c_int64),
+                                                              None if init is None else init.ctypes.data, out.ctypes.data, stream or None))
+        return out
+
+    @_locked
     def set_dedup_unposed(self, on: bool) -> None:
         nat.check(self._lib.salve_bev_set_dedup_unposed(self._h, int(on)))
 

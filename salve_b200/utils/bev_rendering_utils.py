@@ -1,10 +1,9 @@
-"""BEV texture-map rendering entry points (mirror of the reference's
-salve/utils/bev_rendering_utils.py texture functions, :38-45 and :254-663), backed by
-libsalve_bev.so.  Signatures, return conventions (None for an empty cloud, (None, None) for a
-pair) and error behaviour follow the reference; the arithmetic runs on the GPU.
+"""BEV rendering entry points (mirror of the reference's salve/utils/bev_rendering_utils.py: the texture
+functions :38-45 and :254-663 and the layout modality :48-251), backed by libsalve_bev.so.  Signatures, return
+conventions (None for an empty cloud, (None, None) for a pair) and error behaviour follow the reference; the
+arithmetic runs on the GPU.
 
-Out of scope here: the layout modality (rasterize_room_layout_pair and the
-cv2 polygon helpers, reference :48-251) and the dead `is_semantics=True` branches.
+Out of scope here: the dead `is_semantics=True` branches.
 """
 
 from __future__ import annotations
@@ -18,6 +17,7 @@ from typing import Dict, List, Optional, Sequence, Tuple, Union
 import numpy as np
 
 from .. import _ctx
+from ..common import bevparams as bevparams_mod
 from ..common.bevparams import DEFAULT_METERS_PER_PX, BEVParams  # noqa: F401  (re-exported like the reference)
 from ..common.sim2 import Sim2
 from ..renderer import IMG_COLLINEAR, IMG_EMPTY
@@ -225,9 +225,113 @@ def generate_texture_maps_for_pair(
             return
         _imwrite(bev_fpath1, bev_img1)
         _imwrite(bev_fpath2, bev_img2)
-    if "layout" in render_modalities:
-        raise NotImplementedError("the layout modality (rasterize_room_layout_pair) is outside this build's scope")
+    if "layout" not in render_modalities:
+        return
+    # Rasterised layout (:632-661): only for `floor` (the ceiling's would be identical).
+    if surface_type != "floor":
+        return
+    building_layout_save_dir = f"{layout_save_root}/{label_type}/{building_id}"
+    os.makedirs(building_layout_save_dir, exist_ok=True)
+    layout_fpath1 = f"{building_layout_save_dir}/{bev_fname_from_img_fpath(pair_idx, pair_uuid, surface_type, img1_fpath)}"
+    layout_fpath2 = f"{building_layout_save_dir}/{bev_fname_from_img_fpath(pair_idx, pair_uuid, surface_type, img2_fpath)}"
+    if Path(layout_fpath1).exists() and Path(layout_fpath2).exists():
+        print("Both layout images already exist, skipping...")
+        return
+    layoutimg1, layoutimg2 = rasterize_room_layout_pair(i2Ti1=i2Ti1, floor_pose_graph=floor_pose_graph, building_id=building_id,
+                                                        floor_id=floor_id, i1=i1, i2=i2)
+    _imwrite(layout_fpath1, layoutimg1)
+    _imwrite(layout_fpath2, layoutimg2)
 
 
-def rasterize_room_layout_pair(*args, **kwargs):
-    raise NotImplementedError("the layout modality is outside this build's scope (SURVEY.md section 8f, row 4)")
+# ---- layout modality (:48-251): room polygon + window / door / opening strokes, rasterised on the GPU ------------------------
+RED = [255, 0, 0]
+GREEN = [0, 255, 0]
+BLUE = [0, 0, 255]
+WDO_COLOR_DICT_CV2 = {"windows": RED, "doors": GREEN, "openings": BLUE}  # :28-31
+
+
+def _to_px(xy: np.ndarray, bevimg_Sim2_world: Sim2) -> np.ndarray:
+    """World -> integer pixel coordinates exactly as rasterize_polygon / rasterize_polyline do (:193-194, :214-215)."""
+    return np.round(bevimg_Sim2_world.transform_from(np.asarray(xy, np.float64).reshape(-1, 2))).astype(np.int64)
+
+
+def _wdo_in_frame(wdo, i2Ti1: Optional[Sim2]):
+    """(type, (2, 2) vertices) of a W/D/O object, moved into pano 2's frame when a pose is given (pano_data.WDO.transform_from, wdo.py:129-144).
+    Any object with `.type` and `.vertices_local_2d` (or `.pt1` / `.pt2`) will do; the reference's own class is used as it is."""
+    v = np.asarray(wdo.vertices_local_2d if hasattr(wdo, "vertices_local_2d") else [wdo.pt1, wdo.pt2], np.float64).reshape(-1, 2)
+    if i2Ti1 is not None:
+        v = i2Ti1.transform_from(v)
+    return wdo.type, v
+
+
+def _layout_desc(bev_params: BEVParams, room_vertices, wdos, render_mask: bool = True, flip: bool = True) -> dict:
+    """One image's drawing list for BevRenderer.rasterize_layouts (what rasterize_single_layout draws, :101-156)."""
+    S = bev_params.bevimg_Sim2_world
+    thick = bevparams_mod.get_line_width_by_resolution(bevparams_mod.DEFAULT_METERS_PER_PX)  # 8 px at 500 x 500 (:125)
+    room_px = _to_px(np.asarray(room_vertices, np.float64) * HOHO_S_ZIND_SCALE_FACTOR, S)
+    strokes = []
+    polygon = None
+    if render_mask:
+        polygon = room_px
+    else:
+        t = int(thick / 3)
+        strokes += [(*room_px[k], *room_px[k + 1], (255, 255, 255), t) for k in range(len(room_px) - 1)]
+    for wtype, v in wdos:
+        px = _to_px(v * HOHO_S_ZIND_SCALE_FACTOR, S)
+        strokes += [(*px[k], *px[k + 1], WDO_COLOR_DICT_CV2[wtype], thick) for k in range(len(px) - 1)]
+    return dict(polygon=polygon, polygon_rgb=(255, 255, 255), strokes=strokes, flip=flip)
+
+
+def rasterize_single_layout(bev_params: BEVParams, room_vertices: np.ndarray, wdo_objs, render_mask: bool = True) -> np.ndarray:
+    """Room boundary in white (filled mask, or a thin contour), windows / doors / openings as 8-px strokes in their colours, then
+    np.flipud (:101-156)."""
+    r = _renderer_for(bev_params)
+    return r.rasterize_layouts([_layout_desc(bev_params, room_vertices, [_wdo_in_frame(w, None) for w in wdo_objs], render_mask)])[0]
+
+
+def rasterize_room_layout_pair(i2Ti1: Sim2, floor_pose_graph, building_id: str, floor_id: str, i1: int, i2: int):
+    """BEV rasterisation of the two panoramas' room layouts, pano 1's moved into pano 2's frame (:48-98).  `floor_pose_graph.nodes[i]`
+    needs `room_vertices_local_2d`, `doors`, `windows`, `openings` (the reference's PoseGraph2d / PanoData, or anything shaped like them)."""
+    bev_params = BEVParams()
+    n1, n2 = floor_pose_graph.nodes[i1], floor_pose_graph.nodes[i2]
+    v1 = np.asarray(n1.room_vertices_local_2d, np.float64)
+    v2 = np.asarray(n2.room_vertices_local_2d, np.float64)
+    # repeat the first vertex as the last one (:76-77), then pano 1's room goes into pano 2's frame (:79)
+    v1 = i2Ti1.transform_from(np.vstack([v1, v1[0].reshape(-1, 2)]))
+    v2 = np.vstack([v2, v2[0].reshape(-1, 2)])
+    w1 = [_wdo_in_frame(w, i2Ti1) for w in list(n1.doors) + list(n1.windows) + list(n1.openings)]
+    w2 = [_wdo_in_frame(w, None) for w in list(n2.doors) + list(n2.windows) + list(n2.openings)]
+    r = _renderer_for(bev_params)
+    imgs = r.rasterize_layouts([_layout_desc(bev_params, v1, w1), _layout_desc(bev_params, v2, w2)])
+    return imgs[0], imgs[1]
+
+
+def _draw_on(image: np.ndarray, layout: dict) -> np.ndarray:
+    h, w = image.shape[:2]
+    r = _ctx.get(grid_h=h, grid_w=w)
+    out = r.rasterize_layouts([layout], init=np.ascontiguousarray(image, np.uint8)[None])[0]
+    image[:] = out
+    return image
+
+
+def draw_polygon_cv2(points: np.ndarray, image: np.ndarray, color) -> np.ndarray:
+    """cv2.fillPoly of one (possibly non-convex) polygon onto `image` (:159-181)."""
+    return _draw_on(image, dict(polygon=np.asarray(points).astype(np.int32), polygon_rgb=tuple(color), strokes=[], flip=False))
+
+
+def rasterize_polygon(polygon_xy: np.ndarray, bev_img: np.ndarray, bevimg_Sim2_world: Sim2, color) -> np.ndarray:
+    """:184-197"""
+    return draw_polygon_cv2(points=_to_px(polygon_xy, bevimg_Sim2_world), image=bev_img, color=color)
+
+
+def draw_polyline_cv2(line_segments_arr: np.ndarray, image: np.ndarray, color, im_h: int, im_w: int, thickness: int = 2) -> None:
+    """Anti-aliased strokes between consecutive points, drawn onto `image` in place (:220-251)."""
+    p = np.asarray(line_segments_arr, np.int64).reshape(-1, 2)
+    _draw_on(image, dict(polygon=None, strokes=[(*p[k], *p[k + 1], tuple(color), thickness) for k in range(len(p) - 1)], flip=False))
+
+
+def rasterize_polyline(polyline_xy: np.ndarray, bev_img: np.ndarray, bevimg_Sim2_world: Sim2, color, thickness: int) -> np.ndarray:
+    """:200-217"""
+    img_h, img_w, _ = bev_img.shape
+    draw_polyline_cv2(line_segments_arr=_to_px(polyline_xy, bevimg_Sim2_world), image=bev_img, color=color, im_h=img_h, im_w=img_w, thickness=thickness)
+    return bev_img

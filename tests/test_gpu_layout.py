@@ -1,0 +1,155 @@
+"""GPU parity tests of the layout modality: the CUDA rasteriser behind rasterize_room_layout_pair /
+rasterize_single_layout / the cv2-named helpers, against cv2 itself and against images of the unmodified reference
+(tests/golden/layout_c1.npz, scripts/make_golden_layout.py).
+
+Bar: cv2.fillPoly bit-exact for polygons inside the image; strokes (cv2.line LINE_AA, thickness 8) identical in their interior and
+outside them, toleranced on the anti-aliased rim: STROKE_RIM_PX, with the differing fractions printed.
+"""
+
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import layout_synth, synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+STROKE_RIM_PX = 2.0  # pixels farther than this from a stroke's outline must be identical
+RIM_MEAN_ABS = 12.0  # mean |difference| (of 255) over the pixels a stroke touches
+
+
+def _pose(seed):
+    R, t = synth.synth_pose(seed)
+    return R, (t * 0.25).astype(np.float32)
+
+
+def _dist_to_strokes(shape, strokes):
+    """Distance of every pixel to the outline of the nearest stroke (capsule of radius thickness / 2 around the segment)."""
+    yy, xx = np.mgrid[0:shape[0], 0:shape[1]].astype(np.float64)
+    best = np.full(shape, 1e9)
+    for x0, y0, x1, y1, _, th in strokes:
+        dx, dy = x1 - x0, y1 - y0
+        L2 = max(dx * dx + dy * dy, 1e-9)
+        t = np.clip(((xx - x0) * dx + (yy - y0) * dy) / L2, 0, 1)
+        d = np.hypot(xx - (x0 + t * dx), yy - (y0 + t * dy))
+        best = np.minimum(best, np.abs(d - th / 2))
+    return best
+
+
+def test_fillpoly_bit_exact_inside_the_image():
+    import cv2
+
+    from salve_b200.utils import bev_rendering_utils as bru
+
+    rng = np.random.default_rng(11)
+    for k in range(40):
+        n = int(rng.integers(3, 14))
+        lo, hi = ((0, 501), (100, 160), (0, 40), (380, 501))[k % 4]
+        pts = rng.integers(lo, hi, size=(n, 2))
+        if k % 5 == 0:
+            pts[int(rng.integers(0, n))] = pts[int(rng.integers(0, n))]  # a repeated vertex
+        col = tuple(int(v) for v in rng.integers(1, 256, 3))
+        ref = np.zeros((501, 501, 3), np.uint8)
+        cv2.fillPoly(ref, np.array([pts]).astype(np.int32), col)
+        got = bru.draw_polygon_cv2(pts, np.zeros((501, 501, 3), np.uint8), col)
+        assert np.array_equal(got, ref), (k, pts.tolist())
+    # drawn onto an existing image, and through the world -> pixel helper
+    from salve_b200.common.bevparams import BEVParams
+
+    base = rng.integers(0, 256, (501, 501, 3)).astype(np.uint8)
+    poly = np.array([[-2.0, -1.0], [1.5, -2.2], [2.4, 1.9], [-0.3, 0.4], [-2.2, 2.1]])
+    S = BEVParams().bevimg_Sim2_world
+    ref = base.copy()
+    cv2.fillPoly(ref, np.array([np.round(S.transform_from(poly)).astype(np.int32)]), (9, 200, 30))
+    got = bru.rasterize_polygon(poly, base.copy(), S, (9, 200, 30))
+    assert np.array_equal(got, ref)
+
+
+def test_fillpoly_partly_outside_the_image_reports_its_difference():
+    """cv2 re-derives an edge that leaves the image from its integer-clipped end points; the kernel fills the exact polygon.  The
+    difference hugs those edges: bounded here, printed for the record."""
+    import cv2
+
+    from salve_b200.utils import bev_rendering_utils as bru
+
+    rng = np.random.default_rng(12)
+    fr = []
+    for k in range(12):
+        pts = rng.integers(-200, 700, size=(int(rng.integers(3, 8)), 2))
+        ref = np.zeros((501, 501, 3), np.uint8)
+        cv2.fillPoly(ref, np.array([pts]).astype(np.int32), (255, 255, 255))
+        got = bru.draw_polygon_cv2(pts, np.zeros((501, 501, 3), np.uint8), (255, 255, 255))
+        fr.append(float((got != ref).any(2).mean()))
+    print("fillPoly with vertices outside the image: differing pixel fraction per polygon", json.dumps([round(f, 5) for f in fr]))
+    assert max(fr) < 0.02 and float(np.mean(fr)) < 0.005
+
+
+def _check_layout(got, ref, strokes_px, name):
+    d = np.abs(got.astype(int) - ref.astype(int)).max(2)
+    dist = _dist_to_strokes(got.shape[:2], strokes_px)
+    far = dist > STROKE_RIM_PX
+    assert d[far].max() == 0, f"{name}: {int((d[far] > 0).sum())} pixels differ away from the strokes' rims"
+    touched = ((got > 0) | (ref > 0)).any(2) & ~far
+    rep = dict(name=name, rim_px=int((~far).sum()), rim_differ=float((d[~far] > 0).mean()), rim_differ_gt32=float((d[~far] > 32).mean()),
+               rim_mean_abs=float(d[touched].mean()) if touched.any() else 0.0, max_abs=int(d.max()))
+    assert rep["rim_mean_abs"] < RIM_MEAN_ABS, rep
+    return rep
+
+
+def test_room_layout_pair_against_the_reference_golden():
+    """rasterize_room_layout_pair against images of the unmodified reference (cv2): polygon and stroke interiors identical, the
+    strokes' anti-aliased rims within tolerance (fractions printed)."""
+    from salve_b200.common.bevparams import BEVParams
+    from salve_b200.common.sim2 import Sim2
+    from salve_b200.utils import bev_rendering_utils as bru
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "layout_c1.npz"))
+    reps = []
+    for k, (s1, s2, ps) in enumerate([(0, 1, 3), (2, 3, 4), (4, 5, 6)]):
+        graph = layout_synth.nodes([s1, s2])
+        R, t = _pose(ps)
+        T = Sim2(R, t, 1.0)
+        i1, i2 = bru.rasterize_room_layout_pair(T, graph, "b", "f", 0, 1)
+        assert i1.shape == (501, 501, 3) and i1.dtype == np.uint8
+        for img, ref, node, pose_ in ((i1, g[f"case{k}_img1"], graph.nodes[0], T), (i2, g[f"case{k}_img2"], graph.nodes[1], None)):
+            wd = [bru._wdo_in_frame(w, pose_) for w in node.doors + node.windows + node.openings]
+            desc = bru._layout_desc(BEVParams(), node.room_vertices_local_2d, wd)
+            strokes = [(x0, 500 - y0, x1, 500 - y1, c, th) for x0, y0, x1, y1, c, th in desc["strokes"]]  # after np.flipud
+            reps.append(_check_layout(img, ref, strokes, f"case{k}"))
+    print("layout pair vs reference (cv2):", json.dumps(reps))
+
+
+def test_single_layout_contour_mode_and_polyline_helper():
+    """render_mask=False (thin white contour) and draw_polyline_cv2 / rasterize_polyline against cv2.line(LINE_AA)."""
+    import cv2
+
+    from salve_b200.common.bevparams import BEVParams
+    from salve_b200.utils import bev_rendering_utils as bru
+
+    v, wd = layout_synth.synth_room(9)
+    v = np.vstack([v, v[:1]])
+    wdos = [layout_synth.PlainWDO(p1, p2, typ) for typ, p1, p2 in wd]
+    got = bru.rasterize_single_layout(BEVParams(), v, wdos, render_mask=False)
+    # the same drawing with cv2
+    S = BEVParams().bevimg_Sim2_world
+    ref = np.zeros((501, 501, 3), np.uint8)
+    strokes = []
+    px = np.round(S.transform_from(v * 1.5)).astype(np.int64)
+    for a, b in zip(px[:-1], px[1:]):
+        cv2.line(ref, tuple(int(x) for x in a), tuple(int(x) for x in b), (255, 255, 255), thickness=2, lineType=cv2.LINE_AA)
+        strokes.append((a[0], a[1], b[0], b[1], (255, 255, 255), 2))
+    for w in wdos:
+        p = np.round(S.transform_from(w.vertices_local_2d * 1.5)).astype(np.int64)
+        cv2.line(ref, tuple(int(x) for x in p[0]), tuple(int(x) for x in p[1]), bru.WDO_COLOR_DICT_CV2[w.type], thickness=8, lineType=cv2.LINE_AA)
+        strokes.append((p[0][0], p[0][1], p[1][0], p[1][1], None, 8))
+    ref = np.flipud(ref)
+    strokes = [(x0, 500 - y0, x1, 500 - y1, c, th) for x0, y0, x1, y1, c, th in strokes]
+    rep = _check_layout(got, ref, strokes, "contour")
+    print("contour mode vs cv2:", json.dumps(rep))
+    img = np.zeros((501, 501, 3), np.uint8)
+    bru.draw_polyline_cv2(np.array([[50, 60], [300, 90], [320, 400]]), img, (10, 250, 90), 501, 501, thickness=8)
+    ref = np.zeros((501, 501, 3), np.uint8)
+    cv2.line(ref, (50, 60), (300, 90), (10, 250, 90), 8, cv2.LINE_AA); cv2.line(ref, (300, 90), (320, 400), (10, 250, 90), 8, cv2.LINE_AA)
+    _check_layout(img, ref, [(50, 60, 300, 90, None, 8), (300, 90, 320, 400, None, 8)], "polyline")

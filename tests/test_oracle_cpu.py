@@ -227,3 +227,21 @@ def test_resize_at_scale_two_is_the_rounded_box_mean():
     assert np.array_equal(po.resize_linear_u8(big, 32, 48), box.astype(np.uint8))
     cv2 = pytest.importorskip("cv2")
     assert np.array_equal(cv2.resize(big, (48, 32), interpolation=cv2.INTER_LINEAR), box.astype(np.uint8))
+
+
+@pytest.mark.needs_reference
+def test_layout_golden_is_what_the_reference_draws():
+    """tests/golden/layout_c1.npz (scripts/make_golden_layout.py) against the imported, unmodified reference and the real cv2."""
+    import os
+
+    from oracle import layout_synth, ref_import
+
+    ref = ref_import.load()
+    import salve.common.pano_data as pano_data
+
+    g = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "layout_c1.npz"))
+    for k, (s1, s2, ps) in enumerate([(0, 1, 3), (2, 3, 4), (4, 5, 6)]):
+        graph = layout_synth.nodes([s1, s2], wdo_cls=pano_data.WDO, sim2_cls=ref.sim2.Sim2)
+        R, t = synth.synth_pose(ps)
+        i1, i2 = ref.bru.rasterize_room_layout_pair(ref.sim2.Sim2(R, (t * 0.25).astype(np.float32), 1.0), graph, "b", "f", 0, 1)
+        assert np.array_equal(i1, g[f"case{k}_img1"]) and np.array_equal(i2, g[f"case{k}_img2"])
