@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(LAYOUT_NT) layout_raster_kernel(LayoutArgs A) 
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
                     const int col = (int)((rgb >> (8 * c)) & 0xFF), bg = (int)o[c];
-                    o[c] = (uint8_t)(bg + (((col - bg) * ai + 127) / 255));
+                    o[c] = (uint8_t)((bg * (255 - ai) + col * ai + 127) / 255);
                 }
             }
         }
