@@ -411,7 +411,7 @@ def roofline_block(stage_ms, steps, alg, n_rendered, n_jobs, chunks_per_step, va
     tj, tsrc = traffic_table()
     traffic = None
     if tj:
-        per_img = sum((tj[k]["dram_bytes_read"] + tj[k]["dram_bytes_write"]) / tj[k]["images_in_launch"] for k in tj if k != "splat_pano_kernel" and "images_in_launch" in tj[k])
+        per_img = sum((tj[k]["dram_bytes_read"] + tj[k]["dram_bytes_write"]) / tj[k]["images_in_launch"] for k in tj if "_stage_kernel" in k and "images_in_launch" in tj[k])
         traffic = per_img * n_rendered / chunks_per_step if per_img else None
     abh = alg_bytes_per_hyp(H, W)
     return {
