@@ -218,7 +218,9 @@ int salve_bev_choose_elevated(salve_bev_ctx* ctx, const int64_t* host_x, const i
  * Sparse -> dense: replaces interp_dense_grid_from_sparse (interpolation_utils.py:21-54) for
  * method="linear".  points: n x 2 int64 (x = column, y = row), distinct; values: n x 3 float64
  * (truncated to uint8 like interpolation_utils.py:53).  grid_h*grid_w <= 800000, grid_w <= 2047, grid_h <= 1023; grids whose
- * bit rows fit shared memory (e.g. 501x501) use image_kernel, larger ones the explicit-mesh path.  host_img: grid_h x grid_w x 3 uint8, fully overwritten unless *status ==
+ * bit rows fit shared memory (e.g. 501x501) use the staged image pipeline (k_image.cuh), larger ones the explicit-mesh path.  Limits: `values` are
+ * taken as the uint8 colours the render path produces (integral, 0..255: the reference interpolates float64 and truncates afterwards, which is the same
+ * for such values) and every point must lie inside the grid (the Python mirror raises NotImplementedError otherwise).  host_img: grid_h x grid_w x 3 uint8, fully overwritten unless *status ==
  * SALVE_BEV_IMG_DEGENERATE (then untouched, as in the reference).  host_hull (may be NULL):
  * grid_h x grid_w uint8, 1 inside the closed convex hull.
  */
@@ -247,8 +249,10 @@ int salve_bev_rasterize_layouts_host(salve_bev_ctx* ctx, int32_t n_img, const in
                                      const uint8_t* host_init, uint8_t* host_out, void* stream);
 
 /*
- * Stage taps of the most recent render call (parity tests).  image = index within the last internal chunk (for a call that
- * was de-duplicated the chunks hold the unique un-posed images first, then the posed ones).
+ * Stage taps of the most recent render of pano images (render_hypotheses* / render_images; parity tests).  image = index within the
+ * last internal chunk (for a call that was de-duplicated the chunks hold the unique un-posed images first, then the posed ones).
+ * The render consumes (zeroes) its key grids, so a tap re-splats the pano pass that produced the image from the job table of the
+ * last chunk and re-runs the stages on it; the panos of that chunk must still be in their slots.
  * what: see SALVE_BEV_TAP_*.  host_buf must be large enough (sizes in comments, g = grid_h*grid_w,
  * wpr = (grid_w+31)/32).
  */

@@ -1,7 +1,7 @@
 """Fixed workload for ncu: the bench step (or a smaller one), W warm-up passes + 1 profiled pass.
     python scripts/profile_step.py [n_hyp=640] [n_panos=40] [passes=2] [max_images=1480]
-With the defaults one pass is exactly one bench.py step: 1 splat_pano_kernel + 1 image_kernel launch over 1 360 images
-(1 280 posed + 80 un-posed) + 1 replicate_images_kernel launch.
+With the defaults one pass is exactly one bench.py step: one launch each of splat_pano_kernel, the five stage kernels of the image
+pipeline (+ image_order_kernel) over 1 358 images (1 280 posed + 78 un-posed) and replicate_images_kernel.
 """
 import os
 import sys
