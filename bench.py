@@ -587,8 +587,7 @@ def run_building(args):
     same = all(np.array_equal(posed_h[h, s], full0[h, s, 0]) and np.array_equal(unposed_h[idx_h[h], s], full0[h, s, 1]) for h in range(2) for s in range(2))
     n_unique = int(unposed_h.shape[0])
     h2d = N_PANOS * H * W * 5 + N_HYP * (2 * 4 + 6 * 4)
-    d2h_full = (N_HYP * 2 + n_unique * 2) * (IMG_BYTES + 9 * 4)
-    d2h = r2.last_d2h_bytes() + (N_HYP * 2 + n_unique * 2) * 9 * 4  # only the row span of an image that can hold non-zero pixels crosses PCIe
+    d2h = (N_HYP * 2 + n_unique * 2) * (IMG_BYTES + 9 * 4)
 
     # what the host can absorb: the plain device->host copy of the same bytes into the same pinned buffers, all ranks at once
     d_probe = torch.empty(N_HYP * 2 * IMG_BYTES, dtype=torch.uint8, device=dev)
@@ -658,15 +657,14 @@ def run_building(args):
         "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "dtype_detail": "f64 geometry (f32 pose parameters), exact int32/int64 predicates, u8 colour, exact u32 barycentrics",
         "data": "synthetic", "config": workload_config(args.config, world), "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "hypotheses/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "d2h_bytes_full_images": d2h_full, "layout": "compact",
+        "e2e": {"value": e2e_value, "unit": "hypotheses/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "layout": "compact",
                 "layout_note": "img1 of every hypothesis and surface + img2 once per distinct (pano 2, surface) with an index per hypothesis: "
                                "53 % of the bytes of the reference's (img1, img2)-per-hypothesis return shape",
                 "matches_device_path": bool(same and same_b), "steps_in_flight": DEPTH, "value_one_step_at_a_time": e2e_seq_value,
                 "host_ceiling_hyp_s": host_ceiling, "host_d2h_gbs": d2h_gbs, "frac_of_host_ceiling": e2e_value / host_ceiling,
-                "note": "two contexts / streams / host threads alternate steps; every step uploads its panos and brings all its images to "
-                        "pinned host memory inside the timed region (wall clock over all steps): of every image the rows between its first and "
-                        "last site are copied device->host, the blank rows are zeroed by host threads of the library; host_ceiling = the plain "
-                        "device->host copy of the FULL images (d2h_bytes_full_images) into the same pinned buffers on all ranks at once"},
+                "note": "two contexts / streams / host threads alternate steps; every step uploads its panos and copies all its images to "
+                        "pinned host memory inside the timed region (wall clock over all steps); host_ceiling = the plain device->host copy of "
+                        "the same bytes into the same pinned buffers on all ranks at once"},
         "gpu_launches": int(launches), "host_ms_per_call": host_ms / args.steps,
         "value_no_dedup": value_nd, "no_dedup_matches": same_nd, "images_rendered_per_step": int(n_rendered),
         "roofline": roofline, "parity": parity, "cpu_baseline": cpu,

@@ -135,8 +135,7 @@ int salve_bev_render_hypotheses(salve_bev_ctx* ctx, int32_t n_hyp, const int32_t
                                 const float* host_R, const float* host_t, uint32_t surfaces, uint8_t* dev_out,
                                 int32_t* dev_counts, int32_t* dev_status, void* stream);
 /* Same, with host output buffers (device->host copies included; synchronises).  Chunks are double buffered:
- * chunk k+1 renders while chunk k is copied out on a private copy stream; pass page-locked host_out to get the overlap.
- * See salve_bev_last_d2h_bytes for what crosses PCIe. */
+ * chunk k+1 renders while chunk k is copied out on a private copy stream; pass page-locked host_out to get the overlap. */
 int salve_bev_render_hypotheses_host(salve_bev_ctx* ctx, int32_t n_hyp, const int32_t* host_pano1, const int32_t* host_pano2,
                                      const float* host_R, const float* host_t, uint32_t surfaces, uint8_t* host_out,
                                      int32_t* host_counts, int32_t* host_status, void* stream);
@@ -280,10 +279,6 @@ int salve_bev_enable_timing(salve_bev_ctx* ctx, int32_t on);
 
 /* Number of kernel launches issued by this context since creation (bench.py's gpu_launches). */
 int64_t salve_bev_launch_count(salve_bev_ctx* ctx);
-/* Image bytes the most recent salve_bev_render_hypotheses[_compact]_host call copied device -> host.  Of every posed image only the rows
- * between its first and last site cross PCIe (all a render can show lies between them; about a third of the rows of a render are
- * blank); the other rows of the caller's buffer are zeroed by host threads of the library (bench.py's e2e.d2h_bytes_per_step). */
-int64_t salve_bev_last_d2h_bytes(salve_bev_ctx* ctx);
 
 #ifdef __cplusplus
 }

@@ -72,7 +72,6 @@ SYMBOLS = {
     "salve_bev_last_timings": (ctypes.c_int, [c_vp, c_f32p]),
     "salve_bev_enable_timing": (ctypes.c_int, [c_vp, ctypes.c_int32]),
     "salve_bev_launch_count": (ctypes.c_int64, [c_vp]),
-    "salve_bev_last_d2h_bytes": (ctypes.c_int64, [c_vp]),
 }
 
 _lib = None

@@ -5,10 +5,6 @@
 #include <string.h>
 
 #include <algorithm>
-#include <condition_variable>
-#include <deque>
-#include <mutex>
-#include <thread>
 #include <vector>
 
 #include "../../include/salve_bev.h"
@@ -41,47 +37,6 @@ static void set_err(const char* fmt, const char* a, const char* b, int line) { s
 
 constexpr int N_TMP = 8;
 constexpr int N_STAGE_EVENTS = 7;  // chunk start, after: splat, sites, prep, window, shade, finish
-
-// Host threads that zero the rows of an output image no device->host copy writes (see render_hyp_dedup: only the row span that
-// can hold non-zero pixels crosses PCIe).
-struct ZeroPool {
-    std::vector<std::thread> th;
-    std::mutex m;
-    std::condition_variable cv, cv_done;
-    std::deque<std::pair<uint8_t*, size_t>> q;
-    size_t pending = 0;
-    bool stop = false;
-    void start(int n) {
-        for (int i = 0; i < n; i++)
-            th.emplace_back([this] {
-                for (;;) {
-                    std::pair<uint8_t*, size_t> t;
-                    {
-                        std::unique_lock<std::mutex> lk(m);
-                        cv.wait(lk, [this] { return stop || !q.empty(); });
-                        if (q.empty()) return;
-                        t = q.front(); q.pop_front();
-                    }
-                    memset(t.first, 0, t.second);
-                    {
-                        std::lock_guard<std::mutex> lk(m);
-                        if (--pending == 0) cv_done.notify_all();
-                    }
-                }
-            });
-    }
-    void push(uint8_t* p, size_t n) {
-        if (!n) return;
-        { std::lock_guard<std::mutex> lk(m); q.emplace_back(p, n); pending++; }
-        cv.notify_one();
-    }
-    void wait() { std::unique_lock<std::mutex> lk(m); cv_done.wait(lk, [this] { return pending == 0; }); }
-    ~ZeroPool() {
-        { std::lock_guard<std::mutex> lk(m); stop = true; }
-        cv.notify_all();
-        for (auto& t : th) t.join();
-    }
-};
 
 struct salve_bev_ctx {
     salve_bev_config cfg;
@@ -142,13 +97,6 @@ struct salve_bev_ctx {
     SplatJob* h_jobs[2] = {nullptr, nullptr};          // pinned staging of the per-chunk job tables
     const uint8_t** h_src[2] = {nullptr, nullptr};
     int stage_parity = 0;
-    // host-output path: per image of a chunk the output rows that can hold non-zero pixels (written by the finish stage)
-    int32_t* d_span = nullptr;            // [2][max_images][2], double buffered like out_store
-    int32_t* h_span[2] = {nullptr, nullptr};
-    cudaEvent_t ev_span[2] = {nullptr, nullptr};
-    ZeroPool* zero_pool = nullptr;
-    bool host_rowspan = true;             // SALVE_BEV_HOST_FULLCOPY=1: copy whole images (developer switch for A/B timing)
-    int64_t last_d2h_bytes = 0;           // image bytes the last *_host render call copied device -> host
     int32_t* h_meta = nullptr;  // pinned staging of counts/status for the *_host variants (user arrays may be pageable,
     size_t h_meta_cap = 0;      //  and a device->pageable async copy would block the host and serialise the pipeline)
     // growable temporaries
@@ -277,8 +225,6 @@ static int ctx_init(salve_bev_ctx* c, const salve_bev_config* cfg) {
     ALLOC(c->d_jobs, N);
     ALLOC(c->d_color_src, N);
     ALLOC(c->out_store, 2 * N * c->img_bytes);
-    ALLOC(c->d_span, 2 * N * 2);
-    { const char* e = getenv("SALVE_BEV_HOST_FULLCOPY"); c->host_rowspan = !(e && e[0] == '1'); }
 #undef ALLOC
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&c->ev_cache, cudaEventDisableTiming));
@@ -290,8 +236,6 @@ static int ctx_init(salve_bev_ctx* c, const salve_bev_config* cfg) {
         CU(cudaEventCreateWithFlags(&c->ev_copied[k], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&c->ev_staged[k], cudaEventDisableTiming));
         CU(cudaMallocHost((void**)&c->h_jobs[k], sizeof(SplatJob) * N));
-        CU(cudaMallocHost((void**)&c->h_span[k], sizeof(int32_t) * 2 * N));
-        CU(cudaEventCreateWithFlags(&c->ev_span[k], cudaEventDisableTiming));
         CU(cudaMallocHost((void**)&c->h_src[k], sizeof(void*) * N));
         CU(cudaMallocHost((void**)&c->h_dest[k], sizeof(int32_t) * N));
     }
@@ -327,7 +271,7 @@ extern "C" void salve_bev_ctx_destroy(salve_bev_ctx* c) {
     cudaDeviceSynchronize();
     void* ptrs[] = {c->pano_rgb_store, c->pano_rgb2x_store, c->pano_depth_store, c->d_depth_ptr, c->d_tables, c->keygrid, c->color, c->occ, c->nonempty,
                     c->keep, c->tmpbits, c->wprefix, c->tris, c->owner, c->list0, c->list1, c->cand, c->qlist, c->clist, c->qres, c->planes, c->rowarr, c->hdr, c->work_counter, c->d_order, c->cache_out, c->cache_counts, c->cache_status, c->d_dest, c->headers, c->counts,
-                    c->status, c->d_jobs, c->d_color_src, c->out_store, c->d_span};
+                    c->status, c->d_jobs, c->d_color_src, c->out_store};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < N_TMP; i++) if (c->tmp[i]) cudaFree(c->tmp[i]);
     for (cudaEvent_t e : c->events) cudaEventDestroy(e);
@@ -336,8 +280,6 @@ extern "C" void salve_bev_ctx_destroy(salve_bev_ctx* c) {
         if (c->ev_copied[k]) cudaEventDestroy(c->ev_copied[k]);
         if (c->ev_staged[k]) cudaEventDestroy(c->ev_staged[k]);
         if (c->h_jobs[k]) cudaFreeHost(c->h_jobs[k]);
-        if (c->h_span[k]) cudaFreeHost(c->h_span[k]);
-        if (c->ev_span[k]) cudaEventDestroy(c->ev_span[k]);
         if (c->h_src[k]) cudaFreeHost(c->h_src[k]);
         if (c->h_dest[k]) cudaFreeHost(c->h_dest[k]);
     }
@@ -352,7 +294,6 @@ extern "C" void salve_bev_ctx_destroy(salve_bev_ctx* c) {
     if (c->d_taps) cudaFree(c->d_taps);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->h_meta) cudaFreeHost(c->h_meta);
-    delete c->zero_pool;
     delete c;
 }
 
@@ -466,8 +407,7 @@ static int stage_event(salve_bev_ctx* c, cudaStream_t st) {
 // Everything after the splat for images [0, n_img): the four stages of k_image.cuh (sites, prep, window, finish).
 static int run_image_stage(salve_bev_ctx* c, int n_img, const GridParams& G, uint32_t* keygrid, const uint8_t* const* color_src,
                            uint8_t* dev_out, int32_t* dev_counts, int32_t* dev_status, int raw_mode, int skip_empty, uint8_t* hull,
-                           int32_t* qtri, cudaStream_t st, const int32_t* dest = nullptr, int32_t* counts_out = nullptr, bool clear_keys = false, bool timed = false,
-                           int32_t* span = nullptr) {
+                           int32_t* qtri, cudaStream_t st, const int32_t* dest = nullptr, int32_t* counts_out = nullptr, bool clear_keys = false, bool timed = false) {
     const size_t smem = image_smem_bytes(G.grid_h, G.wpr);
     if (smem > (size_t)c->max_smem_optin) FAIL(SALVE_BEV_E_CAPACITY, "grid too large for the image stages' shared memory");
     if (n_img > c->cfg.max_images) FAIL(SALVE_BEV_E_CAPACITY, "more images than the context's scratch holds");
@@ -489,7 +429,6 @@ static int run_image_stage(salve_bev_ctx* c, int n_img, const GridParams& G, uin
             IA.counts_out = counts_out ? counts_out + (size_t)g0 * 8 : nullptr;
         }
         IA.cache_out = c->cache_out; IA.cache_counts = c->cache_counts; IA.cache_status = c->cache_status;
-        IA.span = span ? (dest ? span : span + 2 * (size_t)g0) : nullptr;
         IA.hull = hull ? hull + (size_t)g0 * G.g : nullptr; IA.hull_stride = (size_t)G.g;
         IA.qtri = qtri ? qtri + (size_t)g0 * G.g * 3 : nullptr; IA.qtri_stride = (size_t)G.g * 3;
         IA.planes = c->planes; IA.plane_stride = c->bits_stride;
@@ -579,7 +518,7 @@ static int run_mesh_stages(salve_bev_ctx* c, const GridParams& G, const uint32_t
 // One chunk of pano-sourced images.  jobs / color slots are host arrays.
 static int render_chunk(salve_bev_ctx* c, int n_img, const std::vector<SplatJob>& jobs, const std::vector<int>& img_slot, uint8_t* dev_out,
                         int32_t* dev_counts, int32_t* dev_status, cudaStream_t st, const std::vector<int32_t>* dest = nullptr,
-                        int32_t* counts_out = nullptr, int32_t* span = nullptr) {
+                        int32_t* counts_out = nullptr) {
     if (n_img > c->cfg.max_images || (int)jobs.size() > c->cfg.max_images) FAIL(SALVE_BEV_E_CAPACITY, "chunk exceeds max_images");
     int rc = sync_ptr_tables(c, st); if (rc) return rc;
     // job tables go through pinned, double-buffered staging so that the chunk loop never blocks the host
@@ -612,7 +551,7 @@ static int render_chunk(salve_bev_ctx* c, int n_img, const std::vector<SplatJob>
     c->last_counts = dev_counts;
     c->last_jobs = jobs;
     return run_image_stage(c, n_img, c->G, c->keygrid, c->d_color_src, dev_out, dev_counts, dev_status, 0, 0, nullptr, nullptr, st,
-                           dest ? c->d_dest : nullptr, counts_out, true, true, span);
+                           dest ? c->d_dest : nullptr, counts_out, true, true);
 }
 
 // Copy images between two device buffers at any alignment (an image is 753 003 bytes: consecutive images share no
@@ -704,44 +643,6 @@ static int render_hyp_dedup(salve_bev_ctx* c, int32_t n_hyp, const int32_t* p1, 
     std::vector<SplatJob> jobs;
     std::vector<int> slots;
     std::vector<int32_t> dest;
-    // Host output: the posed images of a chunk go device -> host once the chunk is rendered.  Only the rows of an image that can hold
-    // non-zero pixels (the rows between its first and last site, known on the device when the chunk is done) cross PCIe -- the
-    // copy engine is the bound of this path, and about a third of the rows of a render are blank -- the rest is zeroed by host threads.
-    struct Pending { bool active = false; int par = 0, first_posed = 0, np = 0; size_t fin0 = 0; } pend;
-    const size_t row_bytes = (size_t)c->G.grid_w * 3;
-    const int gh = c->G.grid_h;
-    if (host_out) {
-        c->last_d2h_bytes = 0;
-        if (c->host_rowspan && !c->zero_pool) { c->zero_pool = new ZeroPool(); c->zero_pool->start(4); }
-    }
-    auto drain = [&](Pending& d) -> int {
-        if (!d.active) return SALVE_BEV_OK;
-        d.active = false;
-        const uint8_t* src = c->out_store + d.par * N * ib + (size_t)d.first_posed * ib;
-        const int32_t* cnt_stage = c->counts + d.par * N * 8;
-        const int32_t* st_stage = c->status + d.par * N;
-        const size_t k = full ? 2 : 1;  // posed image i of the call is image k*i of `out`
-        if (c->host_rowspan) {
-            CU(cudaEventSynchronize(c->ev_span[d.par]));
-            for (int i = 0; i < d.np; i++) {
-                const int lo = c->h_span[d.par][2 * (d.first_posed + i)], hi = c->h_span[d.par][2 * (d.first_posed + i) + 1];
-                uint8_t* dst = out + (d.fin0 + i) * k * ib;
-                if (lo > hi) { c->zero_pool->push(dst, ib); continue; }
-                CU(cudaMemcpyAsync(dst + lo * row_bytes, src + (size_t)i * ib + lo * row_bytes, (size_t)(hi - lo + 1) * row_bytes, cudaMemcpyDeviceToHost, c->copy_stream));
-                c->last_d2h_bytes += (int64_t)(hi - lo + 1) * row_bytes;
-                c->zero_pool->push(dst, lo * row_bytes);
-                c->zero_pool->push(dst + (size_t)(hi + 1) * row_bytes, (size_t)(gh - 1 - hi) * row_bytes);
-            }
-        } else {
-            if (full) CU(cudaMemcpy2DAsync(out + d.fin0 * 2 * ib, 2 * ib, src, ib, ib, d.np, cudaMemcpyDeviceToHost, c->copy_stream));
-            else CU(cudaMemcpyAsync(out + d.fin0 * ib, src, (size_t)d.np * ib, cudaMemcpyDeviceToHost, c->copy_stream));
-            c->last_d2h_bytes += (int64_t)d.np * ib;
-        }
-        CU(cudaMemcpy2DAsync(hm_counts + d.fin0 * k * 8, k * 32, cnt_stage + (size_t)d.first_posed * 8, 32, 32, d.np, cudaMemcpyDeviceToHost, c->copy_stream));
-        CU(cudaMemcpy2DAsync(hm_status + d.fin0 * k, k * 4, st_stage + d.first_posed, 4, 4, d.np, cudaMemcpyDeviceToHost, c->copy_stream));
-        CU(cudaEventRecord(c->ev_copied[d.par], c->copy_stream));
-        return SALVE_BEV_OK;
-    };
     int chunk_no = 0;
     for (int j0 = 0; j0 < n_jobs; j0 += jobs_per_chunk, chunk_no++) {
         const int nj = std::min(jobs_per_chunk, n_jobs - j0);
@@ -778,21 +679,20 @@ static int render_hyp_dedup(salve_bev_ctx* c, int32_t n_hyp, const int32_t* p1, 
             uint8_t* stage = c->out_store + par * N * ib;
             int32_t* cnt_stage = c->counts + par * N * 8;
             int32_t* st_stage = c->status + par * N;
-            int32_t* span_stage = c->d_span + par * N * 2;
-            rc = render_chunk(c, n_img, jobs, slots, stage, cnt_stage, st_stage, st, &dest, nullptr, c->host_rowspan ? span_stage : nullptr);
+            rc = render_chunk(c, n_img, jobs, slots, stage, cnt_stage, st_stage, st, &dest, nullptr);
             if (rc) return rc;
-            // the chunk before this one is drained now: its kernels were queued ahead of this chunk's, so its row spans are (about to
-            // be) on the host, and the copies issued here overlap this chunk's kernels
-            if ((rc = drain(pend))) return rc;
             if (first_posed >= 0) {
-                pend.active = true; pend.par = par; pend.first_posed = first_posed; pend.np = n_img - first_posed;
-                pend.fin0 = (size_t)(std::max(j0, nU) - nU) * nsurf;  // index among the posed images
+                const int np = n_img - first_posed;
+                const size_t fin0 = (size_t)(std::max(j0, nU) - nU) * nsurf;  // index among the posed images
                 CU(cudaEventRecord(c->ev_done[par], st));
                 CU(cudaStreamWaitEvent(c->copy_stream, c->ev_done[par], 0));
-                if (c->host_rowspan) {
-                    CU(cudaMemcpyAsync(c->h_span[par], span_stage, sizeof(int32_t) * 2 * n_img, cudaMemcpyDeviceToHost, c->copy_stream));
-                    CU(cudaEventRecord(c->ev_span[par], c->copy_stream));
-                }
+                const uint8_t* src = stage + (size_t)first_posed * ib;
+                const size_t k = full ? 2 : 1;  // posed image i of the call is image k*i of `out`
+                if (full) CU(cudaMemcpy2DAsync(out + fin0 * 2 * ib, 2 * ib, src, ib, ib, np, cudaMemcpyDeviceToHost, c->copy_stream));
+                else CU(cudaMemcpyAsync(out + fin0 * ib, src, (size_t)np * ib, cudaMemcpyDeviceToHost, c->copy_stream));
+                CU(cudaMemcpy2DAsync(hm_counts + fin0 * k * 8, k * 32, cnt_stage + (size_t)first_posed * 8, 32, 32, np, cudaMemcpyDeviceToHost, c->copy_stream));
+                CU(cudaMemcpy2DAsync(hm_status + fin0 * k, k * 4, st_stage + first_posed, 4, 4, np, cudaMemcpyDeviceToHost, c->copy_stream));
+                CU(cudaEventRecord(c->ev_copied[par], c->copy_stream));
             }
             if (j0 < nU && j0 + nj >= nU) {
                 // the cache is complete once this chunk is done: its device->host copies overlap the posed chunks that follow
@@ -803,10 +703,8 @@ static int render_hyp_dedup(salve_bev_ctx* c, int32_t n_hyp, const int32_t* p1, 
                         for (int s = 0; s < nsurf; s++)
                             CU(cudaMemcpyAsync(out + ((size_t)(h * nsurf + s) * 2 + 1) * ib, c->cache_out + (size_t)(plan.uniq_of_hyp[h] * nsurf + s) * ib, ib,
                                                cudaMemcpyDeviceToHost, c->copy_stream));
-                    c->last_d2h_bytes += (int64_t)n_posed * ib;
                 } else {
                     CU(cudaMemcpyAsync(out_unposed, c->cache_out, n_unposed * ib, cudaMemcpyDeviceToHost, c->copy_stream));
-                    c->last_d2h_bytes += (int64_t)n_unposed * ib;
                 }
                 CU(cudaMemcpyAsync(hm_ucounts, c->cache_counts, sizeof(int32_t) * 8 * n_unposed, cudaMemcpyDeviceToHost, c->copy_stream));
                 CU(cudaMemcpyAsync(hm_ustatus, c->cache_status, sizeof(int32_t) * n_unposed, cudaMemcpyDeviceToHost, c->copy_stream));
@@ -847,10 +745,8 @@ static int render_hyp_dedup(salve_bev_ctx* c, int32_t n_hyp, const int32_t* p1, 
         if (status_unposed) CU(cudaMemcpyAsync(status_unposed, c->cache_status, sizeof(int32_t) * n_unposed, cudaMemcpyDeviceToDevice, st));
     }
     if (host_out) {
-        if ((rc = drain(pend))) return rc;
         CU(cudaStreamSynchronize(c->copy_stream));
         CU(cudaStreamSynchronize(st));
-        if (c->zero_pool) c->zero_pool->wait();
         if (full) {
             for (int h = 0; h < n_hyp; h++)
                 for (int s = 0; s < nsurf; s++) {
@@ -1495,4 +1391,3 @@ extern "C" int salve_bev_last_timings(salve_bev_ctx* c, float* host_ms) {
 }
 
 extern "C" int64_t salve_bev_launch_count(salve_bev_ctx* c) { return c ? c->launches : 0; }
-extern "C" int64_t salve_bev_last_d2h_bytes(salve_bev_ctx* c) { return c ? c->last_d2h_bytes : 0; }

@@ -119,7 +119,7 @@ constexpr int IMAGE_MAX_FLIPS = 100000;   // safety cap on one descent (never re
 enum { RA_CNT = 0, RA_FIRST, RA_LAST, RA_NE, RA_UP, RA_DN, RA_HL0, RA_HL1, RA_HR0, RA_HR1, RA_N16 };
 enum { RA_HLF = 0, RA_HRF, RA_NF };
 // per-image header (16 int32)
-enum { HD_STATUS = 0, HD_NQ, HD_EDGE, HD_MASKED, HD_PEND, HD_XTRA, HD_ROW_LO, HD_ROW_HI, HD_N };
+enum { HD_STATUS = 0, HD_NQ, HD_EDGE, HD_MASKED, HD_PEND, HD_XTRA, HD_N };
 constexpr int HD_STRIDE = 16;
 
 struct ImageArgs {
@@ -137,7 +137,6 @@ struct ImageArgs {
     const int32_t* dest;
     int32_t* counts_out;              // final counters by destination, or null (then `counts` is the final array)
     uint8_t* cache_out; int32_t* cache_counts; int32_t* cache_status;
-    int32_t* span;                    // optional, by destination (>= 0 only): first and last OUTPUT row of the image that can hold a non-zero pixel (lo > hi: none)
     uint8_t* hull; size_t hull_stride;        // optional tap: 1 inside the closed convex hull
     int32_t* qtri; size_t qtri_stride;        // optional tap: per pixel the 3 vertex pixel ids of its triangle (pre-filled with -1)
     // state between the stages, per image of the chunk
@@ -1055,8 +1054,6 @@ __global__ void __launch_bounds__(PREP_NT) prep_stage_kernel(ImageArgs A) {
         int32_t* hd = A.hdr + (size_t)img * HD_STRIDE;
         hd[HD_STATUS] = status; hd[HD_NQ] = status == 0 ? s_nitems : 0; hd[HD_EDGE] = status == 0 ? s_nedge : 0; hd[HD_MASKED] = s_masked;
         hd[HD_PEND] = 0; hd[HD_XTRA] = 0;
-        // rows that hold sites: everything the image will ever show lies between them (the hull's rows)
-        hd[HD_ROW_LO] = next_bit(s_rownz, 0, h - 1); hd[HD_ROW_HI] = prev_bit(s_rownz, h - 1, 0);
     }
 }
 
@@ -1438,12 +1435,6 @@ __global__ void __launch_bounds__(FINISH_NT, 2) finish_stage_kernel(ImageArgs A)
         // filled = edge-rule pixels + window-pass pixels (what was handed on, residual ties included, is counted by the cooperative pass)
         counts[5] = status == 0 ? hd[HD_EDGE] + hd[HD_NQ] - s_nitems + s_filled : 0; counts[6] = max(counts[6], s_maxflips); counts[7] += s_flips;
         if (status_final) *status_final = status;
-        if (A.span && dst >= 0) {
-            const int lo = hd[HD_ROW_LO], hi = hd[HD_ROW_HI];
-            const bool blank = status == 1 || status == 2 || lo < 0;  // EMPTY / DEGENERATE renders are all zero
-            A.span[2 * dst] = blank ? 1 : (raw ? lo : h - 1 - hi);
-            A.span[2 * dst + 1] = blank ? 0 : (raw ? hi : h - 1 - lo);
-        }
         if (counts_final) {
 #pragma unroll
             for (int k = 0; k < 8; k++) counts_final[k] = counts[k];

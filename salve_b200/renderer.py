@@ -462,9 +462,5 @@ class BevRenderer:
         d["image"] = d["sites"] + d["prep"] + d["window"] + d["shade"] + d["finish"]
         return d
 
-    def last_d2h_bytes(self) -> int:
-        """Image bytes the last host-output render call copied device -> host (row spans only, see include/salve_bev.h)."""
-        return int(self._lib.salve_bev_last_d2h_bytes(self._h))
-
     def launch_count(self) -> int:
         return int(self._lib.salve_bev_launch_count(self._h))
