@@ -207,7 +207,7 @@ static int ctx_init(salve_bev_ctx* c, const salve_bev_config* cfg) {
     ALLOC(c->cache_counts, 2 * P * 8);
     ALLOC(c->cache_status, 2 * P);
     ALLOC(c->d_dest, N);
-    // mesh scratch (explicit triangulation: grids too large for image_kernel's shared memory, and the triangle tap): ONE image
+    // mesh scratch (explicit triangulation: grids too large for the image stages' shared memory, and the triangle tap): ONE image
     ALLOC(c->color, c->g_stride);
     ALLOC(c->occ, c->bits_stride);
     ALLOC(c->nonempty, c->bits_stride);
@@ -467,7 +467,7 @@ static int run_image_stage(salve_bev_ctx* c, int n_img, const GridParams& G, uin
 }
 
 // Explicit-mesh path on ONE image (mesh scratch): sites + zipper, parallel Lawson flips, and (optionally) the rasteriser.
-// Used for grids that exceed image_kernel's shared memory and for the triangle tap.
+// Used for grids that exceed the image stages' shared memory and for the triangle tap.
 static int run_mesh_stages(salve_bev_ctx* c, const GridParams& G, const uint32_t* keygrid, const uint8_t* const* color_src, uint8_t* dev_out,
                            int32_t* dev_counts, int32_t* dev_status, int raw_mode, int skip_empty, uint8_t* hull, bool raster, cudaStream_t st) {
     SitesArgs SA;

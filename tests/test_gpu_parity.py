@@ -557,7 +557,7 @@ def test_interp_dense_fuzz_against_oracle_and_scipy():
 
 
 def test_interp_dense_on_a_grid_wider_than_512_uses_the_int64_instantiation():
-    """Grids above 512 x 512 run image_kernel<false> (int64 circle parameters in the cooperative pass); the reference's 501 x 501
+    """Grids above 512 x 512 run finish_stage_kernel<false> (int64 circle parameters in the cooperative pass); the reference's 501 x 501
     grid never does.  Sparse sites give circles hundreds of pixels wide, dense ones exercise the window pass near the borders."""
     from salve_b200.renderer import BevRenderer
 
