@@ -63,6 +63,7 @@ struct salve_bev_ctx {
     uint32_t *list0 = nullptr, *list1 = nullptr, *cand = nullptr;
     // state between the stages of the image pipeline (k_image.cuh), per image of a chunk
     uint32_t* planes = nullptr;          // 3 bit planes (occupancy, non-empty, keep)
+    uint32_t* defer_planes = nullptr;    // 1 bit plane: queries handed to the cooperative pass
     unsigned char* rowarr = nullptr;     // row arrays (RA_*), rows_stride bytes per image
     int32_t* hdr = nullptr;              // HD_STRIDE int32 per image
     uint32_t* qlist = nullptr;           // query pixels for the window pass (g entries per image)
@@ -198,6 +199,7 @@ static int ctx_init(salve_bev_ctx* c, const salve_bev_config* cfg) {
     ALLOC(c->clist, N * c->g_stride);
     ALLOC(c->qres, N * c->g_stride);
     ALLOC(c->planes, N * 3 * c->bits_stride);
+    ALLOC(c->defer_planes, N * c->bits_stride);
     c->rows_stride = image_rows_stride(MAX_GRID_H + 1);  // any grid height the generic interp entry point accepts
     ALLOC(c->rowarr, N * c->rows_stride);
     ALLOC(c->hdr, N * HD_STRIDE);
@@ -270,7 +272,7 @@ extern "C" void salve_bev_ctx_destroy(salve_bev_ctx* c) {
     cudaSetDevice(c->cfg.device);
     cudaDeviceSynchronize();
     void* ptrs[] = {c->pano_rgb_store, c->pano_rgb2x_store, c->pano_depth_store, c->d_depth_ptr, c->d_tables, c->keygrid, c->color, c->occ, c->nonempty,
-                    c->keep, c->tmpbits, c->wprefix, c->tris, c->owner, c->list0, c->list1, c->cand, c->qlist, c->clist, c->qres, c->planes, c->rowarr, c->hdr, c->work_counter, c->d_order, c->cache_out, c->cache_counts, c->cache_status, c->d_dest, c->headers, c->counts,
+                    c->keep, c->tmpbits, c->wprefix, c->tris, c->owner, c->list0, c->list1, c->cand, c->qlist, c->clist, c->qres, c->planes, c->defer_planes, c->rowarr, c->hdr, c->work_counter, c->d_order, c->cache_out, c->cache_counts, c->cache_status, c->d_dest, c->headers, c->counts,
                     c->status, c->d_jobs, c->d_color_src, c->out_store};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < N_TMP; i++) if (c->tmp[i]) cudaFree(c->tmp[i]);
@@ -431,7 +433,7 @@ static int run_image_stage(salve_bev_ctx* c, int n_img, const GridParams& G, uin
         IA.cache_out = c->cache_out; IA.cache_counts = c->cache_counts; IA.cache_status = c->cache_status;
         IA.hull = hull ? hull + (size_t)g0 * G.g : nullptr; IA.hull_stride = (size_t)G.g;
         IA.qtri = qtri ? qtri + (size_t)g0 * G.g * 3 : nullptr; IA.qtri_stride = (size_t)G.g * 3;
-        IA.planes = c->planes; IA.plane_stride = c->bits_stride;
+        IA.planes = c->planes; IA.plane_stride = c->bits_stride; IA.defer = c->defer_planes;
         IA.rows = c->rowarr; IA.rows_stride = c->rows_stride; IA.hp = (G.grid_h + 15) & ~15;
         IA.hdr = c->hdr;
         IA.qlist = c->qlist; IA.qlist_stride = c->g_stride; IA.qres = c->qres; IA.clist = c->clist;

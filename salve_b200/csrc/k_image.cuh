@@ -82,7 +82,13 @@ namespace bev {
 #define IMAGE_COOP_BAND_DIV 2 // cooperative pass: band = what is left / (IMAGE_COOP_BAND_DIV * warps)
 #endif
 #ifndef IMAGE_FINISH_THREADS
-#define IMAGE_FINISH_THREADS 512  // finish stage: threads per CTA (two CTAs per SM with both bit planes in shared memory)
+#define IMAGE_FINISH_THREADS 384  // finish stage: threads per CTA (3 x 384 with the deferred plane in global memory beats 2 x 512 with both planes in shared memory by 2 %; 4 x 256 ties, 5 x 128 loses 20 %)
+#endif
+#ifndef IMAGE_FINISH_CTAS
+#define IMAGE_FINISH_CTAS 3       // finish stage: CTAs per SM the launch bounds ask for
+#endif
+#ifndef IMAGE_FINISH_DEFER_GLOBAL
+#define IMAGE_FINISH_DEFER_GLOBAL 1  // finish stage: 1 = the deferred-query bit plane lives in global memory
 #endif
 #ifndef IMAGE_PREP_THREADS
 #define IMAGE_PREP_THREADS 256    // prep stage: threads per CTA
@@ -141,6 +147,7 @@ struct ImageArgs {
     int32_t* qtri; size_t qtri_stride;        // optional tap: per pixel the 3 vertex pixel ids of its triangle (pre-filled with -1)
     // state between the stages, per image of the chunk
     uint32_t* planes; size_t plane_stride;    // [n_img][3][plane_stride] bit rows: occupancy, non-empty, keep
+    uint32_t* defer;                          // [n_img][plane_stride] finish stage: queries handed to the cooperative pass (bit rows)
     unsigned char* rows; size_t rows_stride;  // [n_img] row arrays (RA_*), rows_stride bytes per image
     int32_t hp;                               // entries per row array (grid_h rounded up to 16)
     int32_t* hdr;                             // [n_img][HD_STRIDE]
@@ -174,7 +181,7 @@ __host__ __device__ inline size_t prep_smem_bytes(int h, int wpr) {
     return (size_t)h * wpr * 4 + 13 * image_row_bytes(h) + 2 * (((size_t)h * 4 + 15) & ~(size_t)15) + 64;
 }
 __host__ __device__ inline size_t finish_smem_bytes(int h, int wpr) {
-    return 2 * (size_t)h * wpr * 4 + 9 * image_row_bytes(h) + 2 * (((size_t)h * 4 + 15) & ~(size_t)15) + 64;
+    return (IMAGE_FINISH_DEFER_GLOBAL ? 1 : 2) * (size_t)h * wpr * 4 + 9 * image_row_bytes(h) + 2 * (((size_t)h * 4 + 15) & ~(size_t)15) + 64;
 }
 // the largest of them decides whether a grid can take this path at all (else: explicit-mesh kernels)
 __host__ __device__ inline size_t image_smem_bytes(int h, int wpr) {
@@ -182,7 +189,11 @@ __host__ __device__ inline size_t image_smem_bytes(int h, int wpr) {
     return a > b ? (a > c ? a : c) : (b > c ? b : c);
 }
 
+#if IMAGE_FINISH_DEFER_GLOBAL
+#define DEFER_LD(p) __ldcg(p)   // other warps clear bits with atomics (performed in L2): never read them through L1
+#else
 #define DEFER_LD(p) (*(p))
+#endif
 
 struct Tri2 { int ax, ay, bx, by, cx, cy; };
 
@@ -1192,7 +1203,7 @@ __global__ void __launch_bounds__(256) image_order_kernel(const int32_t* __restr
 
 // ---- stage 4: shade the window pass's results, cooperative pass for what it handed on, masked-out sites, counters ---------
 template <bool SG>
-__global__ void __launch_bounds__(FINISH_NT, 2) finish_stage_kernel(ImageArgs A) {
+__global__ void __launch_bounds__(FINISH_NT, IMAGE_FINISH_CTAS) finish_stage_kernel(ImageArgs A) {
     const int img = A.order ? A.order[blockIdx.x] : blockIdx.x;
     const int h = A.G.grid_h, w = A.G.grid_w, wpr = A.G.wpr;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -1205,7 +1216,11 @@ __global__ void __launch_bounds__(FINISH_NT, 2) finish_stage_kernel(ImageArgs A)
     {
         unsigned char* p = smem_raw;
         S.occ = (uint32_t*)p; p += (size_t)nwords * 4;
+#if IMAGE_FINISH_DEFER_GLOBAL
+        S.tmp = A.defer + (size_t)img * A.plane_stride;
+#else
         S.tmp = (uint32_t*)p; p += (size_t)nwords * 4;
+#endif
         const size_t rows = image_row_bytes(h);
         int16_t** arr[9] = {&S.cnt, &S.first, &S.last, &S.up, &S.dn, &S.hl0, &S.hl1, &S.hr0, &S.hr1};
         for (int i = 0; i < 9; i++) { *arr[i] = (int16_t*)p; p += rows; }
