@@ -36,6 +36,9 @@ static void set_err(const char* fmt, const char* a, const char* b, int line) { s
     } while (0)
 
 constexpr int N_TMP = 8;
+#ifndef IMAGE_LOCAL_RULE
+#define IMAGE_LOCAL_RULE 1
+#endif
 constexpr int N_STAGE_EVENTS = 7;  // chunk start, after: splat, sites, prep, window, shade, finish
 
 struct salve_bev_ctx {
@@ -71,6 +74,8 @@ struct salve_bev_ctx {
     unsigned long long* qres = nullptr;  // per list entry: the triangle the window pass reached
     int32_t* work_counter = nullptr;     // window stage: next block of the chunk-wide query list
     int32_t* d_order = nullptr;          // finish stage: hand-out order (image_order_kernel)
+    uint32_t* local_lut = nullptr;       // prep stage: tables of the local rule (LocalRule::WORDS words)
+    bool local_rule = true;
     size_t rows_stride = 0;
     int n_sm = 0;
     // The key grid is all zero between calls: the sites stage zeroes the keys it consumes, so no chunk pays for a memset of
@@ -153,6 +158,68 @@ static void compute_tables_libm(int H, int W, std::vector<double>& t) {
     }
 }
 
+// Tables of the local rule (k_image.cuh, LocalRule): every counter-clockwise triangle of three of the 12 near neighbours that
+// contains the query (the origin) and whose circle -- the lattice points strictly inside it and on it -- stays within the 5 x 5
+// neighbourhood; per 12-bit neighbour pattern the candidates whose vertices are present and which have none of the pattern's
+// sites strictly inside (at most four: more only when the W-E or N-S pair is present, which the edge rule takes first).
+static const std::vector<uint32_t>& local_rule_tables() {
+    static const std::vector<uint32_t> tab = [] {
+        std::vector<uint32_t> t(LocalRule::WORDS, 0u);
+        struct P { int x, y; };
+        auto pos = [](int k) { const int b = LocalRule::pos_bit(k); return P{b % 5 - 2, b / 5 - 2}; };
+        auto orient = [](P a, P b, P c) { return (b.x - a.x) * (c.y - a.y) - (b.y - a.y) * (c.x - a.x); };
+        auto incircle = [](P a, P b, P c, P d) {
+            const long long ax = a.x - d.x, ay = a.y - d.y, bx = b.x - d.x, by = b.y - d.y, cx = c.x - d.x, cy = c.y - d.y;
+            return (ax * ax + ay * ay) * (bx * cy - by * cx) - (bx * bx + by * by) * (ax * cy - ay * cx) + (cx * cx + cy * cy) * (ax * by - ay * bx);
+        };
+        struct Cand { uint32_t vmask12, inside12; };
+        std::vector<Cand> cands;
+        const P o{0, 0};
+        for (int i = 0; i < LocalRule::NPOS; i++)
+            for (int j = i + 1; j < LocalRule::NPOS; j++)
+                for (int k = j + 1; k < LocalRule::NPOS; k++) {
+                    P a = pos(i), b = pos(j), c = pos(k);
+                    int ib = j, ic = k;
+                    const int orr = orient(a, b, c);
+                    if (orr == 0) continue;
+                    if (orr < 0) { std::swap(b, c); std::swap(ib, ic); }
+                    if (orient(a, b, o) < 0 || orient(b, c, o) < 0 || orient(c, a, o) < 0) continue;
+                    uint32_t inside = 0u, on = 0u;
+                    bool fits = true;
+                    for (int y = -8; y <= 8 && fits; y++)
+                        for (int x = -8; x <= 8; x++) {
+                            const P d{x, y};
+                            if ((x == a.x && y == a.y) || (x == b.x && y == b.y) || (x == c.x && y == c.y)) continue;
+                            const long long inc = incircle(a, b, c, d);
+                            if (inc < 0) continue;
+                            if (x < -2 || x > 2 || y < -2 || y > 2) { fits = false; break; }
+                            if (x == 0 && y == 0) continue;  // the query itself is no site
+                            (inc > 0 ? inside : on) |= 1u << ((y + 2) * 5 + x + 2);
+                        }
+                    if (!fits || (int)cands.size() >= LocalRule::MAXCAND) continue;
+                    const int id = (int)cands.size();
+                    t[LocalRule::OFF_INSIDE + id] = inside;
+                    t[LocalRule::OFF_ON + id] = on;
+                    t[LocalRule::OFF_VERTS + id] = (uint32_t)LocalRule::pos_bit(i) | ((uint32_t)LocalRule::pos_bit(ib) << 5) | ((uint32_t)LocalRule::pos_bit(ic) << 10);
+                    uint32_t in12 = 0u;
+                    for (int m = 0; m < LocalRule::NPOS; m++) if (inside & (1u << LocalRule::pos_bit(m))) in12 |= 1u << m;
+                    cands.push_back({(1u << i) | (1u << j) | (1u << k), in12});
+                }
+        for (uint32_t pat = 0; pat < (uint32_t)LocalRule::NPAT; pat++) {
+            uint32_t e = 0xFFFFFFFFu;
+            int n = 0;
+            for (size_t id = 0; id < cands.size() && n < 4; id++)
+                if ((pat & cands[id].vmask12) == cands[id].vmask12 && !(pat & cands[id].inside12)) {
+                    e = (e & ~(0xFFu << (8 * n))) | ((uint32_t)id << (8 * n));
+                    n++;
+                }
+            t[pat] = e;
+        }
+        return t;
+    }();
+    return tab;
+}
+
 static int ctx_init(salve_bev_ctx* c, const salve_bev_config* cfg);
 
 extern "C" int salve_bev_ctx_create(const salve_bev_config* cfg, salve_bev_ctx** out) {
@@ -205,6 +272,11 @@ static int ctx_init(salve_bev_ctx* c, const salve_bev_config* cfg) {
     ALLOC(c->hdr, N * HD_STRIDE);
     ALLOC(c->work_counter, 1);
     ALLOC(c->d_order, N);
+    ALLOC(c->local_lut, LocalRule::WORDS);
+    {
+        const std::vector<uint32_t>& lut = local_rule_tables();
+        CU(cudaMemcpy(c->local_lut, lut.data(), sizeof(uint32_t) * LocalRule::WORDS, cudaMemcpyHostToDevice));
+    }
     ALLOC(c->cache_out, 2 * P * c->img_bytes + 64);  // +64: replicate_images_kernel reads whole words
     ALLOC(c->cache_counts, 2 * P * 8);
     ALLOC(c->cache_status, 2 * P);
@@ -272,7 +344,7 @@ extern "C" void salve_bev_ctx_destroy(salve_bev_ctx* c) {
     cudaSetDevice(c->cfg.device);
     cudaDeviceSynchronize();
     void* ptrs[] = {c->pano_rgb_store, c->pano_rgb2x_store, c->pano_depth_store, c->d_depth_ptr, c->d_tables, c->keygrid, c->color, c->occ, c->nonempty,
-                    c->keep, c->tmpbits, c->wprefix, c->tris, c->owner, c->list0, c->list1, c->cand, c->qlist, c->clist, c->qres, c->planes, c->defer_planes, c->rowarr, c->hdr, c->work_counter, c->d_order, c->cache_out, c->cache_counts, c->cache_status, c->d_dest, c->headers, c->counts,
+                    c->keep, c->tmpbits, c->wprefix, c->tris, c->owner, c->list0, c->list1, c->cand, c->qlist, c->clist, c->qres, c->planes, c->defer_planes, c->rowarr, c->hdr, c->work_counter, c->d_order, c->local_lut, c->cache_out, c->cache_counts, c->cache_status, c->d_dest, c->headers, c->counts,
                     c->status, c->d_jobs, c->d_color_src, c->out_store};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < N_TMP; i++) if (c->tmp[i]) cudaFree(c->tmp[i]);
@@ -438,6 +510,7 @@ static int run_image_stage(salve_bev_ctx* c, int n_img, const GridParams& G, uin
         IA.hdr = c->hdr;
         IA.qlist = c->qlist; IA.qlist_stride = c->g_stride; IA.qres = c->qres; IA.clist = c->clist;
         IA.work_counter = c->work_counter;
+        IA.local_lut = (IMAGE_LOCAL_RULE && c->local_rule) ? c->local_lut : nullptr;
         IA.raw_mode = raw_mode; IA.skip_empty_check = skip_empty; IA.clear_keys = clear_keys ? 1 : 0;
         CU(cudaMemsetAsync(c->work_counter, 0, sizeof(int32_t), st));
         const bool ev = timed && n_img <= WIN_MAX_IMAGES;  // per-stage events: one group per chunk (else only the chunk total is kept)
@@ -445,6 +518,10 @@ static int run_image_stage(salve_bev_ctx* c, int n_img, const GridParams& G, uin
         sites_stage_kernel<<<dim3((unsigned)((G.grid_h + SITES_WARPS * SITES_GROUPS - 1) / (SITES_WARPS * SITES_GROUPS)), (unsigned)n), SITES_WARPS * 32, sites_smem_bytes(G.grid_w, G.wpr), st>>>(IA);
         if (ev && (rc = stage_event(c, st))) return rc;
         prep_stage_kernel<<<n, PREP_NT, prep_smem_bytes(G.grid_h, G.wpr), st>>>(IA);
+        if (IA.local_lut && !qtri) {  // (with the triangle tap the prep stage leaves the queries in the window list)
+            local_stage_kernel<<<dim3(LOCAL_SPLIT, (unsigned)n), LOCAL_NT, 0, st>>>(IA);
+            c->launches++;
+        }
         if (ev && (rc = stage_event(c, st))) return rc;
         const int win_ctas = std::max(1, std::min(c->n_sm * IMAGE_WIN_CTAS, n * 16));
         window_stage_kernel<IMAGE_WIN_NR><<<win_ctas, WIN_NT, 0, st>>>(IA);

@@ -125,7 +125,7 @@ constexpr int IMAGE_MAX_FLIPS = 100000;   // safety cap on one descent (never re
 enum { RA_CNT = 0, RA_FIRST, RA_LAST, RA_NE, RA_UP, RA_DN, RA_HL0, RA_HL1, RA_HR0, RA_HR1, RA_N16 };
 enum { RA_HLF = 0, RA_HRF, RA_NF };
 // per-image header (16 int32)
-enum { HD_STATUS = 0, HD_NQ, HD_EDGE, HD_MASKED, HD_PEND, HD_XTRA, HD_N };
+enum { HD_STATUS = 0, HD_NQ, HD_EDGE, HD_MASKED, HD_PEND, HD_XTRA, HD_LOCAL, HD_NRAW, HD_N };
 constexpr int HD_STRIDE = 16;
 
 struct ImageArgs {
@@ -155,6 +155,7 @@ struct ImageArgs {
     unsigned long long* qres;                 // per image, per list entry: triangle (3 x 21-bit vertex labels), final if | QRES_DONE
     uint32_t* clist;                          // per image: edge-rule pixels (prep), then the entries handed to the cooperative pass
     int32_t* work_counter;                    // window stage: next block of the chunk-wide list (zeroed by the host)
+    const uint32_t* local_lut;                // local rule tables (LocalRule, built by the host), or null: rule off
     int32_t raw_mode;                 // 1: no keep mask, no flip (interp_dense_grid_from_sparse semantics)
     int32_t skip_empty_check;         // 1: generic interp path (no EMPTY status)
     int32_t clear_keys;               // 1: the sites stage zeroes the keys it consumes (the next chunk needs no memset)
@@ -194,6 +195,30 @@ __host__ __device__ inline size_t image_smem_bytes(int h, int wpr) {
 #else
 #define DEFER_LD(p) (*(p))
 #endif
+
+// ---- local rule: queries whose Delaunay triangle has its three vertices among 12 near neighbours --------------------------
+// After the edge rule, two thirds of the remaining queries lie in a triangle whose vertices are all among the 8 neighbours and the
+// 4 pixels at distance 2 on q's row and column, with a circumcircle that stays inside the 5 x 5 neighbourhood.  For them the
+// whole search is a table look-up on the 12 neighbour bits: the table gives the (at most 4) triangles of those neighbours that
+// contain q and have none of the 12 strictly inside; a candidate is THE triangle of the canonical triangulation over q iff the
+// other lattice points strictly inside its circle (a 25-bit mask of the neighbourhood) are no sites and every site ON the circle
+// loses the symbolic-perturbation test -- the same certificate the window pass and the cooperative pass end with, so the result
+// is identical bit for bit.  The prep stage runs it with one thread per query; what it resolves never reaches the window pass.
+// Neighbourhood bit (dy + 2) * 5 + (dx + 2) <-> pixel (x + dx, r + dy).
+struct LocalRule {
+    static constexpr int NPOS = 12, NPAT = 1 << NPOS, MAXCAND = 128;
+    // words of the table: [NPAT] up to four candidate ids per pattern (a byte each, 0xFF: none), then per candidate
+    // inside mask, on-circle mask, the three vertices (5 bits each: neighbourhood bit indices, counter-clockwise)
+    static constexpr int OFF_INSIDE = NPAT, OFF_ON = NPAT + MAXCAND, OFF_VERTS = NPAT + 2 * MAXCAND, WORDS = NPAT + 3 * MAXCAND;
+    // pattern bit k <-> neighbourhood bit: (0,-2); (-1,-1) (0,-1) (1,-1); (-2,0) (-1,0); (1,0) (2,0); (-1,1) (0,1) (1,1); (0,2)
+    __host__ __device__ static constexpr int pos_bit(int k) {
+        return k == 0 ? 2 : k <= 3 ? 5 + k : k <= 5 ? 6 + k : k <= 7 ? 7 + k : k <= 10 ? 8 + k : 22;
+    }
+    __host__ __device__ static uint32_t pattern_of(uint32_t nb) {
+        return ((nb >> 2) & 1u) | (((nb >> 6) & 7u) << 1) | (((nb >> 10) & 3u) << 4) | (((nb >> 13) & 3u) << 6) | (((nb >> 16) & 7u) << 8) |
+               (((nb >> 22) & 1u) << 11);
+    }
+};
 
 struct Tri2 { int ax, ay, bx, by, cx, cy; };
 
@@ -982,6 +1007,10 @@ __global__ void __launch_bounds__(PREP_NT) prep_stage_kernel(ImageArgs A) {
     uint32_t* qlist = A.qlist + (size_t)img * A.qlist_stride;
     uint32_t* elist = A.clist + (size_t)img * A.qlist_stride;  // edge-rule pixels for the shade stage (the cooperative pass's list is built later)
     const bool edge_rule = A.qtri == nullptr;  // the triangle tap wants every query resolved to a triangle
+    // With the local rule the queries first go to a scratch list (the free top end of the edge list's array, downwards: queries
+    // and edge-rule pixels are disjoint, so both fit), from which the local stage feeds the window pass's list.
+    const bool local_rule = edge_rule && A.local_lut != nullptr && status == 0;
+    const int cap = (int)A.qlist_stride;
     {
         int kc = 0;
         const int nw_pad = (nwords + 31) & ~31;
@@ -1035,7 +1064,8 @@ __global__ void __launch_bounds__(PREP_NT) prep_stage_kernel(ImageArgs A) {
             base_q = __shfl_sync(FULL, base_q, 0) + (excl & 0xFFFF);
             base_e = __shfl_sync(FULL, base_e, 0) + (excl >> 16);
             const uint32_t code0 = ((uint32_t)r << COL_BITS) | (uint32_t)(wi * 32);
-            while (q) { const int b = __ffs(q) - 1; q &= q - 1; qlist[base_q++] = code0 + b; }
+            if (local_rule) { while (q) { const int b = __ffs(q) - 1; q &= q - 1; elist[cap - 1 - base_q++] = code0 + b; } }
+            else { while (q) { const int b = __ffs(q) - 1; q &= q - 1; qlist[base_q++] = code0 + b; } }
             uint32_t m = e;
             while (m) {  // bit 31: W-E pair present, bit 30: N-S pair present
                 const int b = __ffs(m) - 1; m &= m - 1;
@@ -1063,8 +1093,110 @@ __global__ void __launch_bounds__(PREP_NT) prep_stage_kernel(ImageArgs A) {
     if (tid == 0) {
         counts[2] = nS; counts[3] = s_ne_cnt; counts[4] = raw ? 0 : s_keep_cnt; counts[5] = 0; counts[6] = 0; counts[7] = 0;
         int32_t* hd = A.hdr + (size_t)img * HD_STRIDE;
-        hd[HD_STATUS] = status; hd[HD_NQ] = status == 0 ? s_nitems : 0; hd[HD_EDGE] = status == 0 ? s_nedge : 0; hd[HD_MASKED] = s_masked;
-        hd[HD_PEND] = 0; hd[HD_XTRA] = 0;
+        // with the local rule the queries are still in the scratch list: the local stage fills the window list and counts it
+        hd[HD_STATUS] = status; hd[HD_NQ] = status == 0 && !local_rule ? s_nitems : 0; hd[HD_EDGE] = status == 0 ? s_nedge : 0;
+        hd[HD_MASKED] = s_masked; hd[HD_PEND] = 0; hd[HD_XTRA] = 0; hd[HD_LOCAL] = 0; hd[HD_NRAW] = local_rule ? s_nitems : 0;
+    }
+}
+
+// ---- local stage (see LocalRule): one thread per query of the prep stage's scratch list ---------------------------------------
+// Resolved queries go to the top end of the window list with their final triangle (the shade stage takes them from there), the
+// rest is appended to the window pass's list.  grid = (LOCAL_SPLIT, images).
+constexpr int LOCAL_SPLIT = 8;
+constexpr int LOCAL_NT = 256;
+__global__ void __launch_bounds__(LOCAL_NT) local_stage_kernel(ImageArgs A) {
+    const int img = blockIdx.y;
+    int32_t* hd = A.hdr + (size_t)img * HD_STRIDE;
+    const int n = hd[HD_NRAW];
+    if (n == 0) return;
+    const unsigned FULL = 0xffffffffu;
+    const int h = A.G.grid_h, w = A.G.grid_w, wpr = A.G.wpr;
+    const int lane = threadIdx.x & 31;
+    const int cap = (int)A.qlist_stride;
+    const uint32_t* lut = A.local_lut;
+    const uint32_t* occ = A.planes + (size_t)img * 3 * A.plane_stride;
+    const uint32_t* raw_list = A.clist + (size_t)img * A.qlist_stride;
+    uint32_t* qlist = A.qlist + (size_t)img * A.qlist_stride;
+    unsigned long long* qres = A.qres + (size_t)img * A.qlist_stride;
+    const int n_pad = (n + 31) & ~31;
+    for (int i = blockIdx.x * LOCAL_NT + threadIdx.x; i < n_pad; i += LOCAL_SPLIT * LOCAL_NT) {
+        const bool valid = i < n;
+        bool solved = false;
+        uint32_t code = 0u;
+        unsigned long long tri = 0ull;
+        if (valid) {
+            code = __ldg(raw_list + cap - 1 - i);
+            const int x = (int)(code & COL_MASK), r = (int)(code >> COL_BITS);
+            // 5 x 5 neighbourhood bits, branch-free with clamped row / word indices and masks for what lies outside the grid
+            const int c0 = x - 2;
+            const int w0 = c0 >> 5, sh = c0 & 31;  // c0 may be negative: arithmetic shift = floor
+            const int wlo = max(w0, 0), whi = min(w0 + 1, wpr - 1);
+            const uint32_t mlo = w0 >= 0 ? 0xFFFFFFFFu : 0u, mhi = w0 + 1 < wpr ? 0xFFFFFFFFu : 0u;
+            uint32_t nb = 0u;
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                const int y = r + k - 2;
+                const int yc = min(max(y, 0), h - 1);
+                const uint32_t vm = y == yc ? 0xFFFFFFFFu : 0u;
+                const uint32_t* row = occ + yc * wpr;
+                nb |= (__funnelshift_r(__ldg(row + wlo) & mlo & vm, __ldg(row + whi) & mhi & vm, sh) & 31u) << (5 * k);
+            }
+            const uint32_t e = __ldg(lut + LocalRule::pattern_of(nb));
+            // candidates with no site strictly inside their circle: all four slots at once (unused slots hold 0xFF: the mask
+            // index wraps to a table entry, the id test discards it)
+            uint32_t surv = 0u;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t cid = (e >> (8 * k)) & 0xFFu;
+                const uint32_t inside = __ldg(lut + LocalRule::OFF_INSIDE + (cid & (LocalRule::MAXCAND - 1)));
+                if (cid != 0xFFu && !(nb & inside)) surv |= 1u << k;
+            }
+            const int qi = r * w + x;
+            while (surv && !solved) {
+                const int k = __ffs(surv) - 1; surv &= surv - 1;
+                const uint32_t cid = (e >> (8 * k)) & 0xFFu;
+                const uint32_t verts = __ldg(lut + LocalRule::OFF_VERTS + cid);
+                uint32_t ties = nb & __ldg(lut + LocalRule::OFF_ON + cid);
+                const int ia = (int)(verts & 31u), ib = (int)((verts >> 5) & 31u), ic = (int)((verts >> 10) & 31u);
+                const int ay = (ia * 13 >> 6) - 2, ax = ia - 5 * (ay + 2) - 2, by = (ib * 13 >> 6) - 2, bx = ib - 5 * (by + 2) - 2,
+                          cy = (ic * 13 >> 6) - 2, cx = ic - 5 * (cy + 2) - 2;  // i / 5 = i * 13 >> 6 for i < 25
+                bool ok = true;
+                if (ties) {  // sites on the circle: symbolic perturbation, as incircle_pert() (weights < 2^20, |orient| <= 32)
+                    const int wa = pert_weight_idx((uint32_t)(qi + ay * w + ax)), wb = pert_weight_idx((uint32_t)(qi + by * w + bx)),
+                              wc = pert_weight_idx((uint32_t)(qi + cy * w + cx));
+                    const int oabc = (bx - ax) * (cy - ay) - (by - ay) * (cx - ax);
+                    while (ties && ok) {
+                        const int b = __ffs(ties) - 1; ties &= ties - 1;
+                        const int dy = (b * 13 >> 6) - 2, dx = b - 5 * (dy + 2) - 2;
+                        const int wd = pert_weight_idx((uint32_t)(qi + dy * w + dx));
+                        const int obcd = (cx - bx) * (dy - by) - (cy - by) * (dx - bx);
+                        const int oacd = (cx - ax) * (dy - ay) - (cy - ay) * (dx - ax);
+                        const int oabd = (bx - ax) * (dy - ay) - (by - ay) * (dx - ax);
+                        // > 0: the site is inside; = 0: a residual tie, left to the passes that know how the oracle breaks it
+                        if (wa * obcd - wb * oacd + wc * oabd - wd * oabc >= 0) ok = false;
+                    }
+                }
+                if (ok) {
+                    solved = true;
+                    tri = QRES_DONE | (unsigned long long)vlabel(r + ay, x + ax) | ((unsigned long long)vlabel(r + by, x + bx) << 21) |
+                          ((unsigned long long)vlabel(r + cy, x + cx) << 42);
+                }
+            }
+        }
+        const uint32_t m_loc = __ballot_sync(FULL, valid && solved), m_win = __ballot_sync(FULL, valid && !solved);
+        int base_l = 0, base_w = 0;
+        if (lane == 0) {
+            if (m_loc) base_l = atomicAdd(hd + HD_LOCAL, __popc(m_loc));
+            if (m_win) base_w = atomicAdd(hd + HD_NQ, __popc(m_win));
+        }
+        base_l = __shfl_sync(FULL, base_l, 0); base_w = __shfl_sync(FULL, base_w, 0);
+        const uint32_t below = (1u << lane) - 1u;
+        if (valid && solved) {
+            const int slot = cap - 1 - (base_l + __popc(m_loc & below));
+            qlist[slot] = code; qres[slot] = tri;
+        } else if (valid) {
+            qlist[base_w + __popc(m_win & below)] = code;
+        }
     }
 }
 
@@ -1105,6 +1237,7 @@ __global__ void __launch_bounds__(SHADE_NT) shade_stage_kernel(ImageArgs A) {
     int32_t* hd = A.hdr + (size_t)img * HD_STRIDE;
     if (hd[HD_STATUS] != 0) return;
     const int n_edge = hd[HD_EDGE], n_win = hd[HD_NQ];
+    const int n_tri = n_win + hd[HD_LOCAL], cap = (int)A.qlist_stride;  // the local rule's entries sit at the top end of the list, downwards
     const int h = A.G.grid_h, w = A.G.grid_w;
     const bool raw = A.raw_mode != 0;
     int dst;
@@ -1153,14 +1286,15 @@ __global__ void __launch_bounds__(SHADE_NT) shade_stage_kernel(ImageArgs A) {
             p[u][2] = (uint8_t)(((ca[u] >> 16) + (cb[u] >> 16)) >> 1);
         }
     }
-    for (int j0 = blockIdx.x * SHADE_NT + threadIdx.x; j0 < n_win; j0 += SHADE_UNROLL * STRIDE) {
+    for (int j0 = blockIdx.x * SHADE_NT + threadIdx.x; j0 < n_tri; j0 += SHADE_UNROLL * STRIDE) {
         unsigned long long rs[SHADE_UNROLL];
         uint32_t code[SHADE_UNROLL], ca[SHADE_UNROLL], cb[SHADE_UNROLL], cc[SHADE_UNROLL];
 #pragma unroll
         for (int u = 0; u < SHADE_UNROLL; u++) {
             const int j = j0 + u * STRIDE;
-            rs[u] = j < n_win ? qres[j] : 0ull;  // without QRES_DONE: handed on to the cooperative pass (or beyond the list)
-            code[u] = j < n_win ? __ldg(qlist + j) : 0u;
+            const int slot = j < n_win ? j : cap - 1 - (j - n_win);
+            rs[u] = j < n_tri ? qres[slot] : 0ull;  // without QRES_DONE: handed on to the cooperative pass (or beyond the list)
+            code[u] = j < n_tri ? __ldg(qlist + slot) : 0u;
         }
 #pragma unroll
         for (int u = 0; u < SHADE_UNROLL; u++) {
@@ -1448,7 +1582,7 @@ __global__ void __launch_bounds__(FINISH_NT, IMAGE_FINISH_CTAS) finish_stage_ker
     __syncthreads();
     if (tid == 0) {
         // filled = edge-rule pixels + window-pass pixels (what was handed on, residual ties included, is counted by the cooperative pass)
-        counts[5] = status == 0 ? hd[HD_EDGE] + hd[HD_NQ] - s_nitems + s_filled : 0; counts[6] = max(counts[6], s_maxflips); counts[7] += s_flips;
+        counts[5] = status == 0 ? hd[HD_EDGE] + hd[HD_LOCAL] + hd[HD_NQ] - s_nitems + s_filled : 0; counts[6] = max(counts[6], s_maxflips); counts[7] += s_flips;
         if (status_final) *status_final = status;
         if (counts_final) {
 #pragma unroll
