@@ -1119,13 +1119,32 @@ __global__ void __launch_bounds__(LOCAL_NT) local_stage_kernel(ImageArgs A) {
     uint32_t* qlist = A.qlist + (size_t)img * A.qlist_stride;
     unsigned long long* qres = A.qres + (size_t)img * A.qlist_stride;
     const int n_pad = (n + 31) & ~31;
-    for (int i = blockIdx.x * LOCAL_NT + threadIdx.x; i < n_pad; i += LOCAL_SPLIT * LOCAL_NT) {
+    constexpr int STEP = LOCAL_SPLIT * LOCAL_NT;
+    const uint32_t below = (1u << lane) - 1u;
+    // The slots of an iteration's results come from two atomics per warp; their round trip is hidden by writing the results out
+    // one iteration later (p_*: the previous iteration's), and the next list entry is fetched an iteration ahead.
+    bool p_valid = false, p_solved = false;
+    uint32_t p_code = 0u, p_mloc = 0u, p_mwin = 0u;
+    unsigned long long p_tri = 0ull;
+    int p_basel = 0, p_basew = 0;
+    auto write_out = [&]() {
+        const int bl = __shfl_sync(FULL, p_basel, 0), bw = __shfl_sync(FULL, p_basew, 0);
+        if (p_valid && p_solved) {
+            const int slot = cap - 1 - (bl + __popc(p_mloc & below));
+            qlist[slot] = p_code; qres[slot] = p_tri;
+        } else if (p_valid) {
+            qlist[bw + __popc(p_mwin & below)] = p_code;
+        }
+    };
+    int i = blockIdx.x * LOCAL_NT + threadIdx.x;
+    uint32_t next_code = i < n ? __ldg(raw_list + cap - 1 - i) : 0u;
+    for (; i < n_pad; i += STEP) {
         const bool valid = i < n;
         bool solved = false;
-        uint32_t code = 0u;
+        const uint32_t code = next_code;
+        next_code = i + STEP < n ? __ldg(raw_list + cap - 1 - (i + STEP)) : 0u;
         unsigned long long tri = 0ull;
         if (valid) {
-            code = __ldg(raw_list + cap - 1 - i);
             const int x = (int)(code & COL_MASK), r = (int)(code >> COL_BITS);
             // 5 x 5 neighbourhood bits, branch-free with clamped row / word indices and masks for what lies outside the grid
             const int c0 = x - 2;
@@ -1161,19 +1180,22 @@ __global__ void __launch_bounds__(LOCAL_NT) local_stage_kernel(ImageArgs A) {
                 const int ay = (ia * 13 >> 6) - 2, ax = ia - 5 * (ay + 2) - 2, by = (ib * 13 >> 6) - 2, bx = ib - 5 * (by + 2) - 2,
                           cy = (ic * 13 >> 6) - 2, cx = ic - 5 * (cy + 2) - 2;  // i / 5 = i * 13 >> 6 for i < 25
                 bool ok = true;
-                if (ties) {  // sites on the circle: symbolic perturbation, as incircle_pert() (weights < 2^20, |orient| <= 32)
+                if (ties) {
+                    // Sites on the circle: symbolic perturbation, as incircle_pert().  Its first three terms are linear in the
+                    // tested point d: wa * orient(b,c,d) - wb * orient(a,c,d) + wc * orient(a,b,d) = PA * dx + PB * dy + PC
+                    // (weights < 2^20, |coordinates| <= 2: every term and the sum fit int32).
                     const int wa = pert_weight_idx((uint32_t)(qi + ay * w + ax)), wb = pert_weight_idx((uint32_t)(qi + by * w + bx)),
                               wc = pert_weight_idx((uint32_t)(qi + cy * w + cx));
+                    const int PA = -wa * (cy - by) + wb * (cy - ay) - wc * (by - ay);
+                    const int PB = wa * (cx - bx) - wb * (cx - ax) + wc * (bx - ax);
+                    const int PC = wa * (bx * cy - by * cx) - wb * (ax * cy - ay * cx) + wc * (ax * by - ay * bx);
                     const int oabc = (bx - ax) * (cy - ay) - (by - ay) * (cx - ax);
                     while (ties && ok) {
                         const int b = __ffs(ties) - 1; ties &= ties - 1;
                         const int dy = (b * 13 >> 6) - 2, dx = b - 5 * (dy + 2) - 2;
                         const int wd = pert_weight_idx((uint32_t)(qi + dy * w + dx));
-                        const int obcd = (cx - bx) * (dy - by) - (cy - by) * (dx - bx);
-                        const int oacd = (cx - ax) * (dy - ay) - (cy - ay) * (dx - ax);
-                        const int oabd = (bx - ax) * (dy - ay) - (by - ay) * (dx - ax);
                         // > 0: the site is inside; = 0: a residual tie, left to the passes that know how the oracle breaks it
-                        if (wa * obcd - wb * oacd + wc * oabd - wd * oabc >= 0) ok = false;
+                        if (PA * dx + PB * dy + PC - wd * oabc >= 0) ok = false;
                     }
                 }
                 if (ok) {
@@ -1189,15 +1211,10 @@ __global__ void __launch_bounds__(LOCAL_NT) local_stage_kernel(ImageArgs A) {
             if (m_loc) base_l = atomicAdd(hd + HD_LOCAL, __popc(m_loc));
             if (m_win) base_w = atomicAdd(hd + HD_NQ, __popc(m_win));
         }
-        base_l = __shfl_sync(FULL, base_l, 0); base_w = __shfl_sync(FULL, base_w, 0);
-        const uint32_t below = (1u << lane) - 1u;
-        if (valid && solved) {
-            const int slot = cap - 1 - (base_l + __popc(m_loc & below));
-            qlist[slot] = code; qres[slot] = tri;
-        } else if (valid) {
-            qlist[base_w + __popc(m_win & below)] = code;
-        }
+        write_out();  // the previous iteration's
+        p_valid = valid; p_solved = solved; p_code = code; p_tri = tri; p_mloc = m_loc; p_mwin = m_win; p_basel = base_l; p_basew = base_w;
     }
+    write_out();
 }
 
 // ---- exact barycentric value of a query pixel from its final triangle (shade stage, cooperative pass) ----------------------
@@ -1458,11 +1475,23 @@ __global__ void __launch_bounds__(FINISH_NT, IMAGE_FINISH_CTAS) finish_stage_ker
             i0 = __shfl_sync(FULL, i0, 0); band = __shfl_sync(FULL, band, 0);
             if (i0 >= n) break;
             const int i_end = min(n, i0 + band);
-          for (int i = i0; i < i_end; i++) {
-            const uint32_t idx = clist[i];
-            const uint32_t code = qlist[idx];
+          // 32 entries of the band at a time: every lane fetches one entry and watches its deferred bit; the warp takes the
+          // first entry that is still pending (most are filled by the triangle of an earlier descent: skipping them costs one
+          // memory round trip per descent instead of three per entry)
+          for (int g0 = i0; g0 < i_end; g0 += 32) {
+           bool mine = g0 + lane < i_end;
+           uint32_t my_idx = 0u, my_code = 0u;
+           if (mine) { my_idx = clist[g0 + lane]; my_code = qlist[my_idx]; }
+           const int my_x = (int)(my_code & COL_MASK), my_r = (int)(my_code >> COL_BITS);
+           while (true) {
+            const bool still = mine && ((DEFER_LD(&defer[my_r * wpr + (my_x >> 5)]) >> (my_x & 31)) & 1u);
+            const uint32_t pm = __ballot_sync(FULL, still);
+            if (!pm) break;
+            const int src = __ffs(pm) - 1;
+            if (lane == src) mine = false;  // taken once, whatever becomes of it
+            const uint32_t idx = __shfl_sync(FULL, my_idx, src);
+            const uint32_t code = __shfl_sync(FULL, my_code, src);
             const int x = (int)(code & COL_MASK), r = (int)(code >> COL_BITS);
-            if (!((DEFER_LD(&defer[r * wpr + (x >> 5)]) >> (x & 31)) & 1u)) continue;  // already filled by another descent's triangle
             Tri2 t;
             const unsigned long long part = qres[idx];
             if (part != 0ull) {  // continue the window pass's descent (the entry is not QRES_DONE: it is on this list)
@@ -1543,6 +1572,7 @@ __global__ void __launch_bounds__(FINISH_NT, IMAGE_FINISH_CTAS) finish_stage_ker
                 }
             }
             __syncwarp();
+           }
           }
         }
     }
