@@ -1099,11 +1099,24 @@ __global__ void __launch_bounds__(PREP_NT) prep_stage_kernel(ImageArgs A) {
     }
 }
 
-// ---- local stage (see LocalRule): one thread per query of the prep stage's scratch list ---------------------------------------
+// ---- local stage (see LocalRule): the queries of the prep stage's scratch list ------------------------------------------------
 // Resolved queries go to the top end of the window list with their final triangle (the shade stage takes them from there), the
 // rest is appended to the window pass's list.  grid = (LOCAL_SPLIT, images).
-constexpr int LOCAL_SPLIT = 8;
+#ifndef LOCAL_SPLIT_DEF
+#define LOCAL_SPLIT_DEF 16
+#endif
+constexpr int LOCAL_SPLIT = LOCAL_SPLIT_DEF;
 constexpr int LOCAL_NT = 256;
+// Four in ten queries have a candidate with sites ON its circle and go through the perturbation tests, a loop of a few to a dozen
+// trips; with one thread per query the warp walks through the longest of them at 5 to 10 lanes (measured: 534 us per C2 step
+// against 454 us this way).  So a warp takes LOCAL_Q entries per lane and round: the straight-line part (neighbourhood, pattern, the four
+// inside masks, the first candidate's on-circle mask) classifies them into "no candidate" (window list), "first candidate has an
+// empty circle and nothing on it" (done) and "jobs"; the jobs are packed into a warp-private array and every lane then takes
+// one job per trip.  The results of a round are staged per warp and written out with one pair of atomics.
+#ifndef LOCAL_Q_DEF
+#define LOCAL_Q_DEF 4
+#endif
+constexpr int LOCAL_Q = LOCAL_Q_DEF;
 __global__ void __launch_bounds__(LOCAL_NT) local_stage_kernel(ImageArgs A) {
     const int img = blockIdx.y;
     int32_t* hd = A.hdr + (size_t)img * HD_STRIDE;
@@ -1111,110 +1124,140 @@ __global__ void __launch_bounds__(LOCAL_NT) local_stage_kernel(ImageArgs A) {
     if (n == 0) return;
     const unsigned FULL = 0xffffffffu;
     const int h = A.G.grid_h, w = A.G.grid_w, wpr = A.G.wpr;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cap = (int)A.qlist_stride;
     const uint32_t* lut = A.local_lut;
     const uint32_t* occ = A.planes + (size_t)img * 3 * A.plane_stride;
     const uint32_t* raw_list = A.clist + (size_t)img * A.qlist_stride;
     uint32_t* qlist = A.qlist + (size_t)img * A.qlist_stride;
     unsigned long long* qres = A.qres + (size_t)img * A.qlist_stride;
-    const int n_pad = (n + 31) & ~31;
-    constexpr int STEP = LOCAL_SPLIT * LOCAL_NT;
+    constexpr int RQ = 32 * LOCAL_Q;  // entries of a warp's round
+    __shared__ uint32_t s_job_code[LOCAL_NT / 32][RQ], s_job_nb[LOCAL_NT / 32][RQ], s_job_e[LOCAL_NT / 32][RQ];
+    __shared__ uint32_t s_win[LOCAL_NT / 32][RQ], s_loc_code[LOCAL_NT / 32][RQ];
+    __shared__ unsigned long long s_loc_tri[LOCAL_NT / 32][RQ];
+    uint32_t *job_code = s_job_code[warp], *job_nb = s_job_nb[warp], *job_e = s_job_e[warp], *win = s_win[warp], *loc_code = s_loc_code[warp];
+    unsigned long long* loc_tri = s_loc_tri[warp];
     const uint32_t below = (1u << lane) - 1u;
-    // The slots of an iteration's results come from two atomics per warp; their round trip is hidden by writing the results out
-    // one iteration later (p_*: the previous iteration's), and the next list entry is fetched an iteration ahead.
-    bool p_valid = false, p_solved = false;
-    uint32_t p_code = 0u, p_mloc = 0u, p_mwin = 0u;
-    unsigned long long p_tri = 0ull;
-    int p_basel = 0, p_basew = 0;
-    auto write_out = [&]() {
-        const int bl = __shfl_sync(FULL, p_basel, 0), bw = __shfl_sync(FULL, p_basew, 0);
-        if (p_valid && p_solved) {
-            const int slot = cap - 1 - (bl + __popc(p_mloc & below));
-            qlist[slot] = p_code; qres[slot] = p_tri;
-        } else if (p_valid) {
-            qlist[bw + __popc(p_mwin & below)] = p_code;
-        }
+    auto tri_of = [&](uint32_t verts, int x, int r) {
+        const int ia = (int)(verts & 31u), ib = (int)((verts >> 5) & 31u), ic = (int)((verts >> 10) & 31u);
+        const int ay = (ia * 13 >> 6) - 2, ax = ia - 5 * (ay + 2) - 2, by = (ib * 13 >> 6) - 2, bx = ib - 5 * (by + 2) - 2,
+                  cy = (ic * 13 >> 6) - 2, cx = ic - 5 * (cy + 2) - 2;  // i / 5 = i * 13 >> 6 for i < 25
+        return QRES_DONE | (unsigned long long)vlabel(r + ay, x + ax) | ((unsigned long long)vlabel(r + by, x + bx) << 21) |
+               ((unsigned long long)vlabel(r + cy, x + cx) << 42);
     };
-    int i = blockIdx.x * LOCAL_NT + threadIdx.x;
-    uint32_t next_code = i < n ? __ldg(raw_list + cap - 1 - i) : 0u;
-    for (; i < n_pad; i += STEP) {
-        const bool valid = i < n;
-        bool solved = false;
-        const uint32_t code = next_code;
-        next_code = i + STEP < n ? __ldg(raw_list + cap - 1 - (i + STEP)) : 0u;
-        unsigned long long tri = 0ull;
-        if (valid) {
-            const int x = (int)(code & COL_MASK), r = (int)(code >> COL_BITS);
-            // 5 x 5 neighbourhood bits, branch-free with clamped row / word indices and masks for what lies outside the grid
-            const int c0 = x - 2;
-            const int w0 = c0 >> 5, sh = c0 & 31;  // c0 may be negative: arithmetic shift = floor
-            const int wlo = max(w0, 0), whi = min(w0 + 1, wpr - 1);
-            const uint32_t mlo = w0 >= 0 ? 0xFFFFFFFFu : 0u, mhi = w0 + 1 < wpr ? 0xFFFFFFFFu : 0u;
-            uint32_t nb = 0u;
+    const int n_warps = LOCAL_SPLIT * (LOCAL_NT / 32);
+    for (int base = (blockIdx.x * (LOCAL_NT / 32) + warp) * RQ; base < n; base += n_warps * RQ) {
+        int n_job = 0, n_win = 0, n_loc = 0;  // warp-uniform
+        // ---- classify LOCAL_Q entries per lane
 #pragma unroll
-            for (int k = 0; k < 5; k++) {
-                const int y = r + k - 2;
-                const int yc = min(max(y, 0), h - 1);
-                const uint32_t vm = y == yc ? 0xFFFFFFFFu : 0u;
-                const uint32_t* row = occ + yc * wpr;
-                nb |= (__funnelshift_r(__ldg(row + wlo) & mlo & vm, __ldg(row + whi) & mhi & vm, sh) & 31u) << (5 * k);
-            }
-            const uint32_t e = __ldg(lut + LocalRule::pattern_of(nb));
-            // candidates with no site strictly inside their circle: all four slots at once (unused slots hold 0xFF: the mask
-            // index wraps to a table entry, the id test discards it)
-            uint32_t surv = 0u;
+        for (int u = 0; u < LOCAL_Q; u++) {
+            const int i = base + u * 32 + lane;
+            const bool valid = i < n;
+            uint32_t code = 0u, nb = 0u, e = 0xFFFFFFFFu, surv = 0u, ties = 0u, verts = 0u;
+            if (valid) {
+                code = __ldg(raw_list + cap - 1 - i);
+                const int x = (int)(code & COL_MASK), r = (int)(code >> COL_BITS);
+                // 5 x 5 neighbourhood bits, branch-free with clamped row / word indices and masks for what lies outside the grid
+                const int c0 = x - 2;
+                const int w0 = c0 >> 5, sh = c0 & 31;  // c0 may be negative: arithmetic shift = floor
+                const int wlo = max(w0, 0), whi = min(w0 + 1, wpr - 1);
+                const uint32_t mlo = w0 >= 0 ? 0xFFFFFFFFu : 0u, mhi = w0 + 1 < wpr ? 0xFFFFFFFFu : 0u;
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const uint32_t cid = (e >> (8 * k)) & 0xFFu;
-                const uint32_t inside = __ldg(lut + LocalRule::OFF_INSIDE + (cid & (LocalRule::MAXCAND - 1)));
-                if (cid != 0xFFu && !(nb & inside)) surv |= 1u << k;
-            }
-            const int qi = r * w + x;
-            while (surv && !solved) {
-                const int k = __ffs(surv) - 1; surv &= surv - 1;
-                const uint32_t cid = (e >> (8 * k)) & 0xFFu;
-                const uint32_t verts = __ldg(lut + LocalRule::OFF_VERTS + cid);
-                uint32_t ties = nb & __ldg(lut + LocalRule::OFF_ON + cid);
-                const int ia = (int)(verts & 31u), ib = (int)((verts >> 5) & 31u), ic = (int)((verts >> 10) & 31u);
-                const int ay = (ia * 13 >> 6) - 2, ax = ia - 5 * (ay + 2) - 2, by = (ib * 13 >> 6) - 2, bx = ib - 5 * (by + 2) - 2,
-                          cy = (ic * 13 >> 6) - 2, cx = ic - 5 * (cy + 2) - 2;  // i / 5 = i * 13 >> 6 for i < 25
-                bool ok = true;
-                if (ties) {
-                    // Sites on the circle: symbolic perturbation, as incircle_pert().  Its first three terms are linear in the
-                    // tested point d: wa * orient(b,c,d) - wb * orient(a,c,d) + wc * orient(a,b,d) = PA * dx + PB * dy + PC
-                    // (weights < 2^20, |coordinates| <= 2: every term and the sum fit int32).
-                    const int wa = pert_weight_idx((uint32_t)(qi + ay * w + ax)), wb = pert_weight_idx((uint32_t)(qi + by * w + bx)),
-                              wc = pert_weight_idx((uint32_t)(qi + cy * w + cx));
-                    const int PA = -wa * (cy - by) + wb * (cy - ay) - wc * (by - ay);
-                    const int PB = wa * (cx - bx) - wb * (cx - ax) + wc * (bx - ax);
-                    const int PC = wa * (bx * cy - by * cx) - wb * (ax * cy - ay * cx) + wc * (ax * by - ay * bx);
-                    const int oabc = (bx - ax) * (cy - ay) - (by - ay) * (cx - ax);
-                    while (ties && ok) {
-                        const int b = __ffs(ties) - 1; ties &= ties - 1;
-                        const int dy = (b * 13 >> 6) - 2, dx = b - 5 * (dy + 2) - 2;
-                        const int wd = pert_weight_idx((uint32_t)(qi + dy * w + dx));
-                        // > 0: the site is inside; = 0: a residual tie, left to the passes that know how the oracle breaks it
-                        if (PA * dx + PB * dy + PC - wd * oabc >= 0) ok = false;
-                    }
+                for (int k = 0; k < 5; k++) {
+                    const int y = r + k - 2;
+                    const int yc = min(max(y, 0), h - 1);
+                    const uint32_t vm = y == yc ? 0xFFFFFFFFu : 0u;
+                    const uint32_t* row = occ + yc * wpr;
+                    nb |= (__funnelshift_r(__ldg(row + wlo) & mlo & vm, __ldg(row + whi) & mhi & vm, sh) & 31u) << (5 * k);
                 }
-                if (ok) {
-                    solved = true;
-                    tri = QRES_DONE | (unsigned long long)vlabel(r + ay, x + ax) | ((unsigned long long)vlabel(r + by, x + bx) << 21) |
-                          ((unsigned long long)vlabel(r + cy, x + cx) << 42);
+                e = __ldg(lut + LocalRule::pattern_of(nb));
+                // candidates with no site strictly inside their circle: all four slots at once (unused slots hold 0xFF: the
+                // mask index wraps to a table entry, the id test discards it)
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t cid = (e >> (8 * k)) & 0xFFu;
+                    const uint32_t inside = __ldg(lut + LocalRule::OFF_INSIDE + (cid & (LocalRule::MAXCAND - 1)));
+                    if (cid != 0xFFu && !(nb & inside)) surv |= 1u << k;
+                }
+                if (surv) {
+                    const uint32_t cid = (e >> (8 * (__ffs(surv) - 1))) & 0xFFu;
+                    ties = nb & __ldg(lut + LocalRule::OFF_ON + cid);
+                    verts = __ldg(lut + LocalRule::OFF_VERTS + cid);
                 }
             }
+            const bool is_win = valid && !surv, is_loc = valid && surv && !ties, is_job = valid && surv && ties;
+            const uint32_t mw = __ballot_sync(FULL, is_win), ml = __ballot_sync(FULL, is_loc), mj = __ballot_sync(FULL, is_job);
+            if (is_win) win[n_win + __popc(mw & below)] = code;
+            if (is_loc) {
+                const int k = n_loc + __popc(ml & below);
+                loc_code[k] = code; loc_tri[k] = tri_of(verts, (int)(code & COL_MASK), (int)(code >> COL_BITS));
+            }
+            if (is_job) {
+                const int k = n_job + __popc(mj & below);
+                job_code[k] = code | (surv << 24); job_nb[k] = nb; job_e[k] = e;
+            }
+            n_win += __popc(mw); n_loc += __popc(ml); n_job += __popc(mj);
         }
-        const uint32_t m_loc = __ballot_sync(FULL, valid && solved), m_win = __ballot_sync(FULL, valid && !solved);
+        __syncwarp();
+        // ---- the jobs, one per lane and trip
+        for (int j0 = 0; j0 < n_job; j0 += 32) {
+            const bool valid = j0 + lane < n_job;
+            bool solved = false;
+            uint32_t code = 0u;
+            unsigned long long tri = 0ull;
+            if (valid) {
+                const uint32_t cs = job_code[j0 + lane], nb = job_nb[j0 + lane], e = job_e[j0 + lane];
+                code = cs & 0xFFFFFFu;
+                uint32_t surv = cs >> 24;
+                const int x = (int)(code & COL_MASK), r = (int)(code >> COL_BITS);
+                const int qi = r * w + x;
+                while (surv && !solved) {
+                    const int k = __ffs(surv) - 1; surv &= surv - 1;
+                    const uint32_t cid = (e >> (8 * k)) & 0xFFu;
+                    const uint32_t verts = __ldg(lut + LocalRule::OFF_VERTS + cid);
+                    uint32_t ties = nb & __ldg(lut + LocalRule::OFF_ON + cid);
+                    bool ok = true;
+                    if (ties) {
+                        // Sites on the circle: symbolic perturbation, as incircle_pert().  Its first three terms are linear in
+                        // the tested point d: wa * orient(b,c,d) - wb * orient(a,c,d) + wc * orient(a,b,d) = PA * dx + PB * dy + PC
+                        // (weights < 2^20, |coordinates| <= 2: every term and the sum fit int32).
+                        const int ia = (int)(verts & 31u), ib = (int)((verts >> 5) & 31u), ic = (int)((verts >> 10) & 31u);
+                        const int ay = (ia * 13 >> 6) - 2, ax = ia - 5 * (ay + 2) - 2, by = (ib * 13 >> 6) - 2, bx = ib - 5 * (by + 2) - 2,
+                                  cy = (ic * 13 >> 6) - 2, cx = ic - 5 * (cy + 2) - 2;
+                        const int wa = pert_weight_idx((uint32_t)(qi + ay * w + ax)), wb = pert_weight_idx((uint32_t)(qi + by * w + bx)),
+                                  wc = pert_weight_idx((uint32_t)(qi + cy * w + cx));
+                        const int PA = -wa * (cy - by) + wb * (cy - ay) - wc * (by - ay);
+                        const int PB = wa * (cx - bx) - wb * (cx - ax) + wc * (bx - ax);
+                        const int PC = wa * (bx * cy - by * cx) - wb * (ax * cy - ay * cx) + wc * (ax * by - ay * bx);
+                        const int oabc = (bx - ax) * (cy - ay) - (by - ay) * (cx - ax);
+                        while (ties && ok) {
+                            const int b = __ffs(ties) - 1; ties &= ties - 1;
+                            const int dy = (b * 13 >> 6) - 2, dx = b - 5 * (dy + 2) - 2;
+                            const int wd = pert_weight_idx((uint32_t)(qi + dy * w + dx));
+                            // > 0: the site is inside; = 0: a residual tie, left to the passes that know how the oracle breaks it
+                            if (PA * dx + PB * dy + PC - wd * oabc >= 0) ok = false;
+                        }
+                    }
+                    if (ok) { solved = true; tri = tri_of(verts, x, r); }
+                }
+            }
+            const uint32_t ml = __ballot_sync(FULL, valid && solved), mw = __ballot_sync(FULL, valid && !solved);
+            if (valid && solved) { const int k = n_loc + __popc(ml & below); loc_code[k] = code; loc_tri[k] = tri; }
+            else if (valid) win[n_win + __popc(mw & below)] = code;
+            n_loc += __popc(ml); n_win += __popc(mw);
+        }
+        // ---- write the round out
         int base_l = 0, base_w = 0;
         if (lane == 0) {
-            if (m_loc) base_l = atomicAdd(hd + HD_LOCAL, __popc(m_loc));
-            if (m_win) base_w = atomicAdd(hd + HD_NQ, __popc(m_win));
+            if (n_loc) base_l = atomicAdd(hd + HD_LOCAL, n_loc);
+            if (n_win) base_w = atomicAdd(hd + HD_NQ, n_win);
         }
-        write_out();  // the previous iteration's
-        p_valid = valid; p_solved = solved; p_code = code; p_tri = tri; p_mloc = m_loc; p_mwin = m_win; p_basel = base_l; p_basew = base_w;
+        base_l = __shfl_sync(FULL, base_l, 0); base_w = __shfl_sync(FULL, base_w, 0);
+        __syncwarp();
+        for (int k = lane; k < n_win; k += 32) qlist[base_w + k] = win[k];
+        for (int k = lane; k < n_loc; k += 32) { const int slot = cap - 1 - (base_l + k); qlist[slot] = loc_code[k]; qres[slot] = loc_tri[k]; }
+        __syncwarp();  // the staging arrays are reused by the next round
     }
-    write_out();
 }
 
 // ---- exact barycentric value of a query pixel from its final triangle (shade stage, cooperative pass) ----------------------
@@ -1521,6 +1564,9 @@ __global__ void __launch_bounds__(FINISH_NT, IMAGE_FINISH_CTAS) finish_stage_ker
             }
 #endif
             int flips = 0, waves = 0;
+#ifdef IMAGE_FINISH_DBG
+            const int dbg_before = my_filled;
+#endif
             // Each lane keeps the violator its row produced in the last scan.  After a flip these candidates are tested (exactly)
             // against the new circle before any row is scanned again: consecutive circles overlap, so about half of the flips
             // are found this way at a tenth of the cost of a scan.  The descent still ends with a full scan that finds nothing.
@@ -1552,7 +1598,11 @@ __global__ void __launch_bounds__(FINISH_NT, IMAGE_FINISH_CTAS) finish_stage_ker
                 if (v < 0 || !flip_to(t, v, x, r)) break;
                 flips++;
             }
+#ifdef IMAGE_FINISH_DBG
+            if (lane == 0) { my_flips += 1 | (waves << 12); }  // debug build: descents and waves instead of flips
+#else
             if (lane == 0) { my_flips += flips; my_maxflips = max(my_maxflips, flips); }
+#endif
             tp = t; have_prev = true;
             // rasterise t over the deferred pixels it contains: one lane per row of its bounding box
             const uint32_t ca = site_rgb(t.ax, t.ay), cb = site_rgb(t.bx, t.by), cc = site_rgb(t.cx, t.cy);
@@ -1571,6 +1621,9 @@ __global__ void __launch_bounds__(FINISH_NT, IMAGE_FINISH_CTAS) finish_stage_ker
                     if (done) my_filled += __popc(atomicAnd(&defer[y * wpr + wi], ~done) & done);
                 }
             }
+#ifdef IMAGE_FINISH_DBG
+            { const int got = __reduce_add_sync(FULL, my_filled - dbg_before); if (lane == 0 && got <= 2) my_maxflips += 1 | (waves << 10) | (flips << 20); }
+#endif
             __syncwarp();
            }
           }
@@ -1606,13 +1659,24 @@ __global__ void __launch_bounds__(FINISH_NT, IMAGE_FINISH_CTAS) finish_stage_ker
     for (int o = 16; o > 0; o >>= 1) {
         my_filled += __shfl_xor_sync(FULL, my_filled, o);
         my_flips += __shfl_xor_sync(FULL, my_flips, o);
+#ifdef IMAGE_FINISH_DBG
+        my_maxflips += __shfl_xor_sync(FULL, my_maxflips, o);
+#else
         my_maxflips = max(my_maxflips, __shfl_xor_sync(FULL, my_maxflips, o));
+#endif
     }
+    #ifdef IMAGE_FINISH_DBG
+    if (lane == 0) { atomicAdd(&s_filled, my_filled); atomicAdd(&s_flips, my_flips); atomicAdd(&s_maxflips, my_maxflips); }
+#else
     if (lane == 0) { atomicAdd(&s_filled, my_filled); atomicAdd(&s_flips, my_flips); atomicMax(&s_maxflips, my_maxflips); }
+#endif
     __syncthreads();
     if (tid == 0) {
         // filled = edge-rule pixels + window-pass pixels (what was handed on, residual ties included, is counted by the cooperative pass)
         counts[5] = status == 0 ? hd[HD_EDGE] + hd[HD_LOCAL] + hd[HD_NQ] - s_nitems + s_filled : 0; counts[6] = max(counts[6], s_maxflips); counts[7] += s_flips;
+#ifdef IMAGE_FINISH_DBG
+        counts[6] = s_maxflips; counts[7] = s_flips;  // debug build: entries handed on | small descents << 16, descents | waves << 12
+#endif
         if (status_final) *status_final = status;
         if (counts_final) {
 #pragma unroll

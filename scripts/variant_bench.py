@@ -56,6 +56,11 @@ def worker(lib, steps, n_hyp, n_panos):
     h.update(out.cpu().numpy().tobytes())
     h.update(status.cpu().numpy().tobytes())
     h.update(np.ascontiguousarray(counts.cpu().numpy().reshape(n_img, 8)[:, :6]).tobytes())
+    if os.environ.get("VB_DBG"):
+        c = counts.cpu().numpy().reshape(n_img, 8).astype(np.int64)
+        sel = c[:, 2] > 0
+        print("DBG", os.path.basename(lib), "images", int(sel.sum()), "small descents", float((c[sel, 6] & 0x3FF).mean()), "their waves", float(((c[sel, 6] >> 10) & 0x3FF).mean()), "their flips", float((c[sel, 6] >> 20).mean()), "mean descents", float((c[sel, 7] & 0xFFF).mean()),
+              "mean waves", float((c[sel, 7] >> 12).mean()), "mean filled", float(c[sel, 5].mean()), file=sys.stderr)
     print(json.dumps({"lib": os.path.basename(lib), "ms_per_step": tot / steps, "hyp_per_s": n_hyp * steps / (tot / 1e3),
                       "splat_ms": stage["splat"] / steps, "image_ms": stage["image"] / steps, "sha1": h.hexdigest()}))
 
@@ -77,6 +82,9 @@ def main():
             d = json.loads(line)
         except Exception:
             print("FAILED", lib, res.stderr[-800:]); continue
+        for ln in res.stderr.splitlines():
+            if ln.startswith("DBG"):
+                print(ln)
         ref = ref or d["sha1"]
         print("%-28s %8.3f ms/step  %8.0f hyp/s  splat %6.3f  image %7.3f  %s" % (d["lib"], d["ms_per_step"], d["hyp_per_s"], d["splat_ms"], d["image_ms"],
                                                                                    "same" if d["sha1"] == ref else "OUTPUT DIFFERS"))
