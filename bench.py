@@ -382,8 +382,8 @@ class Dist:
             self.dist.destroy_process_group()
 
 
-STAGES = ("splat", "sites", "prep", "window", "shade", "finish")
-KERNEL_NAMES = {"splat": "splat_pano_kernel", "sites": "sites_stage_kernel", "prep": "prep_stage_kernel", "window": "window_stage_kernel",
+STAGES = ("splat", "sites", "prep", "local", "window", "shade", "finish")
+KERNEL_NAMES = {"splat": "splat_pano_kernel", "sites": "sites_stage_kernel", "prep": "prep_stage_kernel", "local": "local_stage_kernel", "window": "window_stage_kernel",
                 "shade": "shade_stage_kernel", "finish": "image_order_kernel + finish_stage_kernel"}
 
 
@@ -415,9 +415,9 @@ def roofline_block(stage_ms, steps, alg, n_rendered, n_jobs, chunks_per_step, va
         traffic = per_img * n_rendered / chunks_per_step if per_img else None
     abh = alg_bytes_per_hyp(H, W)
     return {
-        "kernel": "image pipeline: sites_stage + prep_stage + window_stage + shade_stage + finish_stage kernels (one launch each per chunk)",
+        "kernel": "image pipeline: sites_stage + prep_stage + local_stage + window_stage + shade_stage + finish_stage kernels (one launch each per chunk)",
         "bound": "hbm", "achieved": img_gbs, "peak": peak, "unit": "GB/s", "frac": img_gbs / peak, "traffic": traffic,
-        "traffic_source": (tsrc + " (dram__bytes_read.sum + dram__bytes_write.sum of the five kernels, ncu --set full, scaled to this launch's image count)") if traffic else None,
+        "traffic_source": (tsrc + " (dram__bytes_read.sum + dram__bytes_write.sum of the six kernels, ncu --set full, scaled to this launch's image count)") if traffic else None,
         "peak_source": peak_src, "alg_bytes_per_launch": alg["image"] / chunks_per_step, "avg_launch_ms": img_ms / chunks_per_step,
         "launches_timed": steps * chunks_per_step, "share_of_step": img_ms * steps / max(stage_ms["total"], 1e-9),
         "alg_bytes": "key grid in (4 B x 501^2) + winner colours in (3 B x sites) + final image out (753 003 B), per image",
@@ -623,6 +623,7 @@ def run_building(args):
         # key grid in, winner colours in (3 B gathered per site), sparse image + two bit planes out
         "sites": n_rendered * (IMG * IMG * 4 + IMG_BYTES + 2 * plane) + int(sites.sum()) * 3,
         "prep": n_rendered * 3 * plane,                      # occupancy + non-empty planes in, keep plane out (lists are intermediates)
+        "local": n_rendered * plane,                         # occupancy plane in (lists are intermediates)
         "window": n_rendered * plane,                        # occupancy plane in (lists are intermediates)
         "shade": int(filled.sum()) * (3 * 3 + 3),            # three vertex colours in, one pixel out per interpolated pixel
         "finish": n_rendered * plane,

@@ -270,7 +270,7 @@ int salve_bev_rasterize_layouts_host(salve_bev_ctx* ctx, int32_t n_img, const in
 int salve_bev_tap(salve_bev_ctx* ctx, int32_t image, int32_t what, void* host_buf, int64_t host_buf_bytes, void* stream);
 
 /* Per-stage device time (ms, CUDA events) of the most recent pano render call, summed over its chunks.  host_ms: SALVE_BEV_NTIMINGS floats:
- * [0] splat_pano_kernel  [1] sites stage  [2] prep stage  [3] window stage  [4] shade stage  [5] order + finish stage  [6] reserved (0)
+ * [0] splat_pano_kernel  [1] sites stage  [2] prep stage  [3] window stage  [4] shade stage  [5] order + finish stage  [6] local stage
  * [7] total (chunk start to the end of the finish stage). */
 #define SALVE_BEV_NTIMINGS 8
 int salve_bev_last_timings(salve_bev_ctx* ctx, float* host_ms);

@@ -39,7 +39,7 @@ constexpr int N_TMP = 8;
 #ifndef IMAGE_LOCAL_RULE
 #define IMAGE_LOCAL_RULE 1
 #endif
-constexpr int N_STAGE_EVENTS = 7;  // chunk start, after: splat, sites, prep, window, shade, finish
+constexpr int N_STAGE_EVENTS = 8;  // chunk start, after: splat, sites, prep, local, window, shade, finish
 
 struct salve_bev_ctx {
     salve_bev_config cfg;
@@ -518,6 +518,7 @@ static int run_image_stage(salve_bev_ctx* c, int n_img, const GridParams& G, uin
         sites_stage_kernel<<<dim3((unsigned)((G.grid_h + SITES_WARPS * SITES_GROUPS - 1) / (SITES_WARPS * SITES_GROUPS)), (unsigned)n), SITES_WARPS * 32, sites_smem_bytes(G.grid_w, G.wpr), st>>>(IA);
         if (ev && (rc = stage_event(c, st))) return rc;
         prep_stage_kernel<<<n, PREP_NT, prep_smem_bytes(G.grid_h, G.wpr), st>>>(IA);
+        if (ev && (rc = stage_event(c, st))) return rc;
         if (IA.local_lut && !qtri) {  // (with the triangle tap the prep stage leaves the queries in the window list)
             local_stage_kernel<<<dim3(LOCAL_SPLIT, (unsigned)n), LOCAL_NT, 0, st>>>(IA);
             c->launches++;
@@ -541,7 +542,7 @@ static int run_image_stage(salve_bev_ctx* c, int n_img, const GridParams& G, uin
         CU(cudaGetLastError());
     }
     if (timed && n_img > WIN_MAX_IMAGES)
-        for (int k = 0; k < 4; k++) { int rc = stage_event(c, st); if (rc) return rc; }  // keep the event layout: stages not separated
+        for (int k = 0; k < 5; k++) { int rc = stage_event(c, st); if (rc) return rc; }  // keep the event layout: stages not separated
     return timed ? stage_event(c, st) : SALVE_BEV_OK;
 }
 
@@ -1457,11 +1458,13 @@ extern "C" int salve_bev_last_timings(salve_bev_ctx* c, float* host_ms) {
     if (!c->timing || c->events_used == 0) return SALVE_BEV_OK;
     CU(cudaSetDevice(c->cfg.device));
     CU(cudaEventSynchronize(c->events[c->events_used - 1]));
+    // intervals between the events of a chunk: splat, sites, prep, local, window, shade, finish -> slots 0, 1, 2, 6, 3, 4, 5
+    static const int slot[N_STAGE_EVENTS - 1] = {0, 1, 2, 6, 3, 4, 5};
     for (size_t k = 0; k + N_STAGE_EVENTS <= c->events_used; k += N_STAGE_EVENTS) {
         float ms = 0.f;
-        for (int s = 0; s + 1 < N_STAGE_EVENTS; s++) {  // splat, sites, prep, window, shade, finish
+        for (int s = 0; s + 1 < N_STAGE_EVENTS; s++) {
             CU(cudaEventElapsedTime(&ms, c->events[k + s], c->events[k + s + 1]));
-            host_ms[s] += ms;
+            host_ms[slot[s]] += ms;
         }
         CU(cudaEventElapsedTime(&ms, c->events[k], c->events[k + N_STAGE_EVENTS - 1]));
         host_ms[SALVE_BEV_NTIMINGS - 1] += ms;

@@ -1099,9 +1099,32 @@ __global__ void __launch_bounds__(PREP_NT) prep_stage_kernel(ImageArgs A) {
     }
 }
 
+// ---- exact barycentric value of a query pixel from its final triangle (local stage, shade stage, cooperative pass) ----------------------
+__device__ __forceinline__ uint32_t site_rgb_at(const uint8_t* out, bool raw, int h, int w, int sx, int sy) {
+    return load_rgb(out + ((size_t)(raw ? sy : h - 1 - sy) * w + sx) * 3);
+}
+__device__ __forceinline__ void write_px_at(uint8_t* out, int32_t* qtri, bool raw, int h, int w, const Tri2& t, uint32_t ca, uint32_t cb,
+                                            uint32_t cc, int x, int r) {
+    const uint32_t ua = (uint32_t)orient_i(t.bx, t.by, t.cx, t.cy, x, r), ub = (uint32_t)orient_i(t.cx, t.cy, t.ax, t.ay, x, r),
+                   uc = (uint32_t)orient_i(t.ax, t.ay, t.bx, t.by, x, r);
+    const uint32_t A2 = ua + ub + uc;
+    uint8_t* o = out + ((size_t)(raw ? r : h - 1 - r) * w + x) * 3;
+    o[0] = (uint8_t)((ua * (ca & 0xFF) + ub * (cb & 0xFF) + uc * (cc & 0xFF)) / A2);
+    o[1] = (uint8_t)((ua * ((ca >> 8) & 0xFF) + ub * ((cb >> 8) & 0xFF) + uc * ((cc >> 8) & 0xFF)) / A2);
+    o[2] = (uint8_t)((ua * ((ca >> 16) & 0xFF) + ub * ((cb >> 16) & 0xFF) + uc * ((cc >> 16) & 0xFF)) / A2);
+    if (qtri) {
+        // ascending vertex ids: two warps of the cooperative pass may reach the same triangle with different rotations and
+        // write the same pixel concurrently; in canonical order their stores are identical word for word
+        int32_t* q = qtri + ((size_t)r * w + x) * 3;
+        const int i0 = t.ay * w + t.ax, i1 = t.by * w + t.bx, i2 = t.cy * w + t.cx;
+        const int lo = min(i0, min(i1, i2)), hi = max(i0, max(i1, i2));
+        q[0] = lo; q[1] = i0 + i1 + i2 - lo - hi; q[2] = hi;
+    }
+}
+
 // ---- local stage (see LocalRule): the queries of the prep stage's scratch list ------------------------------------------------
-// Resolved queries go to the top end of the window list with their final triangle (the shade stage takes them from there), the
-// rest is appended to the window pass's list.  grid = (LOCAL_SPLIT, images).
+// Resolved queries are shaded on the spot (three colour gathers, exact integer barycentrics), the rest is appended to the window
+// pass's list.  grid = (LOCAL_SPLIT, images).
 #ifndef LOCAL_SPLIT_DEF
 #define LOCAL_SPLIT_DEF 16
 #endif
@@ -1112,12 +1135,16 @@ constexpr int LOCAL_NT = 256;
 // against 454 us this way).  So a warp takes LOCAL_Q entries per lane and round: the straight-line part (neighbourhood, pattern, the four
 // inside masks, the first candidate's on-circle mask) classifies them into "no candidate" (window list), "first candidate has an
 // empty circle and nothing on it" (done) and "jobs"; the jobs are packed into a warp-private array and every lane then takes
-// one job per trip.  The results of a round are staged per warp and written out with one pair of atomics.
+// one job per trip.  The results of a round are staged per warp: one atomic for the window list's slots, and the resolved
+// queries are shaded one per lane, every gather of a trip in flight together.
 #ifndef LOCAL_Q_DEF
 #define LOCAL_Q_DEF 4
 #endif
 constexpr int LOCAL_Q = LOCAL_Q_DEF;
-__global__ void __launch_bounds__(LOCAL_NT) local_stage_kernel(ImageArgs A) {
+#ifndef LOCAL_MIN_CTAS
+#define LOCAL_MIN_CTAS 5
+#endif
+__global__ void __launch_bounds__(LOCAL_NT, LOCAL_MIN_CTAS) local_stage_kernel(ImageArgs A) {
     const int img = blockIdx.y;
     int32_t* hd = A.hdr + (size_t)img * HD_STRIDE;
     const int n = hd[HD_NRAW];
@@ -1130,7 +1157,9 @@ __global__ void __launch_bounds__(LOCAL_NT) local_stage_kernel(ImageArgs A) {
     const uint32_t* occ = A.planes + (size_t)img * 3 * A.plane_stride;
     const uint32_t* raw_list = A.clist + (size_t)img * A.qlist_stride;
     uint32_t* qlist = A.qlist + (size_t)img * A.qlist_stride;
-    unsigned long long* qres = A.qres + (size_t)img * A.qlist_stride;
+    const bool raw = A.raw_mode != 0;
+    int dst;
+    uint8_t* out = image_out(A, img, dst);
     constexpr int RQ = 32 * LOCAL_Q;  // entries of a warp's round
     __shared__ uint32_t s_job_code[LOCAL_NT / 32][RQ], s_job_nb[LOCAL_NT / 32][RQ], s_job_e[LOCAL_NT / 32][RQ];
     __shared__ uint32_t s_win[LOCAL_NT / 32][RQ], s_loc_code[LOCAL_NT / 32][RQ];
@@ -1247,39 +1276,24 @@ __global__ void __launch_bounds__(LOCAL_NT) local_stage_kernel(ImageArgs A) {
             n_loc += __popc(ml); n_win += __popc(mw);
         }
         // ---- write the round out
-        int base_l = 0, base_w = 0;
+        int base_w = 0;
         if (lane == 0) {
-            if (n_loc) base_l = atomicAdd(hd + HD_LOCAL, n_loc);
+            if (n_loc) atomicAdd(hd + HD_LOCAL, n_loc);  // (a count only: the finish stage reports the filled pixels)
             if (n_win) base_w = atomicAdd(hd + HD_NQ, n_win);
         }
-        base_l = __shfl_sync(FULL, base_l, 0); base_w = __shfl_sync(FULL, base_w, 0);
         __syncwarp();
+        for (int k = lane; k < n_loc; k += 32) {
+            const uint32_t code = loc_code[k];
+            const unsigned long long t3 = loc_tri[k];
+            const uint32_t a = (uint32_t)t3 & M21, b = (uint32_t)(t3 >> 21) & M21, c = (uint32_t)(t3 >> 42) & M21;
+            const Tri2 t = {vcol(a), vrow(a), vcol(b), vrow(b), vcol(c), vrow(c)};
+            const uint32_t ca = site_rgb_at(out, raw, h, w, t.ax, t.ay), cb = site_rgb_at(out, raw, h, w, t.bx, t.by),
+                           cc = site_rgb_at(out, raw, h, w, t.cx, t.cy);
+            write_px_at(out, nullptr, raw, h, w, t, ca, cb, cc, (int)(code & COL_MASK), (int)(code >> COL_BITS));
+        }
+        base_w = __shfl_sync(FULL, base_w, 0);
         for (int k = lane; k < n_win; k += 32) qlist[base_w + k] = win[k];
-        for (int k = lane; k < n_loc; k += 32) { const int slot = cap - 1 - (base_l + k); qlist[slot] = loc_code[k]; qres[slot] = loc_tri[k]; }
         __syncwarp();  // the staging arrays are reused by the next round
-    }
-}
-
-// ---- exact barycentric value of a query pixel from its final triangle (shade stage, cooperative pass) ----------------------
-__device__ __forceinline__ uint32_t site_rgb_at(const uint8_t* out, bool raw, int h, int w, int sx, int sy) {
-    return load_rgb(out + ((size_t)(raw ? sy : h - 1 - sy) * w + sx) * 3);
-}
-__device__ __forceinline__ void write_px_at(uint8_t* out, int32_t* qtri, bool raw, int h, int w, const Tri2& t, uint32_t ca, uint32_t cb,
-                                            uint32_t cc, int x, int r) {
-    const uint32_t ua = (uint32_t)orient_i(t.bx, t.by, t.cx, t.cy, x, r), ub = (uint32_t)orient_i(t.cx, t.cy, t.ax, t.ay, x, r),
-                   uc = (uint32_t)orient_i(t.ax, t.ay, t.bx, t.by, x, r);
-    const uint32_t A2 = ua + ub + uc;
-    uint8_t* o = out + ((size_t)(raw ? r : h - 1 - r) * w + x) * 3;
-    o[0] = (uint8_t)((ua * (ca & 0xFF) + ub * (cb & 0xFF) + uc * (cc & 0xFF)) / A2);
-    o[1] = (uint8_t)((ua * ((ca >> 8) & 0xFF) + ub * ((cb >> 8) & 0xFF) + uc * ((cc >> 8) & 0xFF)) / A2);
-    o[2] = (uint8_t)((ua * ((ca >> 16) & 0xFF) + ub * ((cb >> 16) & 0xFF) + uc * ((cc >> 16) & 0xFF)) / A2);
-    if (qtri) {
-        // ascending vertex ids: two warps of the cooperative pass may reach the same triangle with different rotations and
-        // write the same pixel concurrently; in canonical order their stores are identical word for word
-        int32_t* q = qtri + ((size_t)r * w + x) * 3;
-        const int i0 = t.ay * w + t.ax, i1 = t.by * w + t.bx, i2 = t.cy * w + t.cx;
-        const int lo = min(i0, min(i1, i2)), hi = max(i0, max(i1, i2));
-        q[0] = lo; q[1] = i0 + i1 + i2 - lo - hi; q[2] = hi;
     }
 }
 
@@ -1297,7 +1311,6 @@ __global__ void __launch_bounds__(SHADE_NT) shade_stage_kernel(ImageArgs A) {
     int32_t* hd = A.hdr + (size_t)img * HD_STRIDE;
     if (hd[HD_STATUS] != 0) return;
     const int n_edge = hd[HD_EDGE], n_win = hd[HD_NQ];
-    const int n_tri = n_win + hd[HD_LOCAL], cap = (int)A.qlist_stride;  // the local rule's entries sit at the top end of the list, downwards
     const int h = A.G.grid_h, w = A.G.grid_w;
     const bool raw = A.raw_mode != 0;
     int dst;
@@ -1346,15 +1359,14 @@ __global__ void __launch_bounds__(SHADE_NT) shade_stage_kernel(ImageArgs A) {
             p[u][2] = (uint8_t)(((ca[u] >> 16) + (cb[u] >> 16)) >> 1);
         }
     }
-    for (int j0 = blockIdx.x * SHADE_NT + threadIdx.x; j0 < n_tri; j0 += SHADE_UNROLL * STRIDE) {
+    for (int j0 = blockIdx.x * SHADE_NT + threadIdx.x; j0 < n_win; j0 += SHADE_UNROLL * STRIDE) {
         unsigned long long rs[SHADE_UNROLL];
         uint32_t code[SHADE_UNROLL], ca[SHADE_UNROLL], cb[SHADE_UNROLL], cc[SHADE_UNROLL];
 #pragma unroll
         for (int u = 0; u < SHADE_UNROLL; u++) {
             const int j = j0 + u * STRIDE;
-            const int slot = j < n_win ? j : cap - 1 - (j - n_win);
-            rs[u] = j < n_tri ? qres[slot] : 0ull;  // without QRES_DONE: handed on to the cooperative pass (or beyond the list)
-            code[u] = j < n_tri ? __ldg(qlist + slot) : 0u;
+            rs[u] = j < n_win ? qres[j] : 0ull;  // without QRES_DONE: handed on to the cooperative pass (or beyond the list)
+            code[u] = j < n_win ? __ldg(qlist + j) : 0u;
         }
 #pragma unroll
         for (int u = 0; u < SHADE_UNROLL; u++) {

@@ -454,12 +454,13 @@ class BevRenderer:
 
     @_locked
     def last_timings(self) -> dict:
-        """Per-stage device time (ms) of the last pano render call: splat, the five stages of the image pipeline, `image` (their sum)
+        """Per-stage device time (ms) of the last pano render call: splat, the six stages of the image pipeline, `image` (their sum)
         and `total`."""
         ms = np.zeros(8, np.float32)
         nat.check(self._lib.salve_bev_last_timings(self._h, _ptr(ms, ctypes.c_float)))
-        d = dict(splat=float(ms[0]), sites=float(ms[1]), prep=float(ms[2]), window=float(ms[3]), shade=float(ms[4]), finish=float(ms[5]), total=float(ms[7]))
-        d["image"] = d["sites"] + d["prep"] + d["window"] + d["shade"] + d["finish"]
+        d = dict(splat=float(ms[0]), sites=float(ms[1]), prep=float(ms[2]), local=float(ms[6]), window=float(ms[3]), shade=float(ms[4]),
+                 finish=float(ms[5]), total=float(ms[7]))
+        d["image"] = d["sites"] + d["prep"] + d["local"] + d["window"] + d["shade"] + d["finish"]
         return d
 
     def launch_count(self) -> int:
