@@ -277,6 +277,12 @@ int salve_bev_last_timings(salve_bev_ctx* ctx, float* host_ms);
 /* Enable/disable per-stage event timing (off by default: events add sync points at read time only). */
 int salve_bev_enable_timing(salve_bev_ctx* ctx, int32_t on);
 
+/* The host-built tables of the local rule (k_image.cuh, LocalRule; the prep / local stages' short cut of the Delaunay search of
+ * reference interpolation_utils.py:21-54 for queries whose triangle has its vertices among 12 near neighbours): copies up to
+ * n_words uint32 words into host_words and returns the table's size in words.  No GPU needed; tests/ check it against an independent
+ * enumeration. */
+int64_t salve_bev_local_rule_tables(uint32_t* host_words, int64_t n_words);
+
 /* Number of kernel launches issued by this context since creation (bench.py's gpu_launches). */
 int64_t salve_bev_launch_count(salve_bev_ctx* ctx);
 

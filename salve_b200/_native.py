@@ -71,6 +71,7 @@ SYMBOLS = {
     "salve_bev_tap": (ctypes.c_int, [c_vp, ctypes.c_int32, ctypes.c_int32, c_vp, ctypes.c_int64, c_vp]),
     "salve_bev_last_timings": (ctypes.c_int, [c_vp, c_f32p]),
     "salve_bev_enable_timing": (ctypes.c_int, [c_vp, ctypes.c_int32]),
+    "salve_bev_local_rule_tables": (ctypes.c_int64, [c_vp, ctypes.c_int64]),
     "salve_bev_launch_count": (ctypes.c_int64, [c_vp]),
 }
 

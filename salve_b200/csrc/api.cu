@@ -161,7 +161,8 @@ static void compute_tables_libm(int H, int W, std::vector<double>& t) {
 // Tables of the local rule (k_image.cuh, LocalRule): every counter-clockwise triangle of three of the 12 near neighbours that
 // contains the query (the origin) and whose circle -- the lattice points strictly inside it and on it -- stays within the 5 x 5
 // neighbourhood; per 12-bit neighbour pattern the candidates whose vertices are present and which have none of the pattern's
-// sites strictly inside (at most four: more only when the W-E or N-S pair is present, which the edge rule takes first).
+// sites strictly inside (the first four: 224 patterns with co-circular sites at distance 2 have 7 or 14, and a query whose triangle
+// is one of the others simply goes on to the window pass).
 static const std::vector<uint32_t>& local_rule_tables() {
     static const std::vector<uint32_t> tab = [] {
         std::vector<uint32_t> t(LocalRule::WORDS, 0u);
@@ -1470,6 +1471,13 @@ extern "C" int salve_bev_last_timings(salve_bev_ctx* c, float* host_ms) {
         host_ms[SALVE_BEV_NTIMINGS - 1] += ms;
     }
     return SALVE_BEV_OK;
+}
+
+extern "C" int64_t salve_bev_local_rule_tables(uint32_t* host_words, int64_t n_words) {
+    const std::vector<uint32_t>& t = local_rule_tables();
+    if (host_words)
+        for (int64_t i = 0; i < n_words && i < (int64_t)t.size(); i++) host_words[i] = t[(size_t)i];
+    return (int64_t)t.size();
 }
 
 extern "C" int64_t salve_bev_launch_count(salve_bev_ctx* c) { return c ? c->launches : 0; }

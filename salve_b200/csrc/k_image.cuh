@@ -199,7 +199,7 @@ __host__ __device__ inline size_t image_smem_bytes(int h, int wpr) {
 // ---- local rule: queries whose Delaunay triangle has its three vertices among 12 near neighbours --------------------------
 // After the edge rule, two thirds of the remaining queries lie in a triangle whose vertices are all among the 8 neighbours and the
 // 4 pixels at distance 2 on q's row and column, with a circumcircle that stays inside the 5 x 5 neighbourhood.  For them the
-// whole search is a table look-up on the 12 neighbour bits: the table gives the (at most 4) triangles of those neighbours that
+// whole search is a table look-up on the 12 neighbour bits: the table gives (up to 4 of) the triangles of those neighbours that
 // contain q and have none of the 12 strictly inside; a candidate is THE triangle of the canonical triangulation over q iff the
 // other lattice points strictly inside its circle (a 25-bit mask of the neighbourhood) are no sites and every site ON the circle
 // loses the symbolic-perturbation test -- the same certificate the window pass and the cooperative pass end with, so the result

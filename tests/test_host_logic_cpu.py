@@ -143,3 +143,71 @@ def test_bench_reference_arm_prints_the_contract_line():
     have_ref = os.path.isdir(os.path.join(root, "oracle", "_ref", "salve"))
     assert line["cpu_baseline"]["kind"] == ("reference" if have_ref else "port") and line["cpu_baseline"]["cores"] >= 1
     assert "workload" in line["config"] and line["gpu_launches"] == 0
+
+
+def test_local_rule_tables_against_an_independent_enumeration():
+    """The host-built tables of the local rule (include/salve_bev.h: salve_bev_local_rule_tables; k_image.cuh LocalRule) restated in
+    plain Python: the candidate triangles, their inside / on-circle masks over the 5 x 5 neighbourhood and, for every 12-bit
+    neighbour pattern, the first four candidates whose vertices are present and whose circle holds none of the pattern's sites."""
+    import ctypes
+    import itertools
+
+    from salve_b200 import _native as nat
+
+    lib = nat.load()
+    n = lib.salve_bev_local_rule_tables(None, 0)
+    NPAT, MAXC = 4096, 128
+    assert n == NPAT + 3 * MAXC
+    tab = np.zeros(n, np.uint32)
+    assert lib.salve_bev_local_rule_tables(tab.ctypes.data_as(ctypes.c_void_p), n) == n
+
+    pos = [(0, -2), (-1, -1), (0, -1), (1, -1), (-2, 0), (-1, 0), (1, 0), (2, 0), (-1, 1), (0, 1), (1, 1), (0, 2)]  # (dx, dy) of pattern bit k
+    bit = lambda p: (p[1] + 2) * 5 + p[0] + 2
+    orient = lambda a, b, c: (b[0] - a[0]) * (c[1] - a[1]) - (b[1] - a[1]) * (c[0] - a[0])
+
+    def incircle(a, b, c, d):
+        ax, ay, bx, by, cx, cy = a[0] - d[0], a[1] - d[1], b[0] - d[0], b[1] - d[1], c[0] - d[0], c[1] - d[1]
+        return (ax * ax + ay * ay) * (bx * cy - by * cx) - (bx * bx + by * by) * (ax * cy - ay * cx) + (cx * cx + cy * cy) * (ax * by - ay * bx)
+
+    cands = []
+    for i, j, k in itertools.combinations(range(12), 3):
+        a, b, c = pos[i], pos[j], pos[k]
+        o = orient(a, b, c)
+        if o == 0:
+            continue
+        if o < 0:
+            b, c = c, b
+        if min(orient(a, b, (0, 0)), orient(b, c, (0, 0)), orient(c, a, (0, 0))) < 0:
+            continue
+        inside = on = 0
+        fits = True
+        for y in range(-8, 9):
+            for x in range(-8, 9):
+                if (x, y) in (a, b, c):
+                    continue
+                inc = incircle(a, b, c, (x, y))
+                if inc < 0:
+                    continue
+                if max(abs(x), abs(y)) > 2:
+                    fits = False
+                elif (x, y) != (0, 0):
+                    if inc > 0:
+                        inside |= 1 << bit((x, y))
+                    else:
+                        on |= 1 << bit((x, y))
+        if fits:
+            cands.append(((a, b, c), (1 << i) | (1 << j) | (1 << k), inside, on))
+    assert len(cands) == 96
+    for cid, ((a, b, c), vmask, inside, on) in enumerate(cands):
+        assert int(tab[NPAT + cid]) == inside and int(tab[NPAT + MAXC + cid]) == on
+        assert int(tab[NPAT + 2 * MAXC + cid]) == bit(a) | (bit(b) << 5) | (bit(c) << 10)
+    in12 = [sum(1 << m for m in range(12) if inside & (1 << bit(pos[m]))) for _, _, inside, _ in cands]
+    n_truncated = 0
+    for pat in range(NPAT):
+        want = [cid for cid, (_, vmask, _, _) in enumerate(cands) if (pat & vmask) == vmask and not (pat & in12[cid])]
+        got = [(int(tab[pat]) >> (8 * s)) & 0xFF for s in range(4)]
+        assert got == (want[:4] + [0xFF] * 4)[:4], pat
+        n_truncated += len(want) > 4
+    # more than four viable candidates: 224 patterns with co-circular sites at distance 2 (the table keeps the first four; a query
+    # whose triangle is one of the others goes to the window pass -- coverage, not correctness)
+    assert n_truncated == 224
