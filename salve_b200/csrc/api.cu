@@ -479,7 +479,7 @@ static int stage_event(salve_bev_ctx* c, cudaStream_t st) {
     return SALVE_BEV_OK;
 }
 
-// Everything after the splat for images [0, n_img): the four stages of k_image.cuh (sites, prep, window, finish).
+// Everything after the splat for images [0, n_img): the six stages of k_image.cuh (sites, prep, local, window, shade, finish).
 static int run_image_stage(salve_bev_ctx* c, int n_img, const GridParams& G, uint32_t* keygrid, const uint8_t* const* color_src,
                            uint8_t* dev_out, int32_t* dev_counts, int32_t* dev_status, int raw_mode, int skip_empty, uint8_t* hull,
                            int32_t* qtri, cudaStream_t st, const int32_t* dest = nullptr, int32_t* counts_out = nullptr, bool clear_keys = false, bool timed = false) {

@@ -1,4 +1,4 @@
-// k_image.cuh -- everything after the splat, as a pipeline of four kernels over a chunk of BEV images:
+// k_image.cuh -- everything after the splat, as a pipeline of six kernels over a chunk of BEV images:
 //   winners -> site bit rows, sparse colours, emptiness / keep masks, convex hull,
 //   and the densification itself, with NO triangle mesh in memory.
 //
@@ -20,21 +20,23 @@
 // (perturbed) Delaunay triangulation over q -- bit-identical to rasterising the full mesh, but the
 // only state is the 32 KB occupancy bitmap of the image: no mesh, no atomics, no rounds.
 //
-// The four stages (one launch each per chunk; state between them lives in per-image global scratch that the next stage
+// The six stages (one launch each per chunk; state between them lives in per-image global scratch that the next stage
 // reads through L2):
-//   1 sites_stage_kernel   grid (rows / 8, images), a warp per BEV row: key grid -> winner colours (gather from the pano),
-//                          occupancy / non-empty bit rows, row summaries, the sparse image written with aligned 16-byte stores
-//                          from a row staged in shared memory.  Streaming, HBM bound, 48+ warps per SM.
+//   1 sites_stage_kernel   grid (rows / 32, images), a warp per BEV row: key grid (bulk copies, TMA engine) -> winner colours
+//                          (gather from the pano), occupancy / non-empty bit rows, row summaries, the sparse image written with
+//                          aligned 16-byte stores from a row staged in shared memory.  Streaming, HBM bound.
 //   2 prep_stage_kernel    a CTA per image: guards, exact convex hull (pre-filtered monotone chains), keep mask (separable
 //                          dilation), EDGE RULE (queries between two opposite 4-neighbour sites: mean of two colours) and the
 //                          list of the remaining query pixels.
-//   3 window_stage_kernel  persistent warps over ONE query list for the whole chunk (lanes are filled across image
+//   3 local_stage_kernel   LOCAL RULE: a table look-up on 12 neighbour bits + the empty-circle / perturbation certificate on the
+//                          5 x 5 neighbourhood resolves (and shades) two thirds of those queries; the rest goes on.
+//   4 window_stage_kernel  persistent warps over ONE query list for the whole chunk (lanes are filled across image
 //                          boundaries): small triangles, 7 x 32 window in registers, exact float interval classification;
 //                          what it cannot certify is handed on with the triangle it has reached.
-//   4 finish_stage_kernel  a CTA per image (most handed-on queries first): shades what the window pass resolved, then the
-//                          COOPERATIVE PASS (one warp per query, 32 rows per wave, cached violators, previous final
-//                          triangle as a start; a final triangle is shared by all deferred pixels inside it), masked-out
-//                          sites, counters, status.
+//   5 shade_stage_kernel   one thread per list entry: edge-rule means, exact barycentrics of what the window pass resolved.
+//   6 finish_stage_kernel  a CTA per image (most handed-on queries first): the COOPERATIVE PASS (one warp per query, 32 rows
+//                          per wave, cached violators, previous final triangle as a start; a final triangle is shared by all
+//                          deferred pixels inside it), masked-out sites, counters, status.
 // The closed convex hull decides which pixels are queries at all (outside it griddata gives NaN -> 0).
 #pragma once
 #include <type_traits>

@@ -1,6 +1,6 @@
 """Fixed workload for ncu: the bench step (or a smaller one), W warm-up passes + 1 profiled pass.
     python scripts/profile_step.py [n_hyp=640] [n_panos=40] [passes=2] [max_images=1480]
-With the defaults one pass is exactly one bench.py step: one launch each of splat_pano_kernel, the five stage kernels of the image
+With the defaults one pass is exactly one bench.py step: one launch each of splat_pano_kernel, the six stage kernels of the image
 pipeline (+ image_order_kernel) over 1 358 images (1 280 posed + 78 un-posed) and replicate_images_kernel.
 """
 import os
