@@ -62,6 +62,12 @@ namespace bev {
 #ifndef IMAGE_WIN_VINIT
 #define IMAGE_WIN_VINIT 1     // window pass: initial triangle on the column pair D-U when it is shorter than the row pair L-R
 #endif
+#ifndef IMAGE_WIN_MAXGAP
+#define IMAGE_WIN_MAXGAP 30   // window pass: widest row pair L-R a descent starts from (14: +0.03 ms in the finish stage, which then starts those queries from scratch)
+#endif
+#ifndef IMAGE_WIN_APEX_MASK
+#define IMAGE_WIN_APEX_MASK 0x01FFFF00u  // window pass: columns (bit 16 + dx) searched for the apex of the initial triangle: |dx| <= 8
+#endif
 #ifndef IMAGE_WIN_BLOCK
 #define IMAGE_WIN_BLOCK 256   // window pass: queries a warp takes from the chunk-wide list per atomic
 #endif
@@ -344,7 +350,7 @@ __global__ void __launch_bounds__(WIN_NT, IMAGE_WIN_CTAS) window_stage_kernel(Im
     constexpr int NROW = 2 * NR + 1;
     static_assert(NROW * 9 <= 64, "on-circle candidates are packed 9 bits per row into one 64-bit word");
     static_assert(WIN_MAX_IMAGES % WIN_NT == 0, "prefix table: whole entries per thread");
-    constexpr int MAXGAP = 14, MAXFLIPS = 16;
+    constexpr int MAXGAP = IMAGE_WIN_MAXGAP, MAXFLIPS = 16;
     constexpr int PER = WIN_MAX_IMAGES / WIN_NT;
     const unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -474,8 +480,8 @@ __global__ void __launch_bounds__(WIN_NT, IMAGE_WIN_CTAS) window_stage_kernel(Im
 #pragma unroll
                     for (int k = NR; k >= 1; k--) {
                         const uint32_t u = wr[NR + k], d = wr[NR - k];
-                        if (u & 0x01FFFF00u) { mu = u & 0x01FFFF00u; ku = k; }
-                        if (d & 0x01FFFF00u) { md = d & 0x01FFFF00u; kd = k; }
+                        if (u & IMAGE_WIN_APEX_MASK) { mu = u & IMAGE_WIN_APEX_MASK; ku = k; }
+                        if (d & IMAGE_WIN_APEX_MASK) { md = d & IMAGE_WIN_APEX_MASK; kd = k; }
                         if (u & 0x10000u) yu = k;
                         if (d & 0x10000u) yd = k;
                     }
